@@ -1,0 +1,220 @@
+"""Generate tests/golden/*.npz by running the REFERENCE VERBATIM (oracle/ref_loader.py).
+
+TEST INFRASTRUCTURE ONLY; runs only where /root/reference is mounted (the build container):
+
+    python -m oracle.make_goldens            # everything (the 1000x1000 target tile takes minutes)
+    python -m oracle.make_goldens --quick    # skip the 1000x1000 target-transform tile
+
+Inputs are NOT stored: they are regenerated from the seed by cdnet_b200/synth.py (bit-exact by
+construction) and each file records the sha1 digest of its inputs so a test can verify that.
+The 16-direction goldens are produced in a child process with dt_num_classes=16 in the
+environment, because the reference freezes that setting at import
+(data_prepare/SegFix_offset_helper.py:37-39).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+
+from cdnet_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+# (name, seed, H, W, n_target) -- post-processing tiles
+P_TILES = [
+    ("p_96x128", 11, 96, 128, 9),
+    ("p_200x150", 12, 200, 150, 22),
+    ("p_256", 100, 256, 256, None),
+    ("p_333x517", 13, 333, 517, None),
+    ("p_1000", 100, 1000, 1000, None),
+]
+# target-transform tiles: (name, seed, H, W, n_target)
+T_TILES = [
+    ("t_64_single", 21, 64, 64, 1),
+    ("t_128", 22, 128, 128, 12),
+    ("t_256", 5, 256, 256, 45),
+    ("t_250x300_dense", 23, 250, 300, 330),  # > 255 nuclei: uint8 id wrap
+    ("t_500", 1000, 500, 500, 120),
+]
+T_BIG = ("t_1000", 0, 1000, 1000, 700)
+
+
+def _save(name, meta, **arrays):
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, meta=np.asarray(json.dumps(meta)), **arrays)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024.0), flush=True)
+
+
+def gold_ddm(ns):
+    rng = np.random.default_rng(42)
+    out, meta = {}, {"cases": []}
+    for cls in (5, 9, 17):
+        for i, (H, W) in enumerate(((37, 53), (64, 64), (1, 9), (9, 1))):
+            x = rng.integers(0, cls, size=(H, W)).astype(np.uint8)
+            x[rng.integers(0, 3, size=(H, W)) == 0] = 0
+            key = "c%d_%d" % (cls, i)
+            out[key + "_in"] = x
+            out[key + "_out"] = ns.generate_dd_map(x, cls)
+            meta["cases"].append([key, cls])
+        for key, x in (("c%d_zero" % cls, np.zeros((6, 7), np.uint8)),
+                       ("c%d_const" % cls, np.full((6, 7), 1, np.uint8))):
+            out[key + "_in"] = x
+            out[key + "_out"] = ns.generate_dd_map(x, cls)
+            meta["cases"].append([key, cls])
+    # a real-looking one
+    d = synth.postproc_inputs(100, 256, 256)
+    out["tta0_in"] = d["dcm"][0]
+    out["tta0_out"] = ns.generate_dd_map(d["dcm"][0], 9)
+    meta["cases"].append(["tta0", 9])
+    m = rng.integers(-3, 4, size=(2, 6, 8))
+    shifts = [(1, 1, 1), (1, 1, 0), (2, 1, 1), (3, 0, 1), (4, 0, 1), (3, 1, 1), (3, 1, 0), (4, 1, 1),
+              (1, 2, 3), (4, 0, 0)]
+    out["cs_in"] = m
+    for i, (dd, s1, s2) in enumerate(shifts):
+        out["cs_%d" % i] = ns.circshift(m, dd, s1, s2)
+    meta["circshift"] = shifts
+    _save("ddm", meta, **out)
+
+
+def gold_postproc(ns, quick):
+    for name, seed, H, W, n in P_TILES:
+        t0 = time.time()
+        d = synth.postproc_inputs(seed, H, W, n)
+        meta = {"seed": seed, "H": H, "W": W, "n_target": n, "direction_classes": 9, "min_area": 20,
+                "radius": 2, "digest": synth.digest(d["dcm"], d["prob"], d["point"])}
+        arrays = {}
+        for pp in (0, 1):
+            r = ns.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
+            arrays["dam_pp%d_labels" % pp] = r["pred_labeled"].astype(np.int32)
+            arrays["dam_pp%d_dtype" % pp] = np.asarray(str(r["pred_labeled"].dtype))
+            if pp == 0:
+                arrays["dam_inside"] = np.packbits(r["pred_inside"])
+                arrays["dam_pred2"] = np.packbits(r["pred2"].astype(bool))
+                arrays["dam_ddm_mean16"] = np.round(r["prob_direction_maps"][0] * 16).astype(np.uint8)
+            r = ns.plain_postprocess(d["prob"].copy(), 20, 2, pp)
+            arrays["plain_pp%d_labels" % pp] = r["pred_labeled"].astype(np.int32)
+            arrays["plain_pp%d_dtype" % pp] = np.asarray(str(r["pred_labeled"].dtype))
+        # watershed order exposure: pixels whose label depends on heap mechanics
+        ref_loader.set_watershed_order("heap")
+        rh = ns.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1)
+        ref_loader.set_watershed_order("stable")
+        meta["ws_heap_vs_stable_diff_px"] = int((rh["pred_labeled"] != arrays["dam_pp1_labels"]).sum())
+        meta["seconds"] = round(time.time() - t0, 2)
+        _save(name, meta, **arrays)
+
+
+def gold_process(ns):
+    """postproc_other.process on raw masks incl. edge cases."""
+    out, meta = {}, {"cases": []}
+    rng = np.random.default_rng(7)
+    cases = {}
+    ids = synth.instance_map(31, 180, 220, 40)
+    cases["blobs"] = (ids > 0)
+    m = np.zeros((60, 80), bool)
+    cases["empty"] = m.copy()
+    m2 = m.copy(); m2[20:45, 30:60] = True; m2[30:34, 40:44] = False
+    cases["holed_rect"] = m2
+    m3 = m.copy(); m3[0:25, 0:30] = True; m3[40:60, 60:80] = True
+    cases["border"] = m3
+    m4 = m.copy(); m4[10:30, 10:30] = True; m4[30:50, 30:50] = True  # diagonal-only contact
+    cases["diag"] = m4
+    m5 = m.copy(); m5[5:8, 5:8] = True; m5[20, 20] = True
+    cases["tiny"] = m5
+    yy, xx = np.mgrid[0:90, 0:140]
+    dumb = ((yy - 45) ** 2 + (xx - 45) ** 2 <= 28 ** 2) | ((yy - 45) ** 2 + (xx - 95) ** 2 <= 28 ** 2)
+    cases["dumbbell"] = dumb
+    cases["noise"] = rng.integers(0, 4, size=(70, 90)) > 0
+    for key, mask in cases.items():
+        for ms in (5, 10):
+            src = mask.astype(np.uint8) * 255
+            res = ns.process(src.copy(), "modelName", min_size=ms)
+            out["%s_ms%d" % (key, ms)] = res.astype(np.int32)
+        res = ns.process(mask.astype(np.uint8) * 255, "unet", min_size=10)
+        out["%s_unet" % key] = res.astype(np.int32)
+        out["%s_in" % key] = np.packbits(mask)
+        meta["cases"].append([key, list(mask.shape)])
+    _save("process", meta, **out)
+
+
+def gold_centre(ns):
+    out, meta = {}, {"cases": []}
+    ids = synth.instance_map(33, 120, 160, 14)
+    for k in range(1, int(ids.max()) + 1):
+        m = (ids == k).astype(np.int64)
+        c = ns.get_centerpoint2(m, m.shape[0], m.shape[1])
+        out["c_%d" % k] = np.asarray(c, dtype=np.int64)
+    out["ids"] = ids
+    meta["n"] = int(ids.max())
+    _save("centre", meta, **out)
+
+
+def _t_case(ns, name, seed, H, W, n, num_classes):
+    t0 = time.time()
+    ids = synth.instance_map(seed, H, W, n)
+    lab = synth.as_uint8_label(ids)
+    res = ns.LabelEncoding(3, 1, 1)((None, None, lab))
+    meta = {"seed": seed, "H": H, "W": W, "n_target": n, "num_classes": num_classes,
+            "n_instances": int(ids.max()), "digest": synth.digest(lab),
+            "seconds": round(time.time() - t0, 2)}
+    assert res[4].dtype == np.int64 and res[3].dtype == np.float16
+    _save(name, meta, ternary=np.asarray(res[2]), point=res[3], direction=res[4].astype(np.uint8))
+
+
+def gold_targets(ns, quick, num_classes):
+    sfx = "" if num_classes == 8 else "_d%d" % num_classes
+    tiles = T_TILES if num_classes == 8 else T_TILES[1:3]
+    for name, seed, H, W, n in tiles:
+        _t_case(ns, name + sfx, seed, H, W, n, num_classes)
+    if num_classes == 8:
+        # three-class input (values {0,255}) -> measure.label branch, my_transforms_direction.py:763-774
+        ids = synth.instance_map(24, 128, 160, 14)
+        lab3 = np.repeat(((ids > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+        res = ns.LabelEncoding(3, 1, 1)((None, None, lab3))
+        _save("t_128x160_threeclass", {"seed": 24, "H": 128, "W": 160, "n_target": 14,
+                                       "num_classes": 8, "digest": synth.digest(lab3)},
+              ternary=np.asarray(res[2]), point=res[3], direction=res[4].astype(np.uint8))
+        if not quick:
+            _t_case(ns, T_BIG[0], *T_BIG[1:], num_classes=8)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--child16", action="store_true")
+    a = ap.parse_args()
+    if a.child16:
+        assert os.environ.get("dt_num_classes") == "16"
+        ns = ref_loader.load()
+        assert ns.DTOffsetConfig.num_classes == 16
+        gold_targets(ns, True, 16)
+        return
+    ns = ref_loader.load()
+    assert ns.DTOffsetConfig.num_classes == 8
+    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16"]
+    if "ddm" in todo:
+        gold_ddm(ns)
+    if "process" in todo:
+        gold_process(ns)
+    if "centre" in todo:
+        gold_centre(ns)
+    if "postproc" in todo:
+        gold_postproc(ns, a.quick)
+    if "targets" in todo:
+        gold_targets(ns, a.quick, 8)
+    if "t16" in todo:
+        env = dict(os.environ, dt_num_classes="16")
+        subprocess.check_call([sys.executable, "-m", "oracle.make_goldens", "--child16"], env=env,
+                              cwd=REPO)
+
+
+if __name__ == "__main__":
+    main()
