@@ -1,0 +1,422 @@
+"""Host-side mirror of the reference's callables for the geometry hot path.
+
+Same names, argument meaning, return dtypes/shapes and error behaviour as honglianghe/CDNet, but
+every computation runs in hand-written sm_100a kernels behind the C ABI of libcdnet_b200.so
+(include/cdnet_b200.h).  PyTorch is used only for device memory, pinned staging and streams.
+
+numpy in / numpy out ("drop-in") functions:
+    generate_dd_map, circshift                data_prepare/getDirectionDiffMap.py:14-108
+    process                                   postproc_other.py:15-54
+    dam_postprocess                           test_dam.py:455-563 (inline block, wrapped)
+    plain_postprocess                         test.py:270-295   (inline block, wrapped)
+    label, binary_fill_holes, remove_small_objects, dilation, distance_transform_edt
+                                              the scipy / scikit-image calls on the path
+Device-resident batched variants (`*_cuda`, torch CUDA tensors [B,...]) keep the data on the GPU
+between the CNN and the post-processing, and `DamPostprocessPlan` pre-allocates pinned staging +
+device buffers for repeated host-buffer calls (what bench.py's e2e measures).
+"""
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import CdnetError, check
+
+_ws_cache = {}
+_dev_checked = set()
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise CdnetError("cdnet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
+        if not isinstance(device, torch.device) else device
+    if dev.index not in _dev_checked:
+        if not _cabi.lib().cdnet_device_ok(dev.index):
+            raise CdnetError("device %s is not a compute-capability 10.x GPU; libcdnet_b200 is sm_100a-only" % dev)
+        _dev_checked.add(dev.index)
+    return dev
+
+
+def _workspace(nbytes, dev):
+    key = dev.index
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _ws_cache[key] = None
+        buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _cu8(t):
+    return t.contiguous() if t.dtype == torch.uint8 else t.to(torch.uint8).contiguous()
+
+
+def launch_count():
+    return int(_cabi.lib().cdnet_launch_count())
+
+
+# =====================================================================================================
+# device-resident batched API
+# =====================================================================================================
+def ddm_cuda(cls, direction_classes, return_status=False):
+    """cls uint8 [B,H,W] CUDA -> float32 [B,H,W] (generate_dd_map per tile)."""
+    L = _cabi.lib()
+    dev = _device(cls.device)
+    cls = _cu8(cls)
+    B, H, W = cls.shape
+    out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    nb = L.cdnet_ddm_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_ddm(_ptr(cls), _ptr(out), _ptr(status), B, H, W, int(direction_classes), _ptr(ws), ws.numel(),
+                      _stream()), "cdnet_ddm")
+    return (out, status) if return_status else out
+
+
+def label_cuda(mask, connectivity=4, return_num=False):
+    """mask [B,H,W] (non-zero = foreground) -> int32 labels, raster-first ids."""
+    L = _cabi.lib()
+    dev = _device(mask.device)
+    m = _cu8(mask != 0) if mask.dtype != torch.uint8 else mask.contiguous()
+    B, H, W = m.shape
+    out = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    n = torch.zeros((B,), dtype=torch.int32, device=dev)
+    nb = L.cdnet_ccl_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_ccl(_ptr(m), _ptr(out), _ptr(n), B, H, W, int(connectivity), _ptr(ws), ws.numel(), _stream()),
+          "cdnet_ccl")
+    return (out, n) if return_num else out
+
+
+def fill_holes_cuda(mask):
+    L = _cabi.lib()
+    dev = _device(mask.device)
+    m = _cu8(mask != 0) if mask.dtype != torch.uint8 else mask.contiguous()
+    B, H, W = m.shape
+    out = torch.empty_like(m)
+    nb = L.cdnet_fill_holes_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_fill_holes(_ptr(m), _ptr(out), B, H, W, _ptr(ws), ws.numel(), _stream()), "cdnet_fill_holes")
+    return out
+
+
+def remove_small_mask_cuda(mask, min_size):
+    L = _cabi.lib()
+    dev = _device(mask.device)
+    m = _cu8(mask != 0) if mask.dtype != torch.uint8 else mask.contiguous()
+    B, H, W = m.shape
+    out = torch.empty_like(m)
+    nb = L.cdnet_remove_small_mask_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_remove_small_mask(_ptr(m), _ptr(out), B, H, W, int(min_size), _ptr(ws), ws.numel(), _stream()),
+          "cdnet_remove_small_mask")
+    return out
+
+
+def remove_small_labels_cuda(labels, min_size):
+    """int32 [B,H,W] labels (values in [0, H*W]) -> copy with small labels zeroed."""
+    L = _cabi.lib()
+    dev = _device(labels.device)
+    out = labels.to(torch.int32).contiguous().clone()
+    B, H, W = out.shape
+    nb = L.cdnet_remove_small_labels_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_remove_small_labels(_ptr(out), B, H, W, int(min_size), _ptr(ws), ws.numel(), _stream()),
+          "cdnet_remove_small_labels")
+    return out
+
+
+def label_dilate_cuda(labels, radius, out_dtype=torch.int32):
+    L = _cabi.lib()
+    dev = _device(labels.device)
+    lab = labels.to(torch.int32).contiguous()
+    B, H, W = lab.shape
+    out = torch.empty((B, H, W), dtype=out_dtype, device=dev)
+    check(L.cdnet_label_dilate(_ptr(lab), _ptr(out), out.element_size(), B, H, W, int(radius), _stream()),
+          "cdnet_label_dilate")
+    return out
+
+
+def edt_cuda(mask, return_squared=False):
+    """exact EDT: float64 [B,H,W] (and the int32 squared distances)."""
+    L = _cabi.lib()
+    dev = _device(mask.device)
+    m = _cu8(mask != 0) if mask.dtype != torch.uint8 else mask.contiguous()
+    B, H, W = m.shape
+    d2 = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    dist = torch.empty((B, H, W), dtype=torch.float64, device=dev)
+    nb = L.cdnet_edt_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_edt(_ptr(m), _ptr(d2), _ptr(dist), B, H, W, _ptr(ws), ws.numel(), _stream()), "cdnet_edt")
+    return (dist, d2) if return_squared else dist
+
+
+def process_cuda(pred01, min_size=10, ws=True):
+    """pred01 uint8 [B,H,W] already binarised -> int32 labels (postproc_other.process)."""
+    L = _cabi.lib()
+    dev = _device(pred01.device)
+    m = _cu8(pred01)
+    B, H, W = m.shape
+    out = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    nb = L.cdnet_ws_postproc_workspace_bytes(B, H, W)
+    wsb = _workspace(nb, dev)
+    check(L.cdnet_ws_postproc(_ptr(m), _ptr(out), _ptr(status), B, H, W, int(min_size), 1 if ws else 0, _ptr(wsb),
+                              wsb.numel(), _stream()), "cdnet_ws_postproc")
+    return out
+
+
+def dam_postprocess_cuda(dcm, prob, point, direction_classes=9, min_area=20, radius=2, postproc=0,
+                         write_prob=False, out_dtype=None, out=None, status=None):
+    """dcm uint8 [B,8,H,W], prob float32 [B,3,H,W], point float32 [B,1,H,W] (CUDA) -> labels [B,H,W].
+    out_dtype defaults to what the reference returns: int64 (measure.label) for postproc 0, int32
+    (process) for postproc 1.  Returns (labels, status)."""
+    L = _cabi.lib()
+    dev = _device(dcm.device)
+    assert dcm.dtype == torch.uint8 and prob.dtype == torch.float32 and point.dtype == torch.float32
+    assert dcm.is_contiguous() and prob.is_contiguous() and point.is_contiguous()
+    B, T, H, W = dcm.shape
+    assert T == 8 and tuple(prob.shape) == (B, 3, H, W) and point.numel() == B * H * W
+    if out_dtype is None:
+        out_dtype = torch.int64 if int(postproc) == 0 else torch.int32
+    if out is None:
+        out = torch.empty((B, H, W), dtype=out_dtype, device=dev)
+    if status is None:
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+    nb = L.cdnet_dam_postproc_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_dam_postproc(_ptr(dcm), _ptr(prob), _ptr(point), _ptr(out), out.element_size(), _ptr(status), B, H,
+                               W, int(direction_classes), int(min_area), int(radius), int(postproc),
+                               1 if write_prob else 0, _ptr(ws), ws.numel(), _stream()), "cdnet_dam_postproc")
+    return out, status
+
+
+def plain_postprocess_cuda(prob, min_area=20, radius=2, postproc=0, multi_class=True, out_dtype=None):
+    L = _cabi.lib()
+    dev = _device(prob.device)
+    assert prob.dtype == torch.float32 and prob.is_contiguous()
+    B, C, H, W = prob.shape
+    if out_dtype is None:
+        out_dtype = torch.int64 if int(postproc) == 0 else torch.int32
+    out = torch.empty((B, H, W), dtype=out_dtype, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    nb = L.cdnet_plain_postproc_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_plain_postproc(_ptr(prob), C, _ptr(out), out.element_size(), _ptr(status), B, H, W,
+                                 1 if multi_class else 0, int(min_area), int(radius), int(postproc), _ptr(ws),
+                                 ws.numel(), _stream()), "cdnet_plain_postproc")
+    return out, status
+
+
+# =====================================================================================================
+# numpy drop-ins (reference signatures)
+# =====================================================================================================
+def _h2d(a, dtype=None):
+    a = np.ascontiguousarray(a) if dtype is None else np.ascontiguousarray(a, dtype=dtype)
+    return torch.from_numpy(a).to(_device(), non_blocking=False)
+
+
+def generate_dd_map(label_direction, direction_classes):
+    """data_prepare/getDirectionDiffMap.py:44-108.  [H,W] integer class map -> float32 [H,W];
+    NaN for a constant map, like the reference's 0/0."""
+    lab = np.asarray(label_direction)
+    assert lab.ndim == 2
+    # class ids outside 0..255 are unknown to label_to_vector (zero vector) -> any id >= n works
+    cls = np.where((lab >= 0) & (lab < 255), lab, 255).astype(np.uint8) if lab.dtype != np.uint8 else lab
+    out = ddm_cuda(_h2d(cls)[None], direction_classes)
+    return out[0].cpu().numpy()
+
+
+def circshift(matrix_ori, direction, shiftnum1, shiftnum2):
+    """data_prepare/getDirectionDiffMap.py:14-42: zero-filled shift of a [C,H,W] array."""
+    m = np.ascontiguousarray(matrix_ori)
+    assert m.ndim == 3 and m.dtype.itemsize in (1, 2, 4, 8)
+    L = _cabi.lib()
+    view = {1: np.uint8, 2: np.uint16, 4: np.int32, 8: np.int64}[m.dtype.itemsize]
+    src = _h2d(m.view(view))
+    dst = torch.empty_like(src)
+    C, H, W = m.shape
+    check(L.cdnet_circshift(_ptr(src), _ptr(dst), C, H, W, m.dtype.itemsize, int(direction), int(shiftnum1),
+                            int(shiftnum2), _stream()), "cdnet_circshift")
+    return dst.cpu().numpy().view(m.dtype)
+
+
+def label(input, connectivity=None, return_num=False):
+    """skimage.measure.label (default: 8-connected, int64) for a binary image; pass connectivity=1
+    for scipy.ndimage.label semantics (4-connected, int32)."""
+    x = np.asarray(input)
+    conn = 8 if (connectivity is None or connectivity == 2) else 4
+    lab, n = label_cuda(_h2d((x != 0).astype(np.uint8))[None], conn, return_num=True)
+    res = lab[0].cpu().numpy()
+    res = res.astype(np.int64) if conn == 8 else res
+    return (res, int(n[0])) if return_num else res
+
+
+def binary_fill_holes(input):
+    """scipy.ndimage.binary_fill_holes -> bool [H,W]."""
+    x = np.asarray(input)
+    return fill_holes_cuda(_h2d((x != 0).astype(np.uint8))[None])[0].cpu().numpy().astype(bool)
+
+
+def remove_small_objects(ar, min_size=64, connectivity=1):
+    """skimage.morphology.remove_small_objects (bool: 4-connected components; int: values are labels)."""
+    ar = np.asarray(ar)
+    if min_size == 0:
+        return ar.copy()
+    if ar.dtype == bool:
+        assert connectivity == 1
+        return remove_small_mask_cuda(_h2d(ar.astype(np.uint8))[None], min_size)[0].cpu().numpy().astype(bool)
+    if not np.issubdtype(ar.dtype, np.integer):
+        raise TypeError("Only bool or integer image types are supported. Got %s." % ar.dtype)
+    if ar.size and ar.min() < 0:
+        raise ValueError("Negative value labels are not supported.")
+    if ar.size and ar.max() > ar.size:
+        raise CdnetError("label values above H*W are not supported by the CUDA histogram")
+    out = remove_small_labels_cuda(_h2d(ar.astype(np.int32))[None], min_size)[0].cpu().numpy()
+    return out.astype(ar.dtype)
+
+
+def dilation(image, selem=None, radius=None):
+    """skimage.morphology.dilation(label_image, disk(radius)); selem=None -> the cross (radius 1)."""
+    img = np.asarray(image)
+    if radius is None:
+        radius = 1 if selem is None else (np.asarray(selem).shape[0] - 1) // 2
+        if selem is not None:
+            r = radius
+            yy, xx = np.mgrid[-r:r + 1, -r:r + 1]
+            if not np.array_equal(np.asarray(selem) != 0, (xx * xx + yy * yy) <= r * r):
+                raise CdnetError("only disk(r) footprints are supported")
+    if img.size and img.min() < 0:
+        raise CdnetError("label images must be non-negative")
+    out = label_dilate_cuda(_h2d(img.astype(np.int32))[None], radius)[0].cpu().numpy()
+    return out.astype(img.dtype)
+
+
+def distance_transform_edt(input):
+    """scipy.ndimage.distance_transform_edt -> float64 [H,W]."""
+    x = np.asarray(input)
+    return edt_cuda(_h2d((x != 0).astype(np.uint8))[None])[0].cpu().numpy()
+
+
+def process(pred, model_mode, min_size=10, ws=True):
+    """postproc_other.process (postproc_other.py:15-54).  Binarises `pred` IN PLACE like the reference
+    (:31-32) and returns int32 labels (ids keep gaps)."""
+    if model_mode == "dcan":
+        raise NotImplementedError("the dcan branch (postproc_other.py:69-97) is out of scope")
+    if model_mode == "micronet":
+        raise NotImplementedError("the micronet tail (postproc_other.py:56-68) is out of scope")
+    assert len(pred.shape) == 2, "Prediction shape is not HW"
+    hi = pred > 0.5
+    pred[hi] = 1
+    pred[~hi] = 0
+    if model_mode == "unet":
+        ws = False
+    return process_cuda(_h2d(hi.astype(np.uint8))[None], min_size, ws)[0].cpu().numpy()
+
+
+class DamPostprocessPlan(object):
+    """Pre-allocated pinned staging + device buffers for repeated host-buffer calls of the
+    direction-aware post-processing on B tiles of H x W (test_dam.py:455-563).
+
+    Fill `h_dcm` [B,8,H,W] u8, `h_prob` [B,3,H,W] f32, `h_point` [B,1,H,W] f32 (pinned numpy views),
+    call `run()`, read `h_labels` [B,H,W]."""
+
+    def __init__(self, B, H, W, direction_classes=9, min_area=20, radius=2, postproc=0, write_prob=False,
+                 device=None, out_dtype=None):
+        self.dev = _device(device)
+        self.args = (int(direction_classes), int(min_area), int(radius), int(postproc), bool(write_prob))
+        if out_dtype is None:
+            out_dtype = torch.int64 if int(postproc) == 0 else torch.int32
+        pin = dict(pin_memory=True)
+        self.t_dcm = torch.empty((B, 8, H, W), dtype=torch.uint8, **pin)
+        self.t_prob = torch.empty((B, 3, H, W), dtype=torch.float32, **pin)
+        self.t_point = torch.empty((B, 1, H, W), dtype=torch.float32, **pin)
+        self.t_labels = torch.empty((B, H, W), dtype=out_dtype, **pin)
+        self.t_status = torch.zeros((B,), dtype=torch.int32, **pin)
+        self.h_dcm, self.h_prob, self.h_point = self.t_dcm.numpy(), self.t_prob.numpy(), self.t_point.numpy()
+        self.h_labels, self.h_status = self.t_labels.numpy(), self.t_status.numpy()
+        self.d_dcm = torch.empty_like(self.t_dcm, device=self.dev)
+        self.d_prob = torch.empty_like(self.t_prob, device=self.dev)
+        self.d_point = torch.empty_like(self.t_point, device=self.dev)
+        self.d_labels = torch.empty_like(self.t_labels, device=self.dev)
+        self.d_status = torch.zeros((B,), dtype=torch.int32, device=self.dev)
+        self.h2d_bytes = self.t_dcm.numel() + 4 * self.t_prob.numel() + 4 * self.t_point.numel()
+        self.d2h_bytes = self.t_labels.numel() * self.t_labels.element_size() + 4 * B
+
+    def launch(self):
+        """H2D, kernels, D2H -- all asynchronous on the current stream."""
+        self.d_dcm.copy_(self.t_dcm, non_blocking=True)
+        self.d_prob.copy_(self.t_prob, non_blocking=True)
+        self.d_point.copy_(self.t_point, non_blocking=True)
+        self.launch_device()
+        self.t_labels.copy_(self.d_labels, non_blocking=True)
+        self.t_status.copy_(self.d_status, non_blocking=True)
+        if self.args[4]:
+            self.t_prob[:, 2].copy_(self.d_prob[:, 2], non_blocking=True)
+
+    def launch_device(self):
+        """kernels only, inputs already resident in d_dcm / d_prob / d_point."""
+        dc, ma, ra, pp, wp = self.args
+        dam_postprocess_cuda(self.d_dcm, self.d_prob, self.d_point, dc, ma, ra, pp, wp, out=self.d_labels,
+                             status=self.d_status)
+
+    def run(self):
+        self.launch()
+        torch.cuda.current_stream().synchronize()
+        if (self.h_status & _cabi.S_DDM_CONSTANT).any():
+            # the reference: NaN direction-difference map -> `assert(np.min(enhanced_boundary) >= 0)` fails
+            raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
+        return self.h_labels
+
+
+_plans = {}
+
+
+def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_area=20, radius=2, postproc=0,
+                    model_name="modelName", mutate_prob=True):
+    """test_dam.py:455-563 as a function.
+
+    prob_maps  float32 [3,H,W]  (channel 2 is overwritten in place with the boosted boundary
+                                probability, like the reference does at :536, unless mutate_prob=False)
+    point_maps float32 [1,H,W]
+    dcm_tta    uint8 [8,H,W] or [H,W,8]: prob_dcm, _hf, _vf, _hvf, _r90, _r90_hf, _r90_vf, _r90_hvf
+    Returns pred_labeled [H,W]: int64 (postproc 0, measure.label) or int32 (postproc 1, process)."""
+    if model_name in ("unet", "micronet", "dcan") and int(postproc) == 1:
+        raise NotImplementedError("postproc=1 with model_mode %r is out of scope" % model_name)
+    prob = np.asarray(prob_maps)
+    H, W = prob.shape[1:]
+    dcm = np.asarray(dcm_tta)
+    if dcm.shape == (H, W, 8) and dcm.shape != (8, H, W):
+        dcm = np.moveaxis(dcm, 2, 0)
+    key = (H, W, int(direction_classes), int(min_area), int(radius), int(postproc), bool(mutate_prob),
+           torch.cuda.current_device())
+    plan = _plans.get(key)
+    if plan is None:
+        _plans.clear()
+        plan = _plans[key] = DamPostprocessPlan(1, H, W, direction_classes, min_area, radius, postproc,
+                                                write_prob=mutate_prob)
+    plan.h_dcm[0] = dcm
+    plan.h_prob[0] = prob
+    plan.h_point[0] = np.asarray(point_maps).reshape(1, H, W)
+    labels = plan.run()[0].copy()
+    if mutate_prob and isinstance(prob_maps, np.ndarray):
+        prob_maps[2, :, :] = plan.h_prob[0, 2]
+    return labels
+
+
+def plain_postprocess(prob_maps, min_area=20, radius=2, postproc=0, model_name="modelName", multi_class=True):
+    """test.py:270-295 as a function -> pred_labeled [H,W] (int64 for postproc 0, int32 for 1)."""
+    if model_name in ("unet", "micronet", "dcan") and int(postproc) == 1:
+        raise NotImplementedError("postproc=1 with model_mode %r is out of scope" % model_name)
+    prob = _h2d(np.asarray(prob_maps), np.float32)[None]
+    out, _ = plain_postprocess_cuda(prob, min_area, radius, postproc, multi_class)
+    return out[0].cpu().numpy()

@@ -1,0 +1,426 @@
+// ccl.cu -- union-find connected components with canonical raster-order numbering (K6-K8).
+//
+// Replaces scipy.ndimage.label (4-conn; postproc_other.py:37,44), skimage.measure.label (8-conn;
+// test_dam.py:561, test.py:292, my_transforms_direction.py:755,773), scipy binary_fill_holes
+// (test_dam.py:546, test.py:277, postproc_other.py:42,51) and skimage remove_small_objects
+// (test_dam.py:548, test.py:279, postproc_other.py:46,48,53).
+//
+// Design: one int32 parent plane L per tile.  (1) init: every pixel points at the first pixel of
+// its horizontal run inside its 32-pixel warp segment (ballot + clz, no memory traffic besides the
+// store); (2) merge: only the links that are not implied by a neighbour are united with an
+// atomicMin union-find (first column of each vertical overlap, warp-segment seams, non-redundant
+// diagonals); links always point to the smaller index so the root is the component's first raster
+// pixel; (3) flatten.  Ids = rank of the root among roots in raster order: per-row root counts
+// (ballot/popc), an exclusive scan over rows, and a per-row running rank.
+//
+// fill holes / remove small / 8-connected labelling of the inference post-processing run on ONE
+// forest: equal-value 4-connected components of the mask (foreground and background alike) ->
+// background components that do not touch the frame are holes -> holes are united with their
+// foreground neighbours -> areas -> small components dropped -> surviving components that touch
+// diagonally are united -> numbering.
+#include "internal.h"
+
+namespace cdnet {
+
+constexpr int kBX = 128, kBY = 4;
+#define CCL_COORDS                                             \
+    const int x = blockIdx.x * kBX + threadIdx.x;              \
+    const int y = blockIdx.y * kBY + threadIdx.y;              \
+    const int b = blockIdx.z;                                  \
+    const bool inb = (x < W) && (y < H);                       \
+    const size_t tile = (size_t)b * H * W;                     \
+    const int p = y * W + x;                                   \
+    const int lane = threadIdx.x & 31;                         \
+    (void)lane; (void)p; (void)tile; (void)inb;
+
+static inline dim3 ccl_grid(int B, int H, int W) { return dim3(ceil_div(W, kBX), ceil_div(H, kBY), B); }
+static inline dim3 ccl_block() { return dim3(kBX, kBY); }
+
+// EQ = false: foreground-only components (mask != 0).  EQ = true: equal-value components of a 0/1 mask.
+template <bool EQ>
+__global__ void __launch_bounds__(kBX* kBY) k_ccl_init(const uint8_t* __restrict__ mask, int* __restrict__ L,
+                                                       int* __restrict__ zero1, int* __restrict__ zero2, int H, int W) {
+    CCL_COORDS
+    const int v = inb ? (mask[tile + p] != 0) : -1;
+    const int vl = __shfl_up_sync(0xffffffffu, v, 1);
+    const bool link = inb && lane > 0 && (EQ ? (v == vl) : (v && vl == 1));
+    const unsigned m = __ballot_sync(0xffffffffu, link);
+    if (!inb) return;
+    const int cnt = __clz(~(m << (31 - lane)));  // consecutive linked lanes ending at this one
+    L[tile + p] = p - cnt;
+    if (zero1) zero1[tile + p] = 0;
+    if (zero2) zero2[tile + p] = 0;
+}
+
+template <bool EQ, int CONN>
+__global__ void __launch_bounds__(kBX* kBY) k_ccl_merge(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W) {
+    CCL_COORDS
+    if (!inb) return;
+    const uint8_t* M = mask + tile;
+    int* Lt = L + tile;
+    const int v = M[p] != 0;
+    if (!EQ && !v) return;
+    auto same = [&](int q) -> bool { const int u = M[q] != 0; return EQ ? (u == v) : (u != 0); };
+    const bool hl = x > 0 && same(p - 1);
+    if (hl && lane == 0) uf_union(Lt, p, p - 1);  // seam between two warp segments of one run
+    if (y > 0) {
+        const bool up = same(p - W);
+        if (up) {
+            // implied by the left neighbour's own vertical link when all four pixels agree
+            const bool redundant = hl && same(p - W - 1);
+            if (!redundant) uf_union(Lt, p, p - W);
+        } else if (CONN == 8) {
+            if (x > 0 && !hl && same(p - W - 1)) uf_union(Lt, p, p - W - 1);
+            if (x + 1 < W && same(p - W + 1) && !same(p + 1)) uf_union(Lt, p, p - W + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBX* kBY) k_flatten(int* __restrict__ L, int H, int W) {
+    CCL_COORDS
+    if (!inb) return;
+    int* Lt = L + tile;
+    Lt[p] = uf_find(Lt, p);
+}
+
+// ---- numbering ------------------------------------------------------------------------------------
+// flatten + count roots of kept pixels per row.  keep == nullptr: every pixel with L-root semantics
+// handled by the caller's mask `fg`.
+__global__ void __launch_bounds__(kBX* kBY) k_flatten_count(int* __restrict__ L, const uint8_t* __restrict__ keep,
+                                                            int* __restrict__ rowcnt, int H, int W) {
+    CCL_COORDS
+    bool root = false;
+    if (inb && keep[tile + p]) {
+        int* Lt = L + tile;
+        const int r = uf_find(Lt, p);
+        Lt[p] = r;
+        root = (r == p);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, root);
+    if (lane == 0 && m && y < H) atomicAdd(rowcnt + (size_t)b * H + y, __popc(m));
+}
+
+// exclusive scan of rowcnt over the H rows of each tile (in place); n_out[b] = total
+__global__ void __launch_bounds__(1024) k_scan_rows(int* __restrict__ rowcnt, int* __restrict__ n_out, int H) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int b = blockIdx.x;
+    int* rc = rowcnt + (size_t)b * H;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < H; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < H ? rc[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane == 31) s_warp[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += t;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int incl = s + (wid > 0 ? s_warp[wid - 1] : 0) + carry;
+        if (i < H) rc[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && n_out) n_out[b] = s_carry;
+}
+
+// one warp per row: idmap[root pixel] = 1 + number of roots before it in raster order
+__global__ void __launch_bounds__(256) k_assign_ids(const int* __restrict__ L, const uint8_t* __restrict__ keep,
+                                                    const int* __restrict__ rowbase, int* __restrict__ idmap, int H, int W) {
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.y;
+    if (y >= H) return;
+    const size_t tile = (size_t)b * H * W;
+    int running = rowbase[(size_t)b * H + y] + 1;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const int p = y * W + x;
+        const bool root = x < W && keep[tile + p] && L[tile + p] == p;
+        const unsigned m = __ballot_sync(0xffffffffu, root);
+        if (root) idmap[tile + p] = running + __popc(m & ((1u << lane) - 1));
+        running += __popc(m);
+    }
+}
+
+__global__ void __launch_bounds__(kBX* kBY) k_relabel(const int* __restrict__ L, const uint8_t* __restrict__ keep,
+                                                      const int* __restrict__ idmap, int* __restrict__ out, int H, int W) {
+    CCL_COORDS
+    if (!inb) return;
+    out[tile + p] = keep[tile + p] ? idmap[tile + L[tile + p]] : 0;
+}
+
+static int number_and_relabel(int32_t* L, const uint8_t* keep, int32_t* idmap, int32_t* rowcnt, int32_t* labels,
+                              int32_t* n_out, int B, int H, int W, cudaStream_t st) {
+    CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, sizeof(int32_t) * (size_t)B * H, st));
+    CDNET_LAUNCH(k_flatten_count, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, rowcnt, H, W);
+    CDNET_LAUNCH(k_scan_rows, B, 1024, 0, st, rowcnt, n_out, H);
+    CDNET_LAUNCH(k_assign_ids, dim3(ceil_div(H, 8), B), 256, 0, st, L, keep, rowcnt, idmap, H, W);
+    CDNET_LAUNCH(k_relabel, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, idmap, labels, H, W);
+    return last_error();
+}
+
+int ccl_forest_launch(const uint8_t* mask, int32_t* L, int B, int H, int W, int conn, cudaStream_t st) {
+    CDNET_LAUNCH(k_ccl_init<false>, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, (int*)nullptr, (int*)nullptr, H, W);
+    if (conn == 4) CDNET_LAUNCH((k_ccl_merge<false, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
+    else if (conn == 8) CDNET_LAUNCH((k_ccl_merge<false, 8>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
+    else return CDNET_E_BADARG;
+    return last_error();
+}
+
+int ccl_label_launch(const uint8_t* mask, int32_t* labels, int32_t* n_out, int32_t* L, int32_t* idmap,
+                     int32_t* rowcnt, int B, int H, int W, int conn, cudaStream_t st) {
+    int rc = ccl_forest_launch(mask, L, B, H, W, conn, st);
+    if (rc) return rc;
+    return number_and_relabel(L, mask, idmap, rowcnt, labels, n_out, B, H, W, st);
+}
+
+// ---- fill holes ----------------------------------------------------------------------------------
+// frame pixels that are background mark the root of their background component
+__global__ void k_border_touch(const uint8_t* __restrict__ mask, const int* __restrict__ L, int* __restrict__ touch,
+                               int H, int W) {
+    const int b = blockIdx.y;
+    const size_t tile = (size_t)b * H * W;
+    const int per = 2 * W + 2 * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+        int y, x;
+        if (i < W) { y = 0; x = i; }
+        else if (i < 2 * W) { y = H - 1; x = i - W; }
+        else if (i < 2 * W + H) { y = i - 2 * W; x = 0; }
+        else { y = i - 2 * W - H; x = W - 1; }
+        const int p = y * W + x;
+        if (mask[tile + p] == 0) touch[tile + uf_find(L + tile, p)] = 1;
+    }
+}
+
+// L <- roots; state = 1 foreground, 2 hole (background component that never reaches the frame), 0 else
+__global__ void __launch_bounds__(kBX* kBY) k_flatten_fill(const uint8_t* __restrict__ mask, int* __restrict__ L,
+                                                           const int* __restrict__ touch, uint8_t* __restrict__ state,
+                                                           int H, int W) {
+    CCL_COORDS
+    if (!inb) return;
+    int* Lt = L + tile;
+    const int r = uf_find(Lt, p);
+    Lt[p] = r;
+    const bool fg = mask[tile + p] != 0;
+    state[tile + p] = fg ? 1 : (touch[tile + r] ? 0 : 2);
+}
+
+int fill_holes_state_launch(const uint8_t* mask, uint8_t* state, int32_t* L, int32_t* touch, int B, int H, int W,
+                            cudaStream_t st) {
+    CDNET_LAUNCH(k_ccl_init<true>, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, (int*)nullptr, H, W);
+    CDNET_LAUNCH((k_ccl_merge<true, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
+    CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, mask, L, touch, H, W);
+    CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, state, H, W);
+    return last_error();
+}
+
+// hole pixels join every 4-adjacent foreground pixel -> forest of the filled mask's 4-conn components
+__global__ void __launch_bounds__(kBX* kBY) k_fill_merge(const uint8_t* __restrict__ state, int* __restrict__ L, int H, int W) {
+    CCL_COORDS
+    if (!inb) return;
+    const uint8_t* S = state + tile;
+    if (S[p] != 2) return;
+    int* Lt = L + tile;
+    if (y > 0 && S[p - W] == 1) uf_union(Lt, p, p - W);
+    if (x > 0 && S[p - 1] == 1) uf_union(Lt, p, p - 1);
+    if (x + 1 < W && S[p + 1] == 1) uf_union(Lt, p, p + 1);
+    if (y + 1 < H && S[p + W] == 1) uf_union(Lt, p, p + W);
+}
+
+// flatten + per-root pixel count of the pixels with state != 0 (warp-aggregated atomics)
+__global__ void __launch_bounds__(kBX* kBY) k_flatten_area(const uint8_t* __restrict__ state, int* __restrict__ L,
+                                                           int* __restrict__ area, int H, int W) {
+    CCL_COORDS
+    int r = -1;
+    if (inb && state[tile + p]) {
+        int* Lt = L + tile;
+        r = uf_find(Lt, p);
+        Lt[p] = r;
+    }
+    // lanes of one warp that share a root add once
+    const unsigned peers = __match_any_sync(0xffffffffu, r);
+    if (r >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(area + tile + r, __popc(peers));
+}
+
+__global__ void __launch_bounds__(kBX* kBY) k_keep_large(const uint8_t* __restrict__ state, const int* __restrict__ L,
+                                                         const int* __restrict__ area, uint8_t* __restrict__ keep,
+                                                         int min_area, int H, int W) {
+    CCL_COORDS
+    if (!inb) return;
+    keep[tile + p] = (state[tile + p] && area[tile + L[tile + p]] >= min_area) ? 1 : 0;
+}
+
+// kept 4-connected components that touch only diagonally are one 8-connected component
+__global__ void __launch_bounds__(kBX* kBY) k_diag_merge(const uint8_t* __restrict__ keep, int* __restrict__ L, int H, int W) {
+    CCL_COORDS
+    if (!inb || y == 0) return;
+    const uint8_t* K = keep + tile;
+    if (!K[p] || K[p - W]) return;
+    int* Lt = L + tile;
+    if (x > 0 && K[p - W - 1] && !K[p - 1]) uf_union(Lt, p, p - W - 1);
+    if (x + 1 < W && K[p - W + 1] && !K[p + 1]) uf_union(Lt, p, p - W + 1);
+}
+
+size_t fill_remove_label_workspace(int B, int H, int W) {
+    const size_t n = (size_t)B * H * W;
+    return 3 * pad256(n * 4) + 2 * pad256(n) + pad256((size_t)B * H * 4);
+}
+
+int fill_remove_label_launch(const uint8_t* inside, int32_t* labels, uint8_t* pred2_out, int B, int H, int W,
+                             int min_area, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t n = (size_t)B * H * W;
+    Arena ar(ws, ws_bytes);
+    int32_t* L = ar.take<int32_t>(n);
+    int32_t* aux1 = ar.take<int32_t>(n);  // frame-touch flags, later id map
+    int32_t* aux2 = ar.take<int32_t>(n);  // areas
+    uint8_t* state = ar.take<uint8_t>(n);
+    uint8_t* keep_ws = ar.take<uint8_t>(n);
+    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    uint8_t* keep = pred2_out ? pred2_out : keep_ws;
+    CDNET_LAUNCH(k_ccl_init<true>, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, aux2, H, W);
+    CDNET_LAUNCH((k_ccl_merge<true, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, H, W);
+    CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, aux1, H, W);
+    CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, state, H, W);
+    CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
+    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, H, W);
+    CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, keep, min_area, H, W);
+    CDNET_LAUNCH(k_diag_merge, ccl_grid(B, H, W), ccl_block(), 0, st, keep, L, H, W);
+    return number_and_relabel(L, keep, aux1, rowcnt, labels, nullptr, B, H, W, st);
+}
+
+// ---- integer remove_small_objects ------------------------------------------------------------------
+__global__ void k_label_hist(const int* __restrict__ labels, int* __restrict__ counts, size_t plane) {
+    const int b = blockIdx.y;
+    const int* Lb = labels + (size_t)b * plane;
+    int* cb = counts + (size_t)b * (plane + 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((plane + 31) & ~size_t(31));
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int v = i < plane ? Lb[i] : 0;
+        const unsigned peers = __match_any_sync(0xffffffffu, v);
+        if (v > 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(cb + v, __popc(peers));
+    }
+}
+__global__ void k_label_drop_small(int* __restrict__ labels, const int* __restrict__ counts, size_t plane, int min_size) {
+    const int b = blockIdx.y;
+    int* Lb = labels + (size_t)b * plane;
+    const int* cb = counts + (size_t)b * (plane + 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = Lb[i];
+        if (v > 0 && cb[v] < min_size) Lb[i] = 0;
+    }
+}
+
+int remove_small_labels_launch(int32_t* labels, int32_t* counts, int B, int H, int W, int min_size, cudaStream_t st) {
+    const size_t plane = (size_t)H * W;
+    CDNET_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * (plane + 1), st));
+    dim3 grid((unsigned)((plane + 256 * 4 - 1) / (256 * 4)), B);
+    CDNET_LAUNCH(k_label_hist, grid, 256, 0, st, labels, counts, plane);
+    CDNET_LAUNCH(k_label_drop_small, grid, 256, 0, st, labels, counts, plane, min_size);
+    return last_error();
+}
+
+__global__ void k_state_to_mask(const uint8_t* __restrict__ state, uint8_t* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = state[i] ? 1 : 0;
+}
+
+}  // namespace cdnet
+
+using namespace cdnet;
+
+static bool bad_dims(int B, int H, int W) { return B <= 0 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0; }
+
+extern "C" size_t cdnet_ccl_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    const size_t n = (size_t)B * H * W;
+    return 2 * pad256(n * 4) + pad256((size_t)B * H * 4);
+}
+
+extern "C" int cdnet_ccl(const uint8_t* mask, int32_t* labels, int32_t* n_out, int B, int H, int W, int connectivity,
+                         void* ws, size_t ws_bytes, void* stream) {
+    if (!mask || !labels || bad_dims(B, H, W) || (connectivity != 4 && connectivity != 8)) return CDNET_E_BADARG;
+    Arena ar(ws, ws_bytes);
+    const size_t n = (size_t)B * H * W;
+    int32_t* L = ar.take<int32_t>(n);
+    int32_t* idmap = ar.take<int32_t>(n);
+    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    return ccl_label_launch(mask, labels, n_out, L, idmap, rowcnt, B, H, W, connectivity, (cudaStream_t)stream);
+}
+
+extern "C" size_t cdnet_fill_holes_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    const size_t n = (size_t)B * H * W;
+    return 2 * pad256(n * 4) + pad256(n);
+}
+
+extern "C" int cdnet_fill_holes(const uint8_t* mask, uint8_t* out, int B, int H, int W, void* ws, size_t ws_bytes,
+                                void* stream) {
+    if (!mask || !out || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    Arena ar(ws, ws_bytes);
+    const size_t n = (size_t)B * H * W;
+    int32_t* L = ar.take<int32_t>(n);
+    int32_t* touch = ar.take<int32_t>(n);
+    uint8_t* state = ar.take<uint8_t>(n);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = fill_holes_state_launch(mask, state, L, touch, B, H, W, st);
+    if (rc) return rc;
+    const size_t blocks = (n + 1023) / 1024;
+    CDNET_LAUNCH(k_state_to_mask, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, state, out, n);
+    return last_error();
+}
+
+extern "C" size_t cdnet_remove_small_mask_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    const size_t n = (size_t)B * H * W;
+    return 2 * pad256(n * 4);
+}
+
+extern "C" int cdnet_remove_small_mask(const uint8_t* mask, uint8_t* out, int B, int H, int W, int min_size, void* ws,
+                                       size_t ws_bytes, void* stream) {
+    if (!mask || !out || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    Arena ar(ws, ws_bytes);
+    const size_t n = (size_t)B * H * W;
+    int32_t* L = ar.take<int32_t>(n);
+    int32_t* area = ar.take<int32_t>(n);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    CDNET_LAUNCH(k_ccl_init<false>, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, (int*)nullptr, H, W);
+    CDNET_LAUNCH((k_ccl_merge<false, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
+    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, H, W);
+    CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, out, min_size, H, W);
+    return last_error();
+}
+
+extern "C" size_t cdnet_remove_small_labels_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    return pad256((size_t)B * ((size_t)H * W + 1) * 4);
+}
+
+extern "C" int cdnet_remove_small_labels(int32_t* labels, int B, int H, int W, int min_size, void* ws, size_t ws_bytes,
+                                         void* stream) {
+    if (!labels || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    Arena ar(ws, ws_bytes);
+    int32_t* counts = ar.take<int32_t>((size_t)B * ((size_t)H * W + 1));
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    return remove_small_labels_launch(labels, counts, B, H, W, min_size, (cudaStream_t)stream);
+}

@@ -1,0 +1,86 @@
+// common.cuh -- shared device/host helpers of libcdnet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/cdnet_b200.h"
+
+namespace cdnet {
+
+extern unsigned long long g_launches;  // api.cu
+extern int g_prof_on;                  // api.cu: per-launch CUDA-event timing (cdnet_profile_*)
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+
+#define CDNET_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
+    do {                                                                          \
+        if (::cdnet::g_prof_on) ::cdnet::prof_begin(#kernel, (stream));           \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+        if (::cdnet::g_prof_on) ::cdnet::prof_end((stream));                      \
+        ++::cdnet::g_launches;                                                    \
+    } while (0)
+
+#define CDNET_CUDA_OK(expr)                                 \
+    do {                                                    \
+        cudaError_t e__ = (expr);                           \
+        if (e__ != cudaSuccess) return -(int)e__;           \
+    } while (0)
+
+static inline int last_error() {
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// bump allocator over the caller's workspace (256-byte aligned slices)
+struct Arena {
+    char* base;
+    size_t size, off;
+    bool ok;
+    Arena(void* p, size_t n) : base((char*)p), size(n), off(0), ok(true) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (base == nullptr || off + bytes > size) { ok = false; off += bytes; return nullptr; }
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+static inline size_t pad256(size_t n) { return (n + 255) & ~size_t(255); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- union-find on an int32 parent array; links always point to a smaller index, so the root
+// ---- of a finished component is its first pixel in raster order -------------------------------
+__device__ __forceinline__ int uf_find(const int* __restrict__ L, int p) {
+    int q = __ldcg(L + p);
+    while (q != p) {
+        p = q;
+        q = __ldcg(L + p);
+    }
+    return p;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    for (;;) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(L + a, b);  // a > b: hang a under b
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// float <-> order-preserving uint32 (for atomicMax on floats of any sign)
+__device__ __forceinline__ unsigned int f32_to_ordered(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_f32(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+}  // namespace cdnet

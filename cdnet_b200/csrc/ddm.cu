@@ -1,0 +1,275 @@
+// ddm.cu -- direction-difference map (K1/K2 of SURVEY.md section 2.1).
+//
+// Replaces generate_dd_map / circshift / label_to_vector
+// (data_prepare/getDirectionDiffMap.py:14-108, data_prepare/SegFix_offset_helper.py:50-89,246-261).
+//
+// The reference builds int64 vector planes, eight shifted copies, f64 cosines stored to f32, a
+// channel minimum, np.around and a per-image min-max normalisation.  Exact reformulation
+// (SURVEY.md Appendix B.1): around(f32(cos(v_a, v_b))) in {-1,0,1} depends only on the two class
+// ids, and around is monotone, so d = 1 - min_k LUT[a][b_k] in {0,1,2}.  The LUT is evaluated on
+// the host with the reference's own arithmetic and shipped as two bit-sets per class (pos / neg);
+// a pixel only needs the SET S of classes present in its neighbourhood:
+//     any b in S with LUT[a][b] = -1  -> d = 2 ;  all b in S have LUT = +1 -> d = 0 ;  else d = 1
+// Zero padding == class 0 (zero vector, cos 0).  Output of the first pass is a 2-bit code per
+// (pixel, map) plus three "value present" bits per map for the normalisation.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cdnet {
+
+struct DdmLut {
+    uint32_t pos[32];
+    uint32_t neg[32];
+    int n;           // number of classes incl. background (5, 9, 17)
+    int axial;       // 5 classes: only the 4 axial neighbours (getDirectionDiffMap.py:56-67)
+    int force_zero;  // 17 classes: 8 of 16 cosine channels stay 0 (getDirectionDiffMap.py:90 vs 69-88)
+};
+
+static const int kRing8[8][2] = {{0, -1}, {-1, -1}, {-1, 0}, {-1, 1}, {0, 1}, {1, 1}, {1, 0}, {1, -1}};
+static const int kRing16[16][2] = {{0, -2}, {-1, -2}, {-2, -2}, {-2, -1}, {-2, 0}, {-2, 1}, {-2, 2}, {-1, 2},
+                                   {0, 2},  {1, 2},   {2, 2},   {2, 1},   {2, 0},  {2, -1}, {2, -2}, {1, -2}};
+static const int kDiag4[4][2] = {{-1, -1}, {-1, 1}, {1, 1}, {1, -1}};
+
+// class -> (dh, dw), data_prepare/SegFix_offset_helper.py:50-89 (keys 5, 9, 17)
+bool ddm_build_lut(int n_classes, DdmLut* lut) {
+    int vec[32][2] = {{0, 0}};
+    if (n_classes == 5) {
+        for (int i = 0; i < 4; ++i) { vec[i + 1][0] = kDiag4[i][0]; vec[i + 1][1] = kDiag4[i][1]; }
+    } else if (n_classes == 9) {
+        for (int i = 0; i < 8; ++i) { vec[i + 1][0] = kRing8[i][0]; vec[i + 1][1] = kRing8[i][1]; }
+    } else if (n_classes == 17) {
+        for (int i = 0; i < 16; ++i) { vec[i + 1][0] = kRing16[i][0]; vec[i + 1][1] = kRing16[i][1]; }
+    } else {
+        return false;
+    }
+    lut->n = n_classes;
+    lut->axial = (n_classes == 5);
+    lut->force_zero = (n_classes == 17);
+    for (int a = 0; a < 32; ++a) { lut->pos[a] = 0; lut->neg[a] = 0; }
+    for (int a = 0; a < n_classes; ++a) {
+        for (int b = 0; b < n_classes; ++b) {
+            // getDirectionDiffMap.py:92-97: int64 dot, f64 norms, +1e-6, f64 divide, store to f32
+            const double num = (double)(vec[a][0] * vec[b][0] + vec[a][1] * vec[b][1]);
+            const double den = sqrt((double)(vec[a][0] * vec[a][0] + vec[a][1] * vec[a][1])) *
+                                   sqrt((double)(vec[b][0] * vec[b][0] + vec[b][1] * vec[b][1])) +
+                               0.000001;
+            const float c = (float)(num / den);
+            const float r = nearbyintf(c);  // np.around: half to even (default rounding mode)
+            if (r > 0.5f) lut->pos[a] |= (1u << b);
+            if (r < -0.5f) lut->neg[a] |= (1u << b);
+        }
+    }
+    return true;
+}
+
+constexpr int kRows = 8;  // rows per thread strip
+
+template <bool FAST>
+__device__ __forceinline__ void load_row6(const uint8_t* __restrict__ plane, int H, int W, int y, int x4,
+                                          int n, uint32_t cb[6], uint32_t cls[4]) {
+    // class bits of columns x4-1 .. x4+4 of row y (class 0 outside the image / for invalid ids)
+    uint32_t c[6] = {0, 0, 0, 0, 0, 0};
+    if (y >= 0 && y < H) {
+        const uint8_t* row = plane + (size_t)y * W;
+        if (FAST && x4 + 3 < W) {
+            const uint32_t w = __ldg((const uint32_t*)(row + x4));
+            c[1] = w & 0xff; c[2] = (w >> 8) & 0xff; c[3] = (w >> 16) & 0xff; c[4] = w >> 24;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x4 + i < W) c[1 + i] = __ldg(row + x4 + i);
+        }
+        if (x4 > 0) c[0] = __ldg(row + x4 - 1);
+        if (x4 + 4 < W) c[5] = __ldg(row + x4 + 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const uint32_t ci = c[i] < (uint32_t)n ? c[i] : 0u;  // unknown id: zero vector, like class 0
+        cb[i] = 1u << ci;
+        if (i >= 1 && i <= 4) cls[i - 1] = c[i];
+    }
+}
+
+// codes: uint16 [B,H,W], bits 2t..2t+1 = d of map t.  flags: uint32 [B], bit 3t+d = "map t has value d".
+template <int T, bool FAST>
+__global__ void __launch_bounds__(128) k_ddm_codes(const uint8_t* __restrict__ cls_maps, uint16_t* __restrict__ codes,
+                                                   uint32_t* __restrict__ flags, int H, int W, DdmLut lut) {
+    __shared__ uint32_t s_pos[32], s_neg[32];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 32) { s_pos[tid] = lut.pos[tid]; s_neg[tid] = lut.neg[tid]; }
+    __syncthreads();
+    const int b = blockIdx.z;
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kRows;
+    uint32_t seen = 0;
+    if (x4 < W && y0 < H) {
+        uint32_t acc[kRows][2];  // 4 x uint16 per row
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) { acc[r][0] = 0; acc[r][1] = 0; }
+        const size_t plane_sz = (size_t)H * W;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            const uint8_t* plane = cls_maps + ((size_t)b * T + t) * plane_sz;
+            uint32_t cb_prev[6], cb_cur[6], cb_next[6], cls_prev[4], cls_cur[4], cls_next[4];
+            load_row6<FAST>(plane, H, W, y0 - 1, x4, lut.n, cb_prev, cls_prev);
+            load_row6<FAST>(plane, H, W, y0, x4, lut.n, cb_cur, cls_cur);
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const int y = y0 + r;
+                load_row6<FAST>(plane, H, W, y + 1, x4, lut.n, cb_next, cls_next);
+                if (y < H) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t S;
+                        if (lut.axial) {
+                            S = cb_prev[i + 1] | cb_next[i + 1] | cb_cur[i] | cb_cur[i + 2];
+                        } else {
+                            S = cb_prev[i] | cb_prev[i + 1] | cb_prev[i + 2] | cb_cur[i] | cb_cur[i + 2] |
+                                cb_next[i] | cb_next[i + 1] | cb_next[i + 2];
+                        }
+                        const uint32_t a = cls_cur[i];
+                        uint32_t d = 0;
+                        if (a != 0) {
+                            const uint32_t ai = a < (uint32_t)lut.n ? a : 31u;  // row 31 is empty
+                            if (s_neg[ai] & S) d = 2;
+                            else if ((S & ~s_pos[ai]) != 0 || lut.force_zero) d = 1;
+                        }
+                        if (x4 + i < W) {
+                            seen |= 1u << (3 * t + d);
+                            acc[r][i >> 1] |= d << (2 * t + 16 * (i & 1));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { cb_prev[i] = cb_cur[i]; cb_cur[i] = cb_next[i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cls_cur[i] = cls_next[i];
+            }
+        }
+        uint16_t* cout = codes + (size_t)b * plane_sz;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int y = y0 + r;
+            if (y < H) {
+                uint16_t* dst = cout + (size_t)y * W + x4;
+                if (FAST && x4 + 3 < W) {
+                    *(uint2*)dst = make_uint2(acc[r][0], acc[r][1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (x4 + i < W) dst[i] = (uint16_t)(acc[r][i >> 1] >> (16 * (i & 1)));
+                }
+            }
+        }
+    }
+    seen = __reduce_or_sync(0xffffffffu, seen);
+    if (threadIdx.x == 0 && seen) atomicOr(flags + b, seen);
+}
+
+// normalised value of code d for a map whose present-value bits are f (3 bits): (d-min)/(max-min)
+// in f32 (getDirectionDiffMap.py:104-106); constant map -> 0/0 = NaN.
+__device__ __forceinline__ float ddm_value(uint32_t d, uint32_t f) {
+    const int mn = (f & 1) ? 0 : ((f & 2) ? 1 : 2);
+    const int mx = (f & 4) ? 2 : ((f & 2) ? 1 : 0);
+    return __fdiv_rn((float)((int)d - mn), (float)(mx - mn));
+}
+
+__global__ void k_ddm_normalize(const uint16_t* __restrict__ codes, const uint32_t* __restrict__ flags,
+                                float* __restrict__ out, int32_t* __restrict__ status, size_t plane_sz) {
+    const int b = blockIdx.y;
+    const uint32_t f = flags[b] & 7u;
+    const bool constant = (f == 1u || f == 2u || f == 4u || f == 0u);
+    if (constant && status && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status + b, CDNET_S_DDM_CONSTANT);
+    const float v0 = ddm_value(0, f), v1 = ddm_value(1, f), v2 = ddm_value(2, f);
+    const uint16_t* c = codes + (size_t)b * plane_sz;
+    float* o = out + (size_t)b * plane_sz;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane_sz; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t d = c[i] & 3u;
+        o[i] = d == 0 ? v0 : (d == 1 ? v1 : v2);
+    }
+}
+
+// launcher shared with postproc.cu
+int ddm_codes_launch(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int B, int T, int H, int W,
+                     int n_classes, cudaStream_t st) {
+    DdmLut lut;
+    if (!ddm_build_lut(n_classes, &lut)) return CDNET_E_BADARG;
+    CDNET_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)B, st));
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(W, 128), ceil_div(H, 4 * kRows), B);
+    const bool fast = (W % 4 == 0) && (((uintptr_t)cls_maps & 3) == 0) && (((uintptr_t)codes & 7) == 0);
+    if (T == 8) {
+        if (fast) CDNET_LAUNCH((k_ddm_codes<8, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
+        else CDNET_LAUNCH((k_ddm_codes<8, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
+    } else if (T == 1) {
+        if (fast) CDNET_LAUNCH((k_ddm_codes<1, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
+        else CDNET_LAUNCH((k_ddm_codes<1, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
+    } else {
+        return CDNET_E_BADARG;
+    }
+    return last_error();
+}
+
+}  // namespace cdnet
+
+using namespace cdnet;
+
+extern "C" size_t cdnet_ddm_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return pad256((size_t)B * H * W * sizeof(uint16_t)) + pad256((size_t)B * sizeof(uint32_t));
+}
+
+extern "C" int cdnet_ddm(const uint8_t* cls, float* out, int32_t* status, int B, int H, int W, int n_classes,
+                         void* ws, size_t ws_bytes, void* stream) {
+    if (!cls || !out || B <= 0 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0) return CDNET_E_BADARG;
+    if (ws_bytes < cdnet_ddm_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(ws, ws_bytes);
+    uint16_t* codes = ar.take<uint16_t>((size_t)B * H * W);
+    uint32_t* flags = ar.take<uint32_t>(B);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    int rc = ddm_codes_launch(cls, codes, flags, B, 1, H, W, n_classes, st);
+    if (rc) return rc;
+    const size_t plane = (size_t)H * W;
+    dim3 grid((unsigned)((plane + 256 * 8 - 1) / (256 * 8)), B);
+    CDNET_LAUNCH(k_ddm_normalize, grid, 256, 0, st, codes, flags, out, status, plane);
+    return last_error();
+}
+
+// ---- circshift, data_prepare/getDirectionDiffMap.py:14-42 -------------------------------------
+namespace cdnet {
+template <typename E>
+__global__ void k_circshift(const E* __restrict__ in, E* __restrict__ out, int H, int W, int dy, int dx) {
+    // out[y][x] = in[y+dy][x+dx], zero outside
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const size_t plane = (size_t)H * W * blockIdx.z;
+    if (x >= W) return;
+    const int sy = y + dy, sx = x + dx;
+    E v = 0;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = in[plane + (size_t)sy * W + sx];
+    out[plane + (size_t)y * W + x] = v;
+}
+}  // namespace cdnet
+
+extern "C" int cdnet_circshift(const void* in, void* out, int C, int H, int W, int elem_bytes, int direction,
+                               int shift1, int shift2, void* stream) {
+    if (!in || !out || C <= 0 || H <= 0 || W <= 0 || direction < 1 || direction > 4 || shift1 < 0 || shift2 < 0)
+        return CDNET_E_BADARG;
+    // direction 1/2: rows move up (content of row y+s1 lands on y); 3/4: down.  1/3: columns move
+    // left; 2/4: right.
+    const int dy = (direction <= 2) ? shift1 : -shift1;
+    const int dx = (direction == 1 || direction == 3) ? shift2 : -shift2;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(ceil_div(W, 256), H, C);
+    switch (elem_bytes) {
+        case 1: CDNET_LAUNCH(k_circshift<uint8_t>, grid, 256, 0, st, (const uint8_t*)in, (uint8_t*)out, H, W, dy, dx); break;
+        case 2: CDNET_LAUNCH(k_circshift<uint16_t>, grid, 256, 0, st, (const uint16_t*)in, (uint16_t*)out, H, W, dy, dx); break;
+        case 4: CDNET_LAUNCH(k_circshift<uint32_t>, grid, 256, 0, st, (const uint32_t*)in, (uint32_t*)out, H, W, dy, dx); break;
+        case 8: CDNET_LAUNCH(k_circshift<unsigned long long>, grid, 256, 0, st, (const unsigned long long*)in,
+                             (unsigned long long*)out, H, W, dy, dx); break;
+        default: return CDNET_E_BADARG;
+    }
+    return last_error();
+}

@@ -1,0 +1,224 @@
+// postproc.cu -- inference post-processing pipelines (K3-K5 + orchestration).
+//
+// cdnet_dam_postproc replaces the inline block test_dam.py:455-563 (with its hard-wired switches
+// dcm_combined = 1, voting_firt = 0, DDM_switch = 100, mseloss = 1, direction = 1);
+// cdnet_plain_postproc replaces test.py:270-295.
+//
+// DAM chain per batch of tiles (every kernel is batched over B):
+//   k_ddm_codes<8>    8 TTA class maps -> 2-bit DDM codes (ddm.cu)                 test_dam.py:479-487
+//   k_point_max       per-tile max of the point map                                test_dam.py:530
+//   k_boost_inside    mean of the 8 normalised DDMs (f64), point gate + cross dilation,
+//                     boundary boost of prob[2] (f64 math stored to f32), 3-way argmax,
+//                     inside = (argmax == 1)                                        test_dam.py:489,530-539
+//   fill holes -> remove small (4-conn) -> 8-conn label (ccl.cu, one forest)        test_dam.py:546-561
+//     or process() = watershed chain (watershed.cu) when postproc == 1             test_dam.py:559
+//   k_label_dilate    disk(radius)                                                 test_dam.py:563
+#include "internal.h"
+
+namespace cdnet {
+
+__device__ __forceinline__ float ddm_value_f(uint32_t d, uint32_t f) {
+    const int mn = (f & 1) ? 0 : ((f & 2) ? 1 : 2);
+    const int mx = (f & 4) ? 2 : ((f & 2) ? 1 : 0);
+    return __fdiv_rn((float)((int)d - mn), (float)(mx - mn));
+}
+
+__global__ void __launch_bounds__(256) k_point_max(const float* __restrict__ point, unsigned int* __restrict__ pmax,
+                                                   size_t plane) {
+    __shared__ unsigned int s_max[8];
+    const int b = blockIdx.y;
+    const float* P = point + (size_t)b * plane;
+    unsigned int m = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, f32_to_ordered(P[i]));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        m = s_max[threadIdx.x];
+        m = __reduce_max_sync(0xffu, m);
+        if (threadIdx.x == 0) atomicMax(pmax + b, m);
+    }
+}
+
+// one thread per pixel.  prob: [B,3,H,W]; writes inside u8; optionally prob[2] <- boosted (test_dam.py:536)
+__global__ void __launch_bounds__(256) k_boost_inside(const uint16_t* __restrict__ codes, const uint32_t* __restrict__ flags,
+                                                      const float* __restrict__ point, const unsigned int* __restrict__ pmax,
+                                                      float* __restrict__ prob, uint8_t* __restrict__ inside,
+                                                      int32_t* __restrict__ status, int H, int W, int write_prob) {
+    __shared__ float s_val[8][4];
+    __shared__ int s_const;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) s_const = 0;
+    __syncthreads();
+    if (tid < 32) {
+        const int t = tid >> 2, d = tid & 3;
+        const uint32_t f = (flags[b] >> (3 * t)) & 7u;
+        s_val[t][d] = d < 3 ? ddm_value_f(d, f) : 0.f;
+        if (d == 0 && (f == 0u || f == 1u || f == 2u || f == 4u)) s_const = 1;
+    }
+    __syncthreads();
+    if (s_const && status && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicOr(status + b, CDNET_S_DDM_CONSTANT);
+    const int x = blockIdx.x * 64 + threadIdx.x;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t plane = (size_t)H * W;
+    const int p = y * W + x;
+    const uint32_t c = codes[(size_t)b * plane + p];
+    double sum = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) sum = __dadd_rn(sum, (double)s_val[t][(c >> (2 * t)) & 3u]);
+    const double ddm = __dmul_rn(sum, 0.125);  // np.mean over the 8 maps (exact: dyadic values)
+    // point gate (test_dam.py:530-531): f32 divide by the global max, > 0.2 (f32), cross dilation
+    const float* P = point + (size_t)b * plane;
+    const float mx = ordered_to_f32(pmax[b]);
+    bool g = __fdiv_rn(P[p], mx) > 0.2f;
+    if (y > 0) g = g || (__fdiv_rn(P[p - W], mx) > 0.2f);
+    if (y + 1 < H) g = g || (__fdiv_rn(P[p + W], mx) > 0.2f);
+    if (x > 0) g = g || (__fdiv_rn(P[p - 1], mx) > 0.2f);
+    if (x + 1 < W) g = g || (__fdiv_rn(P[p + 1], mx) > 0.2f);
+    // enhanced_boundary = 2 * (ddm - ddm * gate)   (test_dam.py:532-534), f64
+    const double eb = __dmul_rn(2.0, __dadd_rn(ddm, -__dmul_rn(ddm, g ? 1.0 : 0.0)));
+    float* PR = prob + (size_t)b * 3 * plane;
+    const float p0 = PR[p], p1 = PR[plane + p], p2 = PR[2 * plane + p];
+    // prob[2] = (prob[2] + 0.5*eb) * (1 + eb): f64 arithmetic stored into the f32 array (test_dam.py:536)
+    const float p2n = __double2float_rn(__dmul_rn(__dadd_rn((double)p2, __dmul_rn(0.5, eb)), __dadd_rn(1.0, eb)));
+    if (write_prob) PR[2 * plane + p] = p2n;
+    // np.argmax: first maximum wins, NaN counts as maximum
+    int am = 0;
+    float best = p0;
+    if (p1 > best || (p1 != p1 && best == best)) { am = 1; best = p1; }
+    if (p2n > best || (p2n != p2n && best == best)) { am = 2; }
+    inside[(size_t)b * plane + p] = (am == 1) ? 1 : 0;
+}
+
+// test.py:270-275: inside = argmax over C channels == 1, or prob[0] >= 0.5
+__global__ void __launch_bounds__(256) k_plain_inside(const float* __restrict__ prob, int C, uint8_t* __restrict__ inside,
+                                                      size_t plane, int multi_class) {
+    const int b = blockIdx.y;
+    const float* PR = prob + (size_t)b * C * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        uint8_t r;
+        if (multi_class) {
+            int am = 0;
+            float best = PR[i];
+            for (int c = 1; c < C; ++c) {
+                const float v = PR[(size_t)c * plane + i];
+                if (v > best || (v != v && best == best)) { am = c; best = v; }
+            }
+            r = (am == 1);
+        } else {
+            r = PR[i] >= 0.5f;
+        }
+        inside[(size_t)b * plane + i] = r;
+    }
+}
+
+static size_t tail_workspace(int B, int H, int W) {
+    const size_t a = fill_remove_label_workspace(B, H, W);
+    const size_t c = ws_process_workspace(B, H, W);
+    return a > c ? a : c;
+}
+
+// inside -> labels (postproc 0: fill/remove/label8; 1: process()) -> dilation
+static int tail_launch(const uint8_t* inside, int32_t* labels, void* out, int out_elem_bytes, int32_t* status, int B,
+                       int H, int W, int min_area, int ws_min_size, int radius, int postproc, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    int rc;
+    if (postproc == 1) rc = ws_process_launch(inside, labels, status, B, H, W, ws_min_size, 1, ws, ws_bytes, st);
+    else rc = fill_remove_label_launch(inside, labels, nullptr, B, H, W, min_area, ws, ws_bytes, st);
+    if (rc) return rc;
+    return label_dilate_launch(labels, out, out_elem_bytes, B, H, W, radius, st);
+}
+
+}  // namespace cdnet
+
+using namespace cdnet;
+
+static bool bad_dims(int B, int H, int W) { return B <= 0 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0; }
+
+extern "C" size_t cdnet_dam_postproc_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    const size_t n = (size_t)B * H * W;
+    return pad256(n * 2) + 2 * pad256((size_t)B * 4) + pad256(n) + pad256(n * 4) + tail_workspace(B, H, W);
+}
+
+extern "C" int cdnet_dam_postproc(const uint8_t* dcm, float* prob, const float* point, void* out, int out_elem_bytes,
+                                  int32_t* status, int B, int H, int W, int direction_classes, int min_area, int radius,
+                                  int postproc, int write_prob, void* ws, size_t ws_bytes, void* stream) {
+    if (!dcm || !prob || !point || !out || bad_dims(B, H, W) || (out_elem_bytes != 4 && out_elem_bytes != 8) ||
+        (postproc != 0 && postproc != 1) || radius < 0 || radius > 4)
+        return CDNET_E_BADARG;
+    if (direction_classes != 5 && direction_classes != 9 && direction_classes != 17) return CDNET_E_BADARG;
+    if (ws_bytes < cdnet_dam_postproc_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)B * H * W, plane = (size_t)H * W;
+    Arena ar(ws, ws_bytes);
+    uint16_t* codes = ar.take<uint16_t>(n);
+    uint32_t* flags = ar.take<uint32_t>(B);
+    unsigned int* pmax = ar.take<unsigned int>(B);
+    uint8_t* inside = ar.take<uint8_t>(n);
+    int32_t* labels = ar.take<int32_t>(n);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    void* tail_ws = (char*)ws + ar.off;
+    const size_t tail_bytes = ws_bytes - ar.off;
+    if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
+    int rc = ddm_codes_launch(dcm, codes, flags, B, 8, H, W, direction_classes, st);
+    if (rc) return rc;
+    CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, st));
+    {
+        int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
+        CDNET_LAUNCH(k_point_max, dim3(gx, B), 256, 0, st, point, pmax, plane);
+    }
+    CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point, pmax,
+                 prob, inside, status, H, W, write_prob);
+    rc = last_error();
+    if (rc) return rc;
+    // test_dam.py:559 calls process() with its default min_size = 10
+    return tail_launch(inside, labels, out, out_elem_bytes, status, B, H, W, min_area, 10, radius, postproc, tail_ws,
+                       tail_bytes, st);
+}
+
+extern "C" size_t cdnet_plain_postproc_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    const size_t n = (size_t)B * H * W;
+    return pad256(n) + pad256(n * 4) + tail_workspace(B, H, W);
+}
+
+extern "C" int cdnet_plain_postproc(const float* prob, int C, void* out, int out_elem_bytes, int32_t* status, int B, int H,
+                                    int W, int multi_class, int min_area, int radius, int postproc, void* ws,
+                                    size_t ws_bytes, void* stream) {
+    if (!prob || !out || C <= 0 || bad_dims(B, H, W) || (out_elem_bytes != 4 && out_elem_bytes != 8) ||
+        (postproc != 0 && postproc != 1) || radius < 0 || radius > 4)
+        return CDNET_E_BADARG;
+    if (ws_bytes < cdnet_plain_postproc_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)B * H * W, plane = (size_t)H * W;
+    Arena ar(ws, ws_bytes);
+    uint8_t* inside = ar.take<uint8_t>(n);
+    int32_t* labels = ar.take<int32_t>(n);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    void* tail_ws = (char*)ws + ar.off;
+    const size_t tail_bytes = ws_bytes - ar.off;
+    if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
+    int gx = (int)((plane + 256 * 4 - 1) / (256 * 4));
+    CDNET_LAUNCH(k_plain_inside, dim3(gx, B), 256, 0, st, prob, C, inside, plane, multi_class);
+    // test.py:289-290 passes min_size = min_area to process()
+    return tail_launch(inside, labels, out, out_elem_bytes, status, B, H, W, min_area, min_area, radius, postproc, tail_ws,
+                       tail_bytes, st);
+}
+
+extern "C" size_t cdnet_ws_postproc_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    return ws_process_workspace(B, H, W);
+}
+
+extern "C" int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W, int min_size,
+                                 int ws_flag, void* ws, size_t ws_bytes, void* stream) {
+    if (!pred01 || !labels || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    if (ws_bytes < ws_process_workspace(B, H, W)) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
+    return ws_process_launch(pred01, labels, status, B, H, W, min_size, ws_flag, ws, ws_bytes, st);
+}

@@ -1,0 +1,286 @@
+// watershed.cu -- postproc_other.process (K9-K12): instance distance map, markers, marker-controlled
+// watershed, small-object removal.
+//
+// Replaces postproc_other.py:15-54 (the `ws` branch :36-49 and the unet/micronet head :50-54).
+//
+// O(H*W) reformulation of the reference's O(N_inst*H*W) loop (`gen_inst_dst_map`, :16-27): the EDT
+// of one 4-connected component equals the global EDT of the binary mask restricted to it
+// (SURVEY.md Appendix B.2), so ONE exact EDT plus a per-component maximum (atomicMax on the
+// component root) gives uint8(255 * d / max d) for every instance at once.
+//
+// Watershed (skimage.segmentation.watershed, connectivity 1, compactness 0): a priority flood in
+// (value, age) order that labels a pixel when it is PUSHED.  Values are uint8 (the reference negates
+// a uint8 array, :47), so a 256-bucket FIFO per foreground component reproduces (value, age)
+// exactly; ties between the initial age-0 marker pixels are resolved by raster index (this build's
+// canonical order, SURVEY.md section 7 hard-part 1).  Floods of different components of `pred`
+// never interact, so each component is flooded by one warp: lanes 0-3 fetch the four neighbours
+// (-W, -1, +1, +W) in parallel, lane 0 owns the bucket heads/tails (shared memory) and the `next`
+// links (global).
+#include "internal.h"
+
+namespace cdnet {
+
+constexpr int kBX = 128, kBY = 4;
+static inline dim3 px_grid(int B, int H, int W) { return dim3(ceil_div(W, kBX), ceil_div(H, kBY), B); }
+static inline dim3 px_block() { return dim3(kBX, kBY); }
+#define PX_COORDS                                              \
+    const int x = blockIdx.x * kBX + threadIdx.x;              \
+    const int y = blockIdx.y * kBY + threadIdx.y;              \
+    const int b = blockIdx.z;                                  \
+    const bool inb = (x < W) && (y < H);                       \
+    const size_t tile = (size_t)b * H * W;                     \
+    const int p = y * W + x;                                   \
+    const int lane = threadIdx.x & 31;                         \
+    (void)lane; (void)p; (void)tile; (void)inb;
+
+// L <- roots of pred's 4-conn components; maxd2[root] = max d2 over the component
+__global__ void __launch_bounds__(kBX* kBY) k_comp_stats(const uint8_t* __restrict__ pred, int* __restrict__ L,
+                                                         const int* __restrict__ d2, int* __restrict__ maxd2,
+                                                         int H, int W) {
+    PX_COORDS
+    int r = -1, d = 0;
+    if (inb && pred[tile + p]) {
+        int* Lt = L + tile;
+        r = uf_find(Lt, p);
+        Lt[p] = r;
+        d = d2[tile + p];
+    }
+    if (r >= 0) atomicMax(maxd2 + tile + r, d);
+}
+
+// dist = uint8(255 * (sqrt(d2) / sqrt(max d2)))  (postproc_other.py:24-26, f64, truncating);
+// val = (uint8)(-dist) (:47); marker0 = dist > 125 (:39-41)
+__global__ void __launch_bounds__(kBX* kBY) k_dist_marker(const uint8_t* __restrict__ pred, const int* __restrict__ L,
+                                                          const int* __restrict__ d2, const int* __restrict__ maxd2,
+                                                          uint8_t* __restrict__ val, uint8_t* __restrict__ marker0,
+                                                          int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    uint8_t dist = 0;
+    if (pred[tile + p]) {
+        const double d = __dsqrt_rn((double)d2[tile + p]);
+        const double dm = __dsqrt_rn((double)maxd2[tile + L[tile + p]]);
+        const double s = __dmul_rn(255.0, __ddiv_rn(d, dm));
+        dist = (uint8_t)(int)s;
+    }
+    val[tile + p] = (uint8_t)(0u - (unsigned)dist);
+    marker0[tile + p] = dist > 125;
+}
+
+// binary_erosion(iterations=1): cross structure, border_value 0 (postproc_other.py:43)
+__global__ void __launch_bounds__(kBX* kBY) k_erode_cross(const uint8_t* __restrict__ state, uint8_t* __restrict__ out,
+                                                          int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const uint8_t* S = state + tile;
+    bool k = false;
+    if (x > 0 && y > 0 && x + 1 < W && y + 1 < H) k = S[p] && S[p - 1] && S[p + 1] && S[p - W] && S[p + W];
+    out[tile + p] = k;
+}
+
+// out <- markers * mask (skimage watershed's input validation); bounding box of every component of
+// pred, keyed by its root
+__global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restrict__ pred, const int* __restrict__ L,
+                                                         int* __restrict__ out, int* __restrict__ ymax,
+                                                         int* __restrict__ xmin, int* __restrict__ xmax, int H, int W) {
+    PX_COORDS
+    int r = -1;
+    if (inb) {
+        if (pred[tile + p]) r = L[tile + p];
+        else out[tile + p] = 0;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, r);
+    if (r >= 0) {
+        const int first = __ffs(peers) - 1, last = 31 - __clz(peers);
+        if (lane == first) {
+            atomicMin(xmin + tile + r, x);
+            atomicMax(ymax + tile + r, y);
+        }
+        if (lane == last) atomicMax(xmax + tile + r, x);
+    }
+}
+
+__global__ void __launch_bounds__(kBX* kBY) k_bbox_init(int* __restrict__ ymax, int* __restrict__ xmin,
+                                                        int* __restrict__ xmax, int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    ymax[tile + p] = -1;
+    xmin[tile + p] = 0x7fffffff;
+    xmax[tile + p] = -1;
+}
+
+struct Buckets {
+    int head[256];
+    int tail[256];
+};
+
+// one warp per component of `pred` (the warp that owns the component's root pixel)
+__global__ void __launch_bounds__(128) k_flood(const uint8_t* __restrict__ pred, const int* __restrict__ L,
+                                               const uint8_t* __restrict__ val, volatile int* out, volatile int* next,
+                                               const int* __restrict__ ymax, const int* __restrict__ xmin,
+                                               const int* __restrict__ xmax, int H, int W) {
+    __shared__ Buckets s_b[4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    const size_t tile = (size_t)b * H * W;
+    const int p = y * W + x;
+    const bool is_root = x < W && pred[tile + p] && L[tile + p] == p;
+    unsigned roots = __ballot_sync(0xffffffffu, is_root);
+    if (!roots) return;
+    Buckets& B = s_b[wid];
+    const uint8_t* P = pred + tile;
+    const int* Lt = L + tile;
+    const uint8_t* V = val + tile;
+    volatile int* O = out + tile;
+    volatile int* N = next + tile;
+    while (roots) {
+        const int rl = __ffs(roots) - 1;
+        roots &= roots - 1;
+        const int root = __shfl_sync(0xffffffffu, p, rl);
+        for (int i = lane; i < 256; i += 32) { B.head[i] = -1; B.tail[i] = -1; }
+        __syncwarp();
+        int cur = 256;
+        // ---- age-0 elements: marker pixels of this component in raster order
+        const int y0 = root / W, y1 = ymax[tile + root], x0 = xmin[tile + root], x1 = xmax[tile + root];
+        for (int yy = y0; yy <= y1; ++yy) {
+            for (int xb = x0; xb <= x1; xb += 32) {
+                const int xx = xb + lane;
+                const int q = yy * W + xx;
+                const bool mk = xx <= x1 && P[q] && Lt[q] == root && O[q] != 0;
+                const int v = mk ? V[q] : 0;
+                unsigned m = __ballot_sync(0xffffffffu, mk);
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int qq = __shfl_sync(0xffffffffu, q, l);
+                    const int vv = __shfl_sync(0xffffffffu, v, l);
+                    if (lane == 0) {
+                        N[qq] = -1;
+                        if (B.tail[vv] < 0) B.head[vv] = qq; else N[B.tail[vv]] = qq;
+                        B.tail[vv] = qq;
+                    }
+                    cur = min(cur, vv);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- flood
+        for (;;) {
+            // lowest non-empty bucket >= cur (32 buckets per probe)
+            int found = -1;
+            for (int base = cur & ~31; base < 256; base += 32) {
+                const int idx = base + lane;
+                const unsigned m = __ballot_sync(0xffffffffu, idx >= cur && B.head[idx] >= 0);
+                if (m) { found = base + __ffs(m) - 1; break; }
+            }
+            if (found < 0) break;
+            cur = found;
+            const int e = B.head[cur];
+            const int lbl = O[e];
+            __syncwarp();
+            if (lane == 0) {
+                const int nx = N[e];
+                B.head[cur] = nx;
+                if (nx < 0) B.tail[cur] = -1;
+            }
+            const int ey = e / W, ex = e - ey * W;
+            int q = -1, v = 0;
+            if (lane < 4) {
+                const int qy = ey + (lane == 0 ? -1 : (lane == 3 ? 1 : 0));
+                const int qx = ex + (lane == 1 ? -1 : (lane == 2 ? 1 : 0));
+                if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+                    const int qq = qy * W + qx;
+                    if (P[qq] && O[qq] == 0) { q = qq; v = V[qq]; }
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, q >= 0);
+            __syncwarp();
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const int qq = __shfl_sync(0xffffffffu, q, l);
+                const int vv = __shfl_sync(0xffffffffu, v, l);
+                if (lane == 0) {
+                    O[qq] = lbl;
+                    N[qq] = -1;
+                    if (B.tail[vv] < 0) B.head[vv] = qq; else N[B.tail[vv]] = qq;
+                    B.tail[vv] = qq;
+                }
+                cur = min(cur, vv);
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+size_t ws_process_workspace(int B, int H, int W) {
+    const size_t n = (size_t)B * H * W;
+    return 5 * pad256(n * 4) + pad256((size_t)B * ((size_t)H * W + 1) * 4) + 3 * pad256(n) + pad256((size_t)B * H * 4);
+}
+
+// kernels from ccl.cu used here
+int ccl_forest_launch(const uint8_t* mask, int32_t* L, int B, int H, int W, int conn, cudaStream_t st);
+
+__global__ void k_state_mask(const uint8_t* __restrict__ state, uint8_t* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = state[i] ? 1 : 0;
+}
+
+int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W, int min_size,
+                      int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st) {
+    (void)status;
+    const size_t n = (size_t)B * H * W;
+    Arena ar(ws, ws_bytes);
+    int32_t* A = ar.take<int32_t>(n);    // forest of pred
+    int32_t* Bp = ar.take<int32_t>(n);   // g2 -> touch / idmap -> ymax
+    int32_t* C = ar.take<int32_t>(n);    // d2 -> marker forest -> xmin
+    int32_t* D = ar.take<int32_t>(n);    // max d2 per root -> xmax
+    int32_t* E = ar.take<int32_t>(n);    // next links
+    int32_t* counts = ar.take<int32_t>((size_t)B * ((size_t)H * W + 1));
+    uint8_t* val = ar.take<uint8_t>(n);
+    uint8_t* mk = ar.take<uint8_t>(n);
+    uint8_t* state = ar.take<uint8_t>(n);
+    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    int rc;
+    if (!ws_flag) {
+        // postproc_other.py:50-54: fill holes -> label -> remove small
+        rc = fill_holes_state_launch(pred01, state, A, Bp, B, H, W, st);
+        if (rc) return rc;
+        const size_t blocks = (n + 1023) / 1024;
+        CDNET_LAUNCH(k_state_mask, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, state, mk, n);
+        rc = ccl_label_launch(mk, labels, nullptr, A, Bp, rowcnt, B, H, W, 4, st);
+        if (rc) return rc;
+        return remove_small_labels_launch(labels, counts, B, H, W, min_size, st);
+    }
+    // 1. components of pred (:37) and the exact EDT of the mask (:24 for all instances at once)
+    rc = ccl_forest_launch(pred01, A, B, H, W, 4, st);
+    if (rc) return rc;
+    rc = edt_launch(pred01, C, Bp, B, H, W, st);
+    if (rc) return rc;
+    CDNET_CUDA_OK(cudaMemsetAsync(D, 0, n * 4, st));
+    CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, H, W);
+    // 2. uint8 distance, its negation, markers (:25-26, :39-41, :47)
+    CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, H, W);
+    // 3. fill holes, cross erosion, label, remove small (:42-46)
+    rc = fill_holes_state_launch(mk, state, C, Bp, B, H, W, st);
+    if (rc) return rc;
+    CDNET_LAUNCH(k_erode_cross, px_grid(B, H, W), px_block(), 0, st, state, mk, H, W);
+    rc = ccl_label_launch(mk, labels, nullptr, C, Bp, rowcnt, B, H, W, 4, st);
+    if (rc) return rc;
+    rc = remove_small_labels_launch(labels, counts, B, H, W, min_size, st);
+    if (rc) return rc;
+    // 4. flood (:47)
+    CDNET_LAUNCH(k_bbox_init, px_grid(B, H, W), px_block(), 0, st, Bp, C, D, H, W);
+    CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, H, W);
+    CDNET_LAUNCH(k_flood, dim3(ceil_div(W, 128), H, B), 128, 0, st, pred01, A, val, labels, E, Bp, C, D, H, W);
+    rc = last_error();
+    if (rc) return rc;
+    // 5. remove small (:48)
+    return remove_small_labels_launch(labels, counts, B, H, W, min_size, st);
+}
+
+}  // namespace cdnet

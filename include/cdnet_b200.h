@@ -1,0 +1,164 @@
+/*
+ * cdnet_b200.h -- C ABI of libcdnet_b200.so: CDNet's geometry hot path on B200 (sm_100a).
+ *
+ * The reference (honglianghe/CDNet) has no FFI: its boundary for this path is a set of plain
+ * Python callables on numpy arrays.  Each entry point below names the
+ * reference callable / line range it replaces; the Python mirror with the reference's own
+ * signatures lives in cdnet_b200/api.py and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (dense, row-major, batch first);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and performs
+ *     no host synchronisation and no allocation: scratch comes from the caller's workspace `ws`
+ *     whose size is returned by the matching *_workspace_bytes() (0 on invalid arguments);
+ *   - return value: 0 = ok, <0 = -(cudaError_t), >0 = CDNET_E_* domain error; nothing throws;
+ *   - B tiles of H x W pixels; H*W < 2^31; pixel p = y*W + x; tiles are independent.
+ */
+#ifndef CDNET_B200_H_
+#define CDNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDNET_E_BADARG 1    /* null pointer, unsupported class count / connectivity / radius ... */
+#define CDNET_E_WORKSPACE 2 /* workspace smaller than *_workspace_bytes() */
+
+/* per-tile status bits written by the kernels into `status[b]` (int32, device) */
+#define CDNET_S_DDM_CONSTANT 1 /* a direction map was constant: generate_dd_map's 0/0 -> NaN
+                                  (getDirectionDiffMap.py:104-106); the reference's
+                                  `assert(np.min(enhanced_boundary) >= 0)` (test_dam.py:535) fails */
+#define CDNET_S_WS_OVERFLOW 2  /* watershed queue overflow (cannot happen with the sizes from
+                                  *_workspace_bytes; kept as a guard) */
+
+const char* cdnet_version(void);
+/* 1 if the library was built for the device `device` can run (compute capability 10.x) */
+int cdnet_device_ok(int device);
+
+/* ---- generate_dd_map(label_direction, direction_classes) ------------------------------------
+ * data_prepare/getDirectionDiffMap.py:44-108 (with circshift :14-42 and
+ * DTOffsetHelper.label_to_vector, data_prepare/SegFix_offset_helper.py:246-261).
+ * cls: uint8 [B,H,W] class maps; out: float32 [B,H,W] in {0, .5, 1} (NaN for a constant map,
+ * status bit CDNET_S_DDM_CONSTANT).  n_classes in {5, 9, 17}.  status may be NULL. */
+size_t cdnet_ddm_workspace_bytes(int B, int H, int W);
+int cdnet_ddm(const uint8_t* cls, float* out, int32_t* status, int B, int H, int W, int n_classes,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* ---- circshift(matrix_ori, direction, shiftnum1, shiftnum2) ---------------------------------
+ * data_prepare/getDirectionDiffMap.py:14-42: zero-filled shift of C planes of `elem_bytes`
+ * (1, 2, 4 or 8) byte elements.  direction 1..4. */
+int cdnet_circshift(const void* in, void* out, int C, int H, int W, int elem_bytes, int direction,
+                    int shift1, int shift2, void* stream);
+
+/* ---- connected-component labelling -----------------------------------------------------------
+ * scipy.ndimage.label (4-connected, postproc_other.py:37,44) / skimage.measure.label
+ * (8-connected, test_dam.py:561, test.py:292, my_transforms_direction.py:755,773): non-zero =
+ * foreground, ids 1..n in raster order of each component's first pixel.
+ * mask: uint8 [B,H,W]; labels: int32 [B,H,W]; n_out: int32 [B] component counts (may be NULL). */
+size_t cdnet_ccl_workspace_bytes(int B, int H, int W);
+int cdnet_ccl(const uint8_t* mask, int32_t* labels, int32_t* n_out, int B, int H, int W,
+              int connectivity, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- scipy.ndimage.binary_fill_holes (test_dam.py:546, test.py:277, postproc_other.py:42,51) --
+ * out may alias mask. */
+size_t cdnet_fill_holes_workspace_bytes(int B, int H, int W);
+int cdnet_fill_holes(const uint8_t* mask, uint8_t* out, int B, int H, int W, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* ---- skimage.morphology.remove_small_objects --------------------------------------------------
+ * bool input (test_dam.py:548, test.py:279): 4-connected components smaller than min_size are
+ * cleared.  out may alias mask. */
+size_t cdnet_remove_small_mask_workspace_bytes(int B, int H, int W);
+int cdnet_remove_small_mask(const uint8_t* mask, uint8_t* out, int B, int H, int W, int min_size,
+                            void* ws, size_t ws_bytes, void* stream);
+/* integer input (postproc_other.py:46,48,53): labels whose pixel count is < min_size are zeroed,
+ * no renumbering.  Label values must lie in [0, H*W].  In place. */
+size_t cdnet_remove_small_labels_workspace_bytes(int B, int H, int W);
+int cdnet_remove_small_labels(int32_t* labels, int B, int H, int W, int min_size, void* ws,
+                              size_t ws_bytes, void* stream);
+
+/* ---- skimage.morphology.dilation(labels, disk(radius)) ----------------------------------------
+ * test_dam.py:563, test.py:295, my_transforms_direction.py:760,774,819: max over the disk
+ * footprint (radius 1 = 5-px cross, 2 = 13 px), out-of-image taps ignored.
+ * out_elem_bytes 4 (int32) or 8 (int64, what measure.label hands on). */
+int cdnet_label_dilate(const int32_t* labels, void* out, int out_elem_bytes, int B, int H, int W,
+                       int radius, void* stream);
+
+/* ---- scipy.ndimage.distance_transform_edt ------------------------------------------------------
+ * postproc_other.py:24, my_transforms_direction.py:802,822.  d2: exact squared distance (int32)
+ * to the nearest zero pixel of mask; dist (may be NULL): float64 sqrt of it. */
+size_t cdnet_edt_workspace_bytes(int B, int H, int W);
+int cdnet_edt(const uint8_t* mask, int32_t* d2, double* dist, int B, int H, int W, void* ws,
+              size_t ws_bytes, void* stream);
+
+/* ---- postproc_other.process(pred, model_mode, min_size, ws) -----------------------------------
+ * postproc_other.py:15-54.  pred01: uint8 [B,H,W], already binarised (pred > 0.5, :31-32).
+ * ws != 0: label -> per-instance EDT scaled to uint8 -> markers (>125, fill holes, cross
+ * erosion, label, remove small) -> marker-controlled watershed on the uint8-negated distance,
+ * (value, age, raster index) order -> remove small.  ws == 0 (model_mode unet/micronet, :35,
+ * :50-54): fill holes -> label -> remove small.  labels: int32 [B,H,W], ids keep gaps. */
+size_t cdnet_ws_postproc_workspace_bytes(int B, int H, int W);
+int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W,
+                      int min_size, int ws_flag, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- direction-aware inference post-processing, test_dam.py:455-563 ----------------------------
+ * dcm:   uint8   [B,8,H,W]  the 8 TTA direction-argmax maps (prob_dcm ... prob_dcm_r90_hvf)
+ * prob:  float32 [B,3,H,W]  class probabilities; if write_prob != 0 channel 2 is overwritten
+ *                           with the boosted boundary probability like the reference (:536)
+ * point: float32 [B,1,H,W]  point map
+ * out:   labels [B,H,W], int32 or int64 (out_elem_bytes 4 / 8; the reference returns int64
+ *        from measure.label when postproc == 0 and int32 from process() when postproc == 1)
+ * status: int32 [B] (CDNET_S_*), may be NULL. */
+size_t cdnet_dam_postproc_workspace_bytes(int B, int H, int W);
+int cdnet_dam_postproc(const uint8_t* dcm, float* prob, const float* point, void* out,
+                       int out_elem_bytes, int32_t* status, int B, int H, int W,
+                       int direction_classes, int min_area, int radius, int postproc,
+                       int write_prob, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- plain inference post-processing, test.py:270-295 -------------------------------------------
+ * prob: float32 [B,C,H,W]; multi_class != 0: inside = (argmax == 1) over C channels, else
+ * inside = prob[:,0] >= 0.5.  Then as above without the direction map; process() gets
+ * min_size = min_area (:289-290). */
+size_t cdnet_plain_postproc_workspace_bytes(int B, int H, int W);
+int cdnet_plain_postproc(const float* prob, int C, void* out, int out_elem_bytes, int32_t* status,
+                         int B, int H, int W, int multi_class, int min_area, int radius,
+                         int postproc, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- get_centerpoint2(mask, n, m) for every label at once --------------------------------------
+ * my_transforms_direction.py:651-685.  labels: int32 [B,H,W] (ids in [0, max_label]);
+ * centres: int32 [B, max_label+1, 2] = (row, col) of the first raster-order pixel of maximum
+ * centerness of each id, (-1,-1) for absent ids. */
+size_t cdnet_center_points_workspace_bytes(int B, int H, int W, int max_label);
+int cdnet_center_points(const int32_t* labels, int32_t* centres, int B, int H, int W, int max_label,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* ---- LabelEncoding.__call__ (out_c = 3, do_direction = 1), my_transforms_direction.py:697-885 --
+ * ids:       uint8 [B,H,W]  channel 0 of the label image (data_folder.py:29,37)
+ * ternary:   uint8 [B,H,W]  {0,127,255}
+ * point:     __half [B,H,W] Gaussian point map (sigma 2) as float16 bits
+ * direction: int64 [B,H,W]  classes 0..num_classes
+ * instance_level[b] != 0: ids are instance ids (reference: > 2 unique values), else a {0,255}
+ * three-class label.  num_classes in {8, 16} (env dt_num_classes of the reference).
+ * inst_out (may be NULL): int32 [B,H,W] the dilated instance map (label_instance). */
+size_t cdnet_encode_targets_workspace_bytes(int B, int H, int W);
+int cdnet_encode_targets(const uint8_t* ids, const uint8_t* instance_level, uint8_t* ternary,
+                         uint16_t* point, int64_t* direction, int32_t* inst_out, int32_t* status,
+                         int B, int H, int W, int num_classes, void* ws, size_t ws_bytes,
+                         void* stream);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long cdnet_launch_count(void);
+
+/* optional per-launch CUDA-event timing (bench.py's live roofline numbers): enable, run, then
+ * cdnet_profile_report() synchronises the device and writes "kernel\tlaunches\ttotal_ms\n" lines
+ * into buf; returns the number of distinct kernels and clears the records. */
+void cdnet_profile_enable(int on);
+int cdnet_profile_report(char* buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDNET_B200_H_ */
