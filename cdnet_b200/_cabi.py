@@ -41,8 +41,9 @@ SIGNATURES = {
     "cdnet_center_points_workspace_bytes": (c_size_t, [c_int] * 4),
     "cdnet_center_points": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cdnet_encode_targets_workspace_bytes": (c_size_t, [c_int] * 3),
-    "cdnet_encode_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                     c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "cdnet_label_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cdnet_encode_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdnet_launch_count": (ctypes.c_ulonglong, []),
     "cdnet_profile_enable": (None, [c_int]),
     "cdnet_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),

@@ -420,3 +420,142 @@ def plain_postprocess(prob_maps, min_area=20, radius=2, postproc=0, model_name="
     prob = _h2d(np.asarray(prob_maps), np.float32)[None]
     out, _ = plain_postprocess_cuda(prob, min_area, radius, postproc, multi_class)
     return out[0].cpu().numpy()
+
+
+# =====================================================================================================
+# target transform (my_transforms_direction.py:651-885)
+# =====================================================================================================
+def _gauss_weights():
+    # scipy.ndimage._filters._gaussian_kernel1d(sigma=2, order=0, radius=int(4*2+0.5)) evaluated with the
+    # host's numpy exactly as scipy does, so the weights are bit-identical to the reference's on this host
+    x = np.arange(-8, 9)
+    phi = np.exp(-0.5 / 4.0 * x ** 2)
+    return np.ascontiguousarray(phi / phi.sum(), dtype=np.float64)
+
+
+def label_stats_cuda(ids):
+    """ids uint8 [B,H,W] -> (n_distinct int32 [B], fg_count int32 [B]) on the device."""
+    L = _cabi.lib()
+    dev = _device(ids.device)
+    ids = _cu8(ids)
+    B, H, W = ids.shape
+    pres = torch.empty((B, 256), dtype=torch.int32, device=dev)
+    fg = torch.empty((B,), dtype=torch.int32, device=dev)
+    check(L.cdnet_label_stats(_ptr(ids), _ptr(pres), _ptr(fg), B, H, W, _stream()), "cdnet_label_stats")
+    return pres.sum(dim=1), fg
+
+
+def encode_targets_cuda(ids, instance_level=True, num_classes=8, want_inst=False, want_dir=False):
+    """ids uint8 [B,H,W] (channel 0 of the label image) ->
+    (ternary uint8 [B,H,W], point float16 [B,H,W], direction int64 [B,H,W][, inst int32][, dir f32 [B,H,W,2]])."""
+    L = _cabi.lib()
+    dev = _device(ids.device)
+    ids = _cu8(ids)
+    B, H, W = ids.shape
+    ternary = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    point = torch.empty((B, H, W), dtype=torch.float16, device=dev)
+    direction = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+    inst = torch.empty((B, H, W), dtype=torch.int32, device=dev) if want_inst else None
+    dirm = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev) if want_dir else None
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    nb = L.cdnet_encode_targets_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    gw = _gauss_weights()
+    check(L.cdnet_encode_targets(_ptr(ids), 1 if instance_level else 0, _ptr(ternary), _ptr(point), _ptr(direction),
+                                 _ptr(inst), _ptr(dirm), _ptr(status), B, H, W, int(num_classes), gw.ctypes.data,
+                                 _ptr(ws), ws.numel(), _stream()), "cdnet_encode_targets")
+    res = [ternary, point, direction]
+    if want_inst:
+        res.append(inst)
+    if want_dir:
+        res.append(dirm)
+    return tuple(res)
+
+
+def center_points_cuda(labels, max_label):
+    """labels int32 [B,H,W] -> centres int32 [B, max_label+1, 2] (row, col); (-1,-1) for absent ids."""
+    L = _cabi.lib()
+    dev = _device(labels.device)
+    lab = labels.to(torch.int32).contiguous()
+    B, H, W = lab.shape
+    out = torch.empty((B, int(max_label) + 1, 2), dtype=torch.int32, device=dev)
+    nb = L.cdnet_center_points_workspace_bytes(B, H, W, int(max_label))
+    ws = _workspace(nb, dev)
+    check(L.cdnet_center_points(_ptr(lab), _ptr(out), B, H, W, int(max_label), _ptr(ws), ws.numel(), _stream()),
+          "cdnet_center_points")
+    return out
+
+
+def get_centerpoint2(mask, n=None, m=None):
+    """my_transforms_direction.py:651-685: [row, col] of the first raster-order pixel of maximum centerness
+    of the (single) nucleus `mask > 0`; [-1, -1] for an empty mask."""
+    mk = np.asarray(mask)
+    if n is not None and m is not None:
+        mk = mk[:n, :m]
+    lab = _h2d((mk > 0).astype(np.int32))[None]
+    c = center_points_cuda(lab, 1)[0, 1].cpu().numpy()
+    return [int(c[0]), int(c[1])]
+
+
+class LabelEncoding(object):
+    """Drop-in for my_transforms_direction.LabelEncoding (:687-885): `LabelEncoding(out_c, radius,
+    do_direction)(imgs)` with imgs = (img, weight_map, label) returns
+    (img, weight_map, PIL 'L' ternary label {0,127,255}[, float16 point map, int64 direction classes]).
+
+    The number of direction classes is the reference's env `dt_num_classes` (default 8;
+    data_prepare/SegFix_offset_helper.py:37-39) unless `num_classes` is given.  CUDA cannot be
+    initialised in a forked DataLoader worker: apply this transform in the main process (or use
+    workers started with 'spawn'); `encode_batch` takes a whole batch of label images at once."""
+
+    def __init__(self, out_c=3, radius=1, do_direction=0, num_classes=None):
+        import os
+        self.out_c = out_c
+        self.radius = 1  # the reference ignores its argument (:694)
+        self.do_direction = do_direction
+        self.num_classes = int(os.environ.get("dt_num_classes", 8)) if num_classes is None else int(num_classes)
+        if self.out_c != 3:
+            raise NotImplementedError("out_c != 3 (my_transforms_direction.py:721-739) is out of scope")
+
+    @staticmethod
+    def _channel0(label):
+        if not isinstance(label, np.ndarray):
+            label = np.array(label)
+        inside = label if label.ndim == 2 else label[:, :, 0]
+        if inside.dtype != np.uint8:
+            if inside.size and (inside.min() < 0 or inside.max() > 255):
+                raise CdnetError("label ids must fit uint8, as data_folder.py:29,37 delivers them")
+            inside = inside.astype(np.uint8)
+        return np.ascontiguousarray(inside)
+
+    def encode_batch(self, labels):
+        """labels: list of label images (same H x W) -> list of (ternary u8, point f16, direction int64)."""
+        try:
+            dev = _device()
+        except RuntimeError as e:  # pragma: no cover
+            raise CdnetError("LabelEncoding needs CUDA in this process (forked DataLoader workers cannot "
+                             "initialise it; run the transform post-collate in the main process): %s" % e)
+        ids = np.stack([self._channel0(l) for l in labels])
+        d_ids = torch.from_numpy(ids).to(dev)
+        ndist, _ = label_stats_cuda(d_ids)
+        level = (ndist > 2).cpu().numpy()
+        out = [None] * len(labels)
+        for lv in (True, False):
+            sel = np.nonzero(level == lv)[0]
+            if sel.size == 0:
+                continue
+            sub = d_ids[torch.from_numpy(sel).to(dev)] if sel.size != len(labels) else d_ids
+            tern, point, direction = encode_targets_cuda(sub, instance_level=lv, num_classes=self.num_classes)
+            tern, point, direction = tern.cpu().numpy(), point.cpu().numpy(), direction.cpu().numpy()
+            for j, i in enumerate(sel):
+                out[i] = (tern[j], point[j], direction[j])
+        return out
+
+    def __call__(self, imgs):
+        from PIL import Image
+        out_imgs = list(imgs)
+        tern, point, direction = self.encode_batch([imgs[2]])[0]
+        out_imgs[2] = Image.fromarray(tern)
+        if self.do_direction == 1:
+            out_imgs.append(point)
+            out_imgs.append(direction)
+        return tuple(out_imgs)

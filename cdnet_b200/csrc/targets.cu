@@ -1,8 +1,489 @@
-// targets.cu -- placeholder until the target-transform kernels land (next commit).
+// targets.cu -- instance-label -> training-target transform (K14-K19).
+//
+// Replaces LabelEncoding.__call__ (my_transforms_direction.py:697-885, out_c = 3, do_direction = 1)
+// and get_centerpoint2 (my_transforms_direction.py:651-685), with the quantiser of
+// data_prepare/SegFix_offset_helper.py:311-341,423-450,486-506 and the Sobel kernel of :102-132.
+//
+// O(H*W) reformulation of the reference's per-nucleus full-canvas loop (:800-835), exact by
+// SURVEY.md Appendix B:
+//   * centre of nucleus k = first raster pixel of maximum centerness; computed for ALL labels at
+//     once: every foreground pixel bisects its 8 rays against `inst == own label`, a u64 atomicMax
+//     on the f64 bit pattern picks the maximum per label and an atomicMin the first pixel;
+//   * EDT(1 - point) is the Euclidean distance to the centre; its per-nucleus maximum over the
+//     cross-dilated support is an integer atomicMax of dy^2+dx^2 (sqrt is monotone);
+//   * "last writer wins" compositing == the winner w(p) = max label in p's cross neighbourhood;
+//     dir(p) = sum over the 11x11 taps q of K[q-p] * f32(dc_w(q)), evaluated as the sequential f32
+//     FMA chain in (kh, kw) order that torch's CPU conv2d was measured to produce (zero taps are
+//     exact no-ops, so only taps inside w's dilated support are touched);
+//   * the double quantisation (:853-855) is idempotent: class = align_angle(angle) index;
+//   * Gaussian point map = separable 17-tap f64 correlation (scipy's symmetric summation order,
+//     reflect border) of 255 at the centres, cast to f16.
+#include <cuda_fp16.h>
+#include <math.h>
+
 #include "internal.h"
 
-extern "C" size_t cdnet_center_points_workspace_bytes(int, int, int, int) { return 0; }
-extern "C" int cdnet_center_points(const int32_t*, int32_t*, int, int, int, int, void*, size_t, void*) { return 3; }
-extern "C" size_t cdnet_encode_targets_workspace_bytes(int, int, int) { return 0; }
-extern "C" int cdnet_encode_targets(const uint8_t*, const uint8_t*, uint8_t*, uint16_t*, int64_t*, int32_t*, int32_t*,
-                                    int, int, int, int, void*, size_t, void*) { return 3; }
+namespace cdnet {
+
+__constant__ float c_sobel[2][121];
+__constant__ double c_gauss[17];
+// (sin, cos)(2*pi/8*k) exactly as CPython/numba's libm produces them (my_transforms_direction.py:657-658)
+__constant__ double c_rays[8][2] = {
+    {0x0.0p+0, 0x1.0000000000000p+0},
+    {0x1.6a09e667f3bccp-1, 0x1.6a09e667f3bcdp-1},
+    {0x1.0000000000000p+0, 0x1.1a62633145c07p-54},
+    {0x1.6a09e667f3bcdp-1, -0x1.6a09e667f3bccp-1},
+    {0x1.1a62633145c07p-53, -0x1.0000000000000p+0},
+    {-0x1.6a09e667f3bccp-1, -0x1.6a09e667f3bcep-1},
+    {-0x1.0000000000000p+0, -0x1.a79394c9e8a0ap-53},
+    {-0x1.6a09e667f3bcep-1, 0x1.6a09e667f3bcbp-1},
+};
+
+constexpr int kBX = 128, kBY = 4;
+static inline dim3 px_grid(int B, int H, int W) { return dim3(ceil_div(W, kBX), ceil_div(H, kBY), B); }
+static inline dim3 px_block() { return dim3(kBX, kBY); }
+#define PX_COORDS                                              \
+    const int x = blockIdx.x * kBX + threadIdx.x;              \
+    const int y = blockIdx.y * kBY + threadIdx.y;              \
+    const int b = blockIdx.z;                                  \
+    const bool inb = (x < W) && (y < H);                       \
+    const size_t tile = (size_t)b * H * W;                     \
+    const int p = y * W + x;                                   \
+    const int lane = threadIdx.x & 31;                         \
+    (void)lane; (void)p; (void)tile; (void)inb;
+
+// ---- label statistics ------------------------------------------------------------------------------
+// presence[b][v] = 1 if value v occurs; fg[b] = number of non-zero pixels
+__global__ void __launch_bounds__(256) k_label_stats(const uint8_t* __restrict__ ids, int* __restrict__ presence,
+                                                     int* __restrict__ fg, size_t plane) {
+    __shared__ int s_pres[256];
+    __shared__ int s_cnt;
+    const int b = blockIdx.y;
+    s_pres[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint8_t* I = ids + (size_t)b * plane;
+    int cnt = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = I[i];
+        s_pres[v] = 1;
+        cnt += v != 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (s_pres[threadIdx.x]) presence[b * 256 + threadIdx.x] = 1;
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(fg + b, s_cnt);
+}
+
+// ---- ternary label / interior (my_transforms_direction.py:743-751, 763-770, 781) --------------------
+__global__ void __launch_bounds__(kBX* kBY) k_t_ternary(const uint8_t* __restrict__ ids, const int* __restrict__ fg,
+                                                        int instance_level, uint8_t* __restrict__ ternary,
+                                                        uint8_t* __restrict__ inside, uint8_t* __restrict__ interior,
+                                                        int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const uint8_t* I = ids + tile;
+    auto val = [&](int q) -> int { const int v = I[q]; return instance_level ? v : (v > 127 ? 1 : 0); };
+    const int v = val(p);
+    int mx = v, mn = v;
+    if (y > 0) { const int u = val(p - W); mx = max(mx, u); mn = min(mn, u); }
+    if (y + 1 < H) { const int u = val(p + W); mx = max(mx, u); mn = min(mn, u); }
+    if (x > 0) { const int u = val(p - 1); mx = max(mx, u); mn = min(mn, u); }
+    if (x + 1 < W) { const int u = val(p + 1); mx = max(mx, u); mn = min(mn, u); }
+    int nl = v > 0;
+    // remove_small_objects(new_label, 5) on a {0,1} uint8 image treats the value 1 as ONE object (:746)
+    if (instance_level && fg[b] < 5) nl = 0;
+    const int ins = nl;
+    if (mx != mn) nl = 2;  // dilation(ids) & ~erosion(ids) > 0  <=>  cross-max != cross-min
+    ternary[tile + p] = nl == 0 ? 0 : (nl == 1 ? 127 : 255);
+    inside[tile + p] = ins;
+    interior[tile + p] = nl == 1;
+}
+
+// ---- centre search (my_transforms_direction.py:651-685) ---------------------------------------------
+__device__ __forceinline__ double ray_reach(const int* __restrict__ L, int H, int W, int i, int j, int own, double sy,
+                                            double sx) {
+    double lo = 0.0, hi = 1000.0;
+    const double fi = (double)i, fj = (double)j;
+#pragma unroll 1
+    for (int it = 0; it < 30; ++it) {
+        const double mid = __dmul_rn(__dadd_rn(lo, hi), 0.5);
+        const double ry = rint(__dadd_rn(fi, __dmul_rn(sy, mid)));  // python round(): half to even
+        const double rx = rint(__dadd_rn(fj, __dmul_rn(sx, mid)));
+        bool hit = false;
+        if (ry >= 0.0 && ry < (double)H && rx >= 0.0 && rx < (double)W) hit = L[(int)ry * W + (int)rx] == own;
+        if (hit) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+// table layout per tile: entries 0..tab-1 (label ids)
+__global__ void __launch_bounds__(kBX* kBY) k_t_centerness(const int* __restrict__ inst, double* __restrict__ cness,
+                                                           unsigned long long* __restrict__ best, int tab, int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const int* L = inst + tile;
+    const int own = L[p];
+    if (own <= 0 || own >= tab) return;
+    double far = 0.0, near = 10000000.0;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const double r = ray_reach(L, H, W, y, x, own, c_rays[k][0], c_rays[k][1]);
+        far = fmax(far, r);
+        near = fmin(near, r);
+    }
+    const double c = __ddiv_rn(near, far);
+    cness[tile + p] = c;
+    atomicMax(best + (size_t)b * tab + own, (unsigned long long)__double_as_longlong(c));
+}
+
+__global__ void __launch_bounds__(kBX* kBY) k_t_center_pick(const int* __restrict__ inst, const double* __restrict__ cness,
+                                                            const unsigned long long* __restrict__ best,
+                                                            int* __restrict__ centre, int tab, int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const int own = inst[tile + p];
+    if (own <= 0 || own >= tab) return;
+    if ((unsigned long long)__double_as_longlong(cness[tile + p]) == best[(size_t)b * tab + own])
+        atomicMin(centre + (size_t)b * tab + own, p);  // strict '>' keeps the first raster maximum
+}
+
+__global__ void k_t_table_init(unsigned long long* __restrict__ best, int* __restrict__ centre, int* __restrict__ maxd2,
+                               size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (best) best[i] = 0ull;
+        centre[i] = 0x7fffffff;
+        if (maxd2) maxd2[i] = 0;
+    }
+}
+
+// centres -> [B, tab, 2] (row, col), (-1,-1) for absent ids
+__global__ void k_t_centres_out(const int* __restrict__ centre, int* __restrict__ out, int W, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = centre[i];
+        out[2 * i] = c == 0x7fffffff ? -1 : c / W;
+        out[2 * i + 1] = c == 0x7fffffff ? -1 : c % W;
+    }
+}
+
+// distinct non-zero labels in the cross neighbourhood of p (dilation(nucleus, disk(1)) support, :819)
+__device__ __forceinline__ int cross_labels(const int* __restrict__ L, int H, int W, int y, int x, int out[5]) {
+    const int p = y * W + x;
+    int n = 0;
+    auto add = [&](int v) {
+        if (v <= 0) return;
+        for (int i = 0; i < n; ++i)
+            if (out[i] == v) return;
+        out[n++] = v;
+    };
+    add(L[p]);
+    if (y > 0) add(L[p - W]);
+    if (y + 1 < H) add(L[p + W]);
+    if (x > 0) add(L[p - 1]);
+    if (x + 1 < W) add(L[p + 1]);
+    return n;
+}
+
+// maxd2[k] = max over the dilated support of k of |q - c_k|^2 ; cflag marks the centres (label_point, :816)
+__global__ void __launch_bounds__(kBX* kBY) k_t_support_max(const int* __restrict__ inst, const int* __restrict__ centre,
+                                                            int* __restrict__ maxd2, uint8_t* __restrict__ cflag, int tab,
+                                                            int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const int* L = inst + tile;
+    int labs[5];
+    const int n = cross_labels(L, H, W, y, x, labs);
+    const int own = L[p];
+    uint8_t flag = 0;
+    for (int i = 0; i < n; ++i) {
+        const int k = labs[i];
+        if (k >= tab) continue;
+        const int c = centre[(size_t)b * tab + k];
+        const int dy = y - c / W, dx = x - c % W;
+        atomicMax(maxd2 + (size_t)b * tab + k, dy * dy + dx * dx);
+        if (k == own && c == p) flag = 1;
+    }
+    cflag[tile + p] = flag;
+}
+
+__device__ __forceinline__ int align_index(float a, int n) {
+    // SegFix_offset_helper.py:311-341 (upper-inclusive bins; all thresholds exact in f32 for n = 8, 16)
+    const float step = 360.0f / (float)n, half = step * 0.5f;
+    if (a <= -180.0f + half || a > 180.0f - half) return 0;
+    for (int i = 1; i < n; ++i) {
+        const float mid = -180.0f + step * (float)i;
+        if (a > mid - half && a <= mid + half) return i;
+    }
+    return 0;
+}
+
+constexpr int kDX = 32, kDY = 8, kHalo = 6;  // 11x11 taps + 1 for the cross dilation
+
+// direction class per pixel (:827-834, :848-871)
+__global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict__ inst, const int* __restrict__ centre,
+                                                          const int* __restrict__ maxd2, const uint8_t* __restrict__ inside,
+                                                          long long* __restrict__ direction, float* __restrict__ dir_out,
+                                                          int tab, int n_classes, int H, int W) {
+    __shared__ int s_l[kDY + 2 * kHalo][kDX + 2 * kHalo + 1];
+    const int b = blockIdx.z;
+    const size_t tile = (size_t)b * H * W;
+    const int* L = inst + tile;
+    const int bx0 = blockIdx.x * kDX, by0 = blockIdx.y * kDY;
+    for (int i = threadIdx.y * kDX + threadIdx.x; i < (kDY + 2 * kHalo) * (kDX + 2 * kHalo); i += kDX * kDY) {
+        const int ly = i / (kDX + 2 * kHalo), lx = i % (kDX + 2 * kHalo);
+        const int gy = by0 + ly - kHalo, gx = bx0 + lx - kHalo;
+        s_l[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? L[gy * W + gx] : 0;
+    }
+    __syncthreads();
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int p = y * W + x;
+    const int ly = threadIdx.y + kHalo, lx = threadIdx.x + kHalo;
+    // winner = highest label whose dilated support contains p ("last writer wins", :832-834)
+    int w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])), max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
+    float acc0 = 0.0f, acc1 = 0.0f;
+    if (w > 0 && w < tab) {
+        const int c = centre[(size_t)b * tab + w];
+        const int cy = c / W, cx = c % W;
+        const double denom = __dadd_rn(__dsqrt_rn((double)maxd2[(size_t)b * tab + w]), 0.0000001);
+#pragma unroll 1
+        for (int kh = 0; kh < 11; ++kh) {
+            const int qy = ly + kh - 5;
+            const int gy = y + kh - 5;
+            if (gy < 0 || gy >= H) continue;
+#pragma unroll 1
+            for (int kw = 0; kw < 11; ++kw) {
+                const int qx = lx + kw - 5;
+                const int gx = x + kw - 5;
+                if (gx < 0 || gx >= W) continue;
+                const bool member = s_l[qy][qx] == w || s_l[qy - 1][qx] == w || s_l[qy + 1][qx] == w ||
+                                    s_l[qy][qx - 1] == w || s_l[qy][qx + 1] == w;
+                if (!member) continue;
+                const int dy = gy - cy, dx = gx - cx;
+                const double dist = __dsqrt_rn((double)(dy * dy + dx * dx));
+                // distance_center_i = (1 - int_pos / (int_pos.max() + 1e-7)) * nucleus  (:824), then .float()
+                const float v = __double2float_rn(__dadd_rn(1.0, -__ddiv_rn(dist, denom)));
+                acc0 = __fmaf_rn(c_sobel[0][kh * 11 + kw], v, acc0);
+                acc1 = __fmaf_rn(c_sobel[1][kh * 11 + kw], v, acc1);
+            }
+        }
+    }
+    if (dir_out) {
+        dir_out[(tile + p) * 2] = acc0;
+        dir_out[(tile + p) * 2 + 1] = acc1;
+    }
+    long long cls = 0;
+    if (inside[tile + p]) {
+        // angle = degrees(arctan2(dir0, dir1)) in f32 (:848); the reference's libm/SVML atan2f is not
+        // correctly rounded, this is (f64 atan2 rounded to f32) -- differences are confined to a few
+        // ulp of the angle, i.e. to pixels within ~1e-5 degrees of a bin edge
+        const float ang = __fmul_rn(__double2float_rn(atan2((double)acc0, (double)acc1)), 57.295776f);
+        cls = align_index(ang, n_classes) + 1;
+    }
+    direction[tile + p] = cls;
+}
+
+// ---- Gaussian point map (:842) ----------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // scipy 'reflect': (d c b a | a b c d | d c b a)
+    if (n == 1) return 0;
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+
+constexpr int kGX = 32, kGY = 16, kGR = 8;
+
+__global__ void __launch_bounds__(kGX* kGY) k_t_gauss(const uint8_t* __restrict__ cflag, __half* __restrict__ out, int H,
+                                                      int W) {
+    __shared__ uint8_t s_f[kGY + 2 * kGR][kGX + 2 * kGR];
+    __shared__ double s_v[kGY][kGX + 2 * kGR];
+    const int b = blockIdx.z;
+    const size_t tile = (size_t)b * H * W;
+    const uint8_t* F = cflag + tile;
+    const int bx0 = blockIdx.x * kGX, by0 = blockIdx.y * kGY;
+    const int tid = threadIdx.y * kGX + threadIdx.x;
+    for (int i = tid; i < (kGY + 2 * kGR) * (kGX + 2 * kGR); i += kGX * kGY) {
+        const int ly = i / (kGX + 2 * kGR), lx = i % (kGX + 2 * kGR);
+        const int gy = reflect_idx(by0 + ly - kGR, H), gx = reflect_idx(bx0 + lx - kGR, W);
+        s_f[ly][lx] = F[gy * W + gx];
+    }
+    __syncthreads();
+    // axis 0 first (scipy.ndimage.gaussian_filter iterates axes in order), symmetric summation order of
+    // correlate1d: centre term, then (in[l-j] + in[l+j]) * w[8-j] for j = 8 .. 1
+    for (int i = tid; i < kGY * (kGX + 2 * kGR); i += kGX * kGY) {
+        const int ly = i / (kGX + 2 * kGR), lx = i % (kGX + 2 * kGR);
+        const int cy = ly + kGR;
+        double t = __dmul_rn(s_f[cy][lx] ? 255.0 : 0.0, c_gauss[8]);
+#pragma unroll
+        for (int j = 8; j >= 1; --j) {
+            const double a = s_f[cy - j][lx] ? 255.0 : 0.0, c = s_f[cy + j][lx] ? 255.0 : 0.0;
+            t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), c_gauss[8 - j]));
+        }
+        s_v[ly][lx] = t;
+    }
+    __syncthreads();
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int lx = threadIdx.x + kGR;
+    double t = __dmul_rn(s_v[threadIdx.y][lx], c_gauss[8]);
+#pragma unroll
+    for (int j = 8; j >= 1; --j)
+        t = __dadd_rn(t, __dmul_rn(__dadd_rn(s_v[threadIdx.y][lx - j], s_v[threadIdx.y][lx + j]), c_gauss[8 - j]));
+    out[tile + (size_t)y * W + x] = __double2half(t);
+}
+
+static void sobel_weights(float out[2][121]) {
+    // SegFix_offset_helper.py:102-132: k[j,i] = (i_ or j_) / (i_^2 + j_^2) in f64, stored to f32;
+    // channel 0 = sobel_y (row offset j_), channel 1 = sobel_x (column offset i_)
+    for (int j = 0; j < 11; ++j)
+        for (int i = 0; i < 11; ++i) {
+            const int j_ = j - 5, i_ = i - 5;
+            float ky = 0.f, kx = 0.f;
+            if (i_ != 0 || j_ != 0) {
+                const double r2 = (double)(i_ * i_ + j_ * j_);
+                ky = (float)((double)j_ / r2);
+                kx = (float)((double)i_ / r2);
+            }
+            out[0][j * 11 + i] = ky;
+            out[1][j * 11 + i] = kx;
+        }
+}
+
+static int centres_launch(const int32_t* inst, double* cness, unsigned long long* best, int32_t* centre, int32_t* maxd2,
+                          int tab, int B, int H, int W, cudaStream_t st) {
+    const size_t nt = (size_t)B * tab;
+    const size_t blocks = (nt + 255) / 256;
+    CDNET_LAUNCH(k_t_table_init, (unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, st, best, centre, maxd2, nt);
+    CDNET_LAUNCH(k_t_centerness, px_grid(B, H, W), px_block(), 0, st, inst, cness, best, tab, H, W);
+    CDNET_LAUNCH(k_t_center_pick, px_grid(B, H, W), px_block(), 0, st, inst, cness, best, centre, tab, H, W);
+    return last_error();
+}
+
+}  // namespace cdnet
+
+using namespace cdnet;
+
+static bool bad_dims(int B, int H, int W) { return B <= 0 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0; }
+
+extern "C" int cdnet_label_stats(const uint8_t* ids, int32_t* presence, int32_t* fg_count, int B, int H, int W,
+                                 void* stream) {
+    if (!ids || !presence || !fg_count || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CDNET_CUDA_OK(cudaMemsetAsync(presence, 0, sizeof(int32_t) * 256 * (size_t)B, st));
+    CDNET_CUDA_OK(cudaMemsetAsync(fg_count, 0, sizeof(int32_t) * (size_t)B, st));
+    const size_t plane = (size_t)H * W;
+    int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
+    CDNET_LAUNCH(k_label_stats, dim3(gx, B), 256, 0, st, ids, presence, fg_count, plane);
+    return last_error();
+}
+
+extern "C" size_t cdnet_center_points_workspace_bytes(int B, int H, int W, int max_label) {
+    if (bad_dims(B, H, W) || max_label < 0) return 0;
+    const size_t n = (size_t)B * H * W, nt = (size_t)B * ((size_t)max_label + 1);
+    return pad256(n * 8) + pad256(nt * 8) + pad256(nt * 4);
+}
+
+extern "C" int cdnet_center_points(const int32_t* labels, int32_t* centres, int B, int H, int W, int max_label, void* ws,
+                                   size_t ws_bytes, void* stream) {
+    if (!labels || !centres || bad_dims(B, H, W) || max_label < 0) return CDNET_E_BADARG;
+    const int tab = max_label + 1;
+    Arena ar(ws, ws_bytes);
+    double* cness = ar.take<double>((size_t)B * H * W);
+    unsigned long long* best = ar.take<unsigned long long>((size_t)B * tab);
+    int32_t* centre = ar.take<int32_t>((size_t)B * tab);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = centres_launch(labels, cness, best, centre, nullptr, tab, B, H, W, st);
+    if (rc) return rc;
+    const size_t nt = (size_t)B * tab;
+    const size_t blocks = (nt + 255) / 256;
+    CDNET_LAUNCH(k_t_centres_out, (unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, st, centre, centres, W, nt);
+    return last_error();
+}
+
+extern "C" size_t cdnet_encode_targets_workspace_bytes(int B, int H, int W) {
+    if (bad_dims(B, H, W)) return 0;
+    const size_t n = (size_t)B * H * W, nt = (size_t)B * ((size_t)H * W + 1);
+    return pad256(n * 8) + pad256(nt * 8) + 2 * pad256(nt * 4) + 2 * pad256(n * 4) + 3 * pad256(n) +
+           pad256((size_t)B * 4) + pad256((size_t)B * 1024) + pad256((size_t)B * H * 4) + ws_process_workspace(B, H, W);
+}
+
+extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternary, uint16_t* point,
+                                    int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status, int B, int H,
+                                    int W, int num_classes, const double* gauss_w, void* ws, size_t ws_bytes,
+                                    void* stream) {
+    if (!ids || !ternary || !point || !direction || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    if (num_classes != 8 && num_classes != 16) return CDNET_E_BADARG;
+    if (ws_bytes < cdnet_encode_targets_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)B * H * W;
+    const int tab = (int)((size_t)H * W + 1 > 0x7fffffff ? 0x7fffffff : (size_t)H * W + 1);
+    const size_t nt = (size_t)B * tab;
+    Arena ar(ws, ws_bytes);
+    double* cness = ar.take<double>(n);
+    unsigned long long* best = ar.take<unsigned long long>(nt);
+    int32_t* centre = ar.take<int32_t>(nt);
+    int32_t* maxd2 = ar.take<int32_t>(nt);
+    int32_t* inst_raw = ar.take<int32_t>(n);
+    int32_t* inst_ws = ar.take<int32_t>(n);
+    uint8_t* inside = ar.take<uint8_t>(n);
+    uint8_t* interior = ar.take<uint8_t>(n);
+    uint8_t* cflag = ar.take<uint8_t>(n);
+    int32_t* fg = ar.take<int32_t>(B);
+    int32_t* pres = ar.take<int32_t>((size_t)B * 256);
+    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    void* sub_ws = (char*)ws + ar.off;
+    const size_t sub_bytes = ws_bytes - ar.off;
+    int32_t* inst = inst_out ? inst_out : inst_ws;
+    if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
+
+    // constants
+    float sob[2][121];
+    sobel_weights(sob);
+    CDNET_CUDA_OK(cudaMemcpyToSymbolAsync(c_sobel, sob, sizeof sob, 0, cudaMemcpyHostToDevice, st));
+    double gw[17];
+    if (gauss_w) {
+        for (int i = 0; i < 17; ++i) gw[i] = gauss_w[i];
+    } else {
+        // scipy.ndimage._filters._gaussian_kernel1d(sigma=2, order=0, radius=8)
+        double s = 0.0;
+        for (int i = 0; i < 17; ++i) { const double t = (double)(i - 8); gw[i] = exp(-0.5 / 4.0 * t * t); s += gw[i]; }
+        for (int i = 0; i < 17; ++i) gw[i] /= s;
+    }
+    CDNET_CUDA_OK(cudaMemcpyToSymbolAsync(c_gauss, gw, sizeof gw, 0, cudaMemcpyHostToDevice, st));
+
+    // 1. ternary label, fg mask, interior
+    CDNET_CUDA_OK(cudaMemsetAsync(fg, 0, sizeof(int32_t) * (size_t)B, st));
+    {
+        const size_t plane = (size_t)H * W;
+        int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
+        CDNET_LAUNCH(k_label_stats, dim3(gx, B), 256, 0, st, ids, pres, fg, plane);
+    }
+    CDNET_LAUNCH(k_t_ternary, px_grid(B, H, W), px_block(), 0, st, ids, fg, instance_level, ternary, inside, interior, H, W);
+    // 2. instances: process(interior*255, min_size=5) (:759) or measure.label (:773), then dilation disk(1)
+    int rc;
+    if (instance_level) {
+        rc = ws_process_launch(interior, inst_raw, status, B, H, W, 5, 1, sub_ws, sub_bytes, st);
+    } else {
+        Arena sub(sub_ws, sub_bytes);
+        int32_t* Lp = sub.take<int32_t>(n);
+        int32_t* idmap = sub.take<int32_t>(n);
+        if (!sub.ok) return CDNET_E_WORKSPACE;
+        rc = ccl_label_launch(interior, inst_raw, nullptr, Lp, idmap, rowcnt, B, H, W, 8, st);
+    }
+    if (rc) return rc;
+    rc = label_dilate_launch(inst_raw, inst, 4, B, H, W, 1, st);
+    if (rc) return rc;
+    // 3. centres, support maxima, direction classes, point map
+    rc = centres_launch(inst, cness, best, centre, maxd2, tab, B, H, W, st);
+    if (rc) return rc;
+    CDNET_LAUNCH(k_t_support_max, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, cflag, tab, H, W);
+    CDNET_LAUNCH(k_t_direction, dim3(ceil_div(W, kDX), ceil_div(H, kDY), B), dim3(kDX, kDY), 0, st, inst, centre, maxd2,
+                 inside, (long long*)direction, dir_out, tab, num_classes, H, W);
+    CDNET_LAUNCH(k_t_gauss, dim3(ceil_div(W, kGX), ceil_div(H, kGY), B), dim3(kGX, kGY), 0, st, cflag, (__half*)point, H, W);
+    return last_error();
+}

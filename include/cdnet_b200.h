@@ -135,19 +135,29 @@ size_t cdnet_center_points_workspace_bytes(int B, int H, int W, int max_label);
 int cdnet_center_points(const int32_t* labels, int32_t* centres, int B, int H, int W, int max_label,
                         void* ws, size_t ws_bytes, void* stream);
 
+/* ---- label statistics for LabelEncoding's branch selection -------------------------------------
+ * my_transforms_direction.py:714-719 (`len(np.unique(label_inside)) > 2` = instance-level input).
+ * presence: int32 [B,256], 1 where the value occurs; fg_count: int32 [B] non-zero pixels. */
+int cdnet_label_stats(const uint8_t* ids, int32_t* presence, int32_t* fg_count, int B, int H, int W,
+                      void* stream);
+
 /* ---- LabelEncoding.__call__ (out_c = 3, do_direction = 1), my_transforms_direction.py:697-885 --
  * ids:       uint8 [B,H,W]  channel 0 of the label image (data_folder.py:29,37)
+ * instance_level != 0: ids are instance ids (reference: > 2 unique values, :743-760), else a
+ *            {0,255} three-class label (:763-774); applies to all B tiles of the call
  * ternary:   uint8 [B,H,W]  {0,127,255}
- * point:     __half [B,H,W] Gaussian point map (sigma 2) as float16 bits
- * direction: int64 [B,H,W]  classes 0..num_classes
- * instance_level[b] != 0: ids are instance ids (reference: > 2 unique values), else a {0,255}
- * three-class label.  num_classes in {8, 16} (env dt_num_classes of the reference).
- * inst_out (may be NULL): int32 [B,H,W] the dilated instance map (label_instance). */
+ * point:     float16 bits [B,H,W] Gaussian point map (sigma 2)
+ * direction: int64 [B,H,W]  classes 0..num_classes; num_classes in {8, 16} (the reference's env
+ *            dt_num_classes, data_prepare/SegFix_offset_helper.py:37-39)
+ * inst_out (may be NULL): int32 [B,H,W] the dilated instance map (label_instance)
+ * dir_out  (may be NULL): float32 [B,H,W,2] the composited Sobel direction map (dir_map)
+ * gauss_w  (HOST pointer, may be NULL): the 17 float64 weights of
+ *            scipy.ndimage gaussian_filter(sigma=2); NULL = computed with libm exp(). */
 size_t cdnet_encode_targets_workspace_bytes(int B, int H, int W);
-int cdnet_encode_targets(const uint8_t* ids, const uint8_t* instance_level, uint8_t* ternary,
-                         uint16_t* point, int64_t* direction, int32_t* inst_out, int32_t* status,
-                         int B, int H, int W, int num_classes, void* ws, size_t ws_bytes,
-                         void* stream);
+int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternary, uint16_t* point,
+                         int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status,
+                         int B, int H, int W, int num_classes, const double* gauss_w, void* ws,
+                         size_t ws_bytes, void* stream);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long cdnet_launch_count(void);

@@ -1,0 +1,107 @@
+"""-m gpu parity tests of the target transform (LabelEncoding / get_centerpoint2): CUDA through the C
+ABI vs goldens generated from the verbatim reference and vs the oracle restatement."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+# The reference's float32 angle goes through the host libm / SVML atan2f, which is not correctly
+# rounded and differs between hosts by a few ulp; the direction CLASS can therefore legitimately
+# differ only where the angle sits within EDGE_TOL degrees of a bin edge.  Everything else is bit-exact.
+EDGE_TOL = 1e-4
+
+
+def _labels(meta, three_class=False):
+    from cdnet_b200 import synth
+    ids = synth.instance_map(meta["seed"], meta["H"], meta["W"], meta["n_target"])
+    if three_class:
+        lab = np.repeat(((ids > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    else:
+        lab = synth.as_uint8_label(ids)
+    assert synth.digest(lab) == meta["digest"], "synthetic inputs differ from the goldens'"
+    return lab
+
+
+def _check_direction(got, ref, lab, n, name):
+    if np.array_equal(got, ref):
+        return
+    from oracle import restate as O
+    bad = np.argwhere(got != ref)
+    parts = O.label_encoding(lab, num_classes=n, literal=False, return_parts=True)[3]
+    step = 360.0 / n
+    for y, x in bad:
+        a = float(parts["angle"][y, x])
+        dist_to_edge = abs(((a + 180.0 - step / 2.0) % step))
+        dist_to_edge = min(dist_to_edge, step - dist_to_edge)
+        assert dist_to_edge < EDGE_TOL, "%s: class differs at (%d,%d) away from a bin edge (angle %r)" % (name, y, x, a)
+    assert len(bad) <= max(2, got.size // 200000), "%s: %d near-edge class differences" % (name, len(bad))
+
+
+@pytest.mark.parametrize("name", ["t_64_single", "t_128", "t_256", "t_250x300_dense", "t_500", "t_1000",
+                                  "t_128x160_threeclass", "t_128_d16", "t_256_d16"])
+def test_label_encoding_golden(cuda_api, name):
+    try:
+        z, meta = load_golden(name)
+    except FileNotFoundError:
+        pytest.skip("golden %s not generated" % name)
+    lab = _labels(meta, three_class="threeclass" in name)
+    enc = cuda_api.LabelEncoding(3, 1, 1, num_classes=meta["num_classes"])
+    res = enc((None, None, lab))
+    assert len(res) == 5
+    tern = np.asarray(res[2])
+    assert tern.dtype == np.uint8 and np.array_equal(tern, z["ternary"]), name
+    assert res[3].dtype == np.float16
+    pg, pr = res[3].astype(np.float64), z["point"].astype(np.float64)
+    assert np.allclose(pg, pr, rtol=1e-5, atol=0), name
+    assert np.array_equal(res[3].view(np.uint16), z["point"].view(np.uint16)), name  # in fact bit-exact
+    assert res[4].dtype == np.int64
+    _check_direction(res[4], z["direction"].astype(np.int64), lab, meta["num_classes"], name)
+
+
+def test_centre_points_golden(cuda_api):
+    import torch
+    z, meta = load_golden("centre")
+    ids = z["ids"]
+    c = cuda_api.center_points_cuda(torch.from_numpy(ids)[None].cuda(), int(ids.max()))[0].cpu().numpy()
+    for k in range(1, meta["n"] + 1):
+        assert list(c[k]) == list(z["c_%d" % k]), k
+        m = (ids == k).astype(np.int64)
+        assert cuda_api.get_centerpoint2(m, m.shape[0], m.shape[1]) == list(z["c_%d" % k])
+
+
+@pytest.mark.parametrize("seed,H,W,n,classes", [(401, 97, 143, 14, 8), (402, 256, 200, 60, 8), (403, 180, 180, 30, 16)])
+def test_label_encoding_vs_oracle(cuda_api, seed, H, W, n, classes):
+    import torch
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    ids = synth.instance_map(seed, H, W, n)
+    lab = synth.as_uint8_label(ids)
+    tern, point, direction, parts = O.label_encoding(lab, num_classes=classes, literal=False, return_parts=True)
+    g = cuda_api.encode_targets_cuda(torch.from_numpy(lab[:, :, 0].copy())[None].cuda(), True, classes,
+                                     want_inst=True, want_dir=True)
+    assert np.array_equal(g[0][0].cpu().numpy(), tern)
+    assert np.array_equal(g[3][0].cpu().numpy(), parts["inst"])
+    assert np.array_equal(g[4][0].cpu().numpy().view(np.uint32), parts["dir_map"].view(np.uint32)), "dir_map bits"
+    assert np.array_equal(g[1][0].cpu().numpy().view(np.uint16), point.view(np.uint16))
+    _check_direction(g[2][0].cpu().numpy(), direction, lab, classes, "seed%d" % seed)
+
+
+def test_label_encoding_edge_cases(cuda_api):
+    from oracle import restate as O
+    # empty tile, tiny nucleus (< 5 px), nucleus on the frame
+    H, W = 48, 56
+    cases = {}
+    cases["empty"] = np.zeros((H, W), np.uint8)
+    a = np.zeros((H, W), np.uint8); a[10:12, 10:12] = 7
+    cases["tiny"] = a
+    b = np.zeros((H, W), np.uint8); b[0:14, 0:17] = 3; b[30:48, 40:56] = 9; b[20:30, 20:33] = 200
+    cases["frame"] = b
+    for name, ids in cases.items():
+        lab = np.repeat(ids[:, :, None], 3, axis=2)
+        ref = O.label_encoding(lab, literal=False)
+        res = cuda_api.LabelEncoding(3, 1, 1, num_classes=8)((None, None, lab))
+        assert np.array_equal(np.asarray(res[2]), ref[0]), name
+        assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), name
+        assert np.array_equal(res[4], ref[2]), name
