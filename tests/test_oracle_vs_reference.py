@@ -1,0 +1,66 @@
+"""CPU, build container only: the oracle restatement against the reference executed VERBATIM from
+/root/reference (oracle/ref_loader.py) on fresh seeded inputs.  Skipped where the reference tree is
+not mounted (the GPU box)."""
+import numpy as np
+import pytest
+
+from cdnet_b200 import synth
+from oracle import ref_loader, restate as O
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+def test_generate_dd_map(ref):
+    rng = np.random.default_rng(9)
+    for cls in (5, 9, 17):
+        x = rng.integers(0, cls, size=(41, 67)).astype(np.uint8)
+        x[rng.integers(0, 2, size=x.shape) == 0] = 0
+        assert np.array_equal(ref.generate_dd_map(x, cls), O.generate_dd_map(x, cls), equal_nan=True)
+
+
+def test_quantiser(ref):
+    ang = np.concatenate([np.linspace(-180, 180, 1441), [22.5, 22.500002, 67.5, -157.5, 157.5, 180.0, -180.0]])
+    ang = ang.astype(np.float32)
+    n = ref.DTOffsetConfig.num_classes
+    a_ref, i_ref = ref.DTOffsetHelper.align_angle(ang.copy(), num_classes=n)
+    a_o, i_o = O.align_angle(ang.copy(), n)
+    assert np.array_equal(i_ref, i_o) and np.array_equal(a_ref, a_o)
+    v_ref = ref.DTOffsetHelper.angle_to_vector(ang.copy(), num_classes=n)
+    assert np.array_equal(v_ref, O.angle_to_vector(ang.copy(), n))
+    assert np.array_equal(ref.DTOffsetHelper.vector_to_label(v_ref, num_classes=n), O.vector_to_label(v_ref, n))
+    # Appendix B.6: the double quantisation is idempotent
+    assert np.array_equal(O.vector_to_label(O.angle_to_vector(ang, n), n), i_o)
+    assert np.array_equal(ref.Sobel.kernel(ksize=11).numpy().reshape(2, 11, 11), O.sobel_kernels(11))
+
+
+def test_postprocess_and_process(ref):
+    d = synth.postproc_inputs(777, 150, 170, 20)
+    for pp in (0, 1):
+        r = ref.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
+        o = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
+        assert r["pred_labeled"].dtype == o["pred_labeled"].dtype
+        assert np.array_equal(r["pred_labeled"], o["pred_labeled"])
+    m = (synth.instance_map(778, 120, 140, 18) > 0).astype(np.uint8) * 255
+    assert np.array_equal(ref.process(m.copy(), "modelName", min_size=5), O.process(m.copy(), "modelName", min_size=5))
+
+
+def test_label_encoding(ref):
+    lab = synth.as_uint8_label(synth.instance_map(779, 110, 130, 12))
+    res = ref.LabelEncoding(3, 1, 1)((None, None, lab))
+    n = ref.DTOffsetConfig.num_classes
+    for literal in (True, False):
+        tern, point, direction = O.label_encoding(lab, num_classes=n, literal=literal)
+        assert np.array_equal(np.asarray(res[2]), tern)
+        assert np.array_equal(res[3].view(np.uint16), point.view(np.uint16))
+        assert np.array_equal(res[4], direction)
+
+
+def test_dcm_voting2(ref):
+    rng = np.random.default_rng(3)
+    dm = rng.integers(0, 9, size=(33, 47, 8)).astype(np.uint8)
+    assert np.array_equal(ref.DcmVoting2(dm), O.dcm_voting2(dm))
