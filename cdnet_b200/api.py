@@ -351,17 +351,41 @@ class DamPostprocessPlan(object):
         self.d_status = torch.zeros((B,), dtype=torch.int32, device=self.dev)
         self.h2d_bytes = self.t_dcm.numel() + 4 * self.t_prob.numel() + 4 * self.t_point.numel()
         self.d2h_bytes = self.t_labels.numel() * self.t_labels.element_size() + 4 * B
+        self._s_in = self._s_out = None
 
-    def launch(self):
-        """H2D, kernels, D2H -- all asynchronous on the current stream."""
-        self.d_dcm.copy_(self.t_dcm, non_blocking=True)
-        self.d_prob.copy_(self.t_prob, non_blocking=True)
-        self.d_point.copy_(self.t_point, non_blocking=True)
-        self.launch_device()
-        self.t_labels.copy_(self.d_labels, non_blocking=True)
-        self.t_status.copy_(self.d_status, non_blocking=True)
-        if self.args[4]:
-            self.t_prob[:, 2].copy_(self.d_prob[:, 2], non_blocking=True)
+    def launch(self, chunk=2):
+        """H2D, kernels, D2H.  The batch is cut into chunks of `chunk` tiles: the pinned-host -> device copy
+        of chunk i+1 (copy-in stream) and the device -> host copy of chunk i-1 (copy-out stream) overlap the
+        kernels of chunk i (current stream).  On return the current stream has been made to wait for the last
+        copy-out, so synchronising it (or recording an event on it) covers the whole step."""
+        B = self.t_dcm.shape[0]
+        cur = torch.cuda.current_stream()
+        if self._s_in is None:
+            self._s_in, self._s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        s_in, s_out = self._s_in, self._s_out
+        s_in.wait_stream(cur)   # the previous step may still be reading the device inputs
+        s_out.wait_stream(cur)
+        dc, ma, ra, pp, wp = self.args
+        for a in range(0, B, chunk):
+            b = min(B, a + chunk)
+            with torch.cuda.stream(s_in):
+                self.d_dcm[a:b].copy_(self.t_dcm[a:b], non_blocking=True)
+                self.d_prob[a:b].copy_(self.t_prob[a:b], non_blocking=True)
+                self.d_point[a:b].copy_(self.t_point[a:b], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            cur.wait_event(ev_in)
+            dam_postprocess_cuda(self.d_dcm[a:b], self.d_prob[a:b], self.d_point[a:b], dc, ma, ra, pp, wp,
+                                 out=self.d_labels[a:b], status=self.d_status[a:b])
+            ev_k = torch.cuda.Event()
+            ev_k.record(cur)
+            s_out.wait_event(ev_k)
+            with torch.cuda.stream(s_out):
+                self.t_labels[a:b].copy_(self.d_labels[a:b], non_blocking=True)
+                self.t_status[a:b].copy_(self.d_status[a:b], non_blocking=True)
+                if wp:
+                    self.t_prob[a:b, 2].copy_(self.d_prob[a:b, 2], non_blocking=True)
+        cur.wait_stream(s_out)
 
     def launch_device(self):
         """kernels only, inputs already resident in d_dcm / d_prob / d_point."""

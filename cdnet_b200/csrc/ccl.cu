@@ -37,42 +37,133 @@ static inline dim3 ccl_grid(int B, int H, int W) { return dim3(ceil_div(W, kBX),
 static inline dim3 ccl_block() { return dim3(kBX, kBY); }
 
 // EQ = false: foreground-only components (mask != 0).  EQ = true: equal-value components of a 0/1 mask.
-template <bool EQ>
-__global__ void __launch_bounds__(kBX* kBY) k_ccl_init(const uint8_t* __restrict__ mask, int* __restrict__ L,
-                                                       int* __restrict__ zero1, int* __restrict__ zero2, int H, int W) {
-    CCL_COORDS
-    const int v = inb ? (mask[tile + p] != 0) : -1;
-    const int vl = __shfl_up_sync(0xffffffffu, v, 1);
-    const bool link = inb && lane > 0 && (EQ ? (v == vl) : (v && vl == 1));
+// One block covers whole rows (row_warps warps per row, up to 1024 pixels per row chunk): every pixel
+// points at the first pixel of its horizontal run inside the chunk -- link bits by ballot, the run start
+// by clz on the warp word or, for runs spanning warps, a prefix-max over the chunk's 32 words.
+__global__ void __launch_bounds__(1024) k_ccl_init_rows(const uint8_t* __restrict__ mask, int* __restrict__ L,
+                                                        int* __restrict__ zero1, int* __restrict__ zero2, int H, int W,
+                                                        int row_warps, int rows_per_block, int eq) {
+    __shared__ unsigned s_link[32];
+    __shared__ int s_lastzero[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const size_t tile = (size_t)b * H * W;
+    const int r_in_block = wid / row_warps, seg = wid % row_warps;
+    const int y = blockIdx.y * rows_per_block + r_in_block;
+    const int x = blockIdx.x * (row_warps * 32) + seg * 32 + lane;
+    const bool active = r_in_block < rows_per_block;
+    const bool inb = active && y < H && x < W;
+    const int p = y * W + x;
+    int v = -1;
+    if (inb) v = mask[tile + p] != 0;
+    // link to the left neighbour (same row chunk only; chunk seams are united by the merge kernel)
+    int vl = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) vl = (inb && seg > 0) ? (mask[tile + p - 1] != 0) : -2;
+    const bool link = inb && (eq ? (v == vl) : (v == 1 && vl == 1));
     const unsigned m = __ballot_sync(0xffffffffu, link);
+    s_link[wid] = m;
+    __syncthreads();
+    // highest run-start position (a zero link bit) at or before the end of each warp word, per row
+    if (wid == 0) {
+        const int my_row = lane / row_warps, my_seg = lane % row_warps;
+        const unsigned z = ~s_link[lane];
+        int lz = (31 - __clz(z)) + my_seg * 32;  // z != 0 for segment 0 (bit 0 is never linked)
+        if (z == 0) lz = -1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, lz, d);
+            const int orow = __shfl_up_sync(0xffffffffu, my_row, d);
+            if (lane >= d && orow == my_row) lz = max(lz, o);
+        }
+        s_lastzero[lane] = lz;
+    }
+    __syncthreads();
     if (!inb) return;
-    const int cnt = __clz(~(m << (31 - lane)));  // consecutive linked lanes ending at this one
-    L[tile + p] = p - cnt;
+    const unsigned zmine = ~m & (0xffffffffu >> (31 - lane));
+    int start_in_chunk;
+    if (zmine) start_in_chunk = seg * 32 + (31 - __clz(zmine));
+    else start_in_chunk = s_lastzero[wid - 1];
+    const int start = p - (seg * 32 + lane) + start_in_chunk;
+    L[tile + p] = start;
     if (zero1) zero1[tile + p] = 0;
     if (zero2) zero2[tile + p] = 0;
 }
 
+struct InitGeom {
+    dim3 grid, block;
+    int row_warps, rows_per_block;
+};
+static inline InitGeom init_geom(int B, int H, int W) {
+    InitGeom g;
+    const int rw = ceil_div(W, 32) < 32 ? ceil_div(W, 32) : 32;
+    g.row_warps = rw;
+    g.rows_per_block = 32 / rw;
+    g.block = dim3(1024);
+    g.grid = dim3(ceil_div(W, rw * 32), ceil_div(H, g.rows_per_block), B);
+    return g;
+}
+#define CCL_INIT(EQ, st, mask, L, z1, z2)                                                                       \
+    do {                                                                                                        \
+        InitGeom g__ = init_geom(B, H, W);                                                                      \
+        CDNET_LAUNCH(k_ccl_init_rows, g__.grid, g__.block, 0, st, mask, L, z1, z2, H, W, g__.row_warps,         \
+                     g__.rows_per_block, (EQ) ? 1 : 0);                                                         \
+    } while (0)
+
+// Vertical (and, for CONN 8, diagonal) links between row y and row y-1 for the rows y = (2k+1) << level.
+// Rows are merged in binary-tree order (level 0 joins row pairs, level 1 joins pairs of pairs, ...): every
+// level hangs the roots of the lower strip under roots of the upper strip, so the depth of the forest is
+// bounded by the number of levels (<= log2 H) instead of growing with H when all rows link at once.
 template <bool EQ, int CONN>
-__global__ void __launch_bounds__(kBX* kBY) k_ccl_merge(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W) {
-    CCL_COORDS
-    if (!inb) return;
+__global__ void __launch_bounds__(kBX* kBY) k_ccl_merge(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W,
+                                                        int level) {
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = (2 * (blockIdx.y * kBY + threadIdx.y) + 1) << level;
+    const int b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const size_t tile = (size_t)b * H * W;
+    const int p = y * W + x;
     const uint8_t* M = mask + tile;
     int* Lt = L + tile;
     const int v = M[p] != 0;
     if (!EQ && !v) return;
     auto same = [&](int q) -> bool { const int u = M[q] != 0; return EQ ? (u == v) : (u != 0); };
     const bool hl = x > 0 && same(p - 1);
-    if (hl && lane == 0) uf_union(Lt, p, p - 1);  // seam between two warp segments of one run
-    if (y > 0) {
-        const bool up = same(p - W);
-        if (up) {
-            // implied by the left neighbour's own vertical link when all four pixels agree
-            const bool redundant = hl && same(p - W - 1);
-            if (!redundant) uf_union(Lt, p, p - W);
-        } else if (CONN == 8) {
-            if (x > 0 && !hl && same(p - W - 1)) uf_union(Lt, p, p - W - 1);
-            if (x + 1 < W && same(p - W + 1) && !same(p + 1)) uf_union(Lt, p, p - W + 1);
-        }
+    const bool up = same(p - W);
+    if (up) {
+        // implied by the left neighbour's own vertical link when all four pixels agree
+        const bool redundant = hl && same(p - W - 1);
+        if (!redundant) uf_union(Lt, p, p - W);
+    } else if (CONN == 8) {
+        if (x > 0 && !hl && same(p - W - 1)) uf_union(Lt, p, p - W - 1);
+        if (x + 1 < W && same(p - W + 1) && !same(p + 1)) uf_union(Lt, p, p - W + 1);
+    }
+}
+
+// runs that continue across a 1024-pixel row-chunk seam of the init kernel (only when W > 1024)
+template <bool EQ>
+__global__ void k_ccl_merge_seams(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W) {
+    const int nseam = (W - 1) / 1024;
+    const int b = blockIdx.y;
+    const size_t tile = (size_t)b * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nseam * H; i += gridDim.x * blockDim.x) {
+        const int y = i / nseam, x = (i % nseam + 1) * 1024;
+        const int p = y * W + x;
+        const int v = mask[tile + p] != 0, u = mask[tile + p - 1] != 0;
+        if (EQ ? (u == v) : (u && v)) uf_union(L + tile, p, p - 1);
+    }
+}
+
+template <bool EQ, int CONN>
+static void merge_all(const uint8_t* mask, int* L, int B, int H, int W, cudaStream_t st) {
+    if (W > 1024) {
+        const int n = ((W - 1) / 1024) * H;
+        CDNET_LAUNCH(k_ccl_merge_seams<EQ>, dim3(ceil_div(n, 256), B), 256, 0, st, mask, L, H, W);
+    }
+    for (int level = 0; (1 << level) < H; ++level) {
+        const int nrows = (H - (1 << level) + (2 << level) - 1) / (2 << level);  // rows y = (2k+1)<<level < H
+        if (nrows <= 0) break;
+        CDNET_LAUNCH((k_ccl_merge<EQ, CONN>), dim3(ceil_div(W, kBX), ceil_div(nrows, kBY), B), ccl_block(), 0, st, mask, L,
+                     H, W, level);
     }
 }
 
@@ -177,9 +268,9 @@ static int number_and_relabel(int32_t* L, const uint8_t* keep, int32_t* idmap, i
 }
 
 int ccl_forest_launch(const uint8_t* mask, int32_t* L, int B, int H, int W, int conn, cudaStream_t st) {
-    CDNET_LAUNCH(k_ccl_init<false>, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, (int*)nullptr, (int*)nullptr, H, W);
-    if (conn == 4) CDNET_LAUNCH((k_ccl_merge<false, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
-    else if (conn == 8) CDNET_LAUNCH((k_ccl_merge<false, 8>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
+    CCL_INIT(false, st, mask, L, (int*)nullptr, (int*)nullptr);
+    if (conn == 4) merge_all<false, 4>(mask, L, B, H, W, st);
+    else if (conn == 8) merge_all<false, 8>(mask, L, B, H, W, st);
     else return CDNET_E_BADARG;
     return last_error();
 }
@@ -224,8 +315,8 @@ __global__ void __launch_bounds__(kBX* kBY) k_flatten_fill(const uint8_t* __rest
 
 int fill_holes_state_launch(const uint8_t* mask, uint8_t* state, int32_t* L, int32_t* touch, int B, int H, int W,
                             cudaStream_t st) {
-    CDNET_LAUNCH(k_ccl_init<true>, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, (int*)nullptr, H, W);
-    CDNET_LAUNCH((k_ccl_merge<true, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
+    CCL_INIT(true, st, mask, L, touch, (int*)nullptr);
+    merge_all<true, 4>(mask, L, B, H, W, st);
     CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, mask, L, touch, H, W);
     CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, state, H, W);
     return last_error();
@@ -295,8 +386,8 @@ int fill_remove_label_launch(const uint8_t* inside, int32_t* labels, uint8_t* pr
     int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
     if (!ar.ok) return CDNET_E_WORKSPACE;
     uint8_t* keep = pred2_out ? pred2_out : keep_ws;
-    CDNET_LAUNCH(k_ccl_init<true>, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, aux2, H, W);
-    CDNET_LAUNCH((k_ccl_merge<true, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, H, W);
+    CCL_INIT(true, st, inside, L, aux1, aux2);
+    merge_all<true, 4>(inside, L, B, H, W, st);
     CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, aux1, H, W);
     CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, state, H, W);
     CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
@@ -404,8 +495,8 @@ extern "C" int cdnet_remove_small_mask(const uint8_t* mask, uint8_t* out, int B,
     int32_t* area = ar.take<int32_t>(n);
     if (!ar.ok) return CDNET_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    CDNET_LAUNCH(k_ccl_init<false>, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, (int*)nullptr, H, W);
-    CDNET_LAUNCH((k_ccl_merge<false, 4>), ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, H, W);
+    CCL_INIT(false, st, mask, L, area, (int*)nullptr);
+    merge_all<false, 4>(mask, L, B, H, W, st);
     CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, H, W);
     CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, out, min_size, H, W);
     return last_error();

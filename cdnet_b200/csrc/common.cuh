@@ -62,16 +62,35 @@ __device__ __forceinline__ int uf_find(const int* __restrict__ L, int p) {
     return p;
 }
 
+// find + path compression: every node on the path is re-pointed (atomicMin, so a concurrent union
+// is never lost) at the root that was found
+__device__ __forceinline__ int uf_find_compress(int* L, int p) {
+    const int r = uf_find(L, p);
+    int x = p;
+    while (x != r) {
+        const int nx = __ldcg(L + x);
+        if (nx > r) atomicMin(L + x, r);
+        if (nx >= x) break;
+        x = nx;
+    }
+    return r;
+}
+
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    const int a0 = a, b0 = b;
     for (;;) {
         a = uf_find(L, a);
         b = uf_find(L, b);
-        if (a == b) return;
+        if (a == b) break;
         if (a < b) { int t = a; a = b; b = t; }
         int old = atomicMin(L + a, b);  // a > b: hang a under b
-        if (old == a) return;
+        if (old == a) { a = b; break; }
         a = old;
     }
+    // keep the trees shallow: both starting points now point (almost) at the common root
+    const int r = a < b ? a : b;
+    if (__ldcg(L + a0) > r) atomicMin(L + a0, r);
+    if (__ldcg(L + b0) > r) atomicMin(L + b0, r);
 }
 
 // float <-> order-preserving uint32 (for atomicMax on floats of any sign)

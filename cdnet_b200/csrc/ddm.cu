@@ -13,6 +13,7 @@
 // Zero padding == class 0 (zero vector, cos 0).  Output of the first pass is a 2-bit code per
 // (pixel, map) plus three "value present" bits per map for the normalisation.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -167,6 +168,154 @@ __global__ void __launch_bounds__(128) k_ddm_codes(const uint8_t* __restrict__ c
     if (threadIdx.x == 0 && seen) atomicOr(flags + b, seen);
 }
 
+// ---- byte-SIMD variant for the 5- and 9-class tables (<= 8 direction classes) ----------------------
+// Four pixels travel in one 32-bit register.  Per pixel the neighbourhood class set is ONE BYTE (bit k =
+// direction class k+1 present) plus one "background/zero-vector present" bit; class -> one-hot byte,
+// class -> neg/pos byte masks are 8-entry byte LUTs evaluated for 4 pixels at once with PRMT
+// (__byte_perm), the 3-wide horizontal OR is two funnel shifts + one LOP3, and "byte != 0" tests use
+// the carry-free haszero trick.  ~14 thread-instructions per (pixel, map) instead of ~53.
+__device__ __forceinline__ uint32_t nonzero7(uint32_t v) {  // bit 7 of each byte set iff the byte != 0
+    return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
+}
+
+struct RowSets {
+    uint32_t onehot;  // per byte: 1 << (class-1) for a valid direction class, else 0
+    uint32_t bg;      // per byte: 1 where the pixel acts as the zero vector (class 0, unknown id, outside)
+    uint32_t act7;    // bit 7 per byte: valid direction class
+    uint32_t odd7;    // bit 7 per byte: non-zero but unknown id (centre code is always 1)
+    uint32_t sel;     // PRMT selector nibbles (class-1) & 7
+};
+
+__device__ __forceinline__ RowSets classify4(uint32_t w, uint32_t ge_add) {
+    RowSets r;
+    const uint32_t inv7 = (((w & 0x7f7f7f7fu) + ge_add) | w) & 0x80808080u;  // byte >= n
+    const uint32_t nz7 = nonzero7(w);
+    r.act7 = nz7 & ~inv7;
+    r.odd7 = nz7 & inv7;
+    const uint32_t actmask = (r.act7 >> 7) * 0xffu;
+    uint32_t km = ((w & 0x0f0f0f0fu) + 0x07070707u) & 0x07070707u;  // (class-1) & 7 per byte
+    km = __byte_perm(km, 0u, 0x3120);
+    r.sel = km | (km >> 12);
+    r.onehot = __byte_perm(0x08040201u, 0x80402010u, r.sel) & actmask;
+    r.bg = ((~r.act7) & 0x80808080u) >> 7;
+    return r;
+}
+
+__device__ __forceinline__ void classify1(uint32_t c, int n, uint32_t& onehot, uint32_t& bg) {
+    const bool act = c >= 1u && c < (uint32_t)n;
+    onehot = act ? (1u << (c - 1u)) : 0u;
+    bg = act ? 0u : 1u;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void load_row_v2(const uint8_t* __restrict__ plane, int H, int W, int y, int x4, int n,
+                                            uint32_t ge_add, int lane, RowSets& rs, uint32_t& h3, uint32_t& hb3,
+                                            uint32_t& lr, uint32_t& lrb) {
+    uint32_t w = 0, cl = 0, cr = 0;
+    const bool rowok = (y >= 0 && y < H);
+    if (rowok && x4 < W) {
+        const uint8_t* row = plane + (size_t)y * W;
+        if (FAST && x4 + 3 < W) {
+            w = __ldg((const uint32_t*)(row + x4));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x4 + i < W) w |= (uint32_t)__ldg(row + x4 + i) << (8 * i);
+        }
+        if (lane == 0 && x4 > 0) cl = __ldg(row + x4 - 1);
+        if (lane == 31 && x4 + 4 < W) cr = __ldg(row + x4 + 4);
+    }
+    rs = classify4(w, ge_add);
+    uint32_t ohl = __shfl_up_sync(0xffffffffu, rs.onehot, 1), bgl = __shfl_up_sync(0xffffffffu, rs.bg, 1);
+    uint32_t ohr = __shfl_down_sync(0xffffffffu, rs.onehot, 1), bgr = __shfl_down_sync(0xffffffffu, rs.bg, 1);
+    if (lane == 0) { uint32_t o, g; classify1(cl, n, o, g); ohl = o << 24; bgl = g << 24; }
+    if (lane == 31) { uint32_t o, g; classify1(cr, n, o, g); ohr = o; bgr = g; }
+    const uint32_t L = __funnelshift_l(ohl, rs.onehot, 8), R = __funnelshift_r(rs.onehot, ohr, 8);
+    const uint32_t Lb = __funnelshift_l(bgl, rs.bg, 8), Rb = __funnelshift_r(rs.bg, bgr, 8);
+    lr = L | R;
+    lrb = Lb | Rb;
+    h3 = lr | rs.onehot;
+    hb3 = lrb | rs.bg;
+}
+
+struct DdmLut8 {
+    uint32_t neg_lo, neg_hi, pos_lo, pos_hi;  // byte k = neg/pos set of class k+1 over classes 1..8
+    int n, axial;
+};
+
+template <int T, bool FAST, bool AXIAL, int ROWS>
+__global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restrict__ cls_maps, uint16_t* __restrict__ codes,
+                                                        uint32_t* __restrict__ flags, int H, int W, DdmLut8 lut) {
+    const int b = blockIdx.z;
+    const int lane = threadIdx.x;
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * ROWS;
+    uint32_t seen = 0;
+    const uint32_t ge_add = (uint32_t)(0x80 - lut.n) * 0x01010101u;
+    // pixels of this word that lie inside the image (bit 7 per byte)
+    uint32_t inimg7 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (x4 + i < W) inimg7 |= 0x80u << (8 * i);
+    if (y0 < H) {  // whole warp shares y0: uniform branch (shuffles inside)
+        uint32_t acc[ROWS][2];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) { acc[r][0] = 0; acc[r][1] = 0; }
+        const size_t plane_sz = (size_t)H * W;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const uint8_t* plane = cls_maps + ((size_t)b * T + t) * plane_sz;
+            RowSets rp, rc, rn;
+            uint32_t h3p, hb3p, lrp, lrbp, h3c, hb3c, lrc, lrbc, h3n, hb3n, lrn, lrbn;
+            load_row_v2<FAST>(plane, H, W, y0 - 1, x4, lut.n, ge_add, lane, rp, h3p, hb3p, lrp, lrbp);
+            load_row_v2<FAST>(plane, H, W, y0, x4, lut.n, ge_add, lane, rc, h3c, hb3c, lrc, lrbc);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                load_row_v2<FAST>(plane, H, W, y0 + r + 1, x4, lut.n, ge_add, lane, rn, h3n, hb3n, lrn, lrbn);
+                uint32_t S, BG;
+                if (AXIAL) { S = rp.onehot | rn.onehot | lrc; BG = rp.bg | rn.bg | lrbc; }
+                else { S = h3p | h3c | h3n; BG = hb3p | hb3c | hb3n; }
+                const uint32_t NEGW = __byte_perm(lut.neg_lo, lut.neg_hi, rc.sel);
+                const uint32_t POSW = __byte_perm(lut.pos_lo, lut.pos_hi, rc.sel);
+                const uint32_t anyneg7 = nonzero7(NEGW & S) & rc.act7;
+                const uint32_t notall7 = nonzero7((S & ~POSW) | BG);
+                const uint32_t b1 = anyneg7;
+                const uint32_t b0 = (notall7 & ~anyneg7 & rc.act7) | rc.odd7;
+                const uint32_t cw = ((b1 >> 6) | (b0 >> 7)) & 0x03030303u;
+                acc[r][0] |= __byte_perm(cw, 0u, 0x4140) << (2 * t);
+                acc[r][1] |= __byte_perm(cw, 0u, 0x4342) << (2 * t);
+                if (y0 + r < H) {
+                    const uint32_t z7 = ~(b1 | b0) & inimg7;
+                    seen |= (z7 ? 1u : 0u) << (3 * t);
+                    seen |= (b0 ? 2u : 0u) << (3 * t);
+                    seen |= (b1 ? 4u : 0u) << (3 * t);
+                }
+                rp = rc; rc = rn;
+                h3p = h3c; hb3p = hb3c; h3c = h3n; hb3c = hb3n; lrc = lrn; lrbc = lrbn;
+            }
+        }
+        if (x4 < W) {
+            uint16_t* cout = codes + (size_t)b * plane_sz;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const int y = y0 + r;
+                if (y < H) {
+                    uint16_t* dst = cout + (size_t)y * W + x4;
+                    if (FAST && x4 + 3 < W) {
+                        *(uint2*)dst = make_uint2(acc[r][0], acc[r][1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (x4 + i < W) dst[i] = (uint16_t)(acc[r][i >> 1] >> (16 * (i & 1)));
+                    }
+                }
+            }
+        }
+    }
+    seen = __reduce_or_sync(0xffffffffu, seen);
+    if (threadIdx.x == 0 && seen) atomicOr(flags + b, seen);
+}
+
 // normalised value of code d for a map whose present-value bits are f (3 bits): (d-min)/(max-min)
 // in f32 (getDirectionDiffMap.py:104-106); constant map -> 0/0 = NaN.
 __device__ __forceinline__ float ddm_value(uint32_t d, uint32_t f) {
@@ -191,22 +340,64 @@ __global__ void k_ddm_normalize(const uint16_t* __restrict__ codes, const uint32
 }
 
 // launcher shared with postproc.cu
+template <int T>
+static void launch_simd(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int H, int W, const DdmLut& lut,
+                        bool fast, dim3 grid, dim3 block, cudaStream_t st) {
+    DdmLut8 l8;
+    l8.n = lut.n;
+    l8.axial = lut.axial;
+    l8.neg_lo = l8.neg_hi = l8.pos_lo = l8.pos_hi = 0;
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t ng = (k + 1 < lut.n) ? ((lut.neg[k + 1] >> 1) & 0xffu) : 0u;
+        const uint32_t ps = (k + 1 < lut.n) ? ((lut.pos[k + 1] >> 1) & 0xffu) : 0u;
+        if (k < 4) { l8.neg_lo |= ng << (8 * k); l8.pos_lo |= ps << (8 * k); }
+        else { l8.neg_hi |= ng << (8 * (k - 4)); l8.pos_hi |= ps << (8 * (k - 4)); }
+    }
+    static int rows = 0;
+    if (!rows) {
+        const char* e = getenv("CDNET_DDM_ROWS");
+        rows = (e && atoi(e) == 8) ? 8 : 4;
+    }
+    grid.y = ceil_div(H, 4 * rows);
+    if (rows == 8) {
+        if (lut.axial) {
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, true, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, true, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+        } else {
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+        }
+    } else {
+        if (lut.axial) {
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, true, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, true, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+        } else {
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+        }
+    }
+}
+
+// launcher shared with postproc.cu
 int ddm_codes_launch(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int B, int T, int H, int W,
                      int n_classes, cudaStream_t st) {
     DdmLut lut;
     if (!ddm_build_lut(n_classes, &lut)) return CDNET_E_BADARG;
+    if (T != 1 && T != 8) return CDNET_E_BADARG;
     CDNET_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)B, st));
     dim3 block(32, 4);
     dim3 grid(ceil_div(W, 128), ceil_div(H, 4 * kRows), B);
     const bool fast = (W % 4 == 0) && (((uintptr_t)cls_maps & 3) == 0) && (((uintptr_t)codes & 7) == 0);
-    if (T == 8) {
+    if (n_classes <= 9) {
+        // <= 8 direction classes: byte-SIMD kernel
+        if (T == 8) launch_simd<8>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st);
+        else launch_simd<1>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st);
+    } else if (T == 8) {
         if (fast) CDNET_LAUNCH((k_ddm_codes<8, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
         else CDNET_LAUNCH((k_ddm_codes<8, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
-    } else if (T == 1) {
+    } else {
         if (fast) CDNET_LAUNCH((k_ddm_codes<1, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
         else CDNET_LAUNCH((k_ddm_codes<1, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
-    } else {
-        return CDNET_E_BADARG;
     }
     return last_error();
 }

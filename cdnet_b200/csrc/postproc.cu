@@ -13,6 +13,8 @@
 //   fill holes -> remove small (4-conn) -> 8-conn label (ccl.cu, one forest)        test_dam.py:546-561
 //     or process() = watershed chain (watershed.cu) when postproc == 1             test_dam.py:559
 //   k_label_dilate    disk(radius)                                                 test_dam.py:563
+#include <math.h>
+
 #include "internal.h"
 
 namespace cdnet {
@@ -93,6 +95,114 @@ __global__ void __launch_bounds__(256) k_boost_inside(const uint16_t* __restrict
     inside[(size_t)b * plane + p] = (am == 1) ? 1 : 0;
 }
 
+// ---- vectorised variant (W % 4 == 0): 4 pixels per thread, 128-bit loads --------------------------
+// * the gate `f32(p / max) > 0.2f` is monotone in p for max > 0, so it is evaluated as `p >= thr` with
+//   thr = the smallest float whose IEEE quotient exceeds 0.2f (found per block by a few nextafter steps);
+// * the mean of the 8 normalised maps is an exact multiple of 1/16: two 256-entry integer LUTs over the
+//   low / high byte of the code word give 16*mean;
+// * where the boost is zero (gate open or DDM 0) prob[2] is unchanged bit for bit, so the f64 path only
+//   runs on boundary pixels.
+__device__ __forceinline__ float gate_threshold(float mx) {
+    float t = __fmul_rn(0.2f, mx);
+    for (int i = 0; i < 8 && __fdiv_rn(t, mx) > 0.2f; ++i) t = nextafterf(t, -INFINITY);
+    for (int i = 0; i < 16 && !(__fdiv_rn(t, mx) > 0.2f); ++i) t = nextafterf(t, INFINITY);
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restrict__ codes, const uint32_t* __restrict__ flags,
+                                                       const float* __restrict__ point, const unsigned int* __restrict__ pmax,
+                                                       float* __restrict__ prob, uint8_t* __restrict__ inside,
+                                                       int32_t* __restrict__ status, int H, int W, int write_prob) {
+    __shared__ uint8_t s_lo[256], s_hi[256];
+    __shared__ float s_thr;
+    __shared__ int s_const, s_div;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    {
+        // 2 * normalised value of code d for each map (0, 1, 2); constant maps flagged
+        const uint32_t fl = flags[b];
+        int bad = 0, lo = 0, hi = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const uint32_t f = (fl >> (3 * t)) & 7u;
+            const int mn = (f & 1) ? 0 : ((f & 2) ? 1 : 2);
+            const int mx = (f & 4) ? 2 : ((f & 2) ? 1 : 0);
+            if (mx == mn) bad = 1;
+            const int d = (tid >> (2 * (t & 3))) & 3;
+            const int v2 = (mx > mn && d < 3) ? (2 * (d - mn)) / (mx - mn) : 0;  // exact: (d-mn)/(mx-mn) in {0,.5,1}
+            if (t < 4) lo += v2; else hi += v2;
+        }
+        s_lo[tid] = (uint8_t)lo;
+        s_hi[tid] = (uint8_t)hi;
+        if (tid == 0) {
+            s_const = bad;
+            const float mxv = ordered_to_f32(pmax[b]);
+            const bool ok = mxv > 0.0f && mxv < INFINITY;
+            s_div = ok ? 0 : 1;
+            s_thr = ok ? gate_threshold(mxv) : 0.0f;
+            if (bad && status && blockIdx.x == 0 && blockIdx.y == 0) atomicOr(status + b, CDNET_S_DDM_CONSTANT);
+        }
+    }
+    __syncthreads();
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x4 >= W || y >= H) return;
+    const int plane = H * W;
+    const int p = y * W + x4;
+    const float* P = point + (size_t)b * plane;
+    const float mx = ordered_to_f32(pmax[b]);
+    const float thr = s_thr;
+    const bool usediv = s_div != 0;
+    auto gate = [&](float v) -> bool { return usediv ? (__fdiv_rn(v, mx) > 0.2f) : (v >= thr); };
+    const float4 pc = *(const float4*)(P + p);
+    bool g[4] = {gate(pc.x), gate(pc.y), gate(pc.z), gate(pc.w)};
+    const bool gl = x4 > 0 ? gate(P[p - 1]) : false;
+    const bool gr = x4 + 4 < W ? gate(P[p + 4]) : false;
+    bool d[4];
+    d[0] = g[0] | gl | g[1];
+    d[1] = g[1] | g[0] | g[2];
+    d[2] = g[2] | g[1] | g[3];
+    d[3] = g[3] | g[2] | gr;
+    if (y > 0) {
+        const float4 u = *(const float4*)(P + p - W);
+        d[0] |= gate(u.x); d[1] |= gate(u.y); d[2] |= gate(u.z); d[3] |= gate(u.w);
+    }
+    if (y + 1 < H) {
+        const float4 u = *(const float4*)(P + p + W);
+        d[0] |= gate(u.x); d[1] |= gate(u.y); d[2] |= gate(u.z); d[3] |= gate(u.w);
+    }
+    const uint2 cw = *(const uint2*)(codes + (size_t)b * plane + p);
+    const uint32_t c[4] = {cw.x & 0xffffu, cw.x >> 16, cw.y & 0xffffu, cw.y >> 16};
+    float* PR = prob + (size_t)b * 3 * plane;
+    const float4 q0 = *(const float4*)(PR + p);
+    const float4 q1 = *(const float4*)(PR + plane + p);
+    float4 q2 = *(const float4*)(PR + 2 * plane + p);
+    const float a0[4] = {q0.x, q0.y, q0.z, q0.w}, a1[4] = {q1.x, q1.y, q1.z, q1.w};
+    float a2[4] = {q2.x, q2.y, q2.z, q2.w};
+    const bool isconst = s_const != 0;
+    uint32_t res = 0;
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int s16 = s_lo[c[i] & 0xff] + s_hi[c[i] >> 8];  // 16 * mean of the 8 maps
+        if (isconst) {
+            a2[i] = __int_as_float(0x7fc00000);  // NaN DDM (the reference asserts here)
+            changed = true;
+        } else if (s16 != 0 && !d[i]) {
+            const double eb = (double)s16 * 0.125;  // 2 * ddm
+            a2[i] = __double2float_rn(__dmul_rn(__dadd_rn((double)a2[i], __dmul_rn(0.5, eb)), __dadd_rn(1.0, eb)));
+            changed = true;
+        }
+        int am = 0;
+        float best = a0[i];
+        if (a1[i] > best || (a1[i] != a1[i] && best == best)) { am = 1; best = a1[i]; }
+        if (a2[i] > best || (a2[i] != a2[i] && best == best)) { am = 2; }
+        res |= (am == 1 ? 1u : 0u) << (8 * i);
+    }
+    *(uint32_t*)(inside + (size_t)b * plane + p) = res;
+    if (write_prob && changed) *(float4*)(PR + 2 * plane + p) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+}
+
 // test.py:270-275: inside = argmax over C channels == 1, or prob[0] >= 0.5
 __global__ void __launch_bounds__(256) k_plain_inside(const float* __restrict__ prob, int C, uint8_t* __restrict__ inside,
                                                       size_t plane, int multi_class) {
@@ -171,8 +281,12 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, float* prob, const float* 
         int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
         CDNET_LAUNCH(k_point_max, dim3(gx, B), 256, 0, st, point, pmax, plane);
     }
-    CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point, pmax,
-                 prob, inside, status, H, W, write_prob);
+    if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
+        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
+                     pmax, prob, inside, status, H, W, write_prob);
+    else
+        CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
+                     pmax, prob, inside, status, H, W, write_prob);
     rc = last_error();
     if (rc) return rc;
     // test_dam.py:559 calls process() with its default min_size = 10

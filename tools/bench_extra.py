@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Extra (non-contract) timings with the library's per-kernel CUDA-event profiler:
+   --what targets : BASELINE configs[2]-shaped target generation (B tiles of HxW, LabelEncoding path)
+   --what ws      : DAM post-processing with postproc=1 (watershed chain) on 14 x 1000^2
+Prints one JSON line per run."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def profile(L, fn, steps):
+    import torch
+    L.cdnet_profile_enable(1)
+    for _ in range(steps):
+        fn()
+    buf = ctypes.create_string_buffer(1 << 16)
+    L.cdnet_profile_report(buf, 1 << 16)
+    L.cdnet_profile_enable(0)
+    kern = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, tot = line.split("\t")
+        base = name.strip("()").split("<")[0]
+        k = kern.setdefault(base, [0, 0.0])
+        k[0] += int(cnt)
+        k[1] += float(tot)
+    return {k: round(v[1] / steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])}
+
+
+def timed(fn, steps):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="targets")
+    ap.add_argument("--tiles", type=int, default=64)
+    ap.add_argument("--size", type=int, default=500)
+    ap.add_argument("--nuclei", type=int, default=120)
+    ap.add_argument("--classes", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    import torch
+    from cdnet_b200 import api, synth, _cabi
+    L = _cabi.lib()
+    if a.what == "targets":
+        base = [synth.as_uint8_label(synth.instance_map(1000 + i, a.size, a.size, a.nuclei))[:, :, 0] for i in range(8)]
+        ids = np.stack([base[i % 8] for i in range(a.tiles)])
+        d_ids = torch.from_numpy(ids).cuda()
+        fn = lambda: api.encode_targets_cuda(d_ids, True, a.classes)
+        for _ in range(2):
+            fn()
+        ms = timed(fn, a.steps)
+        mpx = a.tiles * a.size * a.size / 1e6
+        print(json.dumps({"what": "targets", "tiles": a.tiles, "size": a.size, "classes": a.classes, "ms": ms,
+                          "mpx_per_s": mpx / (ms * 1e-3), "kernels_ms": profile(L, fn, a.steps)}))
+    else:
+        tiles = [synth.postproc_inputs(100 + i, 1000, 1000) for i in range(14)]
+        plan = api.DamPostprocessPlan(14, 1000, 1000, 9, 20, 2, 1)
+        for i, t in enumerate(tiles):
+            plan.h_dcm[i], plan.h_prob[i], plan.h_point[i] = t["dcm"], t["prob"], t["point"]
+        plan.run()
+        for _ in range(2):
+            plan.launch_device()
+        ms = timed(plan.launch_device, a.steps)
+        print(json.dumps({"what": "dam postproc=1", "ms": ms, "mpx_per_s": 14.0 / (ms * 1e-3),
+                          "kernels_ms": profile(L, plan.launch_device, a.steps)}))
+
+
+if __name__ == "__main__":
+    main()
