@@ -33,7 +33,7 @@ SIGNATURES = {
     "cdnet_ws_postproc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_size_t, c_void_p]),
     "cdnet_dam_postproc_workspace_bytes": (c_size_t, [c_int] * 3),
-    "cdnet_dam_postproc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+    "cdnet_dam_postproc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cdnet_plain_postproc_workspace_bytes": (c_size_t, [c_int] * 3),
     "cdnet_plain_postproc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -44,6 +44,17 @@ SIGNATURES = {
     "cdnet_label_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cdnet_encode_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdnet_shard_ddm_codes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "cdnet_shard_point_max": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdnet_shard_boost": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int, c_int, c_void_p]),
+    "cdnet_shard_label_stage1": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "cdnet_shard_label_stage2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
+    "cdnet_shard_label_stage3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cdnet_shard_label_stage4": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                         c_void_p]),
+    "cdnet_shard_relabel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cdnet_launch_count": (ctypes.c_ulonglong, []),
     "cdnet_profile_enable": (None, [c_int]),
     "cdnet_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),

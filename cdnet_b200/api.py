@@ -177,7 +177,8 @@ def process_cuda(pred01, min_size=10, ws=True):
 
 def dam_postprocess_cuda(dcm, prob, point, direction_classes=9, min_area=20, radius=2, postproc=0,
                          write_prob=False, out_dtype=None, out=None, status=None):
-    """dcm uint8 [B,8,H,W], prob float32 [B,3,H,W], point float32 [B,1,H,W] (CUDA) -> labels [B,H,W].
+    """dcm uint8 [B,8,H,W] (or [B,1,H,W]: single-map variant, test_dam.py:499-502), prob float32 [B,3,H,W],
+    point float32 [B,1,H,W] (CUDA) -> labels [B,H,W].
     out_dtype defaults to what the reference returns: int64 (measure.label) for postproc 0, int32
     (process) for postproc 1.  Returns (labels, status)."""
     L = _cabi.lib()
@@ -185,7 +186,7 @@ def dam_postprocess_cuda(dcm, prob, point, direction_classes=9, min_area=20, rad
     assert dcm.dtype == torch.uint8 and prob.dtype == torch.float32 and point.dtype == torch.float32
     assert dcm.is_contiguous() and prob.is_contiguous() and point.is_contiguous()
     B, T, H, W = dcm.shape
-    assert T == 8 and tuple(prob.shape) == (B, 3, H, W) and point.numel() == B * H * W
+    assert T in (1, 8) and tuple(prob.shape) == (B, 3, H, W) and point.numel() == B * H * W
     if out_dtype is None:
         out_dtype = torch.int64 if int(postproc) == 0 else torch.int32
     if out is None:
@@ -194,8 +195,8 @@ def dam_postprocess_cuda(dcm, prob, point, direction_classes=9, min_area=20, rad
         status = torch.empty((B,), dtype=torch.int32, device=dev)
     nb = L.cdnet_dam_postproc_workspace_bytes(B, H, W)
     ws = _workspace(nb, dev)
-    check(L.cdnet_dam_postproc(_ptr(dcm), _ptr(prob), _ptr(point), _ptr(out), out.element_size(), _ptr(status), B, H,
-                               W, int(direction_classes), int(min_area), int(radius), int(postproc),
+    check(L.cdnet_dam_postproc(_ptr(dcm), T, _ptr(prob), _ptr(point), _ptr(out), out.element_size(), _ptr(status), B,
+                               H, W, int(direction_classes), int(min_area), int(radius), int(postproc),
                                1 if write_prob else 0, _ptr(ws), ws.numel(), _stream()), "cdnet_dam_postproc")
     return out, status
 

@@ -178,14 +178,15 @@ __global__ void __launch_bounds__(kBX* kBY) k_flatten(int* __restrict__ L, int H
 // flatten + count roots of kept pixels per row.  keep == nullptr: every pixel with L-root semantics
 // handled by the caller's mask `fg`.
 __global__ void __launch_bounds__(kBX* kBY) k_flatten_count(int* __restrict__ L, const uint8_t* __restrict__ keep,
-                                                            int* __restrict__ rowcnt, int H, int W) {
+                                                            int* __restrict__ rowcnt, int H, int W,
+                                                            const uint8_t* __restrict__ excluded) {
     CCL_COORDS
     bool root = false;
     if (inb && keep[tile + p]) {
         int* Lt = L + tile;
         const int r = uf_find(Lt, p);
         Lt[p] = r;
-        root = (r == p);
+        root = (r == p) && !(excluded && excluded[tile + p]);
     }
     const unsigned m = __ballot_sync(0xffffffffu, root);
     if (lane == 0 && m && y < H) atomicAdd(rowcnt + (size_t)b * H + y, __popc(m));
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(1024) k_scan_rows(int* __restrict__ rowcnt, in
 
 // one warp per row: idmap[root pixel] = 1 + number of roots before it in raster order
 __global__ void __launch_bounds__(256) k_assign_ids(const int* __restrict__ L, const uint8_t* __restrict__ keep,
-                                                    const int* __restrict__ rowbase, int* __restrict__ idmap, int H, int W) {
+                                                    const int* __restrict__ rowbase, int* __restrict__ idmap, int H, int W,
+                                                    const uint8_t* __restrict__ excluded) {
     const int lane = threadIdx.x & 31;
     const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int b = blockIdx.y;
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256) k_assign_ids(const int* __restrict__ L, c
     for (int x0 = 0; x0 < W; x0 += 32) {
         const int x = x0 + lane;
         const int p = y * W + x;
-        const bool root = x < W && keep[tile + p] && L[tile + p] == p;
+        const bool root = x < W && keep[tile + p] && L[tile + p] == p && !(excluded && excluded[tile + p]);
         const unsigned m = __ballot_sync(0xffffffffu, root);
         if (root) idmap[tile + p] = running + __popc(m & ((1u << lane) - 1));
         running += __popc(m);
@@ -257,12 +259,19 @@ __global__ void __launch_bounds__(kBX* kBY) k_relabel(const int* __restrict__ L,
     out[tile + p] = keep[tile + p] ? idmap[tile + L[tile + p]] : 0;
 }
 
+static int number_roots(int32_t* L, const uint8_t* keep, const uint8_t* excluded, int32_t* idmap, int32_t* rowcnt,
+                        int32_t* n_out, int B, int H, int W, cudaStream_t st) {
+    CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, sizeof(int32_t) * (size_t)B * H, st));
+    CDNET_LAUNCH(k_flatten_count, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, rowcnt, H, W, excluded);
+    CDNET_LAUNCH(k_scan_rows, B, 1024, 0, st, rowcnt, n_out, H);
+    CDNET_LAUNCH(k_assign_ids, dim3(ceil_div(H, 8), B), 256, 0, st, L, keep, rowcnt, idmap, H, W, excluded);
+    return last_error();
+}
+
 static int number_and_relabel(int32_t* L, const uint8_t* keep, int32_t* idmap, int32_t* rowcnt, int32_t* labels,
                               int32_t* n_out, int B, int H, int W, cudaStream_t st) {
-    CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, sizeof(int32_t) * (size_t)B * H, st));
-    CDNET_LAUNCH(k_flatten_count, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, rowcnt, H, W);
-    CDNET_LAUNCH(k_scan_rows, B, 1024, 0, st, rowcnt, n_out, H);
-    CDNET_LAUNCH(k_assign_ids, dim3(ceil_div(H, 8), B), 256, 0, st, L, keep, rowcnt, idmap, H, W);
+    int rc = number_roots(L, keep, nullptr, idmap, rowcnt, n_out, B, H, W, st);
+    if (rc) return rc;
     CDNET_LAUNCH(k_relabel, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, idmap, labels, H, W);
     return last_error();
 }
@@ -285,7 +294,7 @@ int ccl_label_launch(const uint8_t* mask, int32_t* labels, int32_t* n_out, int32
 // ---- fill holes ----------------------------------------------------------------------------------
 // frame pixels that are background mark the root of their background component
 __global__ void k_border_touch(const uint8_t* __restrict__ mask, const int* __restrict__ L, int* __restrict__ touch,
-                               int H, int W) {
+                               int H, int W, int top_frame, int bottom_frame) {
     const int b = blockIdx.y;
     const size_t tile = (size_t)b * H * W;
     const int per = 2 * W + 2 * H;
@@ -295,6 +304,7 @@ __global__ void k_border_touch(const uint8_t* __restrict__ mask, const int* __re
         else if (i < 2 * W) { y = H - 1; x = i - W; }
         else if (i < 2 * W + H) { y = i - 2 * W; x = 0; }
         else { y = i - 2 * W - H; x = W - 1; }
+        if ((i < W && !top_frame) || (i >= W && i < 2 * W && !bottom_frame)) continue;  // shard seam, not the slide frame
         const int p = y * W + x;
         if (mask[tile + p] == 0) touch[tile + uf_find(L + tile, p)] = 1;
     }
@@ -317,7 +327,7 @@ int fill_holes_state_launch(const uint8_t* mask, uint8_t* state, int32_t* L, int
                             cudaStream_t st) {
     CCL_INIT(true, st, mask, L, touch, (int*)nullptr);
     merge_all<true, 4>(mask, L, B, H, W, st);
-    CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, mask, L, touch, H, W);
+    CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, mask, L, touch, H, W, 1, 1);
     CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, state, H, W);
     return last_error();
 }
@@ -337,13 +347,14 @@ __global__ void __launch_bounds__(kBX* kBY) k_fill_merge(const uint8_t* __restri
 
 // flatten + per-root pixel count of the pixels with state != 0 (warp-aggregated atomics)
 __global__ void __launch_bounds__(kBX* kBY) k_flatten_area(const uint8_t* __restrict__ state, int* __restrict__ L,
-                                                           int* __restrict__ area, int H, int W) {
+                                                           int* __restrict__ area, int H, int W, int row_lo, int row_hi) {
     CCL_COORDS
     int r = -1;
     if (inb && state[tile + p]) {
         int* Lt = L + tile;
         r = uf_find(Lt, p);
         Lt[p] = r;
+        if (y < row_lo || y >= row_hi) r = -1;  // ghost rows of a slide shard are counted by their owner
     }
     // lanes of one warp that share a root add once
     const unsigned peers = __match_any_sync(0xffffffffu, r);
@@ -388,10 +399,10 @@ int fill_remove_label_launch(const uint8_t* inside, int32_t* labels, uint8_t* pr
     uint8_t* keep = pred2_out ? pred2_out : keep_ws;
     CCL_INIT(true, st, inside, L, aux1, aux2);
     merge_all<true, 4>(inside, L, B, H, W, st);
-    CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, aux1, H, W);
+    CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, aux1, H, W, 1, 1);
     CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, state, H, W);
     CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
-    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, H, W);
+    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, H, W, 0, H);
     CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, keep, min_area, H, W);
     CDNET_LAUNCH(k_diag_merge, ccl_grid(B, H, W), ccl_block(), 0, st, keep, L, H, W);
     return number_and_relabel(L, keep, aux1, rowcnt, labels, nullptr, B, H, W, st);
@@ -497,7 +508,7 @@ extern "C" int cdnet_remove_small_mask(const uint8_t* mask, uint8_t* out, int B,
     cudaStream_t st = (cudaStream_t)stream;
     CCL_INIT(false, st, mask, L, area, (int*)nullptr);
     merge_all<false, 4>(mask, L, B, H, W, st);
-    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, H, W);
+    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, H, W, 0, H);
     CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, out, min_size, H, W);
     return last_error();
 }
@@ -514,4 +525,63 @@ extern "C" int cdnet_remove_small_labels(int32_t* labels, int B, int H, int W, i
     int32_t* counts = ar.take<int32_t>((size_t)B * ((size_t)H * W + 1));
     if (!ar.ok) return CDNET_E_WORKSPACE;
     return remove_small_labels_launch(labels, counts, B, H, W, min_size, (cudaStream_t)stream);
+}
+
+// =====================================================================================================
+// whole-slide row shards: the fill-holes / remove-small / 8-conn label chain cut
+// into stages so that the host can reconcile components that straddle shard seams between the stages
+// (cdnet_b200/sharded.py).  One extended tile per call: the shard's own rows plus one ghost row of the
+// neighbouring shard on each inner side.  All planes are [He, W].
+// =====================================================================================================
+extern "C" int cdnet_shard_label_stage1(const uint8_t* inside, int32_t* L, int32_t* touch, int He, int W, int top_is_frame,
+                                        int bottom_is_frame, void* stream) {
+    if (!inside || !L || !touch || bad_dims(1, He, W)) return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = 1, H = He;
+    CCL_INIT(true, st, inside, L, touch, (int*)nullptr);
+    merge_all<true, 4>(inside, L, B, H, W, st);
+    CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, touch, H, W, top_is_frame,
+                 bottom_is_frame);
+    CDNET_LAUNCH(k_flatten, ccl_grid(B, H, W), ccl_block(), 0, st, L, H, W);
+    return last_error();
+}
+
+// touch[] now holds slide-global flags for the roots of seam components.  state, hole merge, areas of the
+// rows [row_lo, row_hi) only (area must be zero-filled by the caller).
+extern "C" int cdnet_shard_label_stage2(const uint8_t* inside, int32_t* L, const int32_t* touch, uint8_t* state,
+                                        int32_t* area, int He, int W, int row_lo, int row_hi, void* stream) {
+    if (!inside || !L || !touch || !state || !area || bad_dims(1, He, W)) return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = 1, H = He;
+    CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, touch, state, H, W);
+    CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
+    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, area, H, W, row_lo, row_hi);
+    return last_error();
+}
+
+// area[] now holds slide-global pixel counts for the roots of seam components.
+extern "C" int cdnet_shard_label_stage3(const uint8_t* state, int32_t* L, const int32_t* area, uint8_t* keep, int min_area,
+                                        int He, int W, void* stream) {
+    if (!state || !L || !area || !keep || bad_dims(1, He, W)) return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = 1, H = He;
+    CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, area, keep, min_area, H, W);
+    CDNET_LAUNCH(k_diag_merge, ccl_grid(B, H, W), ccl_block(), 0, st, keep, L, H, W);
+    CDNET_LAUNCH(k_flatten, ccl_grid(B, H, W), ccl_block(), 0, st, L, H, W);
+    return last_error();
+}
+
+// local ids 1..n_owned (raster order) for the kept roots that are not `excluded`; rowcnt: int32 [He] scratch
+extern "C" int cdnet_shard_label_stage4(int32_t* L, const uint8_t* keep, const uint8_t* excluded, int32_t* idmap,
+                                        int32_t* rowcnt, int32_t* n_owned, int He, int W, void* stream) {
+    if (!L || !keep || !idmap || !rowcnt || !n_owned || bad_dims(1, He, W)) return CDNET_E_BADARG;
+    return number_roots(L, keep, excluded, idmap, rowcnt, n_owned, 1, He, W, (cudaStream_t)stream);
+}
+
+extern "C" int cdnet_shard_relabel(const int32_t* L, const uint8_t* keep, const int32_t* idmap, int32_t* labels, int He,
+                                   int W, void* stream) {
+    if (!L || !keep || !idmap || !labels || bad_dims(1, He, W)) return CDNET_E_BADARG;
+    const int B = 1, H = He;
+    CDNET_LAUNCH(k_relabel, ccl_grid(B, H, W), ccl_block(), 0, (cudaStream_t)stream, L, keep, idmap, labels, H, W);
+    return last_error();
 }

@@ -95,7 +95,8 @@ __device__ __forceinline__ void load_row6(const uint8_t* __restrict__ plane, int
 // codes: uint16 [B,H,W], bits 2t..2t+1 = d of map t.  flags: uint32 [B], bit 3t+d = "map t has value d".
 template <int T, bool FAST>
 __global__ void __launch_bounds__(128) k_ddm_codes(const uint8_t* __restrict__ cls_maps, uint16_t* __restrict__ codes,
-                                                   uint32_t* __restrict__ flags, int H, int W, DdmLut lut) {
+                                                   uint32_t* __restrict__ flags, int H, int W, DdmLut lut, int row_lo,
+                                                   int row_hi) {
     __shared__ uint32_t s_pos[32], s_neg[32];
     const int tid = threadIdx.y * 32 + threadIdx.x;
     if (tid < 32) { s_pos[tid] = lut.pos[tid]; s_neg[tid] = lut.neg[tid]; }
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128) k_ddm_codes(const uint8_t* __restrict__ c
                             else if ((S & ~s_pos[ai]) != 0 || lut.force_zero) d = 1;
                         }
                         if (x4 + i < W) {
-                            seen |= 1u << (3 * t + d);
+                            if (y >= row_lo && y < row_hi) seen |= 1u << (3 * t + d);
                             acc[r][i >> 1] |= d << (2 * t + 16 * (i & 1));
                         }
                     }
@@ -245,7 +246,8 @@ struct DdmLut8 {
 
 template <int T, bool FAST, bool AXIAL, int ROWS>
 __global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restrict__ cls_maps, uint16_t* __restrict__ codes,
-                                                        uint32_t* __restrict__ flags, int H, int W, DdmLut8 lut) {
+                                                        uint32_t* __restrict__ flags, int H, int W, DdmLut8 lut,
+                                                        int row_lo, int row_hi) {
     const int b = blockIdx.z;
     const int lane = threadIdx.x;
     const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restric
                 const uint32_t cw = ((b1 >> 6) | (b0 >> 7)) & 0x03030303u;
                 acc[r][0] |= __byte_perm(cw, 0u, 0x4140) << (2 * t);
                 acc[r][1] |= __byte_perm(cw, 0u, 0x4342) << (2 * t);
-                if (y0 + r < H) {
+                if (y0 + r >= row_lo && y0 + r < row_hi) {
                     const uint32_t z7 = ~(b1 | b0) & inimg7;
                     seen |= (z7 ? 1u : 0u) << (3 * t);
                     seen |= (b0 ? 2u : 0u) << (3 * t);
@@ -342,7 +344,7 @@ __global__ void k_ddm_normalize(const uint16_t* __restrict__ codes, const uint32
 // launcher shared with postproc.cu
 template <int T>
 static void launch_simd(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int H, int W, const DdmLut& lut,
-                        bool fast, dim3 grid, dim3 block, cudaStream_t st) {
+                        bool fast, dim3 grid, dim3 block, cudaStream_t st, int row_lo, int row_hi) {
     DdmLut8 l8;
     l8.n = lut.n;
     l8.axial = lut.axial;
@@ -361,26 +363,27 @@ static void launch_simd(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flag
     grid.y = ceil_div(H, 4 * rows);
     if (rows == 8) {
         if (lut.axial) {
-            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, true, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
-            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, true, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, true, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, true, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
         } else {
-            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
-            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
         }
     } else {
         if (lut.axial) {
-            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, true, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
-            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, true, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, true, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, true, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
         } else {
-            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
-            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8);
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 4>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
         }
     }
 }
 
 // launcher shared with postproc.cu
 int ddm_codes_launch(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int B, int T, int H, int W,
-                     int n_classes, cudaStream_t st) {
+                     int n_classes, cudaStream_t st, int row_lo, int row_hi) {
+    if (row_hi < 0) row_hi = H;
     DdmLut lut;
     if (!ddm_build_lut(n_classes, &lut)) return CDNET_E_BADARG;
     if (T != 1 && T != 8) return CDNET_E_BADARG;
@@ -390,14 +393,14 @@ int ddm_codes_launch(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, 
     const bool fast = (W % 4 == 0) && (((uintptr_t)cls_maps & 3) == 0) && (((uintptr_t)codes & 7) == 0);
     if (n_classes <= 9) {
         // <= 8 direction classes: byte-SIMD kernel
-        if (T == 8) launch_simd<8>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st);
-        else launch_simd<1>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st);
+        if (T == 8) launch_simd<8>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st, row_lo, row_hi);
+        else launch_simd<1>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st, row_lo, row_hi);
     } else if (T == 8) {
-        if (fast) CDNET_LAUNCH((k_ddm_codes<8, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
-        else CDNET_LAUNCH((k_ddm_codes<8, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
+        if (fast) CDNET_LAUNCH((k_ddm_codes<8, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut, row_lo, row_hi);
+        else CDNET_LAUNCH((k_ddm_codes<8, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut, row_lo, row_hi);
     } else {
-        if (fast) CDNET_LAUNCH((k_ddm_codes<1, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
-        else CDNET_LAUNCH((k_ddm_codes<1, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut);
+        if (fast) CDNET_LAUNCH((k_ddm_codes<1, true>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut, row_lo, row_hi);
+        else CDNET_LAUNCH((k_ddm_codes<1, false>), grid, block, 0, st, cls_maps, codes, flags, H, W, lut, row_lo, row_hi);
     }
     return last_error();
 }
@@ -420,7 +423,7 @@ extern "C" int cdnet_ddm(const uint8_t* cls, float* out, int32_t* status, int B,
     uint16_t* codes = ar.take<uint16_t>((size_t)B * H * W);
     uint32_t* flags = ar.take<uint32_t>(B);
     if (!ar.ok) return CDNET_E_WORKSPACE;
-    int rc = ddm_codes_launch(cls, codes, flags, B, 1, H, W, n_classes, st);
+    int rc = ddm_codes_launch(cls, codes, flags, B, 1, H, W, n_classes, st, 0, -1);
     if (rc) return rc;
     const size_t plane = (size_t)H * W;
     dim3 grid((unsigned)((plane + 256 * 8 - 1) / (256 * 8)), B);
@@ -463,4 +466,12 @@ extern "C" int cdnet_circshift(const void* in, void* out, int C, int H, int W, i
         default: return CDNET_E_BADARG;
     }
     return last_error();
+}
+
+// whole-slide shard: codes for T (1 or 8) maps of one extended tile [T,He,W]; the "value present" flags are
+// accumulated over the rows [row_lo, row_hi) only (the shard's own rows) and are all-reduced by the host.
+extern "C" int cdnet_shard_ddm_codes(const uint8_t* dcm, uint16_t* codes, uint32_t* flags, int T, int He, int W,
+                                     int n_classes, int row_lo, int row_hi, void* stream) {
+    if (!dcm || !codes || !flags || He <= 0 || W <= 0 || (double)He * W >= 2147483648.0) return CDNET_E_BADARG;
+    return ddm_codes_launch(dcm, codes, flags, 1, T, He, W, n_classes, (cudaStream_t)stream, row_lo, row_hi);
 }

@@ -6,7 +6,7 @@ namespace cdnet {
 
 // ddm.cu
 int ddm_codes_launch(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int B, int T, int H, int W,
-                     int n_classes, cudaStream_t st);
+                     int n_classes, cudaStream_t st, int row_lo = 0, int row_hi = -1);
 
 // ccl.cu ------------------------------------------------------------------------------------------
 // labels of the connected components of `mask` (non-zero = foreground), raster-first ids 1..n.

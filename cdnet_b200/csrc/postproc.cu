@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) k_point_max(const float* __restrict__ poi
 __global__ void __launch_bounds__(256) k_boost_inside(const uint16_t* __restrict__ codes, const uint32_t* __restrict__ flags,
                                                       const float* __restrict__ point, const unsigned int* __restrict__ pmax,
                                                       float* __restrict__ prob, uint8_t* __restrict__ inside,
-                                                      int32_t* __restrict__ status, int H, int W, int write_prob) {
+                                                      int32_t* __restrict__ status, int H, int W, int write_prob,
+                                                      int n_maps) {
     __shared__ float s_val[8][4];
     __shared__ int s_const;
     const int b = blockIdx.z;
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(256) k_boost_inside(const uint16_t* __restrict
     if (tid < 32) {
         const int t = tid >> 2, d = tid & 3;
         const uint32_t f = (flags[b] >> (3 * t)) & 7u;
-        s_val[t][d] = d < 3 ? ddm_value_f(d, f) : 0.f;
-        if (d == 0 && (f == 0u || f == 1u || f == 2u || f == 4u)) s_const = 1;
+        s_val[t][d] = (d < 3 && t < n_maps) ? ddm_value_f(d, f) : 0.f;
+        if (t < n_maps && d == 0 && (f == 0u || f == 1u || f == 2u || f == 4u)) s_const = 1;
     }
     __syncthreads();
     if (s_const && status && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicOr(status + b, CDNET_S_DDM_CONSTANT);
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) k_boost_inside(const uint16_t* __restrict
     double sum = 0.0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) sum = __dadd_rn(sum, (double)s_val[t][(c >> (2 * t)) & 3u]);
-    const double ddm = __dmul_rn(sum, 0.125);  // np.mean over the 8 maps (exact: dyadic values)
+    const double ddm = n_maps == 8 ? __dmul_rn(sum, 0.125) : sum;  // np.mean over the 8 maps (exact: dyadic values)
     // point gate (test_dam.py:530-531): f32 divide by the global max, > 0.2 (f32), cross dilation
     const float* P = point + (size_t)b * plane;
     const float mx = ordered_to_f32(pmax[b]);
@@ -112,7 +113,8 @@ __device__ __forceinline__ float gate_threshold(float mx) {
 __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restrict__ codes, const uint32_t* __restrict__ flags,
                                                        const float* __restrict__ point, const unsigned int* __restrict__ pmax,
                                                        float* __restrict__ prob, uint8_t* __restrict__ inside,
-                                                       int32_t* __restrict__ status, int H, int W, int write_prob) {
+                                                       int32_t* __restrict__ status, int H, int W, int write_prob,
+                                                       int n_maps) {
     __shared__ uint8_t s_lo[256], s_hi[256];
     __shared__ float s_thr;
     __shared__ int s_const, s_div;
@@ -124,12 +126,14 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
         int bad = 0, lo = 0, hi = 0;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
+            if (t >= n_maps) continue;
             const uint32_t f = (fl >> (3 * t)) & 7u;
             const int mn = (f & 1) ? 0 : ((f & 2) ? 1 : 2);
             const int mx = (f & 4) ? 2 : ((f & 2) ? 1 : 0);
             if (mx == mn) bad = 1;
             const int d = (tid >> (2 * (t & 3))) & 3;
-            const int v2 = (mx > mn && d < 3) ? (2 * (d - mn)) / (mx - mn) : 0;  // exact: (d-mn)/(mx-mn) in {0,.5,1}
+            // exact: (d-mn)/(mx-mn) in {0,.5,1}; scaled so that lo+hi = 16 * mean over the n_maps (1 or 8) maps
+            const int v2 = (mx > mn && d < 3) ? ((16 / n_maps) * (d - mn)) / (mx - mn) : 0;
             if (t < 4) lo += v2; else hi += v2;
         }
         s_lo[tid] = (uint8_t)lo;
@@ -254,11 +258,12 @@ extern "C" size_t cdnet_dam_postproc_workspace_bytes(int B, int H, int W) {
     return pad256(n * 2) + 2 * pad256((size_t)B * 4) + pad256(n) + pad256(n * 4) + tail_workspace(B, H, W);
 }
 
-extern "C" int cdnet_dam_postproc(const uint8_t* dcm, float* prob, const float* point, void* out, int out_elem_bytes,
-                                  int32_t* status, int B, int H, int W, int direction_classes, int min_area, int radius,
-                                  int postproc, int write_prob, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, const float* point, void* out,
+                                  int out_elem_bytes, int32_t* status, int B, int H, int W, int direction_classes,
+                                  int min_area, int radius, int postproc, int write_prob, void* ws, size_t ws_bytes,
+                                  void* stream) {
     if (!dcm || !prob || !point || !out || bad_dims(B, H, W) || (out_elem_bytes != 4 && out_elem_bytes != 8) ||
-        (postproc != 0 && postproc != 1) || radius < 0 || radius > 4)
+        (postproc != 0 && postproc != 1) || radius < 0 || radius > 4 || (n_maps != 1 && n_maps != 8))
         return CDNET_E_BADARG;
     if (direction_classes != 5 && direction_classes != 9 && direction_classes != 17) return CDNET_E_BADARG;
     if (ws_bytes < cdnet_dam_postproc_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
@@ -274,7 +279,7 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, float* prob, const float* 
     void* tail_ws = (char*)ws + ar.off;
     const size_t tail_bytes = ws_bytes - ar.off;
     if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
-    int rc = ddm_codes_launch(dcm, codes, flags, B, 8, H, W, direction_classes, st);
+    int rc = ddm_codes_launch(dcm, codes, flags, B, n_maps, H, W, direction_classes, st);
     if (rc) return rc;
     CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, st));
     {
@@ -283,10 +288,10 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, float* prob, const float* 
     }
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
         CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
-                     pmax, prob, inside, status, H, W, write_prob);
+                     pmax, prob, inside, status, H, W, write_prob, n_maps);
     else
         CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
-                     pmax, prob, inside, status, H, W, write_prob);
+                     pmax, prob, inside, status, H, W, write_prob, n_maps);
     rc = last_error();
     if (rc) return rc;
     // test_dam.py:559 calls process() with its default min_size = 10
@@ -335,4 +340,33 @@ extern "C" int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
     return ws_process_launch(pred01, labels, status, B, H, W, min_size, ws_flag, ws, ws_bytes, st);
+}
+
+// ---- whole-slide shard pieces of the DAM chain (cdnet_b200/sharded.py) -----------------------------
+// max of the shard's own point-map rows as an order-preserving uint32 (the host all-reduces MAX)
+extern "C" int cdnet_shard_point_max(const float* point, uint32_t* pmax, size_t n, void* stream) {
+    if (!point || !pmax || n == 0) return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(uint32_t), st));
+    int gx = (int)((n + 256 * 16 - 1) / (256 * 16));
+    if (gx > 65535) gx = 65535;
+    CDNET_LAUNCH(k_point_max, dim3(gx, 1), 256, 0, st, point, pmax, n);
+    return last_error();
+}
+
+// boost + argmax on one extended tile; flags / pmax hold the slide-global values; n_maps 1 or 8
+extern "C" int cdnet_shard_boost(const uint16_t* codes, const uint32_t* flags, const float* point, const uint32_t* pmax,
+                                 float* prob, uint8_t* inside, int32_t* status, int He, int W, int n_maps, int write_prob,
+                                 void* stream) {
+    if (!codes || !flags || !point || !pmax || !prob || !inside || He <= 0 || W <= 0 || (n_maps != 1 && n_maps != 8))
+        return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int H = He, B = 1;
+    if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
+        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
+                     pmax, prob, inside, status, H, W, write_prob, n_maps);
+    else
+        CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
+                     pmax, prob, inside, status, H, W, write_prob, n_maps);
+    return last_error();
 }

@@ -105,7 +105,9 @@ int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t* status, i
                       int min_size, int ws_flag, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- direction-aware inference post-processing, test_dam.py:455-563 ----------------------------
- * dcm:   uint8   [B,8,H,W]  the 8 TTA direction-argmax maps (prob_dcm ... prob_dcm_r90_hvf)
+ * dcm:   uint8   [B,n_maps,H,W]  n_maps = 8: the 8 TTA direction-argmax maps (prob_dcm ...
+ *                           prob_dcm_r90_hvf, dcm_combined = 1, :455-498); n_maps = 1: the single-map
+ *                           variant (:499-502)
  * prob:  float32 [B,3,H,W]  class probabilities; if write_prob != 0 channel 2 is overwritten
  *                           with the boosted boundary probability like the reference (:536)
  * point: float32 [B,1,H,W]  point map
@@ -113,7 +115,7 @@ int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t* status, i
  *        from measure.label when postproc == 0 and int32 from process() when postproc == 1)
  * status: int32 [B] (CDNET_S_*), may be NULL. */
 size_t cdnet_dam_postproc_workspace_bytes(int B, int H, int W);
-int cdnet_dam_postproc(const uint8_t* dcm, float* prob, const float* point, void* out,
+int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, const float* point, void* out,
                        int out_elem_bytes, int32_t* status, int B, int H, int W,
                        int direction_classes, int min_area, int radius, int postproc,
                        int write_prob, void* ws, size_t ws_bytes, void* stream);
@@ -158,6 +160,34 @@ int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternar
                          int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status,
                          int B, int H, int W, int num_classes, const double* gauss_w, void* ws,
                          size_t ws_bytes, void* stream);
+
+/* ---- whole-slide row shards ---------------------------------------------
+ * One EXTENDED tile per call: the shard's own rows plus one ghost row of the neighbouring shard on
+ * each inner side; planes are [He, W].  The host (cdnet_b200/sharded.py) reconciles what straddles
+ * the shard seams between the stages: scalar all-reduces of the DDM value flags and the point-map
+ * maximum, and a union of the seam components' roots for fill-holes (frame-touch flags),
+ * remove-small (areas) and the canonical raster-order numbering.  No reference counterpart: the
+ * reference post-processes a slide on one CPU (test_dam.py:455-563). */
+int cdnet_shard_ddm_codes(const uint8_t* dcm, uint16_t* codes, uint32_t* flags, int T, int He, int W,
+                          int n_classes, int row_lo, int row_hi, void* stream);
+int cdnet_shard_point_max(const float* point, uint32_t* pmax, size_t n, void* stream);
+int cdnet_shard_boost(const uint16_t* codes, const uint32_t* flags, const float* point,
+                      const uint32_t* pmax, float* prob, uint8_t* inside, int32_t* status, int He,
+                      int W, int n_maps, int write_prob, void* stream);
+/* stage 1: equal-value 4-conn forest (L = root per pixel), frame-touch flags per root */
+int cdnet_shard_label_stage1(const uint8_t* inside, int32_t* L, int32_t* touch, int He, int W,
+                             int top_is_frame, int bottom_is_frame, void* stream);
+/* stage 2: state (0 bg / 1 fg / 2 hole), holes joined, areas over rows [row_lo,row_hi) (area zeroed by caller) */
+int cdnet_shard_label_stage2(const uint8_t* inside, int32_t* L, const int32_t* touch, uint8_t* state,
+                             int32_t* area, int He, int W, int row_lo, int row_hi, void* stream);
+/* stage 3: keep = area >= min_area, diagonal (8-conn) joins, L = root per pixel */
+int cdnet_shard_label_stage3(const uint8_t* state, int32_t* L, const int32_t* area, uint8_t* keep,
+                             int min_area, int He, int W, void* stream);
+/* stage 4: raster-order ids 1..n_owned for kept roots not marked in `excluded` (may be NULL) */
+int cdnet_shard_label_stage4(int32_t* L, const uint8_t* keep, const uint8_t* excluded, int32_t* idmap,
+                             int32_t* rowcnt, int32_t* n_owned, int He, int W, void* stream);
+int cdnet_shard_relabel(const int32_t* L, const uint8_t* keep, const int32_t* idmap, int32_t* labels,
+                        int He, int W, void* stream);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long cdnet_launch_count(void);

@@ -288,10 +288,14 @@ def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_are
     Returns dict(pred_labeled, pred_inside, pred2, ddm_mean)."""
     prob_maps = np.asarray(prob_maps)
     H, W = prob_maps.shape[1:]
-    stack = np.zeros((H, W, 8), dtype=np.float64)
-    for t in range(8):
-        stack[:, :, t] = generate_dd_map(np.asarray(dcm_tta[t]).astype(np.uint8), direction_classes)
-    ddm = np.mean(stack, axis=2)  # :489
+    if len(dcm_tta) == 1:
+        # single-map variant, test_dam.py:499-502 (the `dcm_combined != 1` branch): float32 DDM, no mean
+        ddm = generate_dd_map(np.asarray(dcm_tta[0]).astype(np.uint8), direction_classes)
+    else:
+        stack = np.zeros((H, W, 8), dtype=np.float64)
+        for t in range(8):
+            stack[:, :, t] = generate_dd_map(np.asarray(dcm_tta[t]).astype(np.uint8), direction_classes)
+        ddm = np.mean(stack, axis=2)  # :489
     with np.errstate(invalid="ignore", divide="ignore"):
         gate = (point_maps[0] / np.max(point_maps) > 0.2) * 1  # :530
     gate = dilate(gate, disk(1))  # :531

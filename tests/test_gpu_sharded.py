@@ -1,0 +1,62 @@
+"""-m gpu: whole-slide row partition with the CUDA backend, all ranks simulated on one GPU (SimComm):
+the sharded result must equal the unsharded single-GPU result (and the oracle) bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def _slide(seed, H, W, n, n_maps):
+    from test_sharded_gloo import _slide as mk
+    return mk(seed, H, W, n, n_maps)
+
+
+@pytest.mark.parametrize("G", [2, 3, 4, 7])
+@pytest.mark.parametrize("n_maps", [8, 1])
+def test_sharded_equals_single_gpu(cuda_api, G, n_maps):
+    import torch
+    from cdnet_b200 import sharded
+    H, W = 612, 524
+    dcm, prob, point = _slide(41, H, W, 230, n_maps)
+    single, status = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(prob)[None].cuda(),
+                                                   torch.from_numpy(point)[None].cuda(), 9, 20, 2, 0)
+    assert int(status.sum()) == 0
+    single = single[0].cpu().numpy()
+    parts = sharded.row_partition(H, G)
+    shards = [dict(dcm=dcm[:, a:b].copy(), prob=prob[:, a:b].copy(), point=point[:, a:b].copy()) for a, b in parts]
+    be = sharded.CudaBackend()
+    outs = sharded.postprocess_slide(shards, sharded.SimComm(G), H, W, be, 9, 20, 2)
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    assert got.dtype == single.dtype
+    assert np.array_equal(got, single), int((got != single).sum())
+
+
+def test_sharded_equals_oracle(cuda_api):
+    from cdnet_b200 import sharded
+    from oracle import restate as O
+    H, W = 300, 280
+    dcm, prob, point = _slide(42, H, W, 60, 8)
+    ref = O.dam_postprocess(prob.copy(), point, dcm, 9, 20, 2, 0, literal=False)["pred_labeled"]
+    parts = sharded.row_partition(H, 3)
+    shards = [dict(dcm=dcm[:, a:b].copy(), prob=prob[:, a:b].copy(), point=point[:, a:b].copy()) for a, b in parts]
+    outs = sharded.postprocess_slide(shards, sharded.SimComm(3), H, W, sharded.CudaBackend(), 9, 20, 2)
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    assert np.array_equal(got, ref)
+
+
+def test_single_map_variant_vs_oracle(cuda_api):
+    """n_maps = 1 (test_dam.py:499-502) through the unsharded C ABI"""
+    import torch
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    d = synth.postproc_inputs(43, 200, 240, 30)
+    dcm = d["dcm"][:1].copy()
+    ref = O.dam_postprocess(d["prob"].copy(), d["point"], dcm, 9, 20, 2, 0, literal=False)["pred_labeled"]
+    out, _ = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(d["prob"])[None].cuda(),
+                                           torch.from_numpy(d["point"])[None].cuda(), 9, 20, 2, 0)
+    assert np.array_equal(out[0].cpu().numpy(), ref)
