@@ -53,6 +53,19 @@ class SimComm(object):
         assert len(values) == self.world
         return list(values)
 
+    def exchange(self, be, up, down):
+        """up[i] / down[i]: backend array that local rank i sends to rank-1 / rank+1 (None at the ends).
+        Returns (from_upper, from_lower) lists."""
+        n = self.world
+        from_upper = [down[i - 1] if i > 0 else None for i in range(n)]
+        from_lower = [up[i + 1] if i < n - 1 else None for i in range(n)]
+        return from_upper, from_lower
+
+    def send_up(self, be, tensors, like):
+        """local rank i > 0 sends tensors[i] to rank i-1; returns what each rank receives from rank i+1"""
+        n = self.world
+        return [tensors[i + 1] if i < n - 1 else None for i in range(n)]
+
 
 class DistComm(object):
     """one rank per process over torch.distributed (NCCL with CUDA tensors, gloo on CPU)"""
@@ -64,47 +77,72 @@ class DistComm(object):
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.local_ranks = [self.rank]
+        # small host-side tables (seam roots, counts, id tables) travel over a gloo side group so that they
+        # neither wait for the device stream nor bounce through device memory; bulk halo rows use NCCL p2p
+        self.host_group = group
+        if group is None and dist.get_backend() == "nccl":
+            self.host_group = dist.new_group(backend="gloo")
 
     def allgather(self, values):
-        """values: [one picklable object] -> list over all ranks"""
+        """values: [one small picklable object] -> list over all ranks"""
         assert len(values) == 1
         out = [None] * self.world
-        self.dist.all_gather_object(out, values[0], group=self.group)
+        self.dist.all_gather_object(out, values[0], group=self.host_group)
         return out
+
+    def exchange(self, be, up, down):
+        """point-to-point halo / seam exchange with the two row neighbours (NCCL send/recv on device
+        tensors, gloo on CPU tensors); what arrives from a neighbour has the shape of what is sent to it"""
+        dist = self.dist
+        r, n = self.rank, self.world
+        ops, recv_up, recv_down = [], None, None
+        t_up = be.to_torch(up[0]) if up[0] is not None else None
+        t_down = be.to_torch(down[0]) if down[0] is not None else None
+        if r > 0 and t_up is not None:
+            recv_up = t_up.new_empty(t_up.shape)
+            ops += [dist.P2POp(dist.isend, t_up, r - 1, self.group), dist.P2POp(dist.irecv, recv_up, r - 1, self.group)]
+        if r < n - 1 and t_down is not None:
+            recv_down = t_down.new_empty(t_down.shape)
+            ops += [dist.P2POp(dist.isend, t_down, r + 1, self.group), dist.P2POp(dist.irecv, recv_down, r + 1, self.group)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return ([be.from_torch(recv_up) if recv_up is not None else None],
+                [be.from_torch(recv_down) if recv_down is not None else None])
+
+    def send_up(self, be, tensors, like):
+        """rank r > 0 sends tensors[0] to rank r-1; rank r < n-1 receives a tensor shaped `like` from r+1"""
+        dist = self.dist
+        r, n = self.rank, self.world
+        ops, recv = [], None
+        if r > 0:
+            ops.append(dist.P2POp(dist.isend, be.to_torch(tensors[0]), r - 1, self.group))
+        if r < n - 1:
+            recv = be.to_torch(like).new_empty(like.shape)
+            ops.append(dist.P2POp(dist.irecv, recv, r + 1, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return [be.from_torch(recv) if recv is not None else None]
 
 
 # --------------------------------------------------------------------------------------------------
 # seam reconciliation (host logic; numpy + scipy.sparse.csgraph)
 # --------------------------------------------------------------------------------------------------
-def seam_classes(seam_info, world):
+def seam_classes(edges, keys_list):
     """Union of the rank-local components that meet at shard seams.
 
-    seam_info[r] = dict(top=(gid[2,W], valid[2,W]) or None, bottom=(gid, valid) or None) where gid is
-    the slide-global pixel index of the LOCAL root of each pixel of the two rows shared with the
-    neighbour (rank r: bottom rows = own last row + ghost row; rank r+1: top rows = ghost row + own
-    first row -- the same two slide rows).  Returns (keys sorted unique int64, class_of_key,
-    n_classes): two keys are in one class iff their local components are connected across seams."""
+    edges: int64 [n,2] pairs (gid_a, gid_b) -- slide-global pixel index of the LOCAL root, on the upper and
+    on the lower rank, of one pixel of the two rows the ranks share; keys_list: the seam roots of every
+    rank.  Both are tiny (de-duplicated on the device).  Returns (keys sorted unique, class_of_key, n_classes)."""
     from scipy.sparse import coo_matrix
     from scipy.sparse.csgraph import connected_components
-    a_list, b_list, all_keys = [], [], []
-    for r in range(world - 1):
-        lo, hi = seam_info[r]["bottom"], seam_info[r + 1]["top"]
-        ga, va = lo
-        gb, vb = hi
-        both = va & vb
-        assert np.array_equal(va, vb), "seam pixels must be classified identically on both ranks"
-        a_list.append(ga[both].astype(np.int64))
-        b_list.append(gb[both].astype(np.int64))
-    for r in range(world):
-        for side in ("top", "bottom"):
-            if seam_info[r][side] is not None:
-                g, v = seam_info[r][side]
-                all_keys.append(g[v].astype(np.int64))
-    keys = np.unique(np.concatenate(all_keys)) if all_keys else np.zeros(0, np.int64)
+    ks = [np.asarray(k, dtype=np.int64).ravel() for k in keys_list] + [np.asarray(edges, dtype=np.int64).ravel()]
+    keys = np.unique(np.concatenate(ks)) if ks else np.zeros(0, np.int64)
     if keys.size == 0:
         return keys, np.zeros(0, np.int64), 0
-    a = np.searchsorted(keys, np.concatenate(a_list)) if a_list else np.zeros(0, np.int64)
-    b = np.searchsorted(keys, np.concatenate(b_list)) if b_list else np.zeros(0, np.int64)
+    e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    a, b = np.searchsorted(keys, e[:, 0]), np.searchsorted(keys, e[:, 1])
     n = keys.size
     graph = coo_matrix((np.ones(a.size, np.int8), (a, b)), shape=(n, n))
     ncls, cls = connected_components(graph, directed=False)
@@ -169,6 +207,44 @@ class CudaBackend(object):
 
     def add_scalar(self, plane, v):
         plane += int(v)
+
+    def to_torch(self, t):
+        return t.contiguous()
+
+    def from_torch(self, t):
+        return t
+
+    def seam_gid(self, L, valid, r0, off):
+        """int32 [2,W]: slide-global index of the local root of the pixels of ext rows r0, r0+1 (-1 = not valid)"""
+        g = L[r0:r0 + 2] + int(off)
+        if valid is not None:
+            g = self.torch.where(valid[r0:r0 + 2] != 0, g, self.torch.full_like(g, -1))
+        return g.contiguous()
+
+    def unique_pairs(self, a, b):
+        """host int64 [n,2]: distinct (a,b) over the entries with a >= 0 (b must be valid there too)"""
+        t = self.torch
+        key = (a.reshape(-1).to(t.int64) << 32) | (b.reshape(-1).to(t.int64) & 0xffffffff)
+        key = key[a.reshape(-1) >= 0]
+        if key.numel() == 0:
+            return np.zeros((0, 2), np.int64)
+        keep = t.ones_like(key, dtype=t.bool)
+        keep[1:] = key[1:] != key[:-1]          # runs of one component pair collapse to one entry
+        u = t.unique(key[keep]).cpu().numpy()
+        out = np.stack([u >> 32, (u & 0xffffffff).astype(np.int64)], axis=1)
+        out[:, 1] = np.where(out[:, 1] >= 2 ** 31, out[:, 1] - 2 ** 32, out[:, 1])
+        assert out.min() >= 0, "seam pixels must be classified identically on both ranks"
+        return out
+
+    def unique_vals(self, tensors):
+        t = self.torch
+        v = t.cat([x.reshape(-1) for x in tensors])
+        v = v[v >= 0]
+        if v.numel() == 0:
+            return np.zeros(0, np.int64)
+        keep = t.ones_like(v, dtype=t.bool)
+        keep[1:] = v[1:] != v[:-1]
+        return t.unique(v[keep]).cpu().numpy().astype(np.int64)
 
     def _st(self):
         return self.torch.cuda.current_stream().cuda_stream
@@ -240,10 +316,10 @@ class CudaBackend(object):
                                               rowcnt.data_ptr(), n.data_ptr(), He, W, self._st()), "stage4")
         return idmap, int(n.cpu().numpy()[0])
 
-    def relabel(self, L, keep, idmap):
+    def relabel(self, L, keep, idmap, out=None):
         from ._cabi import check
         He, W = keep.shape
-        labels = self.empty((He, W), "int32")
+        labels = self.empty((He, W), "int32") if out is None else out
         check(self.L.cdnet_shard_relabel(L.data_ptr(), keep.data_ptr(), idmap.data_ptr(), labels.data_ptr(), He, W,
                                          self._st()), "relabel")
         return labels
@@ -261,35 +337,32 @@ class _Shard(object):
     pass
 
 
-def _seam_rows(sh):
-    """ext-row indices of the two rows shared with the upper / lower neighbour"""
-    top = (0, 1) if sh.has_top else None
-    bottom = (sh.He - 2, sh.He - 1) if sh.has_bottom else None
-    return top, bottom
-
-
-def _seam_info(be, sh, L, valid_plane):
-    """per side: (gid[2,W] int64, valid[2,W] bool) of the rows shared with the neighbour"""
-    info = {"top": None, "bottom": None}
-    top, bottom = _seam_rows(sh)
-    for side, rows in (("top", top), ("bottom", bottom)):
-        if rows is None:
-            continue
-        r0 = rows[0]
-        g = be.to_host(L[r0:r0 + 2]).astype(np.int64) + sh.off
-        v = be.to_host(valid_plane[r0:r0 + 2]) != 0 if valid_plane is not None else np.ones(g.shape, bool)
-        info[side] = (g, v)
-    return info
-
-
-def _seam_entries(be, sh, info, attr_plane):
-    """(keys, vals) of this rank's seam roots, de-duplicated per local root: attr_plane[root]"""
-    ks = [info[s][0][info[s][1]] for s in ("top", "bottom") if info[s] is not None]
-    if not ks:
-        return np.zeros(0, np.int64), np.zeros(0, np.int64)
-    keys = np.unique(np.concatenate(ks))
-    vals = be.gather(attr_plane, keys - sh.off) if attr_plane is not None else np.zeros(keys.size, np.int64)
-    return keys, np.asarray(vals).astype(np.int64)
+def _seam_round(be, comm, S, valid_of, attr_of):
+    """One reconciliation round.  For every local shard: gid of the rows shared with each neighbour (device),
+    the lower rank ships its top rows up (point to point), the upper rank de-duplicates the (upper root,
+    lower root) pairs on the device; the tiny edge / root tables are all-gathered and every rank solves the
+    same union on its host.  Returns (keys, cls, ncls, per-shard seam keys, gathered (keys, attr) entries)."""
+    tops, bots = [], []
+    for sh in S:
+        v = valid_of(sh)
+        tops.append(be.seam_gid(sh.L, v, 0, sh.off) if sh.has_top else None)
+        bots.append(be.seam_gid(sh.L, v, sh.He - 2, sh.off) if sh.has_bottom else None)
+    from_lower = comm.send_up(be, tops, next((b for b in bots if b is not None), None))
+    local = []
+    for sh, top, bot, nb in zip(S, tops, bots, from_lower):
+        edges = be.unique_pairs(bot, nb) if sh.has_bottom else np.zeros((0, 2), np.int64)
+        keys = be.unique_vals([t for t in (top, bot) if t is not None]) if (sh.has_top or sh.has_bottom) \
+            else np.zeros(0, np.int64)
+        attr = np.asarray(be.gather(attr_of(sh), keys - sh.off)).astype(np.int64) if (attr_of is not None and keys.size) \
+            else np.zeros(keys.size, np.int64)
+        sh.seam_keys = keys
+        local.append((edges, keys, attr))
+    allv = comm.allgather(local)
+    edges = np.concatenate([v[0] for v in allv]) if allv else np.zeros((0, 2), np.int64)
+    keys, cls, ncls = seam_classes(edges, [v[1] for v in allv])
+    ek = np.concatenate([v[1] for v in allv]) if allv else np.zeros(0, np.int64)
+    ev = np.concatenate([v[2] for v in allv]) if allv else np.zeros(0, np.int64)
+    return keys, cls, ncls, ek, ev
 
 
 def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64"):
@@ -312,33 +385,46 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         sh.He = sh.Hl + sh.lo + (1 if sh.has_bottom else 0)
         sh.off = (sh.r0 - sh.lo) * W              # slide-global index of ext pixel 0
         asdev = lambda a: a if not isinstance(a, np.ndarray) else be.to_dev(a)
-        sh.dcm, sh.prob, sh.point = asdev(d["dcm"]), asdev(d["prob"]), asdev(d["point"])
-        assert sh.dcm.shape[-2] == sh.Hl and sh.dcm.shape[-1] == W
+        if "dcm_ext" in d:
+            # caller-allocated extended buffers (alloc_shard_buffers): own rows already sit at [lo, lo+Hl),
+            # the ghost rows are filled in place -- no plane-sized copies anywhere
+            sh.dcm_ext, sh.prob_ext, sh.point_ext = d["dcm_ext"], d["prob_ext"], d["point_ext"]
+            assert sh.dcm_ext.shape[-2] == sh.He
+        else:
+            dcm, prob, point = asdev(d["dcm"]), asdev(d["prob"]), asdev(d["point"])
+            assert dcm.shape[-2] == sh.Hl and dcm.shape[-1] == W
+            sh.dcm_ext = be.empty((dcm.shape[0], sh.He, W), "uint8")
+            sh.prob_ext = be.empty((3, sh.He, W), "float32")
+            sh.point_ext = be.empty((1, sh.He, W), "float32")
+            sh.dcm_ext[:, sh.lo:sh.lo + sh.Hl] = dcm
+            sh.prob_ext[:, sh.lo:sh.lo + sh.Hl] = prob
+            sh.point_ext[:, sh.lo:sh.lo + sh.Hl] = point
+        sh.dcm = sh.dcm_ext[:, sh.lo:sh.lo + sh.Hl]
+        sh.point = sh.point_ext[:, sh.lo:sh.lo + sh.Hl]
         S.append(sh)
-    n_maps = int(S[0].dcm.shape[0])
+    n_maps = int(S[0].dcm_ext.shape[0])
 
     def halo(get_rows, nrows):
-        """exchange the first / last `nrows` own rows with the neighbours (all-gather of the seam rows)"""
-        mine = [(be.to_host(get_rows(sh, 0, nrows)), be.to_host(get_rows(sh, sh.Hl - nrows, sh.Hl))) for sh in S]
-        allr = comm.allgather(mine)
-        out = []
-        for sh in S:
-            above = be.to_dev(allr[sh.rank - 1][1]) if sh.has_top else None
-            below = be.to_dev(allr[sh.rank + 1][0]) if sh.has_bottom else None
-            out.append((above, below))
-        return out
+        """first / last `nrows` own rows <-> the row neighbours, point to point, device resident"""
+        up = [get_rows(sh, 0, nrows) if sh.has_top else None for sh in S]
+        down = [get_rows(sh, sh.Hl - nrows, sh.Hl) if sh.has_bottom else None for sh in S]
+        fu, fl = comm.exchange(be, up, down)
+        return list(zip(fu, fl))
 
-    def extend(sh, own, above, below):
-        parts_ = ([above] if above is not None else []) + [own] + ([below] if below is not None else [])
-        return be.cat_rows(parts_) if len(parts_) > 1 else own.contiguous()
+    def fill_ghosts(sh, ext, above, below):
+        """write the received halo rows into the ghost rows of an extended plane (rows axis = -2)"""
+        if above is not None:
+            ext[..., 0:above.shape[-2], :] = above
+        if below is not None:
+            ext[..., ext.shape[-2] - below.shape[-2]:, :] = below
 
     # ---- phase 1: DDM codes (1-row class-map halo), global value flags and point maximum
     h_dcm = halo(lambda sh, a, b: sh.dcm[:, a:b], 1)
     h_pt = halo(lambda sh, a, b: sh.point[:, a:b], 1)
     loc = []
     for sh, (da, db), (pa, pb) in zip(S, h_dcm, h_pt):
-        sh.dcm_ext = extend(sh, sh.dcm, da, db)
-        sh.point_ext = extend(sh, sh.point, pa, pb)
+        fill_ghosts(sh, sh.dcm_ext, da, db)
+        fill_ghosts(sh, sh.point_ext, pa, pb)
         sh.codes, fl = be.ddm_codes(sh.dcm_ext, direction_classes, sh.lo, sh.lo + sh.Hl)
         loc.append((fl, be.point_max(sh.point)))
     allv = comm.allgather(loc)
@@ -353,72 +439,52 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
 
     # ---- phase 2: boost + argmax on own rows, then 1-row halo of the inside mask
     for sh in S:
-        if sh.has_top or sh.has_bottom:
-            # prob needs no halo (pointwise); pad the ghost rows with a copy so that the planes line up
-            pa = sh.prob[:, :1] if sh.has_top else None
-            pb = sh.prob[:, -1:] if sh.has_bottom else None
-            prob_ext = extend(sh, sh.prob, pa, pb)
-        else:
-            prob_ext = sh.prob.contiguous()
-        ins = be.boost(sh.codes, flags, sh.point_ext.reshape(sh.He, W), pmax, prob_ext, n_maps)
-        sh.inside_own = ins[sh.lo:sh.lo + sh.Hl]
+        # prob needs no halo (the boost is pointwise in prob); its ghost rows are never looked at
+        sh.inside = be.boost(sh.codes, flags, sh.point_ext.reshape(sh.He, W), pmax, sh.prob_ext, n_maps)
+        sh.inside_own = sh.inside[sh.lo:sh.lo + sh.Hl]
     h_in = halo(lambda sh, a, b: sh.inside_own[a:b], 1)
     for sh, (ia, ib) in zip(S, h_in):
-        sh.inside = extend(sh, sh.inside_own, ia, ib)
+        fill_ghosts(sh, sh.inside, ia, ib)
+
+    def class_of(keys, cls, k):
+        return cls[np.searchsorted(keys, k)]
 
     # ---- phase 3: forest of equal-value components; slide-global frame-touch flags for seam components
-    infos, entries = [], []
     for sh in S:
         sh.L, sh.touch = be.stage1(sh.inside, sh.rank == 0, sh.rank == G - 1)
-        info = _seam_info(be, sh, sh.L, None)
-        infos.append(info)
-        entries.append(_seam_entries(be, sh, info, sh.touch))
-    g_info, g_ent = comm.allgather(infos), comm.allgather(entries)
-    keys, cls, ncls = seam_classes(g_info, G)
+    keys, cls, ncls, ek, ev = _seam_round(be, comm, S, lambda sh: None, lambda sh: sh.touch)
     if ncls:
-        ek = np.concatenate([e[0] for e in g_ent])
-        ev = np.concatenate([e[1] for e in g_ent])
         ctouch = _class_reduce(keys, cls, ncls, ek, ev, "or")
-        for sh, (k, _) in zip(S, entries):
-            be.scatter(sh.touch, k - sh.off, ctouch[cls[np.searchsorted(keys, k)]].astype(np.int32))
+        for sh in S:
+            k = sh.seam_keys
+            be.scatter(sh.touch, k - sh.off, ctouch[class_of(keys, cls, k)].astype(np.int32))
 
-    # ---- phase 4: fill holes, local areas of own rows; slide-global areas for seam components
-    infos, entries = [], []
+    # ---- phase 4: fill holes, areas of own rows; slide-global areas for seam components
     for sh in S:
         sh.state, sh.area = be.stage2(sh.inside, sh.L, sh.touch, sh.lo, sh.lo + sh.Hl)
-        info = _seam_info(be, sh, sh.L, sh.state)
-        infos.append(info)
-        entries.append(_seam_entries(be, sh, info, sh.area))
-    g_info, g_ent = comm.allgather(infos), comm.allgather(entries)
-    keys, cls, ncls = seam_classes(g_info, G)
+    keys, cls, ncls, ek, ev = _seam_round(be, comm, S, lambda sh: sh.state, lambda sh: sh.area)
     if ncls:
-        # a (rank, local root) pair contributes once; equal keys on two ranks are different local parts
-        ek = np.concatenate([e[0] for e in g_ent])
-        ev = np.concatenate([e[1] for e in g_ent])
-        carea = _class_reduce(keys, cls, ncls, ek, ev, "sum")
-        for sh, (k, _) in zip(S, entries):
-            be.scatter(sh.area, k - sh.off, np.minimum(carea[cls[np.searchsorted(keys, k)]], 2 ** 31 - 1).astype(np.int32))
+        # every (rank, local root) contributes once; equal keys on two ranks are two local parts
+        carea = np.minimum(_class_reduce(keys, cls, ncls, ek, ev, "sum"), 2 ** 31 - 1)
+        for sh in S:
+            k = sh.seam_keys
+            be.scatter(sh.area, k - sh.off, carea[class_of(keys, cls, k)].astype(np.int32))
 
-    # ---- phase 5: remove small, 8-connectivity; owners and excluded roots; numbering
-    infos, entries = [], []
+    # ---- phase 5: remove small, 8-connectivity; owners, excluded roots, numbering
     for sh in S:
         sh.keep = be.stage3(sh.state, sh.L, sh.area, min_area)
-        info = _seam_info(be, sh, sh.L, sh.keep)
-        infos.append(info)
-        entries.append(_seam_entries(be, sh, info, None))
-    g_info = comm.allgather(infos)
-    keys, cls, ncls = seam_classes(g_info, G)
+    keys, cls, ncls, ek, ev = _seam_round(be, comm, S, lambda sh: sh.keep, None)
     croot = _class_reduce(keys, cls, ncls, keys, keys, "min") if ncls else np.zeros(0, np.int64)
     counts = []
-    for sh, (k, _) in zip(S, entries):
+    for sh in S:
+        k = sh.seam_keys
+        groot = croot[class_of(keys, cls, k)] if k.size else k
         own_lo, own_hi = sh.r0 * W, sh.r1 * W
-        groot = croot[cls[np.searchsorted(keys, k)]] if k.size else k
+        # a seam root is numbered by the rank that holds the class's first pixel in its OWN rows
         excl = (groot != k) | (k < own_lo) | (k >= own_hi)
-        sh.seam_keys, sh.seam_groot = k, groot
+        sh.seam_groot = groot
         sh.excluded = be.zeros((sh.He, W), "uint8")
         be.scatter(sh.excluded, (k - sh.off)[excl], np.ones(int(excl.sum()), np.uint8))
-        # ghost-row roots that never reach an own row are not seam keys of a *kept own* pixel only if they are
-        # not kept at all; kept ones appear in the shared rows and are covered above
         sh.idmap, n_owned = be.stage4(sh.L, sh.keep, sh.excluded)
         counts.append(n_owned)
     g_counts = comm.allgather(counts)
@@ -441,22 +507,45 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
             pos = np.searchsorted(tk, groot)
             assert np.array_equal(tk[pos], groot), "every seam class must have exactly one owner"
             be.scatter(sh.idmap, k - sh.off, tv[pos].astype(np.int32))
-        sh.labels = be.relabel(sh.L, sh.keep, sh.idmap)
+        # labels of the extended tile land in the middle of a buffer with room for the extra halo rows of
+        # the dilation (the ghost row already carries valid labels; rows beyond it come from the neighbour)
+        r = int(radius)
+        sh.pad_top = max(r - 1, 0) if sh.has_top else 0
+        sh.pad_bot = max(r - 1, 0) if sh.has_bottom else 0
+        sh.lab_big = be.empty((sh.pad_top + sh.He + sh.pad_bot, W), "int32")
+        sh.labels = sh.lab_big[sh.pad_top:sh.pad_top + sh.He]
+        be.relabel(sh.L, sh.keep, sh.idmap, out=sh.labels)
 
-    # ---- phase 6: label dilation by disk(radius) with a `radius`-row label halo
+    # ---- phase 6: label dilation by disk(radius); rows beyond the ghost row come from the neighbour
     r = int(radius)
     outs = []
-    if r > 0:
-        own_labels = lambda sh, a, b: sh.labels[sh.lo:sh.lo + sh.Hl][a:b]
-        h_lab = halo(own_labels, r)
-    for i, sh in enumerate(S):
-        own = sh.labels[sh.lo:sh.lo + sh.Hl]
-        if r > 0:
-            la, lb = h_lab[i]
-            ext = extend(sh, own, la, lb)
-            top = r if sh.has_top else 0
-            out = be.dilate(ext, r, out_dtype)[top:top + sh.Hl]
-        else:
-            out = be.dilate(own.contiguous(), 0, out_dtype)
+    if r > 1:
+        own = lambda sh: sh.labels[sh.lo:sh.lo + sh.Hl]
+        # the neighbour's own rows 2..r (seen from the seam): first send own[1:r] up / own[Hl-r:Hl-1] down
+        up = [own(sh)[1:r] if sh.has_top else None for sh in S]
+        down = [own(sh)[sh.Hl - r:sh.Hl - 1] if sh.has_bottom else None for sh in S]
+        fu, fl = comm.exchange(be, up, down)
+        for sh, a, b in zip(S, fu, fl):
+            if a is not None:
+                sh.lab_big[0:sh.pad_top] = a
+            if b is not None:
+                sh.lab_big[sh.pad_top + sh.He:] = b
+    for sh in S:
+        top = sh.pad_top + sh.lo
+        out = be.dilate(sh.lab_big, r, out_dtype)[top:top + sh.Hl]
         outs.append(out)
     return outs
+
+
+def alloc_shard_buffers(be, rank, world, H, W, n_maps):
+    """Extended device buffers of one rank: dict(dcm_ext [T,He,W] u8, prob_ext [3,He,W] f32, point_ext
+    [1,He,W] f32) plus views dcm / prob / point of the rank's OWN rows to be filled by the caller.  Passing
+    the *_ext entries to postprocess_slide avoids every plane-sized copy."""
+    r0, r1 = row_partition(H, world)[rank]
+    lo = 1 if rank > 0 else 0
+    He = (r1 - r0) + lo + (1 if rank < world - 1 else 0)
+    d = {"dcm_ext": be.empty((n_maps, He, W), "uint8"), "prob_ext": be.empty((3, He, W), "float32"),
+         "point_ext": be.empty((1, He, W), "float32")}
+    for k in ("dcm", "prob", "point"):
+        d[k] = d[k + "_ext"][:, lo:lo + (r1 - r0)]
+    return d

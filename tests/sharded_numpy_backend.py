@@ -59,6 +59,32 @@ class NumpyBackend(object):
     def add_scalar(self, plane, v):
         plane += np.int32(v)
 
+    def to_torch(self, t):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(t))
+
+    def from_torch(self, t):
+        return t.numpy() if hasattr(t, "numpy") else t
+
+    def seam_gid(self, L, valid, r0, off):
+        g = L[r0:r0 + 2].astype(np.int64) + int(off)
+        if valid is not None:
+            g = np.where(valid[r0:r0 + 2] != 0, g, -1)
+        return np.ascontiguousarray(g.astype(np.int32))
+
+    def unique_pairs(self, a, b):
+        m = a >= 0
+        pairs = np.stack([a[m], b[m]], axis=1).astype(np.int64)
+        if pairs.size == 0:
+            return np.zeros((0, 2), np.int64)
+        u = np.unique(pairs, axis=0)
+        assert u.min() >= 0, "seam pixels must be classified identically on both ranks"
+        return u
+
+    def unique_vals(self, arrays):
+        v = np.concatenate([np.asarray(t).reshape(-1) for t in arrays]).astype(np.int64)
+        return np.unique(v[v >= 0])
+
     def ddm_codes(self, dcm_ext, n_classes, row_lo, row_hi):
         T = dcm_ext.shape[0]
         codes = np.zeros(dcm_ext.shape[1:], np.uint16)
@@ -133,8 +159,12 @@ class NumpyBackend(object):
         idmap[roots] = np.arange(1, n + 1)
         return idmap, n
 
-    def relabel(self, L, keep, idmap):
-        return np.where(keep != 0, idmap.reshape(-1)[L], 0).astype(np.int32)
+    def relabel(self, L, keep, idmap, out=None):
+        res = np.where(keep != 0, idmap.reshape(-1)[L], 0).astype(np.int32)
+        if out is None:
+            return res
+        out[...] = res
+        return out
 
     def dilate(self, labels_ext, radius, out_dtype):
         return O.dilate(labels_ext, O.disk(radius)).astype(out_dtype)

@@ -59,7 +59,10 @@ def main():
     be = sharded.CudaBackend()
     r0, r1 = sharded.row_partition(a.H, world)[rank]
     rows = build_rows(r0, r1, a.W, a.maps)
-    dev_rows = {k: be.to_dev(v) for k, v in rows.items()}
+    dev_rows = sharded.alloc_shard_buffers(be, rank, world, a.H, a.W, a.maps)
+    for k, v in rows.items():
+        dev_rows[k].copy_(be.to_dev(v))
+    del rows
 
     def step():
         return sharded.postprocess_slide([dev_rows], comm, a.H, a.W, be, 9, 20, 2)[0]
