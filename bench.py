@@ -40,20 +40,30 @@ ALG_BYTES_PER_PX = 28.0  # 8 u8 maps + 3 f32 + 1 f32 i
 
 # algorithmic bytes per pixel of each kernel at its own boundary (DESIGN.md section "kernels")
 KERNEL_BYTES_PER_PX = {
-    "k_ddm_codes": 10.0,       # 8 class maps (u8) in, 2-byte code word out
-    "k_point_max": 4.0,        # f32 point map in
-    "k_boost_inside": 19.0,    # codes 2 + point 4 + prob 12 in, inside mask 1 out
-    "k_ccl_init": 5.0,         # mask 1 in, parent 4 out (+ 8 for the two zero-filled planes)
-    "k_ccl_merge": 5.0,        # mask 1 + parent 4
-    "k_flatten_fill": 10.0,    # parent 4 in/out, mask 1, state 1
-    "k_fill_merge": 5.0,
-    "k_flatten_area": 9.0,     # parent 4 in/out, state 1
-    "k_keep_large": 10.0,      # state 1 + parent 4 + area 4 in, keep 1 out
-    "k_diag_merge": 5.0,
+    "k_ddm_codes": 10.0,        # 8 class maps (u8) in, 2-byte code word out
+    "k_ddm_codes_simd": 10.0,
+    "k_point_max": 4.0,         # f32 point map in
+    "k_boost_inside": 19.0,     # codes 2 + point 4 + prob 12 in, inside mask 1 out
+    "k_boost_inside4": 19.0,
+    "k_ccl_init_rows": 13.0,    # mask 1 in, parent 4 + two zero-filled planes 8 out
+    "k_ccl_merge": 2.0,         # all levels together read every mask row twice; parent plane touched sparsely
+    "k_ccl_merge4": 2.0,
+    "k_flatten_fill": 10.0,     # parent 4 in/out, mask 1, state 1
+    "k_flatten_fill4": 10.0,
+    "k_fill_merge": 1.0,        # state 1 (unions are sparse)
+    "k_fill_merge4": 1.0,
+    "k_flatten_area": 9.0,      # parent 4 in/out, state 1
+    "k_flatten_area4": 9.0,
+    "k_keep_large": 10.0,       # state 1 + parent 4 + area 4 in, keep 1 out
+    "k_keep_large4": 10.0,
+    "k_diag_merge": 2.0,
+    "k_diag_merge4": 2.0,
     "k_flatten_count": 9.0,
+    "k_flatten_count4": 9.0,
     "k_assign_ids": 5.0,
-    "k_relabel": 13.0,         # parent 4 + keep 1 + idmap 4 in, labels 4 out
-    "k_label_dilate": 12.0,    # labels 4 in, int64 8 out
+    "k_relabel": 13.0,          # parent 4 + keep 1 + idmap 4 in, labels 4 out
+    "k_relabel4": 13.0,
+    "k_label_dilate": 12.0,     # labels 4 in, int64 8 out
 }
 
 
@@ -266,12 +276,14 @@ def main():
     px_per_launch = TILES * H * W
     peak, peak_src = measured_peak()
     top_name, (top_cnt, top_ms) = top
-    per_launch_ms = top_ms / top_cnt
+    # a "launch" of the dominant kernel = everything it does for one step (the row-tree merge is one logical
+    # pass split over log2(H) launches); px_per_launch pixels per step
+    per_launch_ms = top_ms / a.steps
     bpp = KERNEL_BYTES_PER_PX.get(top_name, ALG_BYTES_PER_PX)
     achieved = bpp * px_per_launch / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "alg_bytes_per_px": bpp, "kernel_ms_per_launch": per_launch_ms,
+                "alg_bytes_per_px": bpp, "kernel_ms_per_launch": per_launch_ms, "launches_per_step": top_cnt / a.steps,
                 "kernel_share_of_step": top_ms / total_k,
                 "pipeline_alg_frac": (ALG_BYTES_PER_PX * px_per_launch / (ms_dev / a.steps * 1e-3) / 1e9) / peak,
                 "kernels_ms_per_step": {k: round(v[1] / a.steps, 4) for k, v in

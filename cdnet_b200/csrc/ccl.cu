@@ -139,6 +139,58 @@ __global__ void __launch_bounds__(kBX* kBY) k_ccl_merge(const uint8_t* __restric
     }
 }
 
+// 4 pixels per thread (W % 4 == 0): two 32-bit mask loads + two edge bytes, the link tests on 4-bit vectors;
+// only the (rare) pixels that really need a union touch the parent plane.
+__device__ __forceinline__ uint32_t nz_bits4(uint32_t w) {  // bit i = byte i of w is non-zero
+    const uint32_t n = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+    return ((n >> 7) & 1u) | ((n >> 14) & 2u) | ((n >> 21) & 4u) | ((n >> 28) & 8u);
+}
+
+template <bool EQ, int CONN>
+__global__ void __launch_bounds__(256) k_ccl_merge4(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W,
+                                                    int level) {
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = (2 * (blockIdx.y * 4 + threadIdx.y) + 1) << level;
+    const int b = blockIdx.z;
+    if (x4 >= W || y >= H) return;
+    const size_t tile = (size_t)b * H * W;
+    const int p = y * W + x4;
+    const uint8_t* M = mask + tile;
+    const uint32_t V = nz_bits4(*(const uint32_t*)(M + p));
+    if (!EQ && V == 0) return;
+    const uint32_t U = nz_bits4(*(const uint32_t*)(M + p - W));
+    uint32_t lv = 0, lu = 0, okl = 0xEu;
+    if (x4 > 0) { lv = M[p - 1] != 0; lu = M[p - W - 1] != 0; okl = 0xFu; }
+    const uint32_t VL = ((V << 1) | lv) & 0xFu, UL = ((U << 1) | lu) & 0xFu;
+    uint32_t same_up, hl, same_ul;
+    if (EQ) { same_up = ~(V ^ U); hl = ~(V ^ VL) & okl; same_ul = ~(V ^ UL) & okl; }
+    else { same_up = V & U; hl = V & VL & okl; same_ul = V & UL & okl; }
+    uint32_t need = same_up & ~(hl & same_ul) & 0xFu;
+    int* Lt = L + tile;
+    while (need) {
+        const int i = __ffs(need) - 1;
+        need &= need - 1;
+        uf_union(Lt, p + i, p + i - W);
+    }
+    if (CONN == 8) {
+        uint32_t rv = 0, ru = 0, okr = 0x7u;
+        if (x4 + 4 < W) { rv = M[p + 4] != 0; ru = M[p - W + 4] != 0; okr = 0xFu; }
+        const uint32_t VR = (V >> 1) | (rv << 3), UR = (U >> 1) | (ru << 3);
+        uint32_t dl = V & ~U & ~VL & UL & okl;
+        uint32_t dr = V & ~U & UR & ~VR & okr;
+        while (dl) {
+            const int i = __ffs(dl) - 1;
+            dl &= dl - 1;
+            uf_union(Lt, p + i, p + i - W - 1);
+        }
+        while (dr) {
+            const int i = __ffs(dr) - 1;
+            dr &= dr - 1;
+            uf_union(Lt, p + i, p + i - W + 1);
+        }
+    }
+}
+
 // runs that continue across a 1024-pixel row-chunk seam of the init kernel (only when W > 1024)
 template <bool EQ>
 __global__ void k_ccl_merge_seams(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W) {
@@ -162,8 +214,12 @@ static void merge_all(const uint8_t* mask, int* L, int B, int H, int W, cudaStre
     for (int level = 0; (1 << level) < H; ++level) {
         const int nrows = (H - (1 << level) + (2 << level) - 1) / (2 << level);  // rows y = (2k+1)<<level < H
         if (nrows <= 0) break;
-        CDNET_LAUNCH((k_ccl_merge<EQ, CONN>), dim3(ceil_div(W, kBX), ceil_div(nrows, kBY), B), ccl_block(), 0, st, mask, L,
-                     H, W, level);
+        if (W % 4 == 0 && ((uintptr_t)mask & 3) == 0)
+            CDNET_LAUNCH((k_ccl_merge4<EQ, CONN>), dim3(ceil_div(W, 256), ceil_div(nrows, 4), B), dim3(64, 4), 0, st, mask,
+                         L, H, W, level);
+        else
+            CDNET_LAUNCH((k_ccl_merge<EQ, CONN>), dim3(ceil_div(W, kBX), ceil_div(nrows, kBY), B), ccl_block(), 0, st, mask,
+                         L, H, W, level);
     }
 }
 
@@ -172,6 +228,210 @@ __global__ void __launch_bounds__(kBX* kBY) k_flatten(int* __restrict__ L, int H
     if (!inb) return;
     int* Lt = L + tile;
     Lt[p] = uf_find(Lt, p);
+}
+
+// =====================================================================================================
+// 4-pixels-per-thread variants of the per-pixel passes (W % 4 == 0): 128-bit parent loads/stores, 32-bit
+// mask loads, four independent root chases in flight per thread.  Same results as the scalar kernels.
+// =====================================================================================================
+#define V4_COORDS                                                   \
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;             \
+    const int y = blockIdx.y * 4 + threadIdx.y;                     \
+    const int b = blockIdx.z;                                       \
+    const bool inb = (x4 < W) && (y < H);                           \
+    const size_t tile = (size_t)b * H * W;                          \
+    const int p = y * W + x4;                                       \
+    (void)p; (void)tile; (void)inb;
+static inline dim3 v4_grid(int B, int H, int W) { return dim3(ceil_div(W, 256), ceil_div(H, 4), B); }
+static inline dim3 v4_block() { return dim3(64, 4); }
+static inline bool v4_ok(int W, const void* a, const void* b2 = nullptr, const void* c = nullptr) {
+    return W % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b2 & 15) == 0 && ((uintptr_t)c & 15) == 0;
+}
+
+__device__ __forceinline__ void find4(const int* __restrict__ Lt, int p, int4 l, int r[4]) {
+    const int q[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i > 0 && q[i] == q[i - 1]) { r[i] = r[i - 1]; continue; }  // same run: same root
+        r[i] = (q[i] == p + i) ? q[i] : uf_find(Lt, q[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_flatten_fill4(const uint8_t* __restrict__ mask, int* __restrict__ L,
+                                                       const int* __restrict__ touch, uint8_t* __restrict__ state, int H,
+                                                       int W) {
+    V4_COORDS
+    if (!inb) return;
+    int* Lt = L + tile;
+    int r[4];
+    find4(Lt, p, *(const int4*)(Lt + p), r);
+    *(int4*)(Lt + p) = make_int4(r[0], r[1], r[2], r[3]);
+    const uint32_t m = *(const uint32_t*)(mask + tile + p);
+    uint32_t st = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool fg = (m >> (8 * i)) & 0xffu;
+        uint32_t s;
+        if (fg) s = 1;
+        else if (i > 0 && r[i] == r[i - 1] && !((m >> (8 * (i - 1))) & 0xffu)) s = (st >> (8 * (i - 1))) & 0xffu;
+        else s = touch[tile + r[i]] ? 0u : 2u;
+        st |= s << (8 * i);
+    }
+    *(uint32_t*)(state + tile + p) = st;
+}
+
+__global__ void __launch_bounds__(256) k_fill_merge4(const uint8_t* __restrict__ state, int* __restrict__ L, int H, int W) {
+    V4_COORDS
+    if (!inb) return;
+    const uint8_t* S = state + tile;
+    const uint32_t w = *(const uint32_t*)(S + p);
+    // any byte == 2 ?
+    const uint32_t t = w ^ 0x02020202u;
+    if (!((t - 0x01010101u) & ~t & 0x80808080u)) return;
+    int* Lt = L + tile;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (((w >> (8 * i)) & 0xffu) != 2u) continue;
+        const int q = p + i, x = x4 + i;
+        if (y > 0 && S[q - W] == 1) uf_union(Lt, q, q - W);
+        if (x > 0 && S[q - 1] == 1) uf_union(Lt, q, q - 1);
+        if (x + 1 < W && S[q + 1] == 1) uf_union(Lt, q, q + 1);
+        if (y + 1 < H && S[q + W] == 1) uf_union(Lt, q, q + W);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_flatten_area4(const uint8_t* __restrict__ state, int* __restrict__ L,
+                                                       int* __restrict__ area, int H, int W, int row_lo, int row_hi) {
+    V4_COORDS
+    if (!inb) return;
+    const uint32_t w = *(const uint32_t*)(state + tile + p);
+    if (w == 0) return;
+    int* Lt = L + tile;
+    const int4 l = *(const int4*)(Lt + p);
+    const int q[4] = {l.x, l.y, l.z, l.w};
+    int r[4];
+    bool dirty = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!((w >> (8 * i)) & 0xffu)) { r[i] = -1; continue; }
+        if (i > 0 && r[i - 1] >= 0 && q[i] == q[i - 1]) r[i] = r[i - 1];
+        else r[i] = (q[i] == p + i) ? q[i] : uf_find(Lt, q[i]);
+        dirty |= (r[i] != q[i]);
+    }
+    if (dirty) *(int4*)(Lt + p) = make_int4(r[0] >= 0 ? r[0] : q[0], r[1] >= 0 ? r[1] : q[1], r[2] >= 0 ? r[2] : q[2],
+                                            r[3] >= 0 ? r[3] : q[3]);
+    if (y < row_lo || y >= row_hi) return;
+    int run = 0, cur = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (r[i] == cur) { run += (cur >= 0); continue; }
+        if (cur >= 0) atomicAdd(area + tile + cur, run);
+        cur = r[i];
+        run = 1;
+    }
+    if (cur >= 0) atomicAdd(area + tile + cur, run);
+}
+
+__global__ void __launch_bounds__(256) k_keep_large4(const uint8_t* __restrict__ state, const int* __restrict__ L,
+                                                     const int* __restrict__ area, uint8_t* __restrict__ keep, int min_area,
+                                                     int H, int W) {
+    V4_COORDS
+    if (!inb) return;
+    const uint32_t w = *(const uint32_t*)(state + tile + p);
+    uint32_t k = 0;
+    if (w) {
+        const int4 l = *(const int4*)(L + tile + p);
+        const int q[4] = {l.x, l.y, l.z, l.w};
+        int prev_root = -1;
+        uint32_t prev_keep = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!((w >> (8 * i)) & 0xffu)) continue;
+            uint32_t ki;
+            if (q[i] == prev_root) ki = prev_keep;
+            else ki = area[tile + q[i]] >= min_area ? 1u : 0u;
+            prev_root = q[i];
+            prev_keep = ki;
+            k |= ki << (8 * i);
+        }
+    }
+    *(uint32_t*)(keep + tile + p) = k;
+}
+
+__global__ void __launch_bounds__(256) k_diag_merge4(const uint8_t* __restrict__ keep, int* __restrict__ L, int H, int W) {
+    V4_COORDS
+    if (!inb || y == 0) return;
+    const uint8_t* K = keep + tile;
+    const uint32_t V = nz_bits4(*(const uint32_t*)(K + p));
+    if (!V) return;
+    const uint32_t U = nz_bits4(*(const uint32_t*)(K + p - W));
+    uint32_t lv = 0, lu = 0, okl = 0xEu, rv = 0, ru = 0, okr = 0x7u;
+    if (x4 > 0) { lv = K[p - 1] != 0; lu = K[p - W - 1] != 0; okl = 0xFu; }
+    if (x4 + 4 < W) { rv = K[p + 4] != 0; ru = K[p - W + 4] != 0; okr = 0xFu; }
+    const uint32_t VL = ((V << 1) | lv) & 0xFu, UL = ((U << 1) | lu) & 0xFu;
+    const uint32_t VR = (V >> 1) | (rv << 3), UR = (U >> 1) | (ru << 3);
+    uint32_t dl = V & ~U & UL & ~VL & okl;
+    uint32_t dr = V & ~U & UR & ~VR & okr;
+    int* Lt = L + tile;
+    while (dl) {
+        const int i = __ffs(dl) - 1;
+        dl &= dl - 1;
+        uf_union(Lt, p + i, p + i - W - 1);
+    }
+    while (dr) {
+        const int i = __ffs(dr) - 1;
+        dr &= dr - 1;
+        uf_union(Lt, p + i, p + i - W + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_flatten_count4(int* __restrict__ L, const uint8_t* __restrict__ keep,
+                                                        int* __restrict__ rowcnt, int H, int W,
+                                                        const uint8_t* __restrict__ excluded) {
+    V4_COORDS
+    int cnt = 0;
+    if (inb) {
+        const uint32_t w = *(const uint32_t*)(keep + tile + p);
+        if (w) {
+            int* Lt = L + tile;
+            const int4 l = *(const int4*)(Lt + p);
+            const int q[4] = {l.x, l.y, l.z, l.w};
+            int r[4];
+            bool dirty = false;
+            const uint32_t ex = excluded ? *(const uint32_t*)(excluded + tile + p) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                r[i] = q[i];
+                if (!((w >> (8 * i)) & 0xffu)) continue;
+                if (i > 0 && ((w >> (8 * (i - 1))) & 0xffu) && q[i] == q[i - 1]) r[i] = r[i - 1];
+                else r[i] = (q[i] == p + i) ? q[i] : uf_find(Lt, q[i]);
+                dirty |= (r[i] != q[i]);
+                cnt += (r[i] == p + i) && !((ex >> (8 * i)) & 0xffu);
+            }
+            if (dirty) *(int4*)(Lt + p) = make_int4(r[0], r[1], r[2], r[3]);
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt && y < H) atomicAdd(rowcnt + (size_t)b * H + y, cnt);
+}
+
+__global__ void __launch_bounds__(256) k_relabel4(const int* __restrict__ L, const uint8_t* __restrict__ keep,
+                                                  const int* __restrict__ idmap, int* __restrict__ out, int H, int W) {
+    V4_COORDS
+    if (!inb) return;
+    const uint32_t w = *(const uint32_t*)(keep + tile + p);
+    int o[4] = {0, 0, 0, 0};
+    if (w) {
+        const int4 l = *(const int4*)(L + tile + p);
+        const int q[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!((w >> (8 * i)) & 0xffu)) continue;
+            if (i > 0 && ((w >> (8 * (i - 1))) & 0xffu) && q[i] == q[i - 1]) o[i] = o[i - 1];
+            else o[i] = idmap[tile + q[i]];
+        }
+    }
+    *(int4*)(out + tile + p) = make_int4(o[0], o[1], o[2], o[3]);
 }
 
 // ---- numbering ------------------------------------------------------------------------------------
@@ -262,7 +522,8 @@ __global__ void __launch_bounds__(kBX* kBY) k_relabel(const int* __restrict__ L,
 static int number_roots(int32_t* L, const uint8_t* keep, const uint8_t* excluded, int32_t* idmap, int32_t* rowcnt,
                         int32_t* n_out, int B, int H, int W, cudaStream_t st) {
     CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, sizeof(int32_t) * (size_t)B * H, st));
-    CDNET_LAUNCH(k_flatten_count, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, rowcnt, H, W, excluded);
+    if (v4_ok(W, L, keep, excluded)) CDNET_LAUNCH(k_flatten_count4, v4_grid(B, H, W), v4_block(), 0, st, L, keep, rowcnt, H, W, excluded);
+    else CDNET_LAUNCH(k_flatten_count, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, rowcnt, H, W, excluded);
     CDNET_LAUNCH(k_scan_rows, B, 1024, 0, st, rowcnt, n_out, H);
     CDNET_LAUNCH(k_assign_ids, dim3(ceil_div(H, 8), B), 256, 0, st, L, keep, rowcnt, idmap, H, W, excluded);
     return last_error();
@@ -272,7 +533,8 @@ static int number_and_relabel(int32_t* L, const uint8_t* keep, int32_t* idmap, i
                               int32_t* n_out, int B, int H, int W, cudaStream_t st) {
     int rc = number_roots(L, keep, nullptr, idmap, rowcnt, n_out, B, H, W, st);
     if (rc) return rc;
-    CDNET_LAUNCH(k_relabel, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, idmap, labels, H, W);
+    if (v4_ok(W, L, keep, idmap) && ((uintptr_t)labels & 15) == 0) CDNET_LAUNCH(k_relabel4, v4_grid(B, H, W), v4_block(), 0, st, L, keep, idmap, labels, H, W);
+    else CDNET_LAUNCH(k_relabel, ccl_grid(B, H, W), ccl_block(), 0, st, L, keep, idmap, labels, H, W);
     return last_error();
 }
 
@@ -328,7 +590,8 @@ int fill_holes_state_launch(const uint8_t* mask, uint8_t* state, int32_t* L, int
     CCL_INIT(true, st, mask, L, touch, (int*)nullptr);
     merge_all<true, 4>(mask, L, B, H, W, st);
     CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, mask, L, touch, H, W, 1, 1);
-    CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, state, H, W);
+    if (v4_ok(W, L, mask, state)) CDNET_LAUNCH(k_flatten_fill4, v4_grid(B, H, W), v4_block(), 0, st, mask, L, touch, state, H, W);
+    else CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, state, H, W);
     return last_error();
 }
 
@@ -400,11 +663,16 @@ int fill_remove_label_launch(const uint8_t* inside, int32_t* labels, uint8_t* pr
     CCL_INIT(true, st, inside, L, aux1, aux2);
     merge_all<true, 4>(inside, L, B, H, W, st);
     CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, aux1, H, W, 1, 1);
-    CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, state, H, W);
-    CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
-    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, H, W, 0, H);
-    CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, keep, min_area, H, W);
-    CDNET_LAUNCH(k_diag_merge, ccl_grid(B, H, W), ccl_block(), 0, st, keep, L, H, W);
+    if (v4_ok(W, L, inside, state)) CDNET_LAUNCH(k_flatten_fill4, v4_grid(B, H, W), v4_block(), 0, st, inside, L, aux1, state, H, W);
+    else CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, state, H, W);
+    if (v4_ok(W, L, state)) CDNET_LAUNCH(k_fill_merge4, v4_grid(B, H, W), v4_block(), 0, st, state, L, H, W);
+    else CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
+    if (v4_ok(W, L, state)) CDNET_LAUNCH(k_flatten_area4, v4_grid(B, H, W), v4_block(), 0, st, state, L, aux2, H, W, 0, H);
+    else CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, H, W, 0, H);
+    if (v4_ok(W, L, state, keep)) CDNET_LAUNCH(k_keep_large4, v4_grid(B, H, W), v4_block(), 0, st, state, L, aux2, keep, min_area, H, W);
+    else CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, aux2, keep, min_area, H, W);
+    if (v4_ok(W, L, keep)) CDNET_LAUNCH(k_diag_merge4, v4_grid(B, H, W), v4_block(), 0, st, keep, L, H, W);
+    else CDNET_LAUNCH(k_diag_merge, ccl_grid(B, H, W), ccl_block(), 0, st, keep, L, H, W);
     return number_and_relabel(L, keep, aux1, rowcnt, labels, nullptr, B, H, W, st);
 }
 
@@ -508,8 +776,10 @@ extern "C" int cdnet_remove_small_mask(const uint8_t* mask, uint8_t* out, int B,
     cudaStream_t st = (cudaStream_t)stream;
     CCL_INIT(false, st, mask, L, area, (int*)nullptr);
     merge_all<false, 4>(mask, L, B, H, W, st);
-    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, H, W, 0, H);
-    CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, out, min_size, H, W);
+    if (v4_ok(W, L, mask)) CDNET_LAUNCH(k_flatten_area4, v4_grid(B, H, W), v4_block(), 0, st, mask, L, area, H, W, 0, H);
+    else CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, H, W, 0, H);
+    if (v4_ok(W, L, mask, out)) CDNET_LAUNCH(k_keep_large4, v4_grid(B, H, W), v4_block(), 0, st, mask, L, area, out, min_size, H, W);
+    else CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, out, min_size, H, W);
     return last_error();
 }
 
@@ -553,9 +823,12 @@ extern "C" int cdnet_shard_label_stage2(const uint8_t* inside, int32_t* L, const
     if (!inside || !L || !touch || !state || !area || bad_dims(1, He, W)) return CDNET_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int B = 1, H = He;
-    CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, touch, state, H, W);
-    CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
-    CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, area, H, W, row_lo, row_hi);
+    if (v4_ok(W, L, inside, state)) CDNET_LAUNCH(k_flatten_fill4, v4_grid(B, H, W), v4_block(), 0, st, inside, L, touch, state, H, W);
+    else CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, touch, state, H, W);
+    if (v4_ok(W, L, state)) CDNET_LAUNCH(k_fill_merge4, v4_grid(B, H, W), v4_block(), 0, st, state, L, H, W);
+    else CDNET_LAUNCH(k_fill_merge, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, H, W);
+    if (v4_ok(W, L, state)) CDNET_LAUNCH(k_flatten_area4, v4_grid(B, H, W), v4_block(), 0, st, state, L, area, H, W, row_lo, row_hi);
+    else CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, area, H, W, row_lo, row_hi);
     return last_error();
 }
 
@@ -565,8 +838,10 @@ extern "C" int cdnet_shard_label_stage3(const uint8_t* state, int32_t* L, const 
     if (!state || !L || !area || !keep || bad_dims(1, He, W)) return CDNET_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int B = 1, H = He;
-    CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, area, keep, min_area, H, W);
-    CDNET_LAUNCH(k_diag_merge, ccl_grid(B, H, W), ccl_block(), 0, st, keep, L, H, W);
+    if (v4_ok(W, L, state, keep)) CDNET_LAUNCH(k_keep_large4, v4_grid(B, H, W), v4_block(), 0, st, state, L, area, keep, min_area, H, W);
+    else CDNET_LAUNCH(k_keep_large, ccl_grid(B, H, W), ccl_block(), 0, st, state, L, area, keep, min_area, H, W);
+    if (v4_ok(W, L, keep)) CDNET_LAUNCH(k_diag_merge4, v4_grid(B, H, W), v4_block(), 0, st, keep, L, H, W);
+    else CDNET_LAUNCH(k_diag_merge, ccl_grid(B, H, W), ccl_block(), 0, st, keep, L, H, W);
     CDNET_LAUNCH(k_flatten, ccl_grid(B, H, W), ccl_block(), 0, st, L, H, W);
     return last_error();
 }
@@ -582,6 +857,7 @@ extern "C" int cdnet_shard_relabel(const int32_t* L, const uint8_t* keep, const 
                                    int W, void* stream) {
     if (!L || !keep || !idmap || !labels || bad_dims(1, He, W)) return CDNET_E_BADARG;
     const int B = 1, H = He;
-    CDNET_LAUNCH(k_relabel, ccl_grid(B, H, W), ccl_block(), 0, (cudaStream_t)stream, L, keep, idmap, labels, H, W);
+    if (v4_ok(W, L, keep, idmap) && ((uintptr_t)labels & 15) == 0) CDNET_LAUNCH(k_relabel4, v4_grid(B, H, W), v4_block(), 0, (cudaStream_t)stream, L, keep, idmap, labels, H, W);
+    else CDNET_LAUNCH(k_relabel, ccl_grid(B, H, W), ccl_block(), 0, (cudaStream_t)stream, L, keep, idmap, labels, H, W);
     return last_error();
 }

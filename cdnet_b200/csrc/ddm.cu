@@ -208,29 +208,36 @@ __device__ __forceinline__ void classify1(uint32_t c, int n, uint32_t& onehot, u
     bg = act ? 0u : 1u;
 }
 
+struct RawRow {
+    uint32_t w, e;  // 4 class bytes; edge byte: the pixel left of the word (lane 0) / right of it (lane 31)
+};
+
 template <bool FAST>
-__device__ __forceinline__ void load_row_v2(const uint8_t* __restrict__ plane, int H, int W, int y, int x4, int n,
-                                            uint32_t ge_add, int lane, RowSets& rs, uint32_t& h3, uint32_t& hb3,
-                                            uint32_t& lr, uint32_t& lrb) {
-    uint32_t w = 0, cl = 0, cr = 0;
-    const bool rowok = (y >= 0 && y < H);
-    if (rowok && x4 < W) {
+__device__ __forceinline__ RawRow load_raw(const uint8_t* __restrict__ plane, int H, int W, int y, int x4, int lane) {
+    RawRow r;
+    r.w = 0; r.e = 0;
+    if (y >= 0 && y < H && x4 < W) {
         const uint8_t* row = plane + (size_t)y * W;
         if (FAST && x4 + 3 < W) {
-            w = __ldg((const uint32_t*)(row + x4));
+            r.w = __ldg((const uint32_t*)(row + x4));
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (x4 + i < W) w |= (uint32_t)__ldg(row + x4 + i) << (8 * i);
+                if (x4 + i < W) r.w |= (uint32_t)__ldg(row + x4 + i) << (8 * i);
         }
-        if (lane == 0 && x4 > 0) cl = __ldg(row + x4 - 1);
-        if (lane == 31 && x4 + 4 < W) cr = __ldg(row + x4 + 4);
+        if (lane == 0 && x4 > 0) r.e = __ldg(row + x4 - 1);
+        if (lane == 31 && x4 + 4 < W) r.e = __ldg(row + x4 + 4);
     }
-    rs = classify4(w, ge_add);
+    return r;
+}
+
+__device__ __forceinline__ void classify_row(const RawRow& raw, int n, uint32_t ge_add, int lane, RowSets& rs,
+                                             uint32_t& h3, uint32_t& hb3, uint32_t& lr, uint32_t& lrb) {
+    rs = classify4(raw.w, ge_add);
     uint32_t ohl = __shfl_up_sync(0xffffffffu, rs.onehot, 1), bgl = __shfl_up_sync(0xffffffffu, rs.bg, 1);
     uint32_t ohr = __shfl_down_sync(0xffffffffu, rs.onehot, 1), bgr = __shfl_down_sync(0xffffffffu, rs.bg, 1);
-    if (lane == 0) { uint32_t o, g; classify1(cl, n, o, g); ohl = o << 24; bgl = g << 24; }
-    if (lane == 31) { uint32_t o, g; classify1(cr, n, o, g); ohr = o; bgr = g; }
+    if (lane == 0) { uint32_t o, g; classify1(raw.e, n, o, g); ohl = o << 24; bgl = g << 24; }
+    if (lane == 31) { uint32_t o, g; classify1(raw.e, n, o, g); ohr = o; bgr = g; }
     const uint32_t L = __funnelshift_l(ohl, rs.onehot, 8), R = __funnelshift_r(rs.onehot, ohr, 8);
     const uint32_t Lb = __funnelshift_l(bgl, rs.bg, 8), Rb = __funnelshift_r(rs.bg, bgr, 8);
     lr = L | R;
@@ -264,36 +271,49 @@ __global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restric
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) { acc[r][0] = 0; acc[r][1] = 0; }
         const size_t plane_sz = (size_t)H * W;
+        // all row words of a plane pair are requested before any of them is consumed: the kernel is bound by
+        // load latency, not by issue slots, so memory-level parallelism is what buys time here
+        constexpr int PB = (T >= 2) ? 2 : 1;
+#pragma unroll 1
+        for (int t0 = 0; t0 < T; t0 += PB) {
+            RawRow raw[PB][ROWS + 2];
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const uint8_t* plane = cls_maps + ((size_t)b * T + t) * plane_sz;
-            RowSets rp, rc, rn;
-            uint32_t h3p, hb3p, lrp, lrbp, h3c, hb3c, lrc, lrbc, h3n, hb3n, lrn, lrbn;
-            load_row_v2<FAST>(plane, H, W, y0 - 1, x4, lut.n, ge_add, lane, rp, h3p, hb3p, lrp, lrbp);
-            load_row_v2<FAST>(plane, H, W, y0, x4, lut.n, ge_add, lane, rc, h3c, hb3c, lrc, lrbc);
+            for (int u = 0; u < PB; ++u) {
+                const uint8_t* plane = cls_maps + ((size_t)b * T + t0 + u) * plane_sz;
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                load_row_v2<FAST>(plane, H, W, y0 + r + 1, x4, lut.n, ge_add, lane, rn, h3n, hb3n, lrn, lrbn);
-                uint32_t S, BG;
-                if (AXIAL) { S = rp.onehot | rn.onehot | lrc; BG = rp.bg | rn.bg | lrbc; }
-                else { S = h3p | h3c | h3n; BG = hb3p | hb3c | hb3n; }
-                const uint32_t NEGW = __byte_perm(lut.neg_lo, lut.neg_hi, rc.sel);
-                const uint32_t POSW = __byte_perm(lut.pos_lo, lut.pos_hi, rc.sel);
-                const uint32_t anyneg7 = nonzero7(NEGW & S) & rc.act7;
-                const uint32_t notall7 = nonzero7((S & ~POSW) | BG);
-                const uint32_t b1 = anyneg7;
-                const uint32_t b0 = (notall7 & ~anyneg7 & rc.act7) | rc.odd7;
-                const uint32_t cw = ((b1 >> 6) | (b0 >> 7)) & 0x03030303u;
-                acc[r][0] |= __byte_perm(cw, 0u, 0x4140) << (2 * t);
-                acc[r][1] |= __byte_perm(cw, 0u, 0x4342) << (2 * t);
-                if (y0 + r >= row_lo && y0 + r < row_hi) {
-                    const uint32_t z7 = ~(b1 | b0) & inimg7;
-                    seen |= (z7 ? 1u : 0u) << (3 * t);
-                    seen |= (b0 ? 2u : 0u) << (3 * t);
-                    seen |= (b1 ? 4u : 0u) << (3 * t);
+                for (int r = 0; r < ROWS + 2; ++r) raw[u][r] = load_raw<FAST>(plane, H, W, y0 - 1 + r, x4, lane);
+            }
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const int t = t0 + u;
+                RowSets rp, rc, rn;
+                uint32_t h3p, hb3p, lrp, lrbp, h3c, hb3c, lrc, lrbc, h3n, hb3n, lrn, lrbn;
+                classify_row(raw[u][0], lut.n, ge_add, lane, rp, h3p, hb3p, lrp, lrbp);
+                classify_row(raw[u][1], lut.n, ge_add, lane, rc, h3c, hb3c, lrc, lrbc);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    classify_row(raw[u][r + 2], lut.n, ge_add, lane, rn, h3n, hb3n, lrn, lrbn);
+                    uint32_t S, BG;
+                    if (AXIAL) { S = rp.onehot | rn.onehot | lrc; BG = rp.bg | rn.bg | lrbc; }
+                    else { S = h3p | h3c | h3n; BG = hb3p | hb3c | hb3n; }
+                    const uint32_t NEGW = __byte_perm(lut.neg_lo, lut.neg_hi, rc.sel);
+                    const uint32_t POSW = __byte_perm(lut.pos_lo, lut.pos_hi, rc.sel);
+                    const uint32_t anyneg7 = nonzero7(NEGW & S) & rc.act7;
+                    const uint32_t notall7 = nonzero7((S & ~POSW) | BG);
+                    const uint32_t b1 = anyneg7;
+                    const uint32_t b0 = (notall7 & ~anyneg7 & rc.act7) | rc.odd7;
+                    const uint32_t cw = ((b1 >> 6) | (b0 >> 7)) & 0x03030303u;
+                    acc[r][0] |= __byte_perm(cw, 0u, 0x4140) << (2 * t);
+                    acc[r][1] |= __byte_perm(cw, 0u, 0x4342) << (2 * t);
+                    if (y0 + r >= row_lo && y0 + r < row_hi) {
+                        const uint32_t z7 = ~(b1 | b0) & inimg7;
+                        seen |= (z7 ? 1u : 0u) << (3 * t);
+                        seen |= (b0 ? 2u : 0u) << (3 * t);
+                        seen |= (b1 ? 4u : 0u) << (3 * t);
+                    }
+                    rp = rc; rc = rn;
+                    h3p = h3c; hb3p = hb3c; h3c = h3n; hb3c = hb3n; lrc = lrn; lrbc = lrbn;
                 }
-                rp = rc; rc = rn;
-                h3p = h3c; hb3p = hb3c; h3c = h3n; hb3c = hb3n; lrc = lrn; lrbc = lrbn;
             }
         }
         if (x4 < W) {
