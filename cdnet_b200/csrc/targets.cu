@@ -118,24 +118,51 @@ __device__ __forceinline__ double ray_reach(const int* __restrict__ L, int H, in
     return hi;
 }
 
-// table layout per tile: entries 0..tab-1 (label ids)
-__global__ void __launch_bounds__(kBX* kBY) k_t_centerness(const int* __restrict__ inst, double* __restrict__ cness,
-                                                           unsigned long long* __restrict__ best, int tab, int H, int W) {
-    PX_COORDS
-    if (!inb) return;
+// table layout per tile: entries 0..tab-1 (label ids).  A block owns a 64 x 32 pixel region, queues its
+// instance pixels in shared memory and lets all 256 threads work through the queue, so that lanes are not
+// idle on background (only ~25 % of a tile is nucleus).
+constexpr int kCW = 64, kCH = 32;
+__global__ void __launch_bounds__(256) k_t_centerness(const int* __restrict__ inst, double* __restrict__ cness,
+                                                      unsigned long long* __restrict__ best, int tab, int H, int W) {
+    __shared__ int s_q[kCW * kCH];
+    __shared__ int s_n;
+    const int b = blockIdx.z;
+    const size_t tile = (size_t)b * H * W;
     const int* L = inst + tile;
-    const int own = L[p];
-    if (own <= 0 || own >= tab) return;
-    double far = 0.0, near = 10000000.0;
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) {
-        const double r = ray_reach(L, H, W, y, x, own, c_rays[k][0], c_rays[k][1]);
-        far = fmax(far, r);
-        near = fmin(near, r);
+    const int bx0 = blockIdx.x * kCW, by0 = blockIdx.y * kCH;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCW * kCH; i += 256) {
+        const int x = bx0 + (i % kCW), y = by0 + (i / kCW);
+        bool fg = false;
+        if (x < W && y < H) {
+            const int own = L[y * W + x];
+            fg = own > 0 && own < tab;
+        }
+        // warp-aggregated append
+        const unsigned m = __ballot_sync(0xffffffffu, fg);
+        int base = 0;
+        if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&s_n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (fg) s_q[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = y * W + x;
     }
-    const double c = __ddiv_rn(near, far);
-    cness[tile + p] = c;
-    atomicMax(best + (size_t)b * tab + own, (unsigned long long)__double_as_longlong(c));
+    __syncthreads();
+    const int n = s_n;
+    for (int it = threadIdx.x; it < n; it += 256) {
+        const int p = s_q[it];
+        const int y = p / W, x = p - y * W;
+        const int own = L[p];
+        double far = 0.0, near = 10000000.0;
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            const double r = ray_reach(L, H, W, y, x, own, c_rays[k][0], c_rays[k][1]);
+            far = fmax(far, r);
+            near = fmin(near, r);
+        }
+        const double c = __ddiv_rn(near, far);
+        cness[tile + p] = c;
+        atomicMax(best + (size_t)b * tab + own, (unsigned long long)__double_as_longlong(c));
+    }
 }
 
 __global__ void __launch_bounds__(kBX* kBY) k_t_center_pick(const int* __restrict__ inst, const double* __restrict__ cness,
@@ -195,14 +222,19 @@ __global__ void __launch_bounds__(kBX* kBY) k_t_support_max(const int* __restric
     int labs[5];
     const int n = cross_labels(L, H, W, y, x, labs);
     const int own = L[p];
+    // the farthest support pixel from the centre is never an interior pixel of the nucleus (one of its four
+    // neighbours is farther), so interior pixels skip the atomic
+    const bool interior = n == 1 && labs[0] == own && y > 0 && y + 1 < H && x > 0 && x + 1 < W &&
+                          L[p - W] == own && L[p + W] == own && L[p - 1] == own && L[p + 1] == own;
     uint8_t flag = 0;
     for (int i = 0; i < n; ++i) {
         const int k = labs[i];
         if (k >= tab) continue;
         const int c = centre[(size_t)b * tab + k];
+        if (k == own && c == p) flag = 1;
+        if (interior) continue;
         const int dy = y - c / W, dx = x - c % W;
         atomicMax(maxd2 + (size_t)b * tab + k, dy * dy + dx * dx);
-        if (k == own && c == p) flag = 1;
     }
     cflag[tile + p] = flag;
 }
@@ -218,32 +250,78 @@ __device__ __forceinline__ int align_index(float a, int n) {
     return 0;
 }
 
+// own-label centre-distance value of every instance pixel: f32((1 - |p - c_k| / (M_k + 1e-7))) (:820-824, .float()
+// at :828).  One f64 sqrt + divide per pixel here instead of one per (pixel, tap) in the Sobel kernel.
+__global__ void __launch_bounds__(kBX* kBY) k_t_dcval(const int* __restrict__ inst, const int* __restrict__ centre,
+                                                      const int* __restrict__ maxd2, float* __restrict__ dcv, int tab,
+                                                      int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const int k = inst[tile + p];
+    float v = 0.0f;
+    if (k > 0 && k < tab) {
+        const int c = centre[(size_t)b * tab + k];
+        const int dy = y - c / W, dx = x - c % W;
+        const double denom = __dadd_rn(__dsqrt_rn((double)maxd2[(size_t)b * tab + k]), 0.0000001);
+        v = __double2float_rn(__dadd_rn(1.0, -__ddiv_rn(__dsqrt_rn((double)(dy * dy + dx * dx)), denom)));
+    }
+    dcv[tile + p] = v;
+}
+
 constexpr int kDX = 32, kDY = 8, kHalo = 6;  // 11x11 taps + 1 for the cross dilation
 
 // direction class per pixel (:827-834, :848-871)
-__global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict__ inst, const int* __restrict__ centre,
-                                                          const int* __restrict__ maxd2, const uint8_t* __restrict__ inside,
+__global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict__ inst, const float* __restrict__ dcv,
+                                                          const int* __restrict__ centre, const int* __restrict__ maxd2,
+                                                          const uint8_t* __restrict__ inside,
                                                           long long* __restrict__ direction, float* __restrict__ dir_out,
                                                           int tab, int n_classes, int H, int W) {
     __shared__ int s_l[kDY + 2 * kHalo][kDX + 2 * kHalo + 1];
+    __shared__ float s_v[kDY + 2 * kHalo][kDX + 2 * kHalo + 1];
+    __shared__ int s_list[kDX * kDY];
+    __shared__ int s_n;
     const int b = blockIdx.z;
     const size_t tile = (size_t)b * H * W;
     const int* L = inst + tile;
     const int bx0 = blockIdx.x * kDX, by0 = blockIdx.y * kDY;
-    for (int i = threadIdx.y * kDX + threadIdx.x; i < (kDY + 2 * kHalo) * (kDX + 2 * kHalo); i += kDX * kDY) {
+    const int tid = threadIdx.y * kDX + threadIdx.x;
+    if (tid == 0) s_n = 0;
+    for (int i = tid; i < (kDY + 2 * kHalo) * (kDX + 2 * kHalo); i += kDX * kDY) {
         const int ly = i / (kDX + 2 * kHalo), lx = i % (kDX + 2 * kHalo);
         const int gy = by0 + ly - kHalo, gx = bx0 + lx - kHalo;
-        s_l[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? L[gy * W + gx] : 0;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        s_l[ly][lx] = ok ? L[gy * W + gx] : 0;
+        s_v[ly][lx] = ok ? dcv[tile + gy * W + gx] : 0.0f;
     }
     __syncthreads();
-    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int p = y * W + x;
-    const int ly = threadIdx.y + kHalo, lx = threadIdx.x + kHalo;
-    // winner = highest label whose dilated support contains p ("last writer wins", :832-834)
-    int w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])), max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
-    float acc0 = 0.0f, acc1 = 0.0f;
-    if (w > 0 && w < tab) {
+    // pixels without a winner get (0, 0) at once; the others are queued so that every lane of the block works
+    // on a pixel that has a Sobel sum to evaluate
+    {
+        const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+        const int ly = threadIdx.y + kHalo, lx = threadIdx.x + kHalo;
+        int w = 0;
+        if (x < W && y < H)
+            w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])), max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
+        const bool active = (x < W && y < H) && w > 0 && w < tab;
+        if (x < W && y < H && !active) {
+            const int p = y * W + x;
+            if (dir_out) { dir_out[(tile + p) * 2] = 0.0f; dir_out[(tile + p) * 2 + 1] = 0.0f; }
+            // angle 0 -> class index n/2 for foreground pixels outside every instance support
+            direction[tile + p] = inside[tile + p] ? (long long)(n_classes / 2 + 1) : 0ll;
+        }
+        if (active) s_list[atomicAdd(&s_n, 1)] = tid;
+    }
+    __syncthreads();
+    const int n_act = s_n;
+    for (int it = tid; it < n_act; it += kDX * kDY) {
+        const int id = s_list[it];
+        const int ty = id / kDX, tx = id % kDX;
+        const int x = bx0 + tx, y = by0 + ty;
+        const int p = y * W + x;
+        const int ly = ty + kHalo, lx = tx + kHalo;
+        // winner = highest label whose dilated support contains p ("last writer wins", :832-834)
+        const int w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])), max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
+        float acc0 = 0.0f, acc1 = 0.0f;
         const int c = centre[(size_t)b * tab + w];
         const int cy = c / W, cx = c % W;
         const double denom = __dadd_rn(__dsqrt_rn((double)maxd2[(size_t)b * tab + w]), 0.0000001);
@@ -252,36 +330,39 @@ __global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict_
             const int qy = ly + kh - 5;
             const int gy = y + kh - 5;
             if (gy < 0 || gy >= H) continue;
-#pragma unroll 1
+#pragma unroll
             for (int kw = 0; kw < 11; ++kw) {
                 const int qx = lx + kw - 5;
                 const int gx = x + kw - 5;
-                if (gx < 0 || gx >= W) continue;
-                const bool member = s_l[qy][qx] == w || s_l[qy - 1][qx] == w || s_l[qy + 1][qx] == w ||
-                                    s_l[qy][qx - 1] == w || s_l[qy][qx + 1] == w;
-                if (!member) continue;
-                const int dy = gy - cy, dx = gx - cx;
-                const double dist = __dsqrt_rn((double)(dy * dy + dx * dx));
-                // distance_center_i = (1 - int_pos / (int_pos.max() + 1e-7)) * nucleus  (:824), then .float()
-                const float v = __double2float_rn(__dadd_rn(1.0, -__ddiv_rn(dist, denom)));
+                float v;
+                if (s_l[qy][qx] == w) {
+                    v = s_v[qy][qx];  // own pixel of the winner: value prepared by k_t_dcval
+                } else {
+                    // 1-pixel dilation ring of the winner: same f64 formula, evaluated in place
+                    const bool ring = (gx >= 0 && gx < W) && (s_l[qy - 1][qx] == w || s_l[qy + 1][qx] == w ||
+                                                              s_l[qy][qx - 1] == w || s_l[qy][qx + 1] == w);
+                    if (!ring) continue;
+                    const int dy = gy - cy, dx = gx - cx;
+                    v = __double2float_rn(__dadd_rn(1.0, -__ddiv_rn(__dsqrt_rn((double)(dy * dy + dx * dx)), denom)));
+                }
                 acc0 = __fmaf_rn(c_sobel[0][kh * 11 + kw], v, acc0);
                 acc1 = __fmaf_rn(c_sobel[1][kh * 11 + kw], v, acc1);
             }
         }
+        if (dir_out) {
+            dir_out[(tile + p) * 2] = acc0;
+            dir_out[(tile + p) * 2 + 1] = acc1;
+        }
+        long long cls = 0;
+        if (inside[tile + p]) {
+            // angle = degrees(arctan2(dir0, dir1)) in f32 (:848); the reference's libm/SVML atan2f is not
+            // correctly rounded, this is (f64 atan2 rounded to f32) -- differences are confined to a few
+            // ulp of the angle, i.e. to pixels within ~1e-5 degrees of a bin edge
+            const float ang = __fmul_rn(__double2float_rn(atan2((double)acc0, (double)acc1)), 57.295776f);
+            cls = align_index(ang, n_classes) + 1;
+        }
+        direction[tile + p] = cls;
     }
-    if (dir_out) {
-        dir_out[(tile + p) * 2] = acc0;
-        dir_out[(tile + p) * 2 + 1] = acc1;
-    }
-    long long cls = 0;
-    if (inside[tile + p]) {
-        // angle = degrees(arctan2(dir0, dir1)) in f32 (:848); the reference's libm/SVML atan2f is not
-        // correctly rounded, this is (f64 atan2 rounded to f32) -- differences are confined to a few
-        // ulp of the angle, i.e. to pixels within ~1e-5 degrees of a bin edge
-        const float ang = __fmul_rn(__double2float_rn(atan2((double)acc0, (double)acc1)), 57.295776f);
-        cls = align_index(ang, n_classes) + 1;
-    }
-    direction[tile + p] = cls;
 }
 
 // ---- Gaussian point map (:842) ----------------------------------------------------------------------
@@ -357,7 +438,7 @@ static int centres_launch(const int32_t* inst, double* cness, unsigned long long
     const size_t nt = (size_t)B * tab;
     const size_t blocks = (nt + 255) / 256;
     CDNET_LAUNCH(k_t_table_init, (unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, st, best, centre, maxd2, nt);
-    CDNET_LAUNCH(k_t_centerness, px_grid(B, H, W), px_block(), 0, st, inst, cness, best, tab, H, W);
+    CDNET_LAUNCH(k_t_centerness, dim3(ceil_div(W, kCW), ceil_div(H, kCH), B), 256, 0, st, inst, cness, best, tab, H, W);
     CDNET_LAUNCH(k_t_center_pick, px_grid(B, H, W), px_block(), 0, st, inst, cness, best, centre, tab, H, W);
     return last_error();
 }
@@ -482,8 +563,10 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     rc = centres_launch(inst, cness, best, centre, maxd2, tab, B, H, W, st);
     if (rc) return rc;
     CDNET_LAUNCH(k_t_support_max, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, cflag, tab, H, W);
-    CDNET_LAUNCH(k_t_direction, dim3(ceil_div(W, kDX), ceil_div(H, kDY), B), dim3(kDX, kDY), 0, st, inst, centre, maxd2,
-                 inside, (long long*)direction, dir_out, tab, num_classes, H, W);
+    float* dcv = (float*)cness;  // centerness is dead after the centre pick: reuse its plane for the dc values
+    CDNET_LAUNCH(k_t_dcval, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, dcv, tab, H, W);
+    CDNET_LAUNCH(k_t_direction, dim3(ceil_div(W, kDX), ceil_div(H, kDY), B), dim3(kDX, kDY), 0, st, inst, dcv, centre,
+                 maxd2, inside, (long long*)direction, dir_out, tab, num_classes, H, W);
     CDNET_LAUNCH(k_t_gauss, dim3(ceil_div(W, kGX), ceil_div(H, kGY), B), dim3(kGX, kGY), 0, st, cflag, (__half*)point, H, W);
     return last_error();
 }
