@@ -29,7 +29,7 @@ def _deps():
         [os.path.join(os.path.dirname(HERE), "include", "cdnet_b200.h")]
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra=()):
     if (not force and os.path.exists(LIB)
             and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in _deps())):
         return LIB
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, pr in procs:
         out = pr.communicate()[0].decode()
@@ -55,4 +55,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                extra=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -53,11 +53,14 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- union-find on an int32 parent array; links always point to a smaller index, so the root
 // ---- of a finished component is its first pixel in raster order -------------------------------
-__device__ __forceinline__ int uf_find(const int* __restrict__ L, int p) {
-    int q = __ldcg(L + p);
+// Plain (L1-cached) loads: a stale parent is still a node of the same tree whose chain ends at the
+// current root, and uf_union re-validates the root with the value atomicMin returns, so coherence is
+// not needed here -- and most hops hit L1 instead of paying an L2 round trip.
+__device__ __forceinline__ int uf_find(const int* L, int p) {
+    int q = L[p];
     while (q != p) {
         p = q;
-        q = __ldcg(L + p);
+        q = L[p];
     }
     return p;
 }
@@ -87,10 +90,11 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
         if (old == a) { a = b; break; }
         a = old;
     }
-    // keep the trees shallow: both starting points now point (almost) at the common root
+    // keep the trees shallow: both starting points now point (almost) at the common root.  Results unused ->
+    // fire-and-forget reductions, nothing waits on them.
     const int r = a < b ? a : b;
-    if (__ldcg(L + a0) > r) atomicMin(L + a0, r);
-    if (__ldcg(L + b0) > r) atomicMin(L + b0, r);
+    if (a0 != r) atomicMin(L + a0, r);
+    if (b0 != r) atomicMin(L + b0, r);
 }
 
 // float <-> order-preserving uint32 (for atomicMax on floats of any sign)

@@ -212,21 +212,23 @@ struct RawRow {
     uint32_t w, e;  // 4 class bytes; edge byte: the pixel left of the word (lane 0) / right of it (lane 31)
 };
 
+// colmode: 0 = word outside the image, 1 = full word (32-bit load), 2 = ragged (byte loads); edge_off: offset of
+// this lane's edge byte relative to x4 (-1 / +4) or 0 for "no edge byte" -- all row-invariant, computed once
 template <bool FAST>
-__device__ __forceinline__ RawRow load_raw(const uint8_t* __restrict__ plane, int H, int W, int y, int x4, int lane) {
+__device__ __forceinline__ RawRow load_raw(const uint8_t* __restrict__ plane, int H, int W, int y, int x4, int colmode,
+                                           int edge_off) {
     RawRow r;
     r.w = 0; r.e = 0;
-    if (y >= 0 && y < H && x4 < W) {
-        const uint8_t* row = plane + (size_t)y * W;
-        if (FAST && x4 + 3 < W) {
-            r.w = __ldg((const uint32_t*)(row + x4));
+    if ((unsigned)y < (unsigned)H && colmode) {
+        const uint8_t* row = plane + (size_t)y * W + x4;
+        if (FAST && colmode == 1) {
+            r.w = __ldg((const uint32_t*)row);
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (x4 + i < W) r.w |= (uint32_t)__ldg(row + x4 + i) << (8 * i);
+                if (x4 + i < W) r.w |= (uint32_t)__ldg(row + i) << (8 * i);
         }
-        if (lane == 0 && x4 > 0) r.e = __ldg(row + x4 - 1);
-        if (lane == 31 && x4 + 4 < W) r.e = __ldg(row + x4 + 4);
+        if (edge_off) r.e = __ldg(row + edge_off);
     }
     return r;
 }
@@ -236,8 +238,15 @@ __device__ __forceinline__ void classify_row(const RawRow& raw, int n, uint32_t 
     rs = classify4(raw.w, ge_add);
     uint32_t ohl = __shfl_up_sync(0xffffffffu, rs.onehot, 1), bgl = __shfl_up_sync(0xffffffffu, rs.bg, 1);
     uint32_t ohr = __shfl_down_sync(0xffffffffu, rs.onehot, 1), bgr = __shfl_down_sync(0xffffffffu, rs.bg, 1);
-    if (lane == 0) { uint32_t o, g; classify1(raw.e, n, o, g); ohl = o << 24; bgl = g << 24; }
-    if (lane == 31) { uint32_t o, g; classify1(raw.e, n, o, g); ohr = o; bgr = g; }
+    {
+        // warp edges: the neighbour pixel comes from the edge byte instead of the adjacent lane (selects, no branch)
+        uint32_t o, g;
+        classify1(raw.e, n, o, g);
+        ohl = lane == 0 ? (o << 24) : ohl;
+        bgl = lane == 0 ? (g << 24) : bgl;
+        ohr = lane == 31 ? o : ohr;
+        bgr = lane == 31 ? g : bgr;
+    }
     const uint32_t L = __funnelshift_l(ohl, rs.onehot, 8), R = __funnelshift_r(rs.onehot, ohr, 8);
     const uint32_t Lb = __funnelshift_l(bgl, rs.bg, 8), Rb = __funnelshift_r(rs.bg, bgr, 8);
     lr = L | R;
@@ -251,8 +260,17 @@ struct DdmLut8 {
     int n, axial;
 };
 
+#ifndef CDNET_DDM_PB
+#define CDNET_DDM_PB 2
+#endif
+#ifndef CDNET_DDM_MINB
+#define CDNET_DDM_MINB 5
+#endif
+#ifndef CDNET_DDM_ROWS_DEFAULT
+#define CDNET_DDM_ROWS_DEFAULT 4
+#endif
 template <int T, bool FAST, bool AXIAL, int ROWS>
-__global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restrict__ cls_maps, uint16_t* __restrict__ codes,
+__global__ void __launch_bounds__(128, CDNET_DDM_MINB) k_ddm_codes_simd(const uint8_t* __restrict__ cls_maps, uint16_t* __restrict__ codes,
                                                         uint32_t* __restrict__ flags, int H, int W, DdmLut8 lut,
                                                         int row_lo, int row_hi) {
     const int b = blockIdx.z;
@@ -266,14 +284,17 @@ __global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restric
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (x4 + i < W) inimg7 |= 0x80u << (8 * i);
-    if (y0 < H) {  // whole warp shares y0: uniform branch (shuffles inside)
+    if (y0 >= H) return;  // whole warp shares y0 (one warp per threadIdx.y): uniform exit, nothing to reduce
+    const int colmode = x4 >= W ? 0 : (x4 + 3 < W ? 1 : 2);
+    const int edge_off = (lane == 0 && x4 > 0 && x4 < W) ? -1 : ((lane == 31 && x4 + 4 < W) ? 4 : 0);
+    {
         uint32_t acc[ROWS][2];
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) { acc[r][0] = 0; acc[r][1] = 0; }
         const size_t plane_sz = (size_t)H * W;
         // all row words of a plane pair are requested before any of them is consumed: the kernel is bound by
         // load latency, not by issue slots, so memory-level parallelism is what buys time here
-        constexpr int PB = (T >= 2) ? 2 : 1;
+        constexpr int PB = (T >= 2) ? CDNET_DDM_PB : 1;
 #pragma unroll 1
         for (int t0 = 0; t0 < T; t0 += PB) {
             RawRow raw[PB][ROWS + 2];
@@ -281,13 +302,14 @@ __global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restric
             for (int u = 0; u < PB; ++u) {
                 const uint8_t* plane = cls_maps + ((size_t)b * T + t0 + u) * plane_sz;
 #pragma unroll
-                for (int r = 0; r < ROWS + 2; ++r) raw[u][r] = load_raw<FAST>(plane, H, W, y0 - 1 + r, x4, lane);
+                for (int r = 0; r < ROWS + 2; ++r) raw[u][r] = load_raw<FAST>(plane, H, W, y0 - 1 + r, x4, colmode, edge_off);
             }
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
                 const int t = t0 + u;
                 RowSets rp, rc, rn;
                 uint32_t h3p, hb3p, lrp, lrbp, h3c, hb3c, lrc, lrbc, h3n, hb3n, lrn, lrbn;
+                uint32_t m0 = 0, m1 = 0, m2 = 0;  // "value d present" masks of this map (bit 7 per pixel byte)
                 classify_row(raw[u][0], lut.n, ge_add, lane, rp, h3p, hb3p, lrp, lrbp);
                 classify_row(raw[u][1], lut.n, ge_add, lane, rc, h3c, hb3c, lrc, lrbc);
 #pragma unroll
@@ -306,14 +328,14 @@ __global__ void __launch_bounds__(128) k_ddm_codes_simd(const uint8_t* __restric
                     acc[r][0] |= __byte_perm(cw, 0u, 0x4140) << (2 * t);
                     acc[r][1] |= __byte_perm(cw, 0u, 0x4342) << (2 * t);
                     if (y0 + r >= row_lo && y0 + r < row_hi) {
-                        const uint32_t z7 = ~(b1 | b0) & inimg7;
-                        seen |= (z7 ? 1u : 0u) << (3 * t);
-                        seen |= (b0 ? 2u : 0u) << (3 * t);
-                        seen |= (b1 ? 4u : 0u) << (3 * t);
+                        m2 |= b1;
+                        m1 |= b0;
+                        m0 |= ~(b1 | b0);
                     }
                     rp = rc; rc = rn;
                     h3p = h3c; hb3p = hb3c; h3c = h3n; hb3c = hb3n; lrc = lrn; lrbc = lrbn;
                 }
+                seen |= (((m0 & inimg7) ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u)) << (3 * t);
             }
         }
         if (x4 < W) {
@@ -378,7 +400,8 @@ static void launch_simd(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flag
     static int rows = 0;
     if (!rows) {
         const char* e = getenv("CDNET_DDM_ROWS");
-        rows = (e && atoi(e) == 8) ? 8 : 4;
+        rows = e ? atoi(e) : CDNET_DDM_ROWS_DEFAULT;
+        if (rows != 8 && rows != 4 && rows != 2) rows = 4;
     }
     grid.y = ceil_div(H, 4 * rows);
     if (rows == 8) {
@@ -388,6 +411,14 @@ static void launch_simd(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flag
         } else {
             if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
             else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 8>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+        }
+    } else if (rows == 2) {
+        if (lut.axial) {
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, true, 2>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, true, 2>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+        } else {
+            if (fast) CDNET_LAUNCH((k_ddm_codes_simd<T, true, false, 2>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
+            else CDNET_LAUNCH((k_ddm_codes_simd<T, false, false, 2>), grid, block, 0, st, cls_maps, codes, flags, H, W, l8, row_lo, row_hi);
         }
     } else {
         if (lut.axial) {
