@@ -46,6 +46,7 @@ KERNEL_BYTES_PER_PX = {
     "k_boost_inside": 19.0,     # codes 2 + point 4 + prob 12 in, inside mask 1 out
     "k_boost_inside4": 19.0,
     "k_ccl_init_rows": 13.0,    # mask 1 in, parent 4 + two zero-filled planes 8 out
+    "k_ccl_strip": 13.0,        # same traffic; the unions happen in shared memory
     "k_ccl_merge": 2.0,         # all levels together read every mask row twice; parent plane touched sparsely
     "k_ccl_merge4": 2.0,
     "k_flatten_fill": 10.0,     # parent 4 in/out, mask 1, state 1
@@ -64,6 +65,7 @@ KERNEL_BYTES_PER_PX = {
     "k_relabel": 13.0,          # parent 4 + keep 1 + idmap 4 in, labels 4 out
     "k_relabel4": 13.0,
     "k_label_dilate": 12.0,     # labels 4 in, int64 8 out
+    "k_label_dilate4": 12.0,
 }
 
 
@@ -281,8 +283,15 @@ def main():
     per_launch_ms = top_ms / a.steps
     bpp = KERNEL_BYTES_PER_PX.get(top_name, ALG_BYTES_PER_PX)
     achieved = bpp * px_per_launch / (per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+        if top_name in tj["bytes_per_px"]:
+            traffic = tj["bytes_per_px"][top_name] * px_per_launch  # dram read+write per step, from ncu --set full
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_px": bpp, "kernel_ms_per_launch": per_launch_ms, "launches_per_step": top_cnt / a.steps,
                 "kernel_share_of_step": top_ms / total_k,
                 "pipeline_alg_frac": (ALG_BYTES_PER_PX * px_per_launch / (ms_dev / a.steps * 1e-3) / 1e9) / peak,

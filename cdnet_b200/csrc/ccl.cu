@@ -18,6 +18,8 @@
 // background components that do not touch the frame are holes -> holes are united with their
 // foreground neighbours -> areas -> small components dropped -> surviving components that touch
 // diagonally are united -> numbering.
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace cdnet {
@@ -115,9 +117,10 @@ static inline InitGeom init_geom(int B, int H, int W) {
 // bounded by the number of levels (<= log2 H) instead of growing with H when all rows link at once.
 template <bool EQ, int CONN>
 __global__ void __launch_bounds__(kBX* kBY) k_ccl_merge(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W,
-                                                        int level) {
+                                                        int level, int stride) {
     const int x = blockIdx.x * kBX + threadIdx.x;
-    const int y = (2 * (blockIdx.y * kBY + threadIdx.y) + 1) << level;
+    const int ri = blockIdx.y * kBY + threadIdx.y;
+    const int y = stride > 0 ? (ri + 1) * stride : ((2 * ri + 1) << level);
     const int b = blockIdx.z;
     if (x >= W || y >= H) return;
     const size_t tile = (size_t)b * H * W;
@@ -148,9 +151,10 @@ __device__ __forceinline__ uint32_t nz_bits4(uint32_t w) {  // bit i = byte i of
 
 template <bool EQ, int CONN>
 __global__ void __launch_bounds__(256) k_ccl_merge4(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W,
-                                                    int level) {
+                                                    int level, int stride) {
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
-    const int y = (2 * (blockIdx.y * 4 + threadIdx.y) + 1) << level;
+    const int ri = blockIdx.y * 4 + threadIdx.y;
+    const int y = stride > 0 ? (ri + 1) * stride : ((2 * ri + 1) << level);
     const int b = blockIdx.z;
     if (x4 >= W || y >= H) return;
     const size_t tile = (size_t)b * H * W;
@@ -216,18 +220,132 @@ static void merge_all(const uint8_t* mask, int* L, int B, int H, int W, cudaStre
         if (nrows <= 0) break;
         if (W % 4 == 0 && ((uintptr_t)mask & 3) == 0)
             CDNET_LAUNCH((k_ccl_merge4<EQ, CONN>), dim3(ceil_div(W, 256), ceil_div(nrows, 4), B), dim3(64, 4), 0, st, mask,
-                         L, H, W, level);
+                         L, H, W, level, 0);
         else
             CDNET_LAUNCH((k_ccl_merge<EQ, CONN>), dim3(ceil_div(W, kBX), ceil_div(nrows, kBY), B), ccl_block(), 0, st, mask,
-                         L, H, W, level);
+                         L, H, W, level, 0);
     }
 }
+
+// ---- strip-local labelling in shared memory -------------------------------------------------------------
+// A block owns SR consecutive rows of one tile (SR * W <= 32768 pixels): mask bytes and an int32 parent per
+// pixel live in shared memory, where a union-find hop costs ~30 cycles instead of an L2 round trip.  Runs
+// are initialised per 32-pixel segment (ballot + clz), every link inside the strip is united in shared
+// memory, the strip is flattened and written out with tile-global indices.  What is left for global memory
+// are the links across strip seams: ONE sparse launch (chains are at most H / SR links long).
+__device__ __forceinline__ int sfind(const int* P, int p) {
+    int q = P[p];
+    while (q != p) { p = q; q = P[p]; }
+    return p;
+}
+__device__ __forceinline__ void sunion(int* P, int a, int b) {
+    for (;;) {
+        a = sfind(P, a);
+        b = sfind(P, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicMin(P + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+template <bool EQ, int CONN>
+__global__ void __launch_bounds__(1024) k_ccl_strip(const uint8_t* __restrict__ mask, int* __restrict__ L,
+                                                    int* __restrict__ zero1, int* __restrict__ zero2, int H, int W, int SR) {
+    extern __shared__ int s_par[];
+    uint8_t* s_m = (uint8_t*)(s_par + SR * W);
+    const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    const int y0 = blockIdx.x * SR;
+    const int rows = min(SR, H - y0);
+    const int n = rows * W;
+    const size_t base = (size_t)blockIdx.y * H * W + (size_t)y0 * W;
+    const uint8_t* M = mask + base;
+    for (int i = tid; i < n; i += nt) {
+        s_m[i] = M[i] != 0;
+        if (zero1) zero1[base + i] = 0;
+        if (zero2) zero2[base + i] = 0;
+    }
+    __syncthreads();
+    auto same = [&](int v, int u) -> bool { return EQ ? (v == u) : (v && u); };
+    const int nr = ((n + nt - 1) / nt) * nt;
+    for (int i = tid; i < nr; i += nt) {
+        const bool valid = i < n;
+        const int x = valid ? i % W : 0;
+        const int v = valid ? s_m[i] : 0;
+        const bool link = valid && x > 0 && lane > 0 && same(v, s_m[i - 1]);
+        const unsigned m = __ballot_sync(0xffffffffu, link);
+        if (valid) s_par[i] = i - __clz(~(m << (31 - lane)));
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const int v = s_m[i];
+        if (!EQ && !v) continue;
+        const int y = i / W, x = i - y * W;
+        const bool hl = x > 0 && same(v, s_m[i - 1]);
+        if (hl && lane == 0) sunion(s_par, i, i - 1);
+        if (y > 0) {
+            if (same(v, s_m[i - W])) {
+                if (!(hl && same(v, s_m[i - W - 1]))) sunion(s_par, i, i - W);
+            } else if (CONN == 8) {
+                if (x > 0 && !hl && same(v, s_m[i - W - 1])) sunion(s_par, i, i - W - 1);
+                if (x + 1 < W && same(v, s_m[i - W + 1]) && !same(v, s_m[i + 1])) sunion(s_par, i, i - W + 1);
+            }
+        }
+    }
+    __syncthreads();
+    const int goff = y0 * W;
+    for (int i = tid; i < n; i += nt) L[base + i] = goff + sfind(s_par, i);
+}
+
+static int strip_rows(int H, int W) {
+    if (W > 16384) return 0;  // a strip needs at least 2 rows in 160 KB
+    int sr = 32768 / W;
+    static int cap = 0;
+    if (!cap) { const char* e = getenv("CDNET_STRIP_ROWS"); cap = e ? atoi(e) : 4; if (cap < 2) cap = 4; }
+    if (sr > cap) sr = cap;  // measured best on B200 for 1000-wide tiles: 4 rows x 512 threads (20 KB, many blocks per SM)
+    return sr >= 2 ? sr : 0;
+}
+
+template <bool EQ, int CONN>
+static int forest_build(const uint8_t* mask, int* L, int* zero1, int* zero2, int B, int H, int W, cudaStream_t st);
 
 __global__ void __launch_bounds__(kBX* kBY) k_flatten(int* __restrict__ L, int H, int W) {
     CCL_COORDS
     if (!inb) return;
     int* Lt = L + tile;
     Lt[p] = uf_find(Lt, p);
+}
+
+template <bool EQ, int CONN>
+static int forest_build(const uint8_t* mask, int* L, int* zero1, int* zero2, int B, int H, int W, cudaStream_t st) {
+    const int SR = strip_rows(H, W);
+    static int disable = -1;
+    if (disable < 0) disable = getenv("CDNET_NO_STRIP") ? 1 : 0;
+    if (SR == 0 || disable) {
+        CCL_INIT(EQ, st, mask, L, zero1, zero2);
+        merge_all<EQ, CONN>(mask, L, B, H, W, st);
+        return last_error();
+    }
+    const size_t smem = (size_t)SR * W * 5;
+    static bool attr_done[2][2] = {{false, false}, {false, false}};
+    if (!attr_done[EQ ? 1 : 0][CONN == 8 ? 1 : 0]) {
+        CDNET_CUDA_OK(cudaFuncSetAttribute(k_ccl_strip<EQ, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 163840));
+        attr_done[EQ ? 1 : 0][CONN == 8 ? 1 : 0] = true;
+    }
+    static int nthreads = 0;
+    if (!nthreads) { const char* e = getenv("CDNET_STRIP_THREADS"); nthreads = e ? atoi(e) : 512; }
+    CDNET_LAUNCH((k_ccl_strip<EQ, CONN>), dim3(ceil_div(H, SR), B), nthreads, smem, st, mask, L, zero1, zero2, H, W, SR);
+    const int nseam = (H - 1) / SR;  // rows SR, 2 SR, ... < H
+    if (nseam > 0) {
+        if (W % 4 == 0 && ((uintptr_t)mask & 3) == 0)
+            CDNET_LAUNCH((k_ccl_merge4<EQ, CONN>), dim3(ceil_div(W, 256), ceil_div(nseam, 4), B), dim3(64, 4), 0, st, mask,
+                         L, H, W, 0, SR);
+        else
+            CDNET_LAUNCH((k_ccl_merge<EQ, CONN>), dim3(ceil_div(W, kBX), ceil_div(nseam, kBY), B), ccl_block(), 0, st, mask,
+                         L, H, W, 0, SR);
+    }
+    return last_error();
 }
 
 // =====================================================================================================
@@ -539,11 +657,9 @@ static int number_and_relabel(int32_t* L, const uint8_t* keep, int32_t* idmap, i
 }
 
 int ccl_forest_launch(const uint8_t* mask, int32_t* L, int B, int H, int W, int conn, cudaStream_t st) {
-    CCL_INIT(false, st, mask, L, (int*)nullptr, (int*)nullptr);
-    if (conn == 4) merge_all<false, 4>(mask, L, B, H, W, st);
-    else if (conn == 8) merge_all<false, 8>(mask, L, B, H, W, st);
-    else return CDNET_E_BADARG;
-    return last_error();
+    if (conn == 4) return forest_build<false, 4>(mask, L, nullptr, nullptr, B, H, W, st);
+    if (conn == 8) return forest_build<false, 8>(mask, L, nullptr, nullptr, B, H, W, st);
+    return CDNET_E_BADARG;
 }
 
 int ccl_label_launch(const uint8_t* mask, int32_t* labels, int32_t* n_out, int32_t* L, int32_t* idmap,
@@ -587,8 +703,7 @@ __global__ void __launch_bounds__(kBX* kBY) k_flatten_fill(const uint8_t* __rest
 
 int fill_holes_state_launch(const uint8_t* mask, uint8_t* state, int32_t* L, int32_t* touch, int B, int H, int W,
                             cudaStream_t st) {
-    CCL_INIT(true, st, mask, L, touch, (int*)nullptr);
-    merge_all<true, 4>(mask, L, B, H, W, st);
+    { int rc0 = forest_build<true, 4>(mask, L, touch, nullptr, B, H, W, st); if (rc0) return rc0; }
     CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, mask, L, touch, H, W, 1, 1);
     if (v4_ok(W, L, mask, state)) CDNET_LAUNCH(k_flatten_fill4, v4_grid(B, H, W), v4_block(), 0, st, mask, L, touch, state, H, W);
     else CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, touch, state, H, W);
@@ -660,8 +775,7 @@ int fill_remove_label_launch(const uint8_t* inside, int32_t* labels, uint8_t* pr
     int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
     if (!ar.ok) return CDNET_E_WORKSPACE;
     uint8_t* keep = pred2_out ? pred2_out : keep_ws;
-    CCL_INIT(true, st, inside, L, aux1, aux2);
-    merge_all<true, 4>(inside, L, B, H, W, st);
+    { int rc0 = forest_build<true, 4>(inside, L, aux1, aux2, B, H, W, st); if (rc0) return rc0; }
     CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, aux1, H, W, 1, 1);
     if (v4_ok(W, L, inside, state)) CDNET_LAUNCH(k_flatten_fill4, v4_grid(B, H, W), v4_block(), 0, st, inside, L, aux1, state, H, W);
     else CDNET_LAUNCH(k_flatten_fill, ccl_grid(B, H, W), ccl_block(), 0, st, inside, L, aux1, state, H, W);
@@ -774,8 +888,7 @@ extern "C" int cdnet_remove_small_mask(const uint8_t* mask, uint8_t* out, int B,
     int32_t* area = ar.take<int32_t>(n);
     if (!ar.ok) return CDNET_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    CCL_INIT(false, st, mask, L, area, (int*)nullptr);
-    merge_all<false, 4>(mask, L, B, H, W, st);
+    { int rc0 = forest_build<false, 4>(mask, L, area, nullptr, B, H, W, st); if (rc0) return rc0; }
     if (v4_ok(W, L, mask)) CDNET_LAUNCH(k_flatten_area4, v4_grid(B, H, W), v4_block(), 0, st, mask, L, area, H, W, 0, H);
     else CDNET_LAUNCH(k_flatten_area, ccl_grid(B, H, W), ccl_block(), 0, st, mask, L, area, H, W, 0, H);
     if (v4_ok(W, L, mask, out)) CDNET_LAUNCH(k_keep_large4, v4_grid(B, H, W), v4_block(), 0, st, mask, L, area, out, min_size, H, W);
@@ -808,8 +921,7 @@ extern "C" int cdnet_shard_label_stage1(const uint8_t* inside, int32_t* L, int32
     if (!inside || !L || !touch || bad_dims(1, He, W)) return CDNET_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int B = 1, H = He;
-    CCL_INIT(true, st, inside, L, touch, (int*)nullptr);
-    merge_all<true, 4>(inside, L, B, H, W, st);
+    { int rc0 = forest_build<true, 4>(inside, L, touch, nullptr, B, H, W, st); if (rc0) return rc0; }
     CDNET_LAUNCH(k_border_touch, dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, st, inside, L, touch, H, W, top_is_frame,
                  bottom_is_frame);
     CDNET_LAUNCH(k_flatten, ccl_grid(B, H, W), ccl_block(), 0, st, L, H, W);
