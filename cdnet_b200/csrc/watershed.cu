@@ -82,12 +82,23 @@ __global__ void __launch_bounds__(kBX* kBY) k_erode_cross(const uint8_t* __restr
 // pred, keyed by its root
 __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restrict__ pred, const int* __restrict__ L,
                                                          int* __restrict__ out, int* __restrict__ ymax,
-                                                         int* __restrict__ xmin, int* __restrict__ xmax, int H, int W) {
+                                                         int* __restrict__ xmin, int* __restrict__ xmax,
+                                                         unsigned int* __restrict__ rootlist, int* __restrict__ nroots,
+                                                         int H, int W) {
     PX_COORDS
     int r = -1;
     if (inb) {
         if (pred[tile + p]) r = L[tile + p];
         else out[tile + p] = 0;
+    }
+    {
+        // compact list of component roots: the flood kernel hands them out to persistent warps
+        const bool is_root = r == p;
+        const unsigned m = __ballot_sync(0xffffffffu, is_root);
+        int basei = 0;
+        if (lane == 0 && m) basei = atomicAdd(nroots, __popc(m));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (is_root) rootlist[basei + __popc(m & ((1u << lane) - 1))] = (unsigned int)(tile + p);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, r);
     if (r >= 0) {
@@ -114,36 +125,142 @@ struct Buckets {
     int tail[256];
 };
 
-// one warp per component of `pred` (the warp that owns the component's root pixel)
+// Components whose bounding box has at most kCap pixels (every single nucleus) are flooded entirely in
+// shared memory: labels, values, FIFO links and bucket heads/tails of the box are staged per warp, so a
+// queue step costs shared-memory latency instead of several dependent L2 round trips.  Larger components
+// take the global-memory path with the same queue discipline.
+constexpr int kCap = 1536;
+struct WarpBox {
+    int lab[kCap];              // -1 = not this component, 0 = unlabelled, > 0 = label
+    unsigned short nxt[kCap];   // FIFO link (0xffff = end)
+    unsigned char val[kCap];
+    unsigned short head[256], tail[256];
+};
+
+__device__ __forceinline__ void flood_box(WarpBox& S, const uint8_t* __restrict__ P, const int* __restrict__ Lt,
+                                          const uint8_t* __restrict__ V, volatile int* O, int root, int W, int x0, int y0,
+                                          int bw, int bh, int lane) {
+    const int n = bw * bh;
+    for (int i = lane; i < 256; i += 32) { S.head[i] = 0xffff; S.tail[i] = 0xffff; }
+    for (int idx = lane; idx < n; idx += 32) {
+        const int ly = idx / bw, lx = idx - ly * bw;
+        const int g = (y0 + ly) * W + x0 + lx;
+        const bool in = P[g] && Lt[g] == root;
+        S.lab[idx] = in ? O[g] : -1;
+        S.val[idx] = V[g];
+    }
+    __syncwarp();
+    int cur = 256;
+    // age-0 elements: marker pixels in raster order
+    for (int base = 0; base < n; base += 32) {
+        const int idx = base + lane;
+        const bool mk = idx < n && S.lab[idx] > 0;
+        const int v = mk ? S.val[idx] : 0;
+        unsigned m = __ballot_sync(0xffffffffu, mk);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int vv = __shfl_sync(0xffffffffu, v, l);
+            if (lane == 0) {
+                const int qq = base + l;
+                S.nxt[qq] = 0xffff;
+                if (S.tail[vv] == 0xffff) S.head[vv] = qq; else S.nxt[S.tail[vv]] = qq;
+                S.tail[vv] = qq;
+            }
+            cur = min(cur, vv);
+        }
+    }
+    __syncwarp();
+    for (;;) {
+        int found = -1;
+        for (int base = cur & ~31; base < 256; base += 32) {
+            const int b = base + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, b >= cur && S.head[b] != 0xffff);
+            if (m) { found = base + __ffs(m) - 1; break; }
+        }
+        if (found < 0) break;
+        cur = found;
+        const int e = S.head[cur];
+        const int lbl = S.lab[e];
+        __syncwarp();
+        if (lane == 0) {
+            const int nx = S.nxt[e];
+            S.head[cur] = nx;
+            if (nx == 0xffff) S.tail[cur] = 0xffff;
+        }
+        const int ey = e / bw, ex = e - ey * bw;
+        int q = -1, v = 0;
+        if (lane < 4) {
+            const int qy = ey + (lane == 0 ? -1 : (lane == 3 ? 1 : 0));
+            const int qx = ex + (lane == 1 ? -1 : (lane == 2 ? 1 : 0));
+            if (qy >= 0 && qy < bh && qx >= 0 && qx < bw) {
+                const int qq = qy * bw + qx;
+                if (S.lab[qq] == 0) { q = qq; v = S.val[qq]; }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, q >= 0);
+        __syncwarp();
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int qq = __shfl_sync(0xffffffffu, q, l);
+            const int vv = __shfl_sync(0xffffffffu, v, l);
+            if (lane == 0) {
+                S.lab[qq] = lbl;
+                S.nxt[qq] = 0xffff;
+                if (S.tail[vv] == 0xffff) S.head[vv] = qq; else S.nxt[S.tail[vv]] = qq;
+                S.tail[vv] = qq;
+            }
+            cur = min(cur, vv);
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    for (int idx = lane; idx < n; idx += 32) {
+        const int l = S.lab[idx];
+        if (l >= 0) {
+            const int ly = idx / bw, lx = idx - ly * bw;
+            O[(y0 + ly) * W + x0 + lx] = l;
+        }
+    }
+    __syncwarp();
+}
+
+// persistent warps: every warp pulls component roots from the compact list until it is exhausted
 __global__ void __launch_bounds__(128) k_flood(const uint8_t* __restrict__ pred, const int* __restrict__ L,
                                                const uint8_t* __restrict__ val, volatile int* out, volatile int* next,
                                                const int* __restrict__ ymax, const int* __restrict__ xmin,
-                                               const int* __restrict__ xmax, int H, int W) {
-    __shared__ Buckets s_b[4];
+                                               const int* __restrict__ xmax, const unsigned int* __restrict__ rootlist,
+                                               const int* __restrict__ nroots, int* __restrict__ cursor, int H, int W) {
+    __shared__ WarpBox s_box[4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    const int y = blockIdx.y;
-    const int b = blockIdx.z;
-    const size_t tile = (size_t)b * H * W;
-    const int p = y * W + x;
-    const bool is_root = x < W && pred[tile + p] && L[tile + p] == p;
-    unsigned roots = __ballot_sync(0xffffffffu, is_root);
-    if (!roots) return;
-    Buckets& B = s_b[wid];
-    const uint8_t* P = pred + tile;
-    const int* Lt = L + tile;
-    const uint8_t* V = val + tile;
-    volatile int* O = out + tile;
-    volatile int* N = next + tile;
-    while (roots) {
-        const int rl = __ffs(roots) - 1;
-        roots &= roots - 1;
-        const int root = __shfl_sync(0xffffffffu, p, rl);
-        for (int i = lane; i < 256; i += 32) { B.head[i] = -1; B.tail[i] = -1; }
+    const int total = *nroots;
+    const unsigned int plane = (unsigned int)H * (unsigned int)W;
+    for (;;) {
+        int wi = 0;
+        if (lane == 0) wi = atomicAdd(cursor, 1);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= total) break;
+        const unsigned int g = rootlist[wi];
+        const int b = (int)(g / plane);
+        const int root = (int)(g - (unsigned int)b * plane);
+        const size_t tile = (size_t)b * plane;
+        const uint8_t* P = pred + tile;
+        const int* Lt = L + tile;
+        const uint8_t* V = val + tile;
+        volatile int* O = out + tile;
+        volatile int* N = next + tile;
+        const int y0 = root / W, y1 = ymax[tile + root], x0 = xmin[tile + root], x1 = xmax[tile + root];
+        if ((x1 - x0 + 1) * (y1 - y0 + 1) <= kCap) {
+            flood_box(s_box[wid], P, Lt, V, O, root, W, x0, y0, x1 - x0 + 1, y1 - y0 + 1, lane);
+            continue;
+        }
+        // ---- large component: same queue discipline on global memory (bucket heads/tails reuse the box)
+        int* head = s_box[wid].lab;
+        int* tail = s_box[wid].lab + 256;
+        for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
         __syncwarp();
         int cur = 256;
-        // ---- age-0 elements: marker pixels of this component in raster order
-        const int y0 = root / W, y1 = ymax[tile + root], x0 = xmin[tile + root], x1 = xmax[tile + root];
         for (int yy = y0; yy <= y1; ++yy) {
             for (int xb = x0; xb <= x1; xb += 32) {
                 const int xx = xb + lane;
@@ -158,33 +275,27 @@ __global__ void __launch_bounds__(128) k_flood(const uint8_t* __restrict__ pred,
                     const int vv = __shfl_sync(0xffffffffu, v, l);
                     if (lane == 0) {
                         N[qq] = -1;
-                        if (B.tail[vv] < 0) B.head[vv] = qq; else N[B.tail[vv]] = qq;
-                        B.tail[vv] = qq;
+                        if (tail[vv] < 0) head[vv] = qq; else N[tail[vv]] = qq;
+                        tail[vv] = qq;
                     }
                     cur = min(cur, vv);
                 }
             }
         }
         __syncwarp();
-        // ---- flood
         for (;;) {
-            // lowest non-empty bucket >= cur (32 buckets per probe)
             int found = -1;
             for (int base = cur & ~31; base < 256; base += 32) {
                 const int idx = base + lane;
-                const unsigned m = __ballot_sync(0xffffffffu, idx >= cur && B.head[idx] >= 0);
+                const unsigned m = __ballot_sync(0xffffffffu, idx >= cur && head[idx] >= 0);
                 if (m) { found = base + __ffs(m) - 1; break; }
             }
             if (found < 0) break;
             cur = found;
-            const int e = B.head[cur];
+            const int e = head[cur];
+            // independent loads first: the label of e, its FIFO link and the three planes of its neighbour
             const int lbl = O[e];
-            __syncwarp();
-            if (lane == 0) {
-                const int nx = N[e];
-                B.head[cur] = nx;
-                if (nx < 0) B.tail[cur] = -1;
-            }
+            const int nx = N[e];
             const int ey = e / W, ex = e - ey * W;
             int q = -1, v = 0;
             if (lane < 4) {
@@ -192,8 +303,14 @@ __global__ void __launch_bounds__(128) k_flood(const uint8_t* __restrict__ pred,
                 const int qx = ex + (lane == 1 ? -1 : (lane == 2 ? 1 : 0));
                 if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
                     const int qq = qy * W + qx;
-                    if (P[qq] && O[qq] == 0) { q = qq; v = V[qq]; }
+                    const int pm = P[qq], om = O[qq], vm = V[qq];
+                    if (pm && om == 0) { q = qq; v = vm; }
                 }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                head[cur] = nx;
+                if (nx < 0) tail[cur] = -1;
             }
             unsigned m = __ballot_sync(0xffffffffu, q >= 0);
             __syncwarp();
@@ -205,8 +322,8 @@ __global__ void __launch_bounds__(128) k_flood(const uint8_t* __restrict__ pred,
                 if (lane == 0) {
                     O[qq] = lbl;
                     N[qq] = -1;
-                    if (B.tail[vv] < 0) B.head[vv] = qq; else N[B.tail[vv]] = qq;
-                    B.tail[vv] = qq;
+                    if (tail[vv] < 0) head[vv] = qq; else N[tail[vv]] = qq;
+                    tail[vv] = qq;
                 }
                 cur = min(cur, vv);
             }
@@ -233,6 +350,7 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
                       int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st) {
     (void)status;
     const size_t n = (size_t)B * H * W;
+    if (n >= 4294967296ull) return CDNET_E_BADARG;  // root list holds 32-bit batch-global pixel indices
     Arena ar(ws, ws_bytes);
     int32_t* A = ar.take<int32_t>(n);    // forest of pred
     int32_t* Bp = ar.take<int32_t>(n);   // g2 -> touch / idmap -> ymax
@@ -275,8 +393,20 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     if (rc) return rc;
     // 4. flood (:47)
     CDNET_LAUNCH(k_bbox_init, px_grid(B, H, W), px_block(), 0, st, Bp, C, D, H, W);
-    CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, H, W);
-    CDNET_LAUNCH(k_flood, dim3(ceil_div(W, 128), H, B), 128, 0, st, pred01, A, val, labels, E, Bp, C, D, H, W);
+    // root list lives in the `counts` buffer (free between the two remove-small passes); rowcnt[0] = number
+    // of roots, rowcnt[1] = work-stealing cursor
+    unsigned int* rootlist = (unsigned int*)counts;
+    CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, 2 * sizeof(int32_t), st));
+    CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, H, W);
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    CDNET_LAUNCH(k_flood, dim3(n_sm * 4), 128, 0, st, pred01, A, val, labels, E, Bp, C, D, rootlist, rowcnt, rowcnt + 1, H,
+                 W);
     rc = last_error();
     if (rc) return rc;
     // 5. remove small (:48)
