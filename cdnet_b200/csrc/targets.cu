@@ -268,10 +268,12 @@ __global__ void __launch_bounds__(kBX* kBY) k_t_dcval(const int* __restrict__ in
     dcv[tile + p] = v;
 }
 
-constexpr int kDX = 32, kDY = 8, kHalo = 6;  // 11x11 taps + 1 for the cross dilation
+// region per block kDX x kDY pixels, kDT threads: the region is larger than the block so that the queue of
+// active pixels keeps every lane busy for several rounds
+constexpr int kDX = 32, kDY = 32, kDT = 256, kHalo = 6;  // 11x11 taps + 1 for the cross dilation
 
 // direction class per pixel (:827-834, :848-871)
-__global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict__ inst, const float* __restrict__ dcv,
+__global__ void __launch_bounds__(kDT) k_t_direction(const int* __restrict__ inst, const float* __restrict__ dcv,
                                                           const int* __restrict__ centre, const int* __restrict__ maxd2,
                                                           const uint8_t* __restrict__ inside,
                                                           long long* __restrict__ direction, float* __restrict__ dir_out,
@@ -284,9 +286,9 @@ __global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict_
     const size_t tile = (size_t)b * H * W;
     const int* L = inst + tile;
     const int bx0 = blockIdx.x * kDX, by0 = blockIdx.y * kDY;
-    const int tid = threadIdx.y * kDX + threadIdx.x;
+    const int tid = threadIdx.x;
     if (tid == 0) s_n = 0;
-    for (int i = tid; i < (kDY + 2 * kHalo) * (kDX + 2 * kHalo); i += kDX * kDY) {
+    for (int i = tid; i < (kDY + 2 * kHalo) * (kDX + 2 * kHalo); i += kDT) {
         const int ly = i / (kDX + 2 * kHalo), lx = i % (kDX + 2 * kHalo);
         const int gy = by0 + ly - kHalo, gx = bx0 + lx - kHalo;
         const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
@@ -296,9 +298,10 @@ __global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict_
     __syncthreads();
     // pixels without a winner get (0, 0) at once; the others are queued so that every lane of the block works
     // on a pixel that has a Sobel sum to evaluate
-    {
-        const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
-        const int ly = threadIdx.y + kHalo, lx = threadIdx.x + kHalo;
+    for (int id = tid; id < kDX * kDY; id += kDT) {
+        const int ty = id / kDX, tx = id % kDX;
+        const int x = bx0 + tx, y = by0 + ty;
+        const int ly = ty + kHalo, lx = tx + kHalo;
         int w = 0;
         if (x < W && y < H)
             w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])), max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
@@ -309,11 +312,16 @@ __global__ void __launch_bounds__(kDX* kDY) k_t_direction(const int* __restrict_
             // angle 0 -> class index n/2 for foreground pixels outside every instance support
             direction[tile + p] = inside[tile + p] ? (long long)(n_classes / 2 + 1) : 0ll;
         }
-        if (active) s_list[atomicAdd(&s_n, 1)] = tid;
+        // warp-aggregated append to the work queue
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        int basei = 0;
+        if ((tid & 31) == 0 && m) basei = atomicAdd(&s_n, __popc(m));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (active) s_list[basei + __popc(m & ((1u << (tid & 31)) - 1))] = id;
     }
     __syncthreads();
     const int n_act = s_n;
-    for (int it = tid; it < n_act; it += kDX * kDY) {
+    for (int it = tid; it < n_act; it += kDT) {
         const int id = s_list[it];
         const int ty = id / kDX, tx = id % kDX;
         const int x = bx0 + tx, y = by0 + ty;
@@ -386,12 +394,20 @@ __global__ void __launch_bounds__(kGX* kGY) k_t_gauss(const uint8_t* __restrict_
     const uint8_t* F = cflag + tile;
     const int bx0 = blockIdx.x * kGX, by0 = blockIdx.y * kGY;
     const int tid = threadIdx.y * kGX + threadIdx.x;
+    // the point map is sparse (one pixel per nucleus): a block whose halo window holds no centre writes zeros
+    int any = 0;
     for (int i = tid; i < (kGY + 2 * kGR) * (kGX + 2 * kGR); i += kGX * kGY) {
         const int ly = i / (kGX + 2 * kGR), lx = i % (kGX + 2 * kGR);
         const int gy = reflect_idx(by0 + ly - kGR, H), gx = reflect_idx(bx0 + lx - kGR, W);
-        s_f[ly][lx] = F[gy * W + gx];
+        const uint8_t f = F[gy * W + gx];
+        s_f[ly][lx] = f;
+        any |= f;
     }
-    __syncthreads();
+    if (!__syncthreads_or(any)) {
+        const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+        if (x < W && y < H) out[tile + (size_t)y * W + x] = __double2half(0.0);
+        return;
+    }
     // axis 0 first (scipy.ndimage.gaussian_filter iterates axes in order), symmetric summation order of
     // correlate1d: centre term, then (in[l-j] + in[l+j]) * w[8-j] for j = 8 .. 1
     for (int i = tid; i < kGY * (kGX + 2 * kGR); i += kGX * kGY) {
@@ -565,7 +581,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     CDNET_LAUNCH(k_t_support_max, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, cflag, tab, H, W);
     float* dcv = (float*)cness;  // centerness is dead after the centre pick: reuse its plane for the dc values
     CDNET_LAUNCH(k_t_dcval, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, dcv, tab, H, W);
-    CDNET_LAUNCH(k_t_direction, dim3(ceil_div(W, kDX), ceil_div(H, kDY), B), dim3(kDX, kDY), 0, st, inst, dcv, centre,
+    CDNET_LAUNCH(k_t_direction, dim3(ceil_div(W, kDX), ceil_div(H, kDY), B), kDT, 0, st, inst, dcv, centre,
                  maxd2, inside, (long long*)direction, dir_out, tab, num_classes, H, W);
     CDNET_LAUNCH(k_t_gauss, dim3(ceil_div(W, kGX), ceil_div(H, kGY), B), dim3(kGX, kGY), 0, st, cflag, (__half*)point, H, W);
     return last_error();
