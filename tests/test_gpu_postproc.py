@@ -107,8 +107,11 @@ def test_primitives_vs_scipy(cuda_api):
     from scipy import ndimage as ndi
     from oracle import restate as O
     rng = np.random.default_rng(5)
+    # ragged widths take the scalar kernels, W % 4 == 0 the 4-pixel ones, W > 1024 crosses init row chunks,
+    # W > 16384 takes the row-tree merge instead of the shared-memory strips
     for H, W, p in ((1, 1, 0.5), (1, 40, 0.6), (37, 1, 0.6), (65, 129, 0.55), (200, 333, 0.62), (128, 128, 0.95),
-                    (64, 64, 0.0), (31, 33, 1.0)):
+                    (64, 64, 0.0), (31, 33, 1.0), (7, 8, 0.6), (3, 12, 0.7), (50, 64, 0.58), (5, 2052, 0.6),
+                    (9, 4100, 0.62), (4, 16500, 0.6), (3, 17001, 0.6)):
         m = rng.random((H, W)) < p
         assert np.array_equal(cuda_api.label(m, connectivity=1), ndi.label(m)[0]), (H, W, "label4")
         assert np.array_equal(cuda_api.label(m), O.label8(m)), (H, W, "label8")
@@ -135,3 +138,17 @@ def test_batched_equals_single(cuda_api):
         for i, t in enumerate(tiles):
             single = cuda_api.dam_postprocess(t["prob"].copy(), t["point"], t["dcm"], 9, 20, 2, pp)
             assert np.array_equal(out[i].cpu().numpy(), single)
+
+
+def test_wide_tile_pipeline_vs_oracle(cuda_api):
+    """W > 16384: the whole-slide fallback path (row-chunk init + row-tree merge) through the full pipeline"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    base = synth.postproc_inputs(77, 24, 1100, 40)
+    rep = 16
+    d = {k: np.ascontiguousarray(np.concatenate([base[k]] * rep, axis=-1)) for k in ("dcm", "prob", "point")}
+    assert d["dcm"].shape[-1] == 17600
+    for pp in (0, 1):
+        ref = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp, literal=False)["pred_labeled"]
+        got = cuda_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
+        assert np.array_equal(got, ref), (pp, int((got != ref).sum()))

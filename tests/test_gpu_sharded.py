@@ -60,3 +60,20 @@ def test_single_map_variant_vs_oracle(cuda_api):
     out, _ = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(d["prob"])[None].cuda(),
                                            torch.from_numpy(d["point"])[None].cuda(), 9, 20, 2, 0)
     assert np.array_equal(out[0].cpu().numpy(), ref)
+
+
+def test_sharded_wide_slide(cuda_api):
+    """W > 16384 (what a 40 000-wide slide uses): shards == single GPU"""
+    import torch
+    from cdnet_b200 import sharded, synth
+    base = synth.postproc_inputs(78, 30, 1040, 40)
+    d = {k: np.ascontiguousarray(np.concatenate([base[k]] * 16, axis=-1)) for k in ("dcm", "prob", "point")}
+    H, W = 30, d["dcm"].shape[-1]
+    dcm = d["dcm"][:1].copy()
+    single, _ = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(d["prob"])[None].cuda(),
+                                              torch.from_numpy(d["point"])[None].cuda(), 9, 20, 2, 0)
+    parts = sharded.row_partition(H, 3)
+    shards = [dict(dcm=dcm[:, a:b].copy(), prob=d["prob"][:, a:b].copy(), point=d["point"][:, a:b].copy()) for a, b in parts]
+    outs = sharded.postprocess_slide(shards, sharded.SimComm(3), H, W, sharded.CudaBackend(), 9, 20, 2)
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    assert np.array_equal(got, single[0].cpu().numpy())
