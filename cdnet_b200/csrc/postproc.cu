@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
     const int y = blockIdx.y * 4 + threadIdx.y;
     if (x4 >= W || y >= H) return;
-    const int plane = H * W;
+    const size_t plane = (size_t)H * W;  // 2 * plane overflows int for whole-slide tiles
     const int p = y * W + x4;
     const float* P = point + (size_t)b * plane;
     const float mx = ordered_to_f32(pmax[b]);

@@ -77,10 +77,11 @@ class DistComm(object):
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.local_ranks = [self.rank]
-        # small host-side tables (seam roots, counts, id tables) travel over a gloo side group so that they
-        # neither wait for the device stream nor bounce through device memory; bulk halo rows use NCCL p2p
+        # small host-side tables (seam roots, counts, id tables): all_gather_object on the default (NCCL) group
+        # measured slightly faster at 8 ranks than a gloo side group (CDNET_SHARD_HOSTGROUP=gloo selects that)
         self.host_group = group
-        if group is None and dist.get_backend() == "nccl":
+        import os
+        if group is None and dist.get_backend() == "nccl" and os.environ.get("CDNET_SHARD_HOSTGROUP", "nccl") == "gloo":
             self.host_group = dist.new_group(backend="gloo")
 
     def allgather(self, values):
@@ -221,6 +222,27 @@ class CudaBackend(object):
             g = self.torch.where(valid[r0:r0 + 2] != 0, g, self.torch.full_like(g, -1))
         return g.contiguous()
 
+    def seam_export(self, L, valid, attr, off, He, has_top, has_bottom, nb_top):
+        """One masked select + one device->host copy per round: rows (gid, neighbour gid or -1, attr) for the
+        run starts of the rows shared with the neighbours.  nb_top: the lower rank's gid of my bottom rows."""
+        t = self.torch
+        parts = []
+        for side, r0 in (("top", 0), ("bottom", He - 2)):
+            if (side == "top" and not has_top) or (side == "bottom" and not has_bottom):
+                continue
+            g = L[r0:r0 + 2].to(t.int64) + int(off)
+            if valid is not None:
+                g = t.where(valid[r0:r0 + 2] != 0, g, t.full_like(g, -1))
+            a = attr.view(-1)[(g - int(off)).clamp_(min=0)].to(t.int64) if attr is not None else t.zeros_like(g)
+            nb = nb_top.to(t.int64) if (side == "bottom" and nb_top is not None) else t.full_like(g, -1)
+            parts.append(t.stack([g.reshape(-1), nb.reshape(-1), a.reshape(-1)], dim=1))
+        if not parts:
+            return np.zeros((0, 3), np.int64)
+        rows = t.cat(parts, dim=0)
+        keep = rows[:, 0] >= 0
+        keep[1:] &= (rows[1:, 0] != rows[:-1, 0]) | (rows[1:, 1] != rows[:-1, 1])
+        return rows[keep].cpu().numpy()
+
     def unique_pairs(self, a, b):
         """host int64 [n,2]: distinct (a,b) over the entries with a >= 0 (b must be valid there too)"""
         t = self.torch
@@ -337,32 +359,31 @@ class _Shard(object):
     pass
 
 
-def _seam_round(be, comm, S, valid_of, attr_of):
+def _seam_round(be, comm, S, valid_of, attr_of, extra=None):
     """One reconciliation round.  For every local shard: gid of the rows shared with each neighbour (device),
-    the lower rank ships its top rows up (point to point), the upper rank de-duplicates the (upper root,
-    lower root) pairs on the device; the tiny edge / root tables are all-gathered and every rank solves the
-    same union on its host.  Returns (keys, cls, ncls, per-shard seam keys, gathered (keys, attr) entries)."""
-    tops, bots = [], []
-    for sh in S:
-        v = valid_of(sh)
-        tops.append(be.seam_gid(sh.L, v, 0, sh.off) if sh.has_top else None)
-        bots.append(be.seam_gid(sh.L, v, sh.He - 2, sh.off) if sh.has_bottom else None)
-    from_lower = comm.send_up(be, tops, next((b for b in bots if b is not None), None))
+    the lower rank ships its top rows up (point to point), the run starts of (own root, neighbour root, attr)
+    are selected on the device and copied to the host in one piece; the tiny tables are all-gathered and
+    every rank solves the same union on its host.  `extra(sh)` rides along in the same all-gather.
+    Returns (keys, cls, ncls, entry keys, entry attrs, gathered extras)."""
+    tops = [be.seam_gid(sh.L, valid_of(sh), 0, sh.off) if sh.has_top else None for sh in S]
+    like = next((be.seam_gid(sh.L, valid_of(sh), sh.He - 2, sh.off) for sh in S if sh.has_bottom), None)
+    from_lower = comm.send_up(be, tops, like)
     local = []
-    for sh, top, bot, nb in zip(S, tops, bots, from_lower):
-        edges = be.unique_pairs(bot, nb) if sh.has_bottom else np.zeros((0, 2), np.int64)
-        keys = be.unique_vals([t for t in (top, bot) if t is not None]) if (sh.has_top or sh.has_bottom) \
-            else np.zeros(0, np.int64)
-        attr = np.asarray(be.gather(attr_of(sh), keys - sh.off)).astype(np.int64) if (attr_of is not None and keys.size) \
-            else np.zeros(keys.size, np.int64)
+    for sh, nb in zip(S, from_lower):
+        rows = be.seam_export(sh.L, valid_of(sh), attr_of(sh) if attr_of is not None else None, sh.off, sh.He,
+                              sh.has_top, sh.has_bottom, nb)
+        e = rows[rows[:, 1] >= 0][:, :2]
+        assert e.size == 0 or e.min() >= 0, "seam pixels must be classified identically on both ranks"
+        edges = np.unique(e, axis=0) if e.size else np.zeros((0, 2), np.int64)
+        keys, first = np.unique(rows[:, 0], return_index=True)
         sh.seam_keys = keys
-        local.append((edges, keys, attr))
+        local.append((edges, keys, rows[first, 2], extra(sh) if extra is not None else None))
     allv = comm.allgather(local)
     edges = np.concatenate([v[0] for v in allv]) if allv else np.zeros((0, 2), np.int64)
     keys, cls, ncls = seam_classes(edges, [v[1] for v in allv])
     ek = np.concatenate([v[1] for v in allv]) if allv else np.zeros(0, np.int64)
     ev = np.concatenate([v[2] for v in allv]) if allv else np.zeros(0, np.int64)
-    return keys, cls, ncls, ek, ev
+    return keys, cls, ncls, ek, ev, [v[3] for v in allv]
 
 
 def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64"):
@@ -375,6 +396,18 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
     reference's AssertionError for a constant direction map."""
     G = comm.world
     parts = row_partition(H, G)
+    import os
+    import time
+    _timing = os.environ.get("CDNET_SHARD_TIMING") is not None
+    _marks = []
+
+    def _mark(name):
+        if _timing:
+            import torch
+            torch.cuda.synchronize()
+            _marks.append((name, time.perf_counter()))
+
+    _mark("start")
     S = []
     for rank, d in zip(comm.local_ranks, shards):
         sh = _Shard()
@@ -437,6 +470,7 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         if f in (0, 1, 2, 4):
             raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
 
+    _mark('phase 2: boost')
     # ---- phase 2: boost + argmax on own rows, then 1-row halo of the inside mask
     for sh in S:
         # prob needs no halo (the boost is pointwise in prob); its ghost rows are never looked at
@@ -449,20 +483,22 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
     def class_of(keys, cls, k):
         return cls[np.searchsorted(keys, k)]
 
+    _mark('phase 3: forest')
     # ---- phase 3: forest of equal-value components; slide-global frame-touch flags for seam components
     for sh in S:
         sh.L, sh.touch = be.stage1(sh.inside, sh.rank == 0, sh.rank == G - 1)
-    keys, cls, ncls, ek, ev = _seam_round(be, comm, S, lambda sh: None, lambda sh: sh.touch)
+    keys, cls, ncls, ek, ev, _ = _seam_round(be, comm, S, lambda sh: None, lambda sh: sh.touch)
     if ncls:
         ctouch = _class_reduce(keys, cls, ncls, ek, ev, "or")
         for sh in S:
             k = sh.seam_keys
             be.scatter(sh.touch, k - sh.off, ctouch[class_of(keys, cls, k)].astype(np.int32))
 
+    _mark('phase 4: fill h')
     # ---- phase 4: fill holes, areas of own rows; slide-global areas for seam components
     for sh in S:
         sh.state, sh.area = be.stage2(sh.inside, sh.L, sh.touch, sh.lo, sh.lo + sh.Hl)
-    keys, cls, ncls, ek, ev = _seam_round(be, comm, S, lambda sh: sh.state, lambda sh: sh.area)
+    keys, cls, ncls, ek, ev, _ = _seam_round(be, comm, S, lambda sh: sh.state, lambda sh: sh.area)
     if ncls:
         # every (rank, local root) contributes once; equal keys on two ranks are two local parts
         carea = np.minimum(_class_reduce(keys, cls, ncls, ek, ev, "sum"), 2 ** 31 - 1)
@@ -470,10 +506,11 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
             k = sh.seam_keys
             be.scatter(sh.area, k - sh.off, carea[class_of(keys, cls, k)].astype(np.int32))
 
+    _mark('phase 5: remove')
     # ---- phase 5: remove small, 8-connectivity; owners, excluded roots, numbering
     for sh in S:
         sh.keep = be.stage3(sh.state, sh.L, sh.area, min_area)
-    keys, cls, ncls, ek, ev = _seam_round(be, comm, S, lambda sh: sh.keep, None)
+    keys, cls, ncls, ek, ev, _ = _seam_round(be, comm, S, lambda sh: sh.keep, None)
     croot = _class_reduce(keys, cls, ncls, keys, keys, "min") if ncls else np.zeros(0, np.int64)
     counts = []
     for sh in S:
@@ -487,21 +524,20 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         be.scatter(sh.excluded, (k - sh.off)[excl], np.ones(int(excl.sum()), np.uint8))
         sh.idmap, n_owned = be.stage4(sh.L, sh.keep, sh.excluded)
         counts.append(n_owned)
-    g_counts = comm.allgather(counts)
-    offsets = np.concatenate([[0], np.cumsum(g_counts)])
     tables = []
-    for sh in S:
-        be.add_scalar(sh.idmap, offsets[sh.rank])
+    for sh, n_owned in zip(S, counts):
         k, groot = sh.seam_keys, sh.seam_groot
         own = (groot == k) & (k >= sh.r0 * W) & (k < sh.r1 * W) if k.size else np.zeros(0, bool)
         ids = be.gather(sh.idmap, (k - sh.off)[own]) if own.any() else np.zeros(0, np.int64)
-        tables.append((k[own], np.asarray(ids).astype(np.int64)))
-    g_tab = comm.allgather(tables)
-    tk = np.concatenate([t[0] for t in g_tab]) if g_tab else np.zeros(0, np.int64)
-    tv = np.concatenate([t[1] for t in g_tab]) if g_tab else np.zeros(0, np.int64)
+        tables.append((n_owned, k[own], np.asarray(ids).astype(np.int64)))
+    g_tab = comm.allgather(tables)   # one exchange: per-rank owned-root counts + (seam class root, LOCAL id)
+    offsets = np.concatenate([[0], np.cumsum([t[0] for t in g_tab])])
+    tk = np.concatenate([t[1] for t in g_tab]) if g_tab else np.zeros(0, np.int64)
+    tv = np.concatenate([t[2] + offsets[r] for r, t in enumerate(g_tab)]) if g_tab else np.zeros(0, np.int64)
     order = np.argsort(tk)
     tk, tv = tk[order], tv[order]
     for sh in S:
+        be.add_scalar(sh.idmap, offsets[sh.rank])
         k, groot = sh.seam_keys, sh.seam_groot
         if k.size:
             pos = np.searchsorted(tk, groot)
@@ -516,6 +552,7 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         sh.labels = sh.lab_big[sh.pad_top:sh.pad_top + sh.He]
         be.relabel(sh.L, sh.keep, sh.idmap, out=sh.labels)
 
+    _mark('phase 6: label ')
     # ---- phase 6: label dilation by disk(radius); rows beyond the ghost row come from the neighbour
     r = int(radius)
     outs = []
@@ -534,6 +571,10 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         top = sh.pad_top + sh.lo
         out = be.dilate(sh.lab_big, r, out_dtype)[top:top + sh.Hl]
         outs.append(out)
+    _mark("end")
+    if _timing and S and S[0].rank == 0:
+        print("shard timing (ms):", ", ".join("%s %.2f" % (_marks[i][0], 1e3 * (_marks[i + 1][1] - _marks[i][1]))
+                                              for i in range(len(_marks) - 1)), flush=True)
     return outs
 
 

@@ -72,6 +72,22 @@ class NumpyBackend(object):
             g = np.where(valid[r0:r0 + 2] != 0, g, -1)
         return np.ascontiguousarray(g.astype(np.int32))
 
+    def seam_export(self, L, valid, attr, off, He, has_top, has_bottom, nb_top):
+        parts = []
+        for side, r0 in (("top", 0), ("bottom", He - 2)):
+            if (side == "top" and not has_top) or (side == "bottom" and not has_bottom):
+                continue
+            g = L[r0:r0 + 2].astype(np.int64) + int(off)
+            if valid is not None:
+                g = np.where(valid[r0:r0 + 2] != 0, g, -1)
+            a = attr.reshape(-1)[np.maximum(g - int(off), 0)].astype(np.int64) if attr is not None else np.zeros_like(g)
+            nb = np.asarray(nb_top).astype(np.int64) if (side == "bottom" and nb_top is not None) else np.full_like(g, -1)
+            parts.append(np.stack([g.reshape(-1), nb.reshape(-1), a.reshape(-1)], axis=1))
+        if not parts:
+            return np.zeros((0, 3), np.int64)
+        rows = np.concatenate(parts, axis=0)
+        return rows[rows[:, 0] >= 0]
+
     def unique_pairs(self, a, b):
         m = a >= 0
         pairs = np.stack([a[m], b[m]], axis=1).astype(np.int64)
