@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(256) k_boost_inside(const uint16_t* __restrict
 //   low / high byte of the code word give 16*mean;
 // * where the boost is zero (gate open or DDM 0) prob[2] is unchanged bit for bit, so the f64 path only
 //   runs on boundary pixels.
+constexpr int kBoostRows = 4;
+
 __device__ __forceinline__ float gate_threshold(float mx) {
     float t = __fmul_rn(0.2f, mx);
     for (int i = 0; i < 8 && __fdiv_rn(t, mx) > 0.2f; ++i) t = nextafterf(t, -INFINITY);
@@ -149,15 +151,20 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
     }
     __syncthreads();
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 4 + threadIdx.y;
-    if (x4 >= W || y >= H) return;
+    if (x4 >= W) return;
     const size_t plane = (size_t)H * W;  // 2 * plane overflows int for whole-slide tiles
-    const int p = y * W + x4;
     const float* P = point + (size_t)b * plane;
     const float mx = ordered_to_f32(pmax[b]);
     const float thr = s_thr;
     const bool usediv = s_div != 0;
+    const bool isconst = s_const != 0;
     auto gate = [&](float v) -> bool { return usediv ? (__fdiv_rn(v, mx) > 0.2f) : (v >= thr); };
+    // kBoostRows rows per thread: the per-block LUT / threshold set-up is amortised over 16 rows
+#pragma unroll 1
+    for (int ry = 0; ry < kBoostRows; ++ry) {
+    const int y = (blockIdx.y * kBoostRows + ry) * 4 + threadIdx.y;
+    if (y >= H) break;
+    const int p = y * W + x4;
     const float4 pc = *(const float4*)(P + p);
     bool g[4] = {gate(pc.x), gate(pc.y), gate(pc.z), gate(pc.w)};
     const bool gl = x4 > 0 ? gate(P[p - 1]) : false;
@@ -183,7 +190,6 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
     float4 q2 = *(const float4*)(PR + 2 * plane + p);
     const float a0[4] = {q0.x, q0.y, q0.z, q0.w}, a1[4] = {q1.x, q1.y, q1.z, q1.w};
     float a2[4] = {q2.x, q2.y, q2.z, q2.w};
-    const bool isconst = s_const != 0;
     uint32_t res = 0;
     bool changed = false;
 #pragma unroll
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
     }
     *(uint32_t*)(inside + (size_t)b * plane + p) = res;
     if (write_prob && changed) *(float4*)(PR + 2 * plane + p) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+    }
 }
 
 // test.py:270-275: inside = argmax over C channels == 1, or prob[0] >= 0.5
@@ -287,7 +294,7 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
         CDNET_LAUNCH(k_point_max, dim3(gx, B), 256, 0, st, point, pmax, plane);
     }
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
-        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
+        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes, flags, point,
                      pmax, prob, inside, status, H, W, write_prob, n_maps);
     else
         CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
@@ -363,7 +370,7 @@ extern "C" int cdnet_shard_boost(const uint16_t* codes, const uint32_t* flags, c
     cudaStream_t st = (cudaStream_t)stream;
     const int H = He, B = 1;
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
-        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
+        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes, flags, point,
                      pmax, prob, inside, status, H, W, write_prob, n_maps);
     else
         CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
