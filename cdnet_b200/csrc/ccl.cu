@@ -261,41 +261,72 @@ __global__ void __launch_bounds__(1024) k_ccl_strip(const uint8_t* __restrict__ 
     const int n = rows * W;
     const size_t base = (size_t)blockIdx.y * H * W + (size_t)y0 * W;
     const uint8_t* M = mask + base;
-    for (int i = tid; i < n; i += nt) {
-        s_m[i] = M[i] != 0;
-        if (zero1) zero1[base + i] = 0;
-        if (zero2) zero2[base + i] = 0;
+    const bool vec = (W % 4 == 0) && (((uintptr_t)M & 3) == 0) && (((uintptr_t)(L + base) & 15) == 0) &&
+                     (!zero1 || ((uintptr_t)(zero1 + base) & 15) == 0) && (!zero2 || ((uintptr_t)(zero2 + base) & 15) == 0);
+    if (vec) {
+        const int4 z4 = make_int4(0, 0, 0, 0);
+        for (int i = tid * 4; i < n; i += nt * 4) {
+            const uint32_t w = *(const uint32_t*)(M + i);
+            const uint32_t nz = ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u) >> 7;  // 0/1 per byte
+            *(uint32_t*)(s_m + i) = nz;
+            if (zero1) *(int4*)(zero1 + base + i) = z4;
+            if (zero2) *(int4*)(zero2 + base + i) = z4;
+        }
+    } else {
+        for (int i = tid; i < n; i += nt) {
+            s_m[i] = M[i] != 0;
+            if (zero1) zero1[base + i] = 0;
+            if (zero2) zero2[base + i] = 0;
+        }
     }
     __syncthreads();
     auto same = [&](int v, int u) -> bool { return EQ ? (v == u) : (v && u); };
-    const int nr = ((n + nt - 1) / nt) * nt;
-    for (int i = tid; i < nr; i += nt) {
-        const bool valid = i < n;
-        const int x = valid ? i % W : 0;
-        const int v = valid ? s_m[i] : 0;
-        const bool link = valid && x > 0 && lane > 0 && same(v, s_m[i - 1]);
-        const unsigned m = __ballot_sync(0xffffffffu, link);
-        if (valid) s_par[i] = i - __clz(~(m << (31 - lane)));
+    // rows are walked explicitly (no per-pixel division); a warp always covers x0 .. x0+31 of one row, so the
+    // 32-pixel segments start at multiples of 32 in every row
+    const int wbase = tid - lane;
+    for (int r = 0; r < rows; ++r) {
+        const int rb = r * W;
+        for (int x0 = wbase; x0 < W; x0 += nt) {
+            const int x = x0 + lane;
+            const bool valid = x < W;
+            const int v = valid ? s_m[rb + x] : 0;
+            const bool link = valid && lane > 0 && same(v, s_m[rb + x - 1]);
+            const unsigned m = __ballot_sync(0xffffffffu, link);
+            if (valid) s_par[rb + x] = rb + x - __clz(~(m << (31 - lane)));
+        }
     }
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-        const int v = s_m[i];
-        if (!EQ && !v) continue;
-        const int y = i / W, x = i - y * W;
-        const bool hl = x > 0 && same(v, s_m[i - 1]);
-        if (hl && lane == 0) sunion(s_par, i, i - 1);
-        if (y > 0) {
-            if (same(v, s_m[i - W])) {
-                if (!(hl && same(v, s_m[i - W - 1]))) sunion(s_par, i, i - W);
-            } else if (CONN == 8) {
-                if (x > 0 && !hl && same(v, s_m[i - W - 1])) sunion(s_par, i, i - W - 1);
-                if (x + 1 < W && same(v, s_m[i - W + 1]) && !same(v, s_m[i + 1])) sunion(s_par, i, i - W + 1);
+    for (int r = 0; r < rows; ++r) {
+        const int rb = r * W;
+        for (int x = tid; x < W; x += nt) {
+            const int i = rb + x;
+            const int v = s_m[i];
+            if (!EQ && !v) continue;
+            const bool hl = x > 0 && same(v, s_m[i - 1]);
+            if (hl && lane == 0) sunion(s_par, i, i - 1);
+            if (r > 0) {
+                if (same(v, s_m[i - W])) {
+                    if (!(hl && same(v, s_m[i - W - 1]))) sunion(s_par, i, i - W);
+                } else if (CONN == 8) {
+                    if (x > 0 && !hl && same(v, s_m[i - W - 1])) sunion(s_par, i, i - W - 1);
+                    if (x + 1 < W && same(v, s_m[i - W + 1]) && !same(v, s_m[i + 1])) sunion(s_par, i, i - W + 1);
+                }
             }
         }
     }
     __syncthreads();
     const int goff = y0 * W;
-    for (int i = tid; i < n; i += nt) L[base + i] = goff + sfind(s_par, i);
+    if (vec) {
+        for (int i = tid * 4; i < n; i += nt * 4) {
+            int r0 = sfind(s_par, i);
+            int r1 = s_par[i + 1] == s_par[i] ? r0 : sfind(s_par, i + 1);
+            int r2 = s_par[i + 2] == s_par[i + 1] ? r1 : sfind(s_par, i + 2);
+            int r3 = s_par[i + 3] == s_par[i + 2] ? r2 : sfind(s_par, i + 3);
+            *(int4*)(L + base + i) = make_int4(goff + r0, goff + r1, goff + r2, goff + r3);
+        }
+    } else {
+        for (int i = tid; i < n; i += nt) L[base + i] = goff + sfind(s_par, i);
+    }
 }
 
 static int strip_rows(int H, int W) {
