@@ -35,6 +35,7 @@ SIGNATURES = {
     "cdnet_dam_postproc_workspace_bytes": (c_size_t, [c_int] * 3),
     "cdnet_dam_postproc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "cdnet_dcm_voting2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cdnet_plain_postproc_workspace_bytes": (c_size_t, [c_int] * 3),
     "cdnet_plain_postproc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_void_p, c_size_t, c_void_p]),

@@ -447,6 +447,38 @@ def plain_postprocess(prob_maps, min_area=20, radius=2, postproc=0, model_name="
     return out[0].cpu().numpy()
 
 
+def dcm_voting2_cuda(dcm):
+    """dcm uint8 [B,8,H,W] -> voted direction class uint8 [B,H,W] (utils.py:1150-1159)."""
+    L = _cabi.lib()
+    dev = _device(dcm.device)
+    d = _cu8(dcm)
+    B, T, H, W = d.shape
+    assert T == 8
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    check(L.cdnet_dcm_voting2(_ptr(d), _ptr(out), B, H, W, _stream()), "cdnet_dcm_voting2")
+    return out
+
+
+def DcmVoting2(direct_map):
+    """utils.py:1150-1159: direct_map uint8 [H,W,8] -> int64 [H,W] (np.argmax of the per-class votes)."""
+    dm = np.asarray(direct_map)
+    assert dm.ndim == 3 and dm.shape[2] == 8
+    d = _h2d(np.ascontiguousarray(np.moveaxis(dm, 2, 0)).astype(np.uint8))[None]
+    return dcm_voting2_cuda(d)[0].cpu().numpy().astype(np.int64)
+
+
+def direction_argmax_cuda(mask_logits, direction_logits):
+    """Device-resident hand-off from the CNN (test_dam.py:984-1013): softmax of the
+    3-class mask head and of the direction head, direction[0] *= mask[0], argmax -> (prob float32 [B,3,H,W],
+    direction class uint8 [B,H,W]).  Stock torch ops on the tensors the CNN already holds on the GPU (this is
+    exactly what the reference runs before its .cpu().numpy()); the point is that nothing leaves the device
+    before dam_postprocess_cuda."""
+    prob = torch.softmax(mask_logits, dim=1)
+    dprob = torch.softmax(direction_logits, dim=1)
+    dprob[:, 0] = dprob[:, 0] * prob[:, 0]
+    return prob.contiguous(), torch.argmax(dprob, dim=1).to(torch.uint8).contiguous()
+
+
 # =====================================================================================================
 # target transform (my_transforms_direction.py:651-885)
 # =====================================================================================================
@@ -569,7 +601,13 @@ class LabelEncoding(object):
             if sel.size == 0:
                 continue
             sub = d_ids[torch.from_numpy(sel).to(dev)] if sel.size != len(labels) else d_ids
-            tern, point, direction = encode_targets_cuda(sub, instance_level=lv, num_classes=self.num_classes)
+            tern, point, direction, inst = encode_targets_cuda(sub, instance_level=lv, num_classes=self.num_classes,
+                                                               want_inst=True)
+            # the reference skips the first entry of np.unique(label_instance) as "background" (:797-800); on a
+            # tile whose dilated instances leave no background pixel that drops a nucleus and its
+            # `assert int(label_point.sum() / 255) == markers_len` (:836) fires
+            if int(inst.reshape(inst.shape[0], -1).min(dim=1).values.max()) > 0:
+                raise AssertionError("label_instance has no background pixel (my_transforms_direction.py:836)")
             tern, point, direction = tern.cpu().numpy(), point.cpu().numpy(), direction.cpu().numpy()
             for j, i in enumerate(sel):
                 out[i] = (tern[j], point[j], direction[j])

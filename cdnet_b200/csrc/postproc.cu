@@ -377,3 +377,41 @@ extern "C" int cdnet_shard_boost(const uint16_t* codes, const uint32_t* flags, c
                      pmax, prob, inside, status, H, W, write_prob, n_maps);
     return last_error();
 }
+
+// ---- DcmVoting2, utils.py:1150-1159 ("next" row of SURVEY.md section 8f) ---------------------------
+// The 8 TTA direction maps are brought into the un-flipped frame by fixed class permutations and voted per
+// pixel over the 9 classes; np.argmax keeps the first maximum.
+namespace cdnet {
+__constant__ uint8_t c_vote_perm[8][9] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8}, {0, 5, 4, 3, 2, 1, 8, 7, 6}, {0, 1, 8, 7, 6, 5, 4, 3, 2}, {0, 5, 6, 7, 8, 1, 2, 3, 4},
+    {0, 3, 4, 5, 6, 7, 8, 1, 2}, {0, 7, 6, 5, 4, 3, 2, 1, 8}, {0, 3, 2, 1, 8, 7, 6, 5, 4}, {0, 7, 8, 1, 2, 3, 4, 5, 6}};
+
+__global__ void __launch_bounds__(256) k_dcm_voting2(const uint8_t* __restrict__ dcm, uint8_t* __restrict__ out, size_t plane) {
+    const int b = blockIdx.y;
+    const uint8_t* D = dcm + (size_t)b * 8 * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long votes = 0;  // nine 4-bit counters (max 8 votes)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = D[(size_t)t * plane + i];
+            if (c <= 8) votes += 1ull << (4 * c_vote_perm[t][c]);
+        }
+        int best = 0, bestv = (int)(votes & 15);
+#pragma unroll
+        for (int c = 1; c < 9; ++c) {
+            const int v = (int)((votes >> (4 * c)) & 15);
+            if (v > bestv) { bestv = v; best = c; }
+        }
+        out[(size_t)b * plane + i] = (uint8_t)best;
+    }
+}
+}  // namespace cdnet
+
+extern "C" int cdnet_dcm_voting2(const uint8_t* dcm, uint8_t* out, int B, int H, int W, void* stream) {
+    if (!dcm || !out || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    const size_t plane = (size_t)H * W;
+    int gx = (int)((plane + 256 * 4 - 1) / (256 * 4));
+    if (gx > 65535) gx = 65535;
+    CDNET_LAUNCH(cdnet::k_dcm_voting2, dim3(gx, B), 256, 0, (cudaStream_t)stream, dcm, out, plane);
+    return cdnet::last_error();
+}

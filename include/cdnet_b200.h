@@ -120,6 +120,11 @@ int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, const float*
                        int direction_classes, int min_area, int radius, int postproc,
                        int write_prob, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- DcmVoting2(direct_map), utils.py:1150-1159 (dead by default in the reference: voting_firt = 0,
+ * test_dam.py:471; SURVEY.md section 8f "next") -----------------------------------------------
+ * dcm: uint8 [B,8,H,W] the 8 TTA direction maps (classes 0..8); out: uint8 [B,H,W] voted class. */
+int cdnet_dcm_voting2(const uint8_t* dcm, uint8_t* out, int B, int H, int W, void* stream);
+
 /* ---- plain inference post-processing, test.py:270-295 -------------------------------------------
  * prob: float32 [B,C,H,W]; multi_class != 0: inside = (argmax == 1) over C channels, else
  * inside = prob[:,0] >= 0.5.  Then as above without the direction map; process() gets

@@ -152,3 +152,28 @@ def test_wide_tile_pipeline_vs_oracle(cuda_api):
         ref = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp, literal=False)["pred_labeled"]
         got = cuda_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
         assert np.array_equal(got, ref), (pp, int((got != ref).sum()))
+
+
+def test_dcm_voting2_vs_oracle(cuda_api):
+    from oracle import restate as O
+    rng = np.random.default_rng(11)
+    dm = rng.integers(0, 9, size=(57, 83, 8)).astype(np.uint8)
+    got = cuda_api.DcmVoting2(dm)
+    assert got.dtype == np.int64 and np.array_equal(got, O.dcm_voting2(dm))
+
+
+def test_direction_argmax_handoff(cuda_api):
+    """device-resident hand-off == the reference's softmax / argmax done by torch (test_dam.py:984-1013)"""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(3)
+    mask_logits = torch.randn((2, 3, 40, 48), generator=g)
+    dir_logits = torch.randn((2, 9, 40, 48), generator=g)
+    prob, cls = cuda_api.direction_argmax_cuda(mask_logits.cuda(), dir_logits.cuda())
+    for i in range(2):
+        p = torch.softmax(mask_logits[i].cuda(), dim=0)
+        d = torch.softmax(dir_logits[i].cuda(), dim=0)
+        d[0] = d[0] * p[0]
+        top2 = torch.topk(d, 2, dim=0).values
+        clear = (top2[0] - top2[1]) > 1e-6   # an exact tie-break is a property of torch's kernels, not ours
+        assert torch.equal(cls[i].long()[clear], torch.argmax(d, dim=0)[clear])
+        assert torch.allclose(prob[i], p, rtol=1e-6, atol=1e-7)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # rebuild the library with a few DDM kernel shapes ON THE GPU BOX and time the kernel (tuning aid)
-for cfg in "4 2 1" "4 1 5" "2 2 6" "2 1 8" "4 2 5"; do
+for cfg in "4 2 5" "8 1 4" "8 1 5" "8 2 4" "4 2 6" "4 1 6"; do
   set -- $cfg
   python -m cdnet_b200.build --force -DCDNET_DDM_ROWS_DEFAULT=$1 -DCDNET_DDM_PB=$2 -DCDNET_DDM_MINB=$3 > /dev/null 2>&1
   python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
