@@ -250,126 +250,138 @@ __device__ __forceinline__ int align_index(float a, int n) {
     return 0;
 }
 
-// own-label centre-distance value of every instance pixel: f32((1 - |p - c_k| / (M_k + 1e-7))) (:820-824, .float()
-// at :828).  One f64 sqrt + divide per pixel here instead of one per (pixel, tap) in the Sobel kernel.
-__global__ void __launch_bounds__(kBX* kBY) k_t_dcval(const int* __restrict__ inst, const int* __restrict__ centre,
-                                                      const int* __restrict__ maxd2, float* __restrict__ dcv, int tab,
-                                                      int H, int W) {
+// defaults for the pixels no instance support covers: dir = (0, 0) -> angle 0 -> class index n/2 (+1) on
+// foreground, 0 on background (:848-871); the per-label kernel overwrites the covered pixels
+__global__ void __launch_bounds__(kBX* kBY) k_t_dir_default(const uint8_t* __restrict__ inside,
+                                                            long long* __restrict__ direction, float* __restrict__ dir_out,
+                                                            int n_classes, int H, int W) {
     PX_COORDS
     if (!inb) return;
-    const int k = inst[tile + p];
-    float v = 0.0f;
-    if (k > 0 && k < tab) {
-        const int c = centre[(size_t)b * tab + k];
-        const int dy = y - c / W, dx = x - c % W;
-        const double denom = __dadd_rn(__dsqrt_rn((double)maxd2[(size_t)b * tab + k]), 0.0000001);
-        v = __double2float_rn(__dadd_rn(1.0, -__ddiv_rn(__dsqrt_rn((double)(dy * dy + dx * dx)), denom)));
-    }
-    dcv[tile + p] = v;
+    direction[tile + p] = inside[tile + p] ? (long long)(n_classes / 2 + 1) : 0ll;
+    if (dir_out) { dir_out[(tile + p) * 2] = 0.0f; dir_out[(tile + p) * 2 + 1] = 0.0f; }
 }
 
-// region per block kDX x kDY pixels, kDT threads: the region is larger than the block so that the queue of
-// active pixels keeps every lane busy for several rounds
-constexpr int kDX = 32, kDY = 32, kDT = 256, kHalo = 6;  // 11x11 taps + 1 for the cross dilation
+// compact list of the labels that exist: (tile << 32) | label
+__global__ void k_t_label_list(const int* __restrict__ centre, unsigned long long* __restrict__ list, int* __restrict__ count,
+                               int tab, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~size_t(31));
+         i += (size_t)gridDim.x * blockDim.x) {
+        const bool present = i < n && (i % tab) != 0 && centre[i] != 0x7fffffff;
+        const unsigned m = __ballot_sync(0xffffffffu, present);
+        int base = 0;
+        if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (present)
+            list[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] =
+                ((unsigned long long)(i / tab) << 32) | (unsigned long long)(i % tab);
+    }
+}
 
-// direction class per pixel (:827-834, :848-871)
-__global__ void __launch_bounds__(kDT) k_t_direction(const int* __restrict__ inst, const float* __restrict__ dcv,
-                                                          const int* __restrict__ centre, const int* __restrict__ maxd2,
-                                                          const uint8_t* __restrict__ inside,
-                                                          long long* __restrict__ direction, float* __restrict__ dir_out,
-                                                          int tab, int n_classes, int H, int W) {
-    __shared__ int s_l[kDY + 2 * kHalo][kDX + 2 * kHalo + 1];
-    __shared__ float s_v[kDY + 2 * kHalo][kDX + 2 * kHalo + 1];
-    __shared__ int s_list[kDX * kDY];
-    __shared__ int s_n;
-    const int b = blockIdx.z;
-    const size_t tile = (size_t)b * H * W;
-    const int* L = inst + tile;
-    const int bx0 = blockIdx.x * kDX, by0 = blockIdx.y * kDY;
+constexpr int kLC = 32;              // output chunk edge
+constexpr int kLV = kLC + 10;        // value tile edge (5-pixel tap halo)
+constexpr int kLI = kLC + 12;        // label tile edge (+1 for the cross dilation)
+
+// Direction map per LABEL (:819-834, :848-871).  "Last writer wins" means pixel p takes the Sobel response of
+// the highest label w whose cross-dilated support contains p, and that response only sees w's own
+// centre-distance map.  So a block takes one label k at a time (persistent, work-stealing over the label
+// list): it stages the label tile, evaluates f32((1 - |q - c_k| / (M_k + 1e-7))) for the support pixels of k
+// in shared memory (0 elsewhere) and every pixel whose winner is k runs the 121-tap sequential f32 FMA chain
+// in (kh, kw) order straight from that tile -- unconditionally, because a zero operand leaves the chain
+// bit-identical.  All support pixels of k lie within floor(sqrt(M_k^2)) of its centre, which bounds the window.
+__global__ void __launch_bounds__(128) k_t_direction_lab(const int* __restrict__ inst, const int* __restrict__ centre,
+                                                         const int* __restrict__ maxd2, const uint8_t* __restrict__ inside,
+                                                         long long* __restrict__ direction, float* __restrict__ dir_out,
+                                                         const unsigned long long* __restrict__ list,
+                                                         const int* __restrict__ count, int* __restrict__ cursor, int tab,
+                                                         int n_classes, int H, int W) {
+    __shared__ int s_l[kLI][kLI + 1];
+    __shared__ float s_v[kLV][kLV + 1];
+    __shared__ int s_item;
     const int tid = threadIdx.x;
-    if (tid == 0) s_n = 0;
-    for (int i = tid; i < (kDY + 2 * kHalo) * (kDX + 2 * kHalo); i += kDT) {
-        const int ly = i / (kDX + 2 * kHalo), lx = i % (kDX + 2 * kHalo);
-        const int gy = by0 + ly - kHalo, gx = bx0 + lx - kHalo;
-        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        s_l[ly][lx] = ok ? L[gy * W + gx] : 0;
-        s_v[ly][lx] = ok ? dcv[tile + gy * W + gx] : 0.0f;
-    }
-    __syncthreads();
-    // pixels without a winner get (0, 0) at once; the others are queued so that every lane of the block works
-    // on a pixel that has a Sobel sum to evaluate
-    for (int id = tid; id < kDX * kDY; id += kDT) {
-        const int ty = id / kDX, tx = id % kDX;
-        const int x = bx0 + tx, y = by0 + ty;
-        const int ly = ty + kHalo, lx = tx + kHalo;
-        int w = 0;
-        if (x < W && y < H)
-            w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])), max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
-        const bool active = (x < W && y < H) && w > 0 && w < tab;
-        if (x < W && y < H && !active) {
-            const int p = y * W + x;
-            if (dir_out) { dir_out[(tile + p) * 2] = 0.0f; dir_out[(tile + p) * 2 + 1] = 0.0f; }
-            // angle 0 -> class index n/2 for foreground pixels outside every instance support
-            direction[tile + p] = inside[tile + p] ? (long long)(n_classes / 2 + 1) : 0ll;
-        }
-        // warp-aggregated append to the work queue
-        const unsigned m = __ballot_sync(0xffffffffu, active);
-        int basei = 0;
-        if ((tid & 31) == 0 && m) basei = atomicAdd(&s_n, __popc(m));
-        basei = __shfl_sync(0xffffffffu, basei, 0);
-        if (active) s_list[basei + __popc(m & ((1u << (tid & 31)) - 1))] = id;
-    }
-    __syncthreads();
-    const int n_act = s_n;
-    for (int it = tid; it < n_act; it += kDT) {
-        const int id = s_list[it];
-        const int ty = id / kDX, tx = id % kDX;
-        const int x = bx0 + tx, y = by0 + ty;
-        const int p = y * W + x;
-        const int ly = ty + kHalo, lx = tx + kHalo;
-        // winner = highest label whose dilated support contains p ("last writer wins", :832-834)
-        const int w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])), max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
-        float acc0 = 0.0f, acc1 = 0.0f;
-        const int c = centre[(size_t)b * tab + w];
+    const int total = *count;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(cursor, 1);
+        __syncthreads();
+        const int item = s_item;
+        __syncthreads();
+        if (item >= total) break;
+        const unsigned long long e = list[item];
+        const int b = (int)(e >> 32), k = (int)(e & 0xffffffffu);
+        const size_t tile = (size_t)b * H * W;
+        const int* L = inst + tile;
+        const int c = centre[(size_t)b * tab + k];
         const int cy = c / W, cx = c % W;
-        const double denom = __dadd_rn(__dsqrt_rn((double)maxd2[(size_t)b * tab + w]), 0.0000001);
-#pragma unroll 1
-        for (int kh = 0; kh < 11; ++kh) {
-            const int qy = ly + kh - 5;
-            const int gy = y + kh - 5;
-            if (gy < 0 || gy >= H) continue;
-#pragma unroll
-            for (int kw = 0; kw < 11; ++kw) {
-                const int qx = lx + kw - 5;
-                const int gx = x + kw - 5;
-                float v;
-                if (s_l[qy][qx] == w) {
-                    v = s_v[qy][qx];  // own pixel of the winner: value prepared by k_t_dcval
-                } else {
-                    // 1-pixel dilation ring of the winner: same f64 formula, evaluated in place
-                    const bool ring = (gx >= 0 && gx < W) && (s_l[qy - 1][qx] == w || s_l[qy + 1][qx] == w ||
-                                                              s_l[qy][qx - 1] == w || s_l[qy][qx + 1] == w);
-                    if (!ring) continue;
-                    const int dy = gy - cy, dx = gx - cx;
-                    v = __double2float_rn(__dadd_rn(1.0, -__ddiv_rn(__dsqrt_rn((double)(dy * dy + dx * dx)), denom)));
+        const int m2 = maxd2[(size_t)b * tab + k];
+        const double denom = __dadd_rn(__dsqrt_rn((double)m2), 0.0000001);
+        int R = (int)sqrt((double)m2);
+        while ((long long)(R + 1) * (R + 1) <= (long long)m2) ++R;
+        while ((long long)R * R > (long long)m2) --R;
+        const int wy0 = max(cy - R, 0), wy1 = min(cy + R, H - 1), wx0 = max(cx - R, 0), wx1 = min(cx + R, W - 1);
+        for (int oy = wy0; oy <= wy1; oy += kLC) {
+            for (int ox = wx0; ox <= wx1; ox += kLC) {
+                // label tile: rows oy-6 .. oy+kLC+5
+                for (int i = tid; i < kLI * kLI; i += 128) {
+                    const int ly = i / kLI, lx = i % kLI;
+                    const int gy = oy - 6 + ly, gx = ox - 6 + lx;
+                    s_l[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? L[gy * W + gx] : 0;
                 }
-                acc0 = __fmaf_rn(c_sobel[0][kh * 11 + kw], v, acc0);
-                acc1 = __fmaf_rn(c_sobel[1][kh * 11 + kw], v, acc1);
+                __syncthreads();
+                // value tile: rows oy-5 .. oy+kLC+4  (label tile index = value tile index + 1)
+                for (int i = tid; i < kLV * kLV; i += 128) {
+                    const int vy = i / kLV, vx = i % kLV;
+                    const int ly = vy + 1, lx = vx + 1;
+                    const bool sup = s_l[ly][lx] == k || s_l[ly - 1][lx] == k || s_l[ly + 1][lx] == k ||
+                                     s_l[ly][lx - 1] == k || s_l[ly][lx + 1] == k;
+                    float v = 0.0f;
+                    if (sup) {
+                        const int gy = oy - 5 + vy, gx = ox - 5 + vx;
+                        // an out-of-image pixel can have an in-image neighbour with label k: it is not part of
+                        // the image, hence not part of the support
+                        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                            const int dy = gy - cy, dx = gx - cx;
+                            v = __double2float_rn(
+                                __dadd_rn(1.0, -__ddiv_rn(__dsqrt_rn((double)(dy * dy + dx * dx)), denom)));
+                        }
+                    }
+                    s_v[vy][vx] = v;
+                }
+                __syncthreads();
+                for (int i = tid; i < kLC * kLC; i += 128) {
+                    const int ty = i / kLC, tx = i % kLC;
+                    const int y = oy + ty, x = ox + tx;
+                    if (y > wy1 || x > wx1) continue;
+                    const int ly = ty + 6, lx = tx + 6;
+                    const int w = max(max(s_l[ly][lx], max(s_l[ly - 1][lx], s_l[ly + 1][lx])),
+                                      max(s_l[ly][lx - 1], s_l[ly][lx + 1]));
+                    if (w != k) continue;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 1
+                    for (int kh = 0; kh < 11; ++kh) {
+#pragma unroll
+                        for (int kw = 0; kw < 11; ++kw) {
+                            const float v = s_v[ty + kh][tx + kw];
+                            acc0 = __fmaf_rn(c_sobel[0][kh * 11 + kw], v, acc0);
+                            acc1 = __fmaf_rn(c_sobel[1][kh * 11 + kw], v, acc1);
+                        }
+                    }
+                    const int p = y * W + x;
+                    if (dir_out) {
+                        dir_out[(tile + p) * 2] = acc0;
+                        dir_out[(tile + p) * 2 + 1] = acc1;
+                    }
+                    long long cls = 0;
+                    if (inside[tile + p]) {
+                        // angle = degrees(arctan2(dir0, dir1)) in f32 (:848); the reference's libm/SVML atan2f is
+                        // not correctly rounded, this is (f64 atan2 rounded to f32) -- differences are confined to
+                        // a few ulp of the angle, i.e. to pixels within ~1e-5 degrees of a bin edge
+                        const float ang = __fmul_rn(__double2float_rn(atan2((double)acc0, (double)acc1)), 57.295776f);
+                        cls = align_index(ang, n_classes) + 1;
+                    }
+                    direction[tile + p] = cls;
+                }
+                __syncthreads();
             }
         }
-        if (dir_out) {
-            dir_out[(tile + p) * 2] = acc0;
-            dir_out[(tile + p) * 2 + 1] = acc1;
-        }
-        long long cls = 0;
-        if (inside[tile + p]) {
-            // angle = degrees(arctan2(dir0, dir1)) in f32 (:848); the reference's libm/SVML atan2f is not
-            // correctly rounded, this is (f64 atan2 rounded to f32) -- differences are confined to a few
-            // ulp of the angle, i.e. to pixels within ~1e-5 degrees of a bin edge
-            const float ang = __fmul_rn(__double2float_rn(atan2((double)acc0, (double)acc1)), 57.295776f);
-            cls = align_index(ang, n_classes) + 1;
-        }
-        direction[tile + p] = cls;
     }
 }
 
@@ -579,10 +591,24 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     rc = centres_launch(inst, cness, best, centre, maxd2, tab, B, H, W, st);
     if (rc) return rc;
     CDNET_LAUNCH(k_t_support_max, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, cflag, tab, H, W);
-    float* dcv = (float*)cness;  // centerness is dead after the centre pick: reuse its plane for the dc values
-    CDNET_LAUNCH(k_t_dcval, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, dcv, tab, H, W);
-    CDNET_LAUNCH(k_t_direction, dim3(ceil_div(W, kDX), ceil_div(H, kDY), B), kDT, 0, st, inst, dcv, centre,
-                 maxd2, inside, (long long*)direction, dir_out, tab, num_classes, H, W);
+    {
+        // label list in the (now dead) centerness plane; [0] of rowcnt = count, [1] = work-stealing cursor
+        unsigned long long* lablist = (unsigned long long*)cness;
+        CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, 2 * sizeof(int32_t), st));
+        const size_t nblk = (nt + 255) / 256;
+        CDNET_LAUNCH(k_t_label_list, (unsigned)(nblk > 65535 ? 65535 : nblk), 256, 0, st, centre, lablist, rowcnt, tab, nt);
+        CDNET_LAUNCH(k_t_dir_default, px_grid(B, H, W), px_block(), 0, st, inside, (long long*)direction, dir_out,
+                     num_classes, H, W);
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (n_sm <= 0) n_sm = 148;
+        }
+        CDNET_LAUNCH(k_t_direction_lab, n_sm * 8, 128, 0, st, inst, centre, maxd2, inside, (long long*)direction, dir_out,
+                     lablist, rowcnt, rowcnt + 1, tab, num_classes, H, W);
+    }
     CDNET_LAUNCH(k_t_gauss, dim3(ceil_div(W, kGX), ceil_div(H, kGY), B), dim3(kGX, kGY), 0, st, cflag, (__half*)point, H, W);
     return last_error();
 }
