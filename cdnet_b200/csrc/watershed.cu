@@ -137,17 +137,47 @@ struct WarpBox {
     unsigned short head[256], tail[256];
 };
 
+// The box is staged with a one-pixel border of "not this component" cells, so the four neighbours of cell e are
+// e - pw, e - 1, e + 1, e + pw without any bounds test or division (pw = box width + 2).
 __device__ __forceinline__ void flood_box(WarpBox& S, const uint8_t* __restrict__ P, const int* __restrict__ Lt,
                                           const uint8_t* __restrict__ V, volatile int* O, int root, int W, int x0, int y0,
                                           int bw, int bh, int lane) {
-    const int n = bw * bh;
+    const int pw = bw + 2, ph = bh + 2;
+    const int n = pw * ph;
     for (int i = lane; i < 256; i += 32) { S.head[i] = 0xffff; S.tail[i] = 0xffff; }
-    for (int idx = lane; idx < n; idx += 32) {
-        const int ly = idx / bw, lx = idx - ly * bw;
-        const int g = (y0 + ly) * W + x0 + lx;
-        const bool in = P[g] && Lt[g] == root;
-        S.lab[idx] = in ? O[g] : -1;
-        S.val[idx] = V[g];
+    // stage: all four planes are requested independently (no load waits on another load's result)
+    int lmn = 0x7fffffff, lmx = 0;
+    for (int ly = 0; ly < ph; ++ly) {
+        const int gy = y0 + ly - 1;
+        for (int lx = lane; lx < pw; lx += 32) {
+            const int idx = ly * pw + lx;
+            int lab = -1, v = 0;
+            if (ly > 0 && ly <= bh && lx > 0 && lx <= bw) {
+                const int g = gy * W + x0 + lx - 1;
+                const int pm = P[g], lr = Lt[g], ov = O[g];
+                v = V[g];
+                if (pm && lr == root) lab = ov;
+            }
+            if (lab > 0) { lmn = min(lmn, lab); lmx = max(lmx, lab); }
+            S.lab[idx] = lab;
+            S.val[idx] = (unsigned char)v;
+        }
+    }
+    // a component that holds a single marker label is simply filled with it (every pixel of a 4-connected
+    // component is reached, and nobody competes); one without markers stays unlabelled.  Only components
+    // with two or more markers -- touching nuclei -- need the ordered flood.
+    __syncwarp();
+    lmn = __reduce_min_sync(0xffffffffu, lmn);
+    lmx = __reduce_max_sync(0xffffffffu, lmx);
+    if (lmx == 0) return;
+    if (lmn == lmx) {
+        for (int ly = 1; ly <= bh; ++ly) {
+            const int gy = y0 + ly - 1;
+            for (int lx = 1 + lane; lx <= bw; lx += 32)
+                if (S.lab[ly * pw + lx] == 0) O[gy * W + x0 + lx - 1] = lmn;
+        }
+        __syncwarp();
+        return;
     }
     __syncwarp();
     int cur = 256;
@@ -172,33 +202,32 @@ __device__ __forceinline__ void flood_box(WarpBox& S, const uint8_t* __restrict_
     }
     __syncwarp();
     for (;;) {
-        int found = -1;
-        for (int base = cur & ~31; base < 256; base += 32) {
-            const int b = base + lane;
-            const unsigned m = __ballot_sync(0xffffffffu, b >= cur && S.head[b] != 0xffff);
-            if (m) { found = base + __ffs(m) - 1; break; }
+        // next non-empty bucket: usually the current one
+        int e = cur < 256 ? S.head[cur] : 0xffff;
+        if (e == 0xffff) {
+            int found = -1;
+            for (int base = cur & ~31; base < 256; base += 32) {
+                const int b = base + lane;
+                const unsigned m = __ballot_sync(0xffffffffu, b >= cur && S.head[b] != 0xffff);
+                if (m) { found = base + __ffs(m) - 1; break; }
+            }
+            if (found < 0) break;
+            cur = found;
+            e = S.head[cur];
         }
-        if (found < 0) break;
-        cur = found;
-        const int e = S.head[cur];
         const int lbl = S.lab[e];
-        __syncwarp();
+        const int nx = S.nxt[e];
+        // lanes 0..3 probe the neighbours in skimage's order (-W, -1, +1, +W)
+        int q = -1, v = 0;
+        if (lane < 4) {
+            const int qq = e + (lane == 0 ? -pw : (lane == 1 ? -1 : (lane == 2 ? 1 : pw)));
+            if (S.lab[qq] == 0) { q = qq; v = S.val[qq]; }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, q >= 0);
         if (lane == 0) {
-            const int nx = S.nxt[e];
             S.head[cur] = nx;
             if (nx == 0xffff) S.tail[cur] = 0xffff;
         }
-        const int ey = e / bw, ex = e - ey * bw;
-        int q = -1, v = 0;
-        if (lane < 4) {
-            const int qy = ey + (lane == 0 ? -1 : (lane == 3 ? 1 : 0));
-            const int qx = ex + (lane == 1 ? -1 : (lane == 2 ? 1 : 0));
-            if (qy >= 0 && qy < bh && qx >= 0 && qx < bw) {
-                const int qq = qy * bw + qx;
-                if (S.lab[qq] == 0) { q = qq; v = S.val[qq]; }
-            }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, q >= 0);
         __syncwarp();
         while (m) {
             const int l = __ffs(m) - 1;
@@ -216,11 +245,11 @@ __device__ __forceinline__ void flood_box(WarpBox& S, const uint8_t* __restrict_
         __syncwarp();
     }
     __syncwarp();
-    for (int idx = lane; idx < n; idx += 32) {
-        const int l = S.lab[idx];
-        if (l >= 0) {
-            const int ly = idx / bw, lx = idx - ly * bw;
-            O[(y0 + ly) * W + x0 + lx] = l;
+    for (int ly = 1; ly <= bh; ++ly) {
+        const int gy = y0 + ly - 1;
+        for (int lx = 1 + lane; lx <= bw; lx += 32) {
+            const int l = S.lab[ly * pw + lx];
+            if (l >= 0) O[gy * W + x0 + lx - 1] = l;
         }
     }
     __syncwarp();
@@ -251,7 +280,7 @@ __global__ void __launch_bounds__(128) k_flood(const uint8_t* __restrict__ pred,
         volatile int* O = out + tile;
         volatile int* N = next + tile;
         const int y0 = root / W, y1 = ymax[tile + root], x0 = xmin[tile + root], x1 = xmax[tile + root];
-        if ((x1 - x0 + 1) * (y1 - y0 + 1) <= kCap) {
+        if ((x1 - x0 + 3) * (y1 - y0 + 3) <= kCap) {
             flood_box(s_box[wid], P, Lt, V, O, root, W, x0, y0, x1 - x0 + 1, y1 - y0 + 1, lane);
             continue;
         }
