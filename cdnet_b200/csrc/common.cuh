@@ -65,20 +65,6 @@ __device__ __forceinline__ int uf_find(const int* L, int p) {
     return p;
 }
 
-// find + path compression: every node on the path is re-pointed (atomicMin, so a concurrent union
-// is never lost) at the root that was found
-__device__ __forceinline__ int uf_find_compress(int* L, int p) {
-    const int r = uf_find(L, p);
-    int x = p;
-    while (x != r) {
-        const int nx = __ldcg(L + x);
-        if (nx > r) atomicMin(L + x, r);
-        if (nx >= x) break;
-        x = nx;
-    }
-    return r;
-}
-
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     const int a0 = a, b0 = b;
     for (;;) {

@@ -193,9 +193,6 @@ class CudaBackend(object):
     def empty(self, shape, dtype):
         return self.torch.empty(shape, dtype=getattr(self.torch, dtype), device=self.dev)
 
-    def cat_rows(self, parts):
-        return self.torch.cat(parts, dim=-2).contiguous()
-
     def scatter(self, plane, flat_idx, vals):
         if len(flat_idx):
             idx = self.torch.from_numpy(np.asarray(flat_idx, dtype=np.int64)).to(self.dev)
@@ -242,31 +239,6 @@ class CudaBackend(object):
         keep = rows[:, 0] >= 0
         keep[1:] &= (rows[1:, 0] != rows[:-1, 0]) | (rows[1:, 1] != rows[:-1, 1])
         return rows[keep].cpu().numpy()
-
-    def unique_pairs(self, a, b):
-        """host int64 [n,2]: distinct (a,b) over the entries with a >= 0 (b must be valid there too)"""
-        t = self.torch
-        key = (a.reshape(-1).to(t.int64) << 32) | (b.reshape(-1).to(t.int64) & 0xffffffff)
-        key = key[a.reshape(-1) >= 0]
-        if key.numel() == 0:
-            return np.zeros((0, 2), np.int64)
-        keep = t.ones_like(key, dtype=t.bool)
-        keep[1:] = key[1:] != key[:-1]          # runs of one component pair collapse to one entry
-        u = t.unique(key[keep]).cpu().numpy()
-        out = np.stack([u >> 32, (u & 0xffffffff).astype(np.int64)], axis=1)
-        out[:, 1] = np.where(out[:, 1] >= 2 ** 31, out[:, 1] - 2 ** 32, out[:, 1])
-        assert out.min() >= 0, "seam pixels must be classified identically on both ranks"
-        return out
-
-    def unique_vals(self, tensors):
-        t = self.torch
-        v = t.cat([x.reshape(-1) for x in tensors])
-        v = v[v >= 0]
-        if v.numel() == 0:
-            return np.zeros(0, np.int64)
-        keep = t.ones_like(v, dtype=t.bool)
-        keep[1:] = v[1:] != v[:-1]
-        return t.unique(v[keep]).cpu().numpy().astype(np.int64)
 
     def _st(self):
         return self.torch.cuda.current_stream().cuda_stream

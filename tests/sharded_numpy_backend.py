@@ -46,9 +46,6 @@ class NumpyBackend(object):
     def empty(self, shape, dtype):
         return np.zeros(shape, dtype=dtype)
 
-    def cat_rows(self, parts):
-        return np.ascontiguousarray(np.concatenate(parts, axis=-2))
-
     def scatter(self, plane, flat_idx, vals):
         if len(flat_idx):
             plane.reshape(-1)[np.asarray(flat_idx, dtype=np.int64)] = np.asarray(vals).astype(plane.dtype)
@@ -87,19 +84,6 @@ class NumpyBackend(object):
             return np.zeros((0, 3), np.int64)
         rows = np.concatenate(parts, axis=0)
         return rows[rows[:, 0] >= 0]
-
-    def unique_pairs(self, a, b):
-        m = a >= 0
-        pairs = np.stack([a[m], b[m]], axis=1).astype(np.int64)
-        if pairs.size == 0:
-            return np.zeros((0, 2), np.int64)
-        u = np.unique(pairs, axis=0)
-        assert u.min() >= 0, "seam pixels must be classified identically on both ranks"
-        return u
-
-    def unique_vals(self, arrays):
-        v = np.concatenate([np.asarray(t).reshape(-1) for t in arrays]).astype(np.int64)
-        return np.unique(v[v >= 0])
 
     def ddm_codes(self, dcm_ext, n_classes, row_lo, row_hi):
         T = dcm_ext.shape[0]
