@@ -56,6 +56,15 @@ SIGNATURES = {
     "cdnet_shard_label_stage4": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                          c_void_p]),
     "cdnet_shard_relabel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "cdnet_seam_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cdnet_seam_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "cdnet_seam_solve": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
+    "cdnet_seam_ids_export": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdnet_seam_ids_apply": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
     "cdnet_launch_count": (ctypes.c_ulonglong, []),
     "cdnet_profile_enable": (None, [c_int]),
     "cdnet_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),

@@ -194,6 +194,26 @@ int cdnet_shard_label_stage4(int32_t* L, const uint8_t* keep, const uint8_t* exc
 int cdnet_shard_relabel(const int32_t* L, const uint8_t* keep, const int32_t* idmap, int32_t* labels,
                         int He, int W, void* stream);
 
+/* ---- device-side seam reconciliation for row shards (csrc/seam.cu) ---------------------------------
+ * A rank exports the run starts of the rows it shares with its neighbours as a table of int32x4 rows
+ * (gid, neighbour gid or -1, attr, attr-once-per-root); row 0 = (count, error bits, 0, 0).  The host
+ * all-gathers the tables ([nranks, cap, 4] int32, NCCL) and every rank solves the same union on its
+ * device: mode 0 = OR of attr per class -> plane at the local roots, 1 = SUM, 2 = mark the seam roots
+ * this rank does not own in `excluded` (then cdnet_seam_ids_export / _apply hand out the class ids).
+ * No host synchronisation anywhere.  ws: cdnet_seam_workspace_bytes(nranks, cap), reused across a round. */
+size_t cdnet_seam_workspace_bytes(int nranks, int cap);
+int cdnet_seam_export(const int32_t* L, const uint8_t* valid, const int32_t* attr, int32_t* emitted,
+                      int round_id, int off, int He, int W, int has_top, int has_bottom,
+                      const int32_t* nb_gid, int32_t* tbl, int cap, void* stream);
+int cdnet_seam_solve(const int32_t* gathered, int nranks, int cap, int my_rank, int mode, int off,
+                     int own_lo, int own_hi, int32_t* plane, uint8_t* excluded, void* ws, size_t ws_bytes,
+                     void* stream);
+int cdnet_seam_ids_export(const int32_t* gathered, int nranks, int cap, int my_rank, int off, int own_lo,
+                          int own_hi, const int32_t* idmap, int32_t* emitted, int round_id, int32_t* tbl2,
+                          void* ws, size_t ws_bytes, void* stream);
+int cdnet_seam_ids_apply(const int32_t* gathered, const int32_t* gathered2, int nranks, int cap,
+                         int my_rank, int off, int32_t* idmap, void* ws, size_t ws_bytes, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long cdnet_launch_count(void);
 

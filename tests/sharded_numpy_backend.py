@@ -53,8 +53,8 @@ class NumpyBackend(object):
     def gather(self, plane, flat_idx):
         return plane.reshape(-1)[np.asarray(flat_idx, dtype=np.int64)]
 
-    def add_scalar(self, plane, v):
-        plane += np.int32(v)
+    def stack(self, arrays):
+        return np.ascontiguousarray(np.stack(arrays, axis=0))
 
     def to_torch(self, t):
         import torch
@@ -63,27 +63,134 @@ class NumpyBackend(object):
     def from_torch(self, t):
         return t.numpy() if hasattr(t, "numpy") else t
 
+    # -- scalars
+    def pack_scalars(self, flags, pmax):
+        return np.array([flags[0], pmax[0]], dtype=np.int32)
+
+    def combine_scalars(self, gathered):
+        g = np.asarray(gathered)
+        flags = np.bitwise_or.reduce(g[:, 0].astype(np.int64) & 0xffffffff)
+        pm = (g[:, 1].astype(np.int64) & 0xffffffff).max()
+        return (np.array([flags], dtype=np.int64).astype(np.uint32).view(np.int32),
+                np.array([pm], dtype=np.int64).astype(np.uint32).view(np.int32))
+
+    def flags_to_host(self, flags):
+        return int(np.asarray(flags).view(np.uint32)[0])
+
+    def exclusive_offset(self, gathered_counts, rank):
+        return np.array([int(np.asarray(gathered_counts).reshape(-1)[:rank].sum())], dtype=np.int32)
+
+    def add_offset(self, plane, offset):
+        plane += np.int32(offset[0])
+
+    # -- seam rounds: same table contract as csrc/seam.cu, solved with scipy on the host
+    def seam_init(self, sh, world, W):
+        sh.cap = 4 * W + 1
+        sh.emitted = np.zeros((sh.He, W), np.int32)
+        sh.world = world
+
     def seam_gid(self, L, valid, r0, off):
         g = L[r0:r0 + 2].astype(np.int64) + int(off)
         if valid is not None:
             g = np.where(valid[r0:r0 + 2] != 0, g, -1)
         return np.ascontiguousarray(g.astype(np.int32))
 
-    def seam_export(self, L, valid, attr, off, He, has_top, has_bottom, nb_top):
-        parts = []
-        for side, r0 in (("top", 0), ("bottom", He - 2)):
-            if (side == "top" and not has_top) or (side == "bottom" and not has_bottom):
+    def seam_export(self, sh, valid, attr, round_id, nb_gid):
+        W = sh.L.shape[1]
+        rows = []
+        err = 0
+        for side, r0 in ((0, 0), (1, sh.He - 2)):
+            if (side == 0 and not sh.has_top) or (side == 1 and not sh.has_bottom):
                 continue
-            g = L[r0:r0 + 2].astype(np.int64) + int(off)
-            if valid is not None:
-                g = np.where(valid[r0:r0 + 2] != 0, g, -1)
-            a = attr.reshape(-1)[np.maximum(g - int(off), 0)].astype(np.int64) if attr is not None else np.zeros_like(g)
-            nb = np.asarray(nb_top).astype(np.int64) if (side == "bottom" and nb_top is not None) else np.full_like(g, -1)
-            parts.append(np.stack([g.reshape(-1), nb.reshape(-1), a.reshape(-1)], axis=1))
-        if not parts:
-            return np.zeros((0, 3), np.int64)
-        rows = np.concatenate(parts, axis=0)
-        return rows[rows[:, 0] >= 0]
+            g = self.seam_gid(sh.L, valid, r0, sh.off).astype(np.int64)
+            nb = np.asarray(nb_gid).astype(np.int64) if (side == 1 and nb_gid is not None) else np.full_like(g, -1)
+            if side == 1 and nb_gid is not None and ((g >= 0) != (nb >= 0)).any():
+                err |= 1
+            for r in range(2):
+                start = np.ones(W, bool)
+                start[1:] = (g[r, 1:] != g[r, :-1]) | (nb[r, 1:] != nb[r, :-1])
+                sel = start & (g[r] >= 0)
+                for x in np.nonzero(sel)[0]:
+                    root = int(g[r, x] - sh.off)
+                    a = int(attr.reshape(-1)[root]) if attr is not None else 0
+                    first = sh.emitted.reshape(-1)[root] != round_id
+                    sh.emitted.reshape(-1)[root] = round_id
+                    rows.append((int(g[r, x]), int(nb[r, x]), a, a if first else 0))
+        tbl = np.zeros((sh.cap, 4), np.int32)
+        tbl[0] = (len(rows), err, 0, 0)
+        if rows:
+            tbl[1:1 + len(rows)] = np.asarray(rows, dtype=np.int64).astype(np.int32)
+        return tbl
+
+    @staticmethod
+    def _classes(gathered):
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        ent = [np.asarray(gathered[r][1:1 + int(gathered[r][0, 0])]).astype(np.int64) for r in range(len(gathered))]
+        allent = np.concatenate(ent) if ent else np.zeros((0, 4), np.int64)
+        keys = np.unique(np.concatenate([allent[:, 0], allent[:, 1][allent[:, 1] >= 0]])) if len(allent) else np.zeros(0, np.int64)
+        if keys.size == 0:
+            return ent, keys, np.zeros(0, np.int64), 0
+        e = allent[allent[:, 1] >= 0]
+        a, b = np.searchsorted(keys, e[:, 0]), np.searchsorted(keys, e[:, 1])
+        ncls, cls = connected_components(coo_matrix((np.ones(a.size, np.int8), (a, b)), shape=(keys.size, keys.size)),
+                                         directed=False)
+        return ent, keys, cls.astype(np.int64), int(ncls)
+
+    def seam_solve(self, sh, gathered, mode, W, plane=None, excluded=None):
+        ent, keys, cls, ncls = self._classes(gathered)
+        sh._seam = (ent, keys, cls, ncls)
+        if ncls == 0:
+            return
+        allent = np.concatenate(ent)
+        cidx = cls[np.searchsorted(keys, allent[:, 0])]
+        mine = ent[sh.rank]
+        mcls = cls[np.searchsorted(keys, mine[:, 0])] if len(mine) else np.zeros(0, np.int64)
+        if mode == 0:
+            val = np.zeros(ncls, np.int64)
+            np.maximum.at(val, cidx, (allent[:, 2] != 0).astype(np.int64))
+            plane.reshape(-1)[mine[:, 0] - sh.off] = val[mcls].astype(np.int32)
+        elif mode == 1:
+            val = np.zeros(ncls, np.int64)
+            np.add.at(val, cidx, allent[:, 3])
+            plane.reshape(-1)[mine[:, 0] - sh.off] = np.minimum(val[mcls], 2 ** 31 - 1).astype(np.int32)
+        else:
+            croot = np.full(ncls, np.iinfo(np.int64).max, np.int64)
+            np.minimum.at(croot, cls, keys)
+            sh._croot = croot
+            g = mine[:, 0]
+            ex = (croot[mcls] != g) | (g < sh.r0 * W) | (g >= sh.r1 * W)
+            excluded.reshape(-1)[(g - sh.off)[ex]] = 1
+
+    def seam_ids_export(self, sh, gathered, idmap, round_id, W):
+        ent, keys, cls, ncls = sh._seam
+        mine = ent[sh.rank]
+        tbl2 = np.zeros((sh.cap, 4), np.int32)
+        if len(mine):
+            g = np.unique(mine[:, 0])
+            own = (sh._croot[cls[np.searchsorted(keys, g)]] == g) & (g >= sh.r0 * W) & (g < sh.r1 * W)
+            go = g[own]
+            tbl2[0, 0] = len(go)
+            tbl2[1:1 + len(go), 0] = go.astype(np.int32)
+            tbl2[1:1 + len(go), 1] = idmap.reshape(-1)[go - sh.off]
+        return tbl2
+
+    def seam_ids_apply(self, sh, gathered, gathered2, idmap):
+        ent, keys, cls, ncls = sh._seam
+        mine = ent[sh.rank]
+        if not len(mine):
+            return
+        t2 = np.concatenate([np.asarray(gathered2[r][1:1 + int(gathered2[r][0, 0])]).astype(np.int64)
+                             for r in range(len(gathered2))])
+        order = np.argsort(t2[:, 0])
+        tk, tv = t2[order, 0], t2[order, 1]
+        groot = sh._croot[cls[np.searchsorted(keys, mine[:, 0])]]
+        pos = np.searchsorted(tk, groot)
+        assert np.array_equal(tk[pos], groot), "every seam class must have exactly one owner"
+        idmap.reshape(-1)[mine[:, 0] - sh.off] = tv[pos].astype(np.int32)
+
+    def seam_errors(self, tables):
+        return int(max(int(t[0, 1]) for t in tables)) if tables else 0
 
     def ddm_codes(self, dcm_ext, n_classes, row_lo, row_hi):
         T = dcm_ext.shape[0]
@@ -94,12 +201,14 @@ class NumpyBackend(object):
             codes |= d << (2 * t)
             for v in np.unique(d[row_lo:row_hi]):
                 flags |= 1 << (3 * t + int(v))
-        return codes, flags
+        return codes, np.array([flags], dtype=np.uint32).view(np.int32)
 
     def point_max(self, point_own):
-        return _f32_to_ordered(np.max(point_own))
+        return np.array([_f32_to_ordered(np.max(point_own))], dtype=np.uint32).view(np.int32)
 
     def boost(self, codes, flags, point_ext, pmax, prob_ext, n_maps):
+        flags = int(np.asarray(flags).view(np.uint32)[0])
+        pmax = int(np.asarray(pmax).view(np.uint32)[0])
         vals = []
         for t in range(n_maps):
             f = (flags >> (3 * t)) & 7
@@ -157,7 +266,7 @@ class NumpyBackend(object):
         idmap = np.zeros(L.shape, np.int32)
         n = int(roots.sum())
         idmap[roots] = np.arange(1, n + 1)
-        return idmap, n
+        return idmap, np.array([n], dtype=np.int32)
 
     def relabel(self, L, keep, idmap, out=None):
         res = np.where(keep != 0, idmap.reshape(-1)[L], 0).astype(np.int32)
