@@ -77,3 +77,24 @@ def test_sharded_wide_slide(cuda_api):
     outs = sharded.postprocess_slide(shards, sharded.SimComm(3), H, W, sharded.CudaBackend(), 9, 20, 2)
     got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
     assert np.array_equal(got, single[0].cpu().numpy())
+
+
+@pytest.mark.parametrize("seed,H,W,G", [(51, 64, 40, 8), (52, 97, 132, 6), (54, 120, 64, 7)])
+def test_sharded_thin_shards(cuda_api, seed, H, W, G):
+    """thin shards: components and holes that cross several seams (device-side seam rounds)"""
+    import torch
+    from cdnet_b200 import sharded
+    from test_sharded_gloo import _slide as mk
+    rng = np.random.default_rng(seed)
+    dcm, prob, point = mk(seed, H, W, max(4, H * W // 900), 8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    snake = ((yy // 3) % 2 == 0) & (xx > 2) & (xx < W - 3)
+    link = ((yy % 6) == 3) & (xx >= W - 6) & (xx < W - 3) | ((yy % 6) == 0) & (xx > 2) & (xx <= 5) & (yy > 0)
+    prob[1][(snake | link) & (rng.random((H, W)) < 0.97)] += np.float32(3.0)
+    single, _ = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(prob)[None].cuda(),
+                                              torch.from_numpy(point)[None].cuda(), 9, 20, 2, 0)
+    parts = sharded.row_partition(H, G)
+    shards = [dict(dcm=dcm[:, a:b].copy(), prob=prob[:, a:b].copy(), point=point[:, a:b].copy()) for a, b in parts]
+    outs = sharded.postprocess_slide(shards, sharded.SimComm(G), H, W, sharded.CudaBackend(), 9, 20, 2)
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    assert np.array_equal(got, single[0].cpu().numpy()), int((got != single[0].cpu().numpy()).sum())

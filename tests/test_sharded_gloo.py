@@ -98,3 +98,19 @@ def test_constant_direction_map_asserts():
     dcm[2] = 0
     with pytest.raises(AssertionError):
         sharded.postprocess_slide(_split(dcm, prob, point, H, 2), sharded.SimComm(2), H, W, NumpyBackend(), 9, 20, 2)
+
+
+@pytest.mark.parametrize("seed,H,W,G", [(51, 64, 40, 8), (52, 97, 131, 6), (53, 33, 300, 4), (54, 120, 64, 7)])
+def test_slide_many_ranks_small_shards(seed, H, W, G):
+    """thin shards (a few rows each): components cross several seams, holes span many shards"""
+    rng = np.random.default_rng(seed)
+    dcm, prob, point = _slide(seed, H, W, max(4, H * W // 900), 8)
+    # serpentine foreground that winds through every shard, plus random specks on the seams
+    yy, xx = np.mgrid[0:H, 0:W]
+    snake = ((yy // 3) % 2 == 0) & (xx > 2) & (xx < W - 3)
+    link = ((yy % 6) == 3) & (xx >= W - 6) & (xx < W - 3) | ((yy % 6) == 0) & (xx > 2) & (xx <= 5) & (yy > 0)
+    prob[1][(snake | link) & (rng.random((H, W)) < 0.97)] += np.float32(3.0)
+    ref = O.dam_postprocess(prob.copy(), point, dcm, 9, 20, 2, 0, literal=False)["pred_labeled"]
+    outs = sharded.postprocess_slide(_split(dcm, prob, point, H, G), sharded.SimComm(G), H, W, NumpyBackend(), 9, 20, 2)
+    got = np.concatenate(outs, axis=0)
+    assert np.array_equal(got, ref), int((got != ref).sum())
