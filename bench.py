@@ -43,6 +43,7 @@ KERNEL_BYTES_PER_PX = {
     "k_ddm_codes": 10.0,        # 8 class maps (u8) in, 2-byte code word out
     "k_ddm_codes_simd": 10.0,
     "k_point_max": 4.0,         # f32 point map in
+    "k_point_max4": 4.0,
     "k_boost_inside": 19.0,     # codes 2 + point 4 + prob 12 in, inside mask 1 out
     "k_boost_inside4": 19.0,
     "k_ccl_init_rows": 13.0,    # mask 1 in, parent 4 + two zero-filled planes 8 out

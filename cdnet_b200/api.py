@@ -622,3 +622,59 @@ class LabelEncoding(object):
             out_imgs.append(point)
             out_imgs.append(direction)
         return tuple(out_imgs)
+
+
+class EncodeTargetsPlan(object):
+    """Pre-allocated pinned staging + device buffers for repeated host-buffer calls of the target transform on
+    B label tiles of H x W (LabelEncoding path, my_transforms_direction.py:697-885, instance-level labels).
+
+    Fill `h_ids` [B,H,W] uint8 (channel 0 of the label images), call `run()`, read `h_ternary` (uint8),
+    `h_point` (float16) and `h_direction` (int64).  Copies of chunk i+1 / i-1 overlap the kernels of chunk i."""
+
+    def __init__(self, B, H, W, num_classes=8, instance_level=True, device=None):
+        self.dev = _device(device)
+        self.num_classes, self.instance_level = int(num_classes), bool(instance_level)
+        pin = dict(pin_memory=True)
+        self.t_ids = torch.empty((B, H, W), dtype=torch.uint8, **pin)
+        self.t_ternary = torch.empty((B, H, W), dtype=torch.uint8, **pin)
+        self.t_point = torch.empty((B, H, W), dtype=torch.float16, **pin)
+        self.t_direction = torch.empty((B, H, W), dtype=torch.int64, **pin)
+        self.h_ids, self.h_ternary = self.t_ids.numpy(), self.t_ternary.numpy()
+        self.h_point, self.h_direction = self.t_point.numpy(), self.t_direction.numpy()
+        self.d_ids = torch.empty_like(self.t_ids, device=self.dev)
+        self.h2d_bytes = self.t_ids.numel()
+        self.d2h_bytes = self.t_ids.numel() * (1 + 2 + 8)
+        self._s_in = self._s_out = None
+
+    def launch(self, chunk=32):
+        B = self.t_ids.shape[0]
+        cur = torch.cuda.current_stream()
+        if self._s_in is None:
+            self._s_in, self._s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        s_in, s_out = self._s_in, self._s_out
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        for a in range(0, B, chunk):
+            b = min(B, a + chunk)
+            with torch.cuda.stream(s_in):
+                self.d_ids[a:b].copy_(self.t_ids[a:b], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            cur.wait_event(ev_in)
+            tern, point, direction = encode_targets_cuda(self.d_ids[a:b], self.instance_level, self.num_classes)
+            ev_k = torch.cuda.Event()
+            ev_k.record(cur)
+            s_out.wait_event(ev_k)
+            with torch.cuda.stream(s_out):
+                self.t_ternary[a:b].copy_(tern, non_blocking=True)
+                self.t_point[a:b].copy_(point, non_blocking=True)
+                self.t_direction[a:b].copy_(direction, non_blocking=True)
+                # keep the device results alive until the copies have run
+                for t in (tern, point, direction):
+                    t.record_stream(s_out)
+        cur.wait_stream(s_out)
+
+    def run(self):
+        self.launch()
+        torch.cuda.current_stream().synchronize()
+        return self.h_ternary, self.h_point, self.h_direction

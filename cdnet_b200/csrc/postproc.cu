@@ -25,21 +25,61 @@ __device__ __forceinline__ float ddm_value_f(uint32_t d, uint32_t f) {
     return __fdiv_rn((float)((int)d - mn), (float)(mx - mn));
 }
 
-__global__ void __launch_bounds__(256) k_point_max(const float* __restrict__ point, unsigned int* __restrict__ pmax,
-                                                   size_t plane) {
+__device__ __forceinline__ void block_max_to(unsigned int m, unsigned int* dst) {
     __shared__ unsigned int s_max[8];
-    const int b = blockIdx.y;
-    const float* P = point + (size_t)b * plane;
-    unsigned int m = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x)
-        m = max(m, f32_to_ordered(P[i]));
     m = __reduce_max_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x < 8) {
         m = s_max[threadIdx.x];
         m = __reduce_max_sync(0xffu, m);
-        if (threadIdx.x == 0) atomicMax(pmax + b, m);
+        if (threadIdx.x == 0) atomicMax(dst, m);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_point_max(const float* __restrict__ point, unsigned int* __restrict__ pmax,
+                                                   size_t plane) {
+    const int b = blockIdx.y;
+    const float* P = point + (size_t)b * plane;
+    unsigned int m = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, f32_to_ordered(P[i]));
+    block_max_to(m, pmax + b);
+}
+
+// plane % 4 == 0 and 16-byte aligned planes: four independent 16-byte loads in flight per thread
+__global__ void __launch_bounds__(256) k_point_max4(const float4* __restrict__ point, unsigned int* __restrict__ pmax,
+                                                    size_t plane4) {
+    const int b = blockIdx.y;
+    const float4* P = point + (size_t)b * plane4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned int m = 0;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < plane4; i += 4 * stride) {
+        const float4 a = __ldg(P + i), c = __ldg(P + i + stride), d = __ldg(P + i + 2 * stride), e = __ldg(P + i + 3 * stride);
+        const unsigned int m0 = max(max(f32_to_ordered(a.x), f32_to_ordered(a.y)), max(f32_to_ordered(a.z), f32_to_ordered(a.w)));
+        const unsigned int m1 = max(max(f32_to_ordered(c.x), f32_to_ordered(c.y)), max(f32_to_ordered(c.z), f32_to_ordered(c.w)));
+        const unsigned int m2 = max(max(f32_to_ordered(d.x), f32_to_ordered(d.y)), max(f32_to_ordered(d.z), f32_to_ordered(d.w)));
+        const unsigned int m3 = max(max(f32_to_ordered(e.x), f32_to_ordered(e.y)), max(f32_to_ordered(e.z), f32_to_ordered(e.w)));
+        m = max(m, max(max(m0, m1), max(m2, m3)));
+    }
+    for (; i < plane4; i += stride) {
+        const float4 a = __ldg(P + i);
+        m = max(m, max(max(f32_to_ordered(a.x), f32_to_ordered(a.y)), max(f32_to_ordered(a.z), f32_to_ordered(a.w))));
+    }
+    block_max_to(m, pmax + b);
+}
+
+static void point_max_launch(const float* point, unsigned int* pmax, int B, size_t plane, cudaStream_t st) {
+    if (plane % 4 == 0 && ((uintptr_t)point & 15) == 0) {
+        const size_t p4 = plane / 4;
+        size_t gx = (p4 + 256 * 4 - 1) / (256 * 4);
+        if (gx > 65535) gx = 65535;
+        CDNET_LAUNCH(k_point_max4, dim3((unsigned)gx, B), 256, 0, st, (const float4*)point, pmax, p4);
+    } else {
+        size_t gx = (plane + 256 * 16 - 1) / (256 * 16);
+        if (gx > 65535) gx = 65535;
+        CDNET_LAUNCH(k_point_max, dim3((unsigned)gx, B), 256, 0, st, point, pmax, plane);
     }
 }
 
@@ -289,10 +329,7 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
     int rc = ddm_codes_launch(dcm, codes, flags, B, n_maps, H, W, direction_classes, st);
     if (rc) return rc;
     CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, st));
-    {
-        int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
-        CDNET_LAUNCH(k_point_max, dim3(gx, B), 256, 0, st, point, pmax, plane);
-    }
+    point_max_launch(point, pmax, B, plane, st);
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
         CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes, flags, point,
                      pmax, prob, inside, status, H, W, write_prob, n_maps);
@@ -355,9 +392,7 @@ extern "C" int cdnet_shard_point_max(const float* point, uint32_t* pmax, size_t 
     if (!point || !pmax || n == 0) return CDNET_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(uint32_t), st));
-    int gx = (int)((n + 256 * 16 - 1) / (256 * 16));
-    if (gx > 65535) gx = 65535;
-    CDNET_LAUNCH(k_point_max, dim3(gx, 1), 256, 0, st, point, pmax, n);
+    point_max_launch(point, pmax, 1, n, st);
     return last_error();
 }
 

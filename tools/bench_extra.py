@@ -66,8 +66,32 @@ def main():
             fn()
         ms = timed(fn, a.steps)
         mpx = a.tiles * a.size * a.size / 1e6
+        kern = profile(L, fn, a.steps)
+        plan = api.EncodeTargetsPlan(a.tiles, a.size, a.size, a.classes)
+        plan.h_ids[:] = ids
+        t0, p0, d0 = [x.copy() for x in plan.run()]
+        ref = fn()
+        assert np.array_equal(t0, ref[0].cpu().numpy()) and np.array_equal(d0, ref[2].cpu().numpy())
+        sweep = {}
+        for ch in (8, 16, 32, 64):
+            for _ in range(2):
+                plan.launch(chunk=ch)
+            sweep[ch] = timed(lambda: plan.launch(chunk=ch), a.steps)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dd = torch.empty_like(plan.t_direction, device="cuda")
+        plan.t_direction.copy_(dd, non_blocking=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(5):
+            plan.t_direction.copy_(dd, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        d2h_gbs = dd.numel() * 8 * 5 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        print(json.dumps({"e2e_chunk_sweep_ms": sweep, "d2h_only_GBps": d2h_gbs}))
+        ms_e2e = min(sweep.values())
         print(json.dumps({"what": "targets", "tiles": a.tiles, "size": a.size, "classes": a.classes, "ms": ms,
-                          "mpx_per_s": mpx / (ms * 1e-3), "kernels_ms": profile(L, fn, a.steps)}))
+                          "mpx_per_s": mpx / (ms * 1e-3), "e2e_ms": ms_e2e, "e2e_mpx_per_s": mpx / (ms_e2e * 1e-3),
+                          "h2d_bytes": plan.h2d_bytes, "d2h_bytes": plan.d2h_bytes, "kernels_ms": kern}))
     else:
         tiles = [synth.postproc_inputs(100 + i, 1000, 1000) for i in range(14)]
         plan = api.DamPostprocessPlan(14, 1000, 1000, 9, 20, 2, 1)
