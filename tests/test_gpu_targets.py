@@ -105,3 +105,30 @@ def test_label_encoding_edge_cases(cuda_api):
         assert np.array_equal(np.asarray(res[2]), ref[0]), name
         assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), name
         assert np.array_equal(res[4], ref[2]), name
+
+
+def test_encode_targets_plan_host_buffers(cuda_api):
+    """The pinned host-buffer plan (chunked copy/compute overlap) returns what the one-shot call returns."""
+    import torch
+    from cdnet_b200 import synth
+    B, H, W = 5, 120, 136
+    ids = np.stack([synth.as_uint8_label(synth.instance_map(700 + i, H, W, 12))[:, :, 0] for i in range(B)])
+    ref = [t.cpu().numpy() for t in cuda_api.encode_targets_cuda(torch.from_numpy(ids).cuda(), True, 8)]
+    plan = cuda_api.EncodeTargetsPlan(B, H, W, 8)
+    for chunk in (2, 32):
+        plan.h_ids[:] = ids
+        plan.h_ternary[:] = 7
+        plan.launch(chunk=chunk)
+        torch.cuda.synchronize()
+        assert np.array_equal(plan.h_ternary, ref[0])
+        assert np.array_equal(plan.h_point.view(np.uint16), ref[1].view(np.uint16))
+        assert np.array_equal(plan.h_direction, ref[2])
+    # golden anchor for one tile through the plan
+    z, meta = load_golden("t_128")
+    lab = _labels(meta)
+    p1 = cuda_api.EncodeTargetsPlan(1, meta["H"], meta["W"], meta["num_classes"])
+    p1.h_ids[0] = lab[:, :, 0]
+    tern, point, direction = p1.run()
+    assert np.array_equal(tern[0], z["ternary"])
+    assert np.array_equal(point[0].view(np.uint16), z["point"].view(np.uint16))
+    _check_direction(direction[0], z["direction"].astype(np.int64), lab, meta["num_classes"], "plan t_128")
