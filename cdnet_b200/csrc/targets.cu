@@ -102,20 +102,28 @@ __global__ void __launch_bounds__(kBX* kBY) k_t_ternary(const uint8_t* __restric
 }
 
 // ---- centre search (my_transforms_direction.py:651-685) ---------------------------------------------
+// The reference bisects [l, r] = [0, 1000] thirty times with mid = (l + r) / 2 and returns r (:668-678).  Every
+// l, r, mid is a multiple of 1000 / 2^30 below 2^11, so all of that arithmetic is exact in f64 and the pair can be
+// carried as (lo, width): mid = lo + width/2, r_final = lo_final + 1000 / 2^30.  Python's round() (half to even)
+// of the f64 position is taken with the 1.5 * 2^52 trick: one DADD in round-to-nearest-even leaves the integer
+// in the low word -- no FRND / F2I / f64 compares in the loop.
 __device__ __forceinline__ double ray_reach(const int* __restrict__ L, int H, int W, int i, int j, int own, double sy,
                                             double sx) {
-    double lo = 0.0, hi = 1000.0;
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+    double lo = 0.0, half = 500.0;
     const double fi = (double)i, fj = (double)j;
-#pragma unroll 1
+    asm volatile("" : "+l"(L));  // keep the tile base in one register pair: one IMAD.WIDE per probe
+#pragma unroll
     for (int it = 0; it < 30; ++it) {
-        const double mid = __dmul_rn(__dadd_rn(lo, hi), 0.5);
-        const double ry = rint(__dadd_rn(fi, __dmul_rn(sy, mid)));  // python round(): half to even
-        const double rx = rint(__dadd_rn(fj, __dmul_rn(sx, mid)));
+        const double mid = __dadd_rn(lo, half);
+        const int ry = __double2loint(__dadd_rn(__dadd_rn(fi, __dmul_rn(sy, mid)), kMagic));
+        const int rx = __double2loint(__dadd_rn(__dadd_rn(fj, __dmul_rn(sx, mid)), kMagic));
         bool hit = false;
-        if (ry >= 0.0 && ry < (double)H && rx >= 0.0 && rx < (double)W) hit = L[(int)ry * W + (int)rx] == own;
-        if (hit) lo = mid; else hi = mid;
+        if ((unsigned)ry < (unsigned)H && (unsigned)rx < (unsigned)W) hit = __ldg(L + (ry * W + rx)) == own;
+        lo = hit ? mid : lo;
+        half = half * 0.5;  // exact; folds to a constant per unrolled step
     }
-    return hi;
+    return __dadd_rn(lo, 0x1.f4p-21);  // + 1000 / 2^30
 }
 
 // table layout per tile: entries 0..tab-1 (label ids).  A block owns a 64 x 32 pixel region, queues its
