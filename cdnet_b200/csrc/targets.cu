@@ -126,6 +126,28 @@ __device__ __forceinline__ double ray_reach(const int* __restrict__ L, int H, in
     return __dadd_rn(lo, 0x1.f4p-21);  // + 1000 / 2^30
 }
 
+// Rays 0, 2, 4, 6 run along an image axis: (sin, cos) is (0 | +-1, +-1 | ~1e-16), the product with mid is +-mid
+// exactly on the axis and below 2e-13 across it, which rounds away -- the cross coordinate stays put.
+// Probe index = r * stride + off with r = round(c +- mid) in [0, limit).
+__device__ __forceinline__ double ray_reach_axis(const int* __restrict__ L, int limit, int stride, int off, int c, int own,
+                                                 long long sign) {
+    const double kMagic = 6755399441055744.0;
+    double lo = 0.0, half = 500.0;
+    const double fc = (double)c;
+    asm volatile("" : "+l"(L));
+#pragma unroll
+    for (int it = 0; it < 30; ++it) {
+        const double mid = __dadd_rn(lo, half);
+        const double step = __longlong_as_double(__double_as_longlong(mid) ^ sign);
+        const int r = __double2loint(__dadd_rn(__dadd_rn(fc, step), kMagic));
+        bool hit = false;
+        if ((unsigned)r < (unsigned)limit) hit = __ldg(L + (r * stride + off)) == own;
+        lo = hit ? mid : lo;
+        half = half * 0.5;
+    }
+    return __dadd_rn(lo, 0x1.f4p-21);
+}
+
 // table layout per tile: entries 0..tab-1 (label ids).  A block owns a 64 x 32 pixel region, queues its
 // instance pixels in shared memory and lets all 256 threads work through the queue, so that lanes are not
 // idle on background (only ~25 % of a tile is nucleus).
@@ -162,7 +184,15 @@ __global__ void __launch_bounds__(256) k_t_centerness(const int* __restrict__ in
         const int own = L[p];
         double far = 0.0, near = 10000000.0;
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
+        for (int a = 0; a < 4; ++a) {  // rays 0 (+x), 2 (+y), 4 (-x), 6 (-y)
+            const bool vert = a & 1;
+            const double r = ray_reach_axis(L, vert ? H : W, vert ? W : 1, vert ? x : y * W, vert ? y : x, own,
+                                            (a & 2) ? (long long)0x8000000000000000ull : 0ll);
+            far = fmax(far, r);
+            near = fmin(near, r);
+        }
+#pragma unroll 1
+        for (int k = 1; k < 8; k += 2) {
             const double r = ray_reach(L, H, W, y, x, own, c_rays[k][0], c_rays[k][1]);
             far = fmax(far, r);
             near = fmin(near, r);
@@ -405,26 +435,51 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 constexpr int kGX = 32, kGY = 16, kGR = 8;
 
+// The point map is sparse (one pixel per nucleus) and every term of scipy's correlate1d is >= +0: adding a zero
+// term never changes the sum, so elements whose 17-tap window holds no non-zero input are written as +0 without
+// arithmetic and the others run the full tap sequence in scipy's order.  Presence is tracked as bit masks: one
+// 32-bit word per window column (the window is exactly 32 rows), one 64-bit word per row of the first pass.
+static_assert(kGY + 2 * kGR == 32 && kGX + 2 * kGR <= 64, "mask widths");
 __global__ void __launch_bounds__(kGX* kGY) k_t_gauss(const uint8_t* __restrict__ cflag, __half* __restrict__ out, int H,
                                                       int W) {
-    __shared__ uint8_t s_f[kGY + 2 * kGR][kGX + 2 * kGR];
+    __shared__ uint32_t s_col[kGX + 2 * kGR];
+    __shared__ unsigned long long s_row[kGY];
     __shared__ double s_v[kGY][kGX + 2 * kGR];
     const int b = blockIdx.z;
     const size_t tile = (size_t)b * H * W;
     const uint8_t* F = cflag + tile;
     const int bx0 = blockIdx.x * kGX, by0 = blockIdx.y * kGY;
     const int tid = threadIdx.y * kGX + threadIdx.x;
-    // the point map is sparse (one pixel per nucleus): a block whose halo window holds no centre writes zeros
+    if (tid < kGX + 2 * kGR) s_col[tid] = 0u;
+    if (tid < kGY) s_row[tid] = 0ull;
+    __syncthreads();
     int any = 0;
-    for (int i = tid; i < (kGY + 2 * kGR) * (kGX + 2 * kGR); i += kGX * kGY) {
-        const int ly = i / (kGX + 2 * kGR), lx = i % (kGX + 2 * kGR);
-        const int gy = reflect_idx(by0 + ly - kGR, H), gx = reflect_idx(bx0 + lx - kGR, W);
-        const uint8_t f = F[gy * W + gx];
-        s_f[ly][lx] = f;
-        any |= f;
+    constexpr int kWW = (kGX + 2 * kGR) / 4;  // window words per row
+    if (by0 >= kGR && by0 + kGY + kGR <= H && bx0 >= kGR && bx0 + kGX + kGR <= W && (W & 3) == 0 &&
+        ((uintptr_t)F & 3) == 0) {
+        // window inside the image: one aligned 4-byte load per thread, no reflection
+        if (tid < (kGY + 2 * kGR) * kWW) {
+            const int ly = tid / kWW, wx = tid % kWW;
+            const uint32_t w = __ldg((const uint32_t*)(F + (size_t)(by0 + ly - kGR) * W + (bx0 - kGR + 4 * wx)));
+            if (w) {
+                any = 1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((w >> (8 * k)) & 0xffu) atomicOr(&s_col[4 * wx + k], 1u << ly);
+            }
+        }
+    } else {
+        for (int i = tid; i < (kGY + 2 * kGR) * (kGX + 2 * kGR); i += kGX * kGY) {
+            const int ly = i / (kGX + 2 * kGR), lx = i % (kGX + 2 * kGR);
+            const int gy = reflect_idx(by0 + ly - kGR, H), gx = reflect_idx(bx0 + lx - kGR, W);
+            if (F[gy * W + gx]) {
+                atomicOr(&s_col[lx], 1u << ly);
+                any = 1;
+            }
+        }
     }
-    if (!__syncthreads_or(any)) {
-        const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    if (!__syncthreads_or(any)) {  // no centre in the halo window: the whole block is zero
         if (x < W && y < H) out[tile + (size_t)y * W + x] = __double2half(0.0);
         return;
     }
@@ -432,23 +487,29 @@ __global__ void __launch_bounds__(kGX* kGY) k_t_gauss(const uint8_t* __restrict_
     // correlate1d: centre term, then (in[l-j] + in[l+j]) * w[8-j] for j = 8 .. 1
     for (int i = tid; i < kGY * (kGX + 2 * kGR); i += kGX * kGY) {
         const int ly = i / (kGX + 2 * kGR), lx = i % (kGX + 2 * kGR);
-        const int cy = ly + kGR;
-        double t = __dmul_rn(s_f[cy][lx] ? 255.0 : 0.0, c_gauss[8]);
+        const uint32_t win = (s_col[lx] >> ly) & 0x1ffffu;  // window rows ly .. ly+16, centre = bit 8
+        double t = 0.0;
+        if (win) {
+            t = __dmul_rn((win >> 8) & 1u ? 255.0 : 0.0, c_gauss[8]);
 #pragma unroll
-        for (int j = 8; j >= 1; --j) {
-            const double a = s_f[cy - j][lx] ? 255.0 : 0.0, c = s_f[cy + j][lx] ? 255.0 : 0.0;
-            t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), c_gauss[8 - j]));
+            for (int j = 8; j >= 1; --j) {
+                const double a = (win >> (8 - j)) & 1u ? 255.0 : 0.0, c = (win >> (8 + j)) & 1u ? 255.0 : 0.0;
+                t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), c_gauss[8 - j]));
+            }
+            if (t != 0.0) atomicOr(&s_row[ly], 1ull << lx);
         }
         s_v[ly][lx] = t;
     }
     __syncthreads();
-    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
     if (x >= W || y >= H) return;
     const int lx = threadIdx.x + kGR;
-    double t = __dmul_rn(s_v[threadIdx.y][lx], c_gauss[8]);
+    double t = 0.0;
+    if ((s_row[threadIdx.y] >> threadIdx.x) & 0x1ffffull) {  // columns lx-8 .. lx+8 of the first pass
+        t = __dmul_rn(s_v[threadIdx.y][lx], c_gauss[8]);
 #pragma unroll
-    for (int j = 8; j >= 1; --j)
-        t = __dadd_rn(t, __dmul_rn(__dadd_rn(s_v[threadIdx.y][lx - j], s_v[threadIdx.y][lx + j]), c_gauss[8 - j]));
+        for (int j = 8; j >= 1; --j)
+            t = __dadd_rn(t, __dmul_rn(__dadd_rn(s_v[threadIdx.y][lx - j], s_v[threadIdx.y][lx + j]), c_gauss[8 - j]));
+    }
     out[tile + (size_t)y * W + x] = __double2half(t);
 }
 
@@ -523,7 +584,7 @@ extern "C" int cdnet_center_points(const int32_t* labels, int32_t* centres, int 
 
 extern "C" size_t cdnet_encode_targets_workspace_bytes(int B, int H, int W) {
     if (bad_dims(B, H, W)) return 0;
-    const size_t n = (size_t)B * H * W, nt = (size_t)B * ((size_t)H * W + 1);
+    const size_t n = (size_t)B * H * W, nt = (size_t)B * ((size_t)H * W / 2 + 2);
     return pad256(n * 8) + pad256(nt * 8) + 2 * pad256(nt * 4) + 2 * pad256(n * 4) + 3 * pad256(n) +
            pad256((size_t)B * 4) + pad256((size_t)B * 1024) + pad256((size_t)B * H * 4) + ws_process_workspace(B, H, W);
 }
@@ -537,7 +598,9 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     if (ws_bytes < cdnet_encode_targets_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)B * H * W;
-    const int tab = (int)((size_t)H * W + 1 > 0x7fffffff ? 0x7fffffff : (size_t)H * W + 1);
+    // instance ids are handed out 1..M by a 4- or 8-connected labelling (watershed keeps the marker ids):
+    // M <= ceil(H*W/2), so the per-label tables need H*W/2 + 2 entries per tile
+    const int tab = (int)((size_t)H * W / 2 + 2);
     const size_t nt = (size_t)B * tab;
     Arena ar(ws, ws_bytes);
     double* cness = ar.take<double>(n);
