@@ -65,6 +65,10 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdnet_seam_ids_apply": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+    "cdnet_label_pairs_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cdnet_label_pairs": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_void_p, c_size_t, c_void_p]),
+    "cdnet_remap_labels": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
     "cdnet_launch_count": (ctypes.c_ulonglong, []),
     "cdnet_profile_enable": (None, [c_int]),
     "cdnet_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),

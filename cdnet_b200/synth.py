@@ -193,3 +193,32 @@ def postproc_inputs(seed, H, W, n_target=None, n_dir=8, flip_frac=0.02):
     point = np.maximum(pt.astype(np.float32) + noise * np.float32(0.75), np.float32(0.0))
     return {"dcm": dcm, "prob": prob.astype(np.float32), "point": point[None].astype(np.float32),
             "ids": ids}
+
+
+def contiguous_ids(ids):
+    """ids renumbered 1..N in ascending order of the old id (what stats_utils.remap_label does), int32."""
+    u = np.unique(ids)
+    u = u[u != 0]
+    lut = np.zeros(int(u.max()) + 1 if u.size else 1, dtype=np.int32)
+    lut[u] = np.arange(1, u.size + 1, dtype=np.int32)
+    return lut[ids]
+
+
+def metric_pair(seed, H, W, n_target, mode=1):
+    """(true, pred) int32 label images with contiguous ids for the instance metrics (stats_utils.py).
+    mode 0: two unrelated instance maps; mode 1: pred = true shifted by (2, -3) px with ~1/6 of the nuclei
+    dropped and ~1/10 merged into another id -- misses, false positives and splits like a real prediction."""
+    true = instance_map(seed, H, W, n_target).astype(np.int32)
+    if mode == 0:
+        pred = instance_map(seed + 1000, H, W, n_target).astype(np.int32)
+    else:
+        pred = np.roll(true, (2, -3), axis=(0, 1)).copy()
+        rng = np.random.default_rng(seed)
+        ids = np.unique(pred)
+        ids = ids[ids > 0]
+        if ids.size:
+            for v in rng.choice(ids, size=max(1, ids.size // 6), replace=False):
+                pred[pred == v] = 0
+            for v in rng.choice(ids, size=max(1, ids.size // 10), replace=False):
+                pred[pred == v] = int(rng.choice(ids))
+    return contiguous_ids(true), contiguous_ids(pred)

@@ -34,6 +34,9 @@ extern "C" {
 #define CDNET_S_WS_OVERFLOW 2  /* watershed queue overflow (cannot happen with the sizes from
                                   *_workspace_bytes; kept as a guard) */
 
+#define CDNET_S_PAIR_OVERFLOW 4 /* cdnet_label_pairs: more distinct (true, pred) pairs than `cap` */
+#define CDNET_S_PAIR_RANGE 8    /* cdnet_label_pairs: a label id is negative or above INT32_MAX */
+
 const char* cdnet_version(void);
 /* 1 if the library was built for the device `device` can run (compute capability 10.x) */
 int cdnet_device_ok(int device);
@@ -213,6 +216,23 @@ int cdnet_seam_ids_export(const int32_t* gathered, int nranks, int cap, int my_r
                           void* ws, size_t ws_bytes, void* stream);
 int cdnet_seam_ids_apply(const int32_t* gathered, const int32_t* gathered2, int nranks, int cap,
                          int my_rank, int off, int32_t* idmap, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- instance metrics: pair table of two label images (SURVEY.md section 8f "next", rank 2) --------
+ * The one reduction behind stats_utils.py:7-98 get_fast_aji, :101-177 get_fast_aji_plus, :182-275
+ * get_fast_pq, :279-318 get_fast_dice_2, :324-334 get_dice_1, :338-357 get_dice_2 and :361-389
+ * remap_label (called from test.py:342-345, test_dam.py:616-621): for every tile the distinct pairs
+ * (t, q) = (true[p], pred[p]) with their pixel counts (they add up to H * W).  true_lab / pred_lab: int32 or int64
+ * [B,H,W] (elem_bytes 4 / 8), ids in [0, INT32_MAX]; keys: uint64 [B,cap] = t << 32 | q; counts: int32
+ * [B,cap]; n_out: int32 [B] pairs written (arbitrary order); status: int32 [B], CDNET_S_PAIR_*.
+ * Areas are the row / column sums of the table; the float64 epilogue is host code (cdnet_b200/metrics.py). */
+size_t cdnet_label_pairs_workspace_bytes(int B, int cap);
+int cdnet_label_pairs(const void* true_lab, const void* pred_lab, int elem_bytes, uint64_t* keys,
+                      int32_t* counts, int32_t* n_out, int32_t* status, int B, int H, int W, int cap,
+                      void* ws, size_t ws_bytes, void* stream);
+/* remap_label's gather (stats_utils.py:386-388): out[i] = new_ids[j] where sorted_ids[j] == in[i], else 0.
+ * in: int32 / int64 [n]; out: int32 [n]; sorted_ids ascending, new_ids: int32 [n_ids] (device). */
+int cdnet_remap_labels(const void* in, int elem_bytes, int32_t* out, const int32_t* sorted_ids,
+                       const int32_t* new_ids, int n_ids, size_t n, void* stream);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long cdnet_launch_count(void);

@@ -185,12 +185,61 @@ def gold_targets(ns, quick, num_classes):
             _t_case(ns, T_BIG[0], *T_BIG[1:], num_classes=8)
 
 
+# instance metrics: (name, seed, H, W, n_target, mode)
+M_CASES = [
+    ("m_64x80_unrelated", 1, 64, 80, 6, 0),
+    ("m_128", 2, 128, 128, 20, 1),
+    ("m_200x150", 3, 200, 150, 40, 1),
+    ("m_256_unrelated", 4, 256, 256, 60, 0),
+    ("m_500", 6, 500, 500, 150, 1),
+    ("m_1000", 7, 1000, 1000, 700, 1),
+]
+
+
+def gold_metrics():
+    """stats_utils.py executed verbatim (it only needs numpy + scipy) on synth.metric_pair inputs."""
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("ref_stats_utils", os.path.join(ref_loader.find_reference(), "stats_utils.py"))
+    R = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(R)
+    out, meta = {}, {"cases": []}
+    for name, seed, H, W, n, mode in M_CASES:
+        t0 = time.time()
+        true, pred = synth.metric_pair(seed, H, W, n, mode)
+        with contextlib.redirect_stdout(io.StringIO()):
+            aji = R.get_fast_aji(true, pred)
+        out[name + "_aji"] = np.asarray(aji, dtype=np.float64)
+        out[name + "_aji_plus"] = np.asarray(R.get_fast_aji_plus(true, pred), dtype=np.float64)
+        for mi in (0.5, 0.3):
+            (dq, sq, pq), (pt, pp, ut, up) = R.get_fast_pq(true, pred, mi)
+            tag = name + "_pq%02d" % int(mi * 10)
+            out[tag] = np.asarray([dq, sq, pq], dtype=np.float64)
+            out[tag + "_paired_true"] = np.asarray(pt, dtype=np.int64)
+            out[tag + "_paired_pred"] = np.asarray(pp, dtype=np.int64)
+            out[tag + "_unpaired_true"] = np.asarray(ut, dtype=np.int64)
+            out[tag + "_unpaired_pred"] = np.asarray(up, dtype=np.int64)
+        out[name + "_dice1"] = np.asarray(R.get_dice_1(true, pred), dtype=np.float64)
+        out[name + "_dice2"] = np.asarray(R.get_fast_dice_2(true, pred), dtype=np.float64)
+        raw = (true.astype(np.int64) * 3 + (true > 0) * 5).astype(np.int32)   # non-contiguous ids
+        out[name + "_remap"] = R.remap_label(raw).astype(np.int32)
+        out[name + "_remap_by_size"] = R.remap_label(raw, by_size=True).astype(np.int32)
+        meta["cases"].append({"name": name, "seed": seed, "H": H, "W": W, "n_target": n, "mode": mode,
+                              "digest": synth.digest(true, pred)})
+        print("%s: %.1fs (aji %.4f)" % (name, time.time() - t0, float(aji[0])), flush=True)
+    _save("metrics", meta, **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--child16", action="store_true")
     a = ap.parse_args()
+    if a.only == "metrics":
+        gold_metrics()
+        return
     if a.child16:
         assert os.environ.get("dt_num_classes") == "16"
         ns = ref_loader.load()
@@ -199,7 +248,7 @@ def main():
         return
     ns = ref_loader.load()
     assert ns.DTOffsetConfig.num_classes == 8
-    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16"]
+    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16", "metrics"]
     if "ddm" in todo:
         gold_ddm(ns)
     if "process" in todo:
@@ -210,6 +259,8 @@ def main():
         gold_postproc(ns, a.quick)
     if "targets" in todo:
         gold_targets(ns, a.quick, 8)
+    if "metrics" in todo:
+        gold_metrics()
     if "t16" in todo:
         env = dict(os.environ, dt_num_classes="16")
         subprocess.check_call([sys.executable, "-m", "oracle.make_goldens", "--child16"], env=env,

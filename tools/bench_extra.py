@@ -103,6 +103,51 @@ def main():
         ms = timed(plan.launch_device, a.steps)
         print(json.dumps({"what": "dam postproc=1", "ms": ms, "mpx_per_s": 14.0 / (ms * 1e-3),
                           "kernels_ms": profile(L, plan.launch_device, a.steps)}))
+    elif a.what == "metrics":
+        # instance metrics (stats_utils.py drop-ins): pair-table reduction for 14 x 1000^2 label pairs on the device,
+        # then the full host-buffer call per tile (H2D + kernels + D2H of the table + float64 epilogue), and the
+        # oracle port on one tile as the CPU yardstick (the reference itself: 2.4 s get_fast_aji + 1.7 s get_fast_pq
+        # per 1000^2 tile with ~700 nuclei, measured in the build container)
+        import contextlib
+        import io
+        from cdnet_b200 import metrics as M
+        pairs = [synth.metric_pair(900 + i, 1000, 1000, 700, 1) for i in range(2)]
+        t = torch.from_numpy(np.stack([pairs[i % 2][0] for i in range(14)])).cuda()
+        p = torch.from_numpy(np.stack([pairs[i % 2][1] for i in range(14)])).cuda()
+        cap = 31250
+        keys = torch.empty((14, cap), dtype=torch.int64, device="cuda")
+        counts = torch.empty((14, cap), dtype=torch.int32, device="cuda")
+        n_out = torch.empty((14,), dtype=torch.int32, device="cuda")
+        status = torch.empty((14,), dtype=torch.int32, device="cuda")
+        ws = torch.empty(L.cdnet_label_pairs_workspace_bytes(14, cap), dtype=torch.uint8, device="cuda")
+
+        def fn():
+            rc = L.cdnet_label_pairs(t.data_ptr(), p.data_ptr(), 4, keys.data_ptr(), counts.data_ptr(), n_out.data_ptr(),
+                                     status.data_ptr(), 14, 1000, 1000, cap, ws.data_ptr(), ws.numel(),
+                                     torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, rc
+        for _ in range(3):
+            fn()
+        ms = timed(fn, a.steps)
+        kern = profile(L, fn, a.steps)
+        assert int(status.max()) == 0
+        tt, pp = pairs[0]
+        with contextlib.redirect_stdout(io.StringIO()):
+            M.get_fast_aji(tt, pp)
+            t0 = time.time()
+            for _ in range(5):
+                aji = M.get_fast_aji(tt, pp)
+                pq = M.get_fast_pq(tt, pp)
+                dice = M.get_dice_1(tt, pp)
+            host_ms = (time.time() - t0) / 5 * 1e3
+            t0 = time.time()
+            res = M.instance_metrics_cuda(t, p)
+            batch_ms = (time.time() - t0) * 1e3
+        print(json.dumps({"what": "metrics", "pair_table_ms_14x1000x1000": ms, "mpx_per_s": 14.0 / (ms * 1e-3),
+                          "alg_GBps": 14e6 * 8 / (ms * 1e-3) / 1e9, "pairs_per_tile": int(n_out[0]),
+                          "dropin_aji_pq_dice_ms_per_tile_host_buffers": host_ms,
+                          "instance_metrics_cuda_ms_14_tiles_device_resident": batch_ms,
+                          "aji": float(aji[0]), "pq": float(pq[0][2]), "dice": float(dice), "kernels_ms": kern}))
 
 
 if __name__ == "__main__":
