@@ -92,7 +92,7 @@ def main():
         print(json.dumps({"what": "targets", "tiles": a.tiles, "size": a.size, "classes": a.classes, "ms": ms,
                           "mpx_per_s": mpx / (ms * 1e-3), "e2e_ms": ms_e2e, "e2e_mpx_per_s": mpx / (ms_e2e * 1e-3),
                           "h2d_bytes": plan.h2d_bytes, "d2h_bytes": plan.d2h_bytes, "kernels_ms": kern}))
-    else:
+    elif a.what == "ws":
         tiles = [synth.postproc_inputs(100 + i, 1000, 1000) for i in range(14)]
         plan = api.DamPostprocessPlan(14, 1000, 1000, 9, 20, 2, 1)
         for i, t in enumerate(tiles):
@@ -103,7 +103,8 @@ def main():
         ms = timed(plan.launch_device, a.steps)
         print(json.dumps({"what": "dam postproc=1", "ms": ms, "mpx_per_s": 14.0 / (ms * 1e-3),
                           "kernels_ms": profile(L, plan.launch_device, a.steps)}))
-    elif a.what == "metrics":
+    else:
+        assert a.what == "metrics", a.what
         # instance metrics (stats_utils.py drop-ins): pair-table reduction for 14 x 1000^2 label pairs on the device,
         # then the full host-buffer call per tile (H2D + kernels + D2H of the table + float64 epilogue), and the
         # oracle port on one tile as the CPU yardstick (the reference itself: 2.4 s get_fast_aji + 1.7 s get_fast_pq
