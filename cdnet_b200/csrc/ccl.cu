@@ -429,6 +429,11 @@ __global__ void __launch_bounds__(256) k_flatten_fill4(const uint8_t* __restrict
     *(uint32_t*)(state + tile + p) = st;
 }
 
+// Hole pixels (state 2) join the foreground components around them.  The forest was flattened by the previous
+// pass, so L holds roots (or, under concurrent unions, nodes one hop from them): all neighbour states and parents
+// of the word's hole pixels are loaded first (independent loads in flight together), duplicates are dropped (a
+// hole is nearly always enclosed by ONE component) and the unions start at roots -- a short dependent chain
+// instead of four full find/union walks per hole pixel.
 __global__ void __launch_bounds__(256) k_fill_merge4(const uint8_t* __restrict__ state, int* __restrict__ L, int H, int W) {
     V4_COORDS
     if (!inb) return;
@@ -438,14 +443,36 @@ __global__ void __launch_bounds__(256) k_fill_merge4(const uint8_t* __restrict__
     const uint32_t t = w ^ 0x02020202u;
     if (!((t - 0x01010101u) & ~t & 0x80808080u)) return;
     int* Lt = L + tile;
+    int own[4], cand[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+        own[i] = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cand[i][k] = -1;
         if (((w >> (8 * i)) & 0xffu) != 2u) continue;
         const int q = p + i, x = x4 + i;
-        if (y > 0 && S[q - W] == 1) uf_union(Lt, q, q - W);
-        if (x > 0 && S[q - 1] == 1) uf_union(Lt, q, q - 1);
-        if (x + 1 < W && S[q + 1] == 1) uf_union(Lt, q, q + 1);
-        if (y + 1 < H && S[q + W] == 1) uf_union(Lt, q, q + W);
+        own[i] = Lt[q];
+        if (y > 0 && S[q - W] == 1) cand[i][0] = Lt[q - W];
+        if (x > 0 && S[q - 1] == 1) cand[i][1] = Lt[q - 1];
+        if (x + 1 < W && S[q + 1] == 1) cand[i][2] = Lt[q + 1];
+        if (y + 1 < H && S[q + W] == 1) cand[i][3] = Lt[q + W];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (own[i] < 0) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = cand[i][k];
+            if (c < 0) continue;
+            bool dup = false;
+#pragma unroll
+            for (int j = 0; j < k; ++j) dup |= (cand[i][j] == c);
+            if (i > 0 && own[i - 1] == own[i]) {  // the previous pixel of the same hole already joined this one
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dup |= (cand[i - 1][j] == c);
+            }
+            if (!dup) uf_union(Lt, own[i], c);
+        }
     }
 }
 
