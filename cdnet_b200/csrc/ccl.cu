@@ -253,7 +253,7 @@ __device__ __forceinline__ void sunion(int* P, int a, int b) {
 template <bool EQ, int CONN>
 __global__ void __launch_bounds__(1024) k_ccl_strip(const uint8_t* __restrict__ mask, int* __restrict__ L,
                                                     int* __restrict__ zero1, int* __restrict__ zero2, int H, int W, int SR) {
-    extern __shared__ int s_par[];
+    CDNET_DYN_SHARED(int, s_par);
     uint8_t* s_m = (uint8_t*)(s_par + SR * W);
     const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
     const int y0 = blockIdx.x * SR;

@@ -13,6 +13,10 @@ extern int g_prof_on;                  // api.cu: per-launch CUDA-event timing (
 void prof_begin(const char* name, cudaStream_t st);
 void prof_end(cudaStream_t st);
 
+// CDNET_LAUNCH / CDNET_DYN_SHARED / CDNET_KEEP_IN_REG64 are the only three places where the sources use
+// syntax a host compiler cannot parse; tests/simt/ (a SIMT emulator used by the CPU test tier to execute the
+// kernels' logic, never by the product) pre-defines them.
+#ifndef CDNET_LAUNCH
 #define CDNET_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
     do {                                                                          \
         if (::cdnet::g_prof_on) ::cdnet::prof_begin(#kernel, (stream));           \
@@ -20,6 +24,11 @@ void prof_end(cudaStream_t st);
         if (::cdnet::g_prof_on) ::cdnet::prof_end((stream));                      \
         ++::cdnet::g_launches;                                                    \
     } while (0)
+// dynamic shared memory of the running block, viewed as `type name[]`
+#define CDNET_DYN_SHARED(type, name) extern __shared__ type name[]
+// pins a 64-bit value in one register pair (stops ptxas from rematerialising it per use)
+#define CDNET_KEEP_IN_REG64(x) asm volatile("" : "+l"(x))
+#endif
 
 #define CDNET_CUDA_OK(expr)                                 \
     do {                                                    \

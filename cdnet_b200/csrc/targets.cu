@@ -112,7 +112,7 @@ __device__ __forceinline__ double ray_reach(const int* __restrict__ L, int H, in
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
     double lo = 0.0, half = 500.0;
     const double fi = (double)i, fj = (double)j;
-    asm volatile("" : "+l"(L));  // keep the tile base in one register pair: one IMAD.WIDE per probe
+    CDNET_KEEP_IN_REG64(L);  // keep the tile base in one register pair: one IMAD.WIDE per probe
 #pragma unroll
     for (int it = 0; it < 30; ++it) {
         const double mid = __dadd_rn(lo, half);
@@ -134,7 +134,7 @@ __device__ __forceinline__ double ray_reach_axis(const int* __restrict__ L, int 
     const double kMagic = 6755399441055744.0;
     double lo = 0.0, half = 500.0;
     const double fc = (double)c;
-    asm volatile("" : "+l"(L));
+    CDNET_KEEP_IN_REG64(L);
 #pragma unroll
     for (int it = 0; it < 30; ++it) {
         const double mid = __dadd_rn(lo, half);

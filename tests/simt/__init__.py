@@ -1,0 +1,136 @@
+"""SIMT emulator: runs the kernel sources of cdnet_b200/csrc on the host for the CPU test tier.
+
+TEST INFRASTRUCTURE ONLY.  `emulated_api()` builds tests/simt/_build/libcdnet_b200_simt.so (g++; the same
+.cu files, compiled against shims of the CUDA headers, see include/cuda_runtime.h and simt_runtime.cpp)
+and yields cdnet_b200.api re-pointed at it for the duration of the `with` block: the emulated library's
+"device pointers" are host pointers, so the host layer is given CPU tensors, no-op streams/events and
+unpinned staging buffers.  Everything else -- argument marshalling, workspace sizing, status handling,
+dtype conventions, every kernel -- is the product's own code.
+
+The product never does any of this: cdnet_b200 has no CPU path and raises CdnetError without a GPU
+(tests/test_cabi_symbols.py checks that the package does not reference tests/ or oracle/).
+"""
+import contextlib
+import ctypes
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        from . import build as _build
+        from cdnet_b200 import _cabi
+        L = ctypes.CDLL(_build.build())
+        for name, (res, args) in _cabi.SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class _NoStream(object):
+    cuda_stream = None
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, s):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _NoEvent(object):
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, s=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _CudaProxy(object):
+    Stream, Event = _NoStream, _NoEvent
+
+    def __init__(self):
+        self._cur = _NoStream()
+
+    def is_available(self):
+        return True
+
+    def current_device(self):
+        return 0
+
+    def current_stream(self, device=None):
+        return self._cur
+
+    def stream(self, s):
+        return contextlib.nullcontext()
+
+    def synchronize(self, device=None):
+        pass
+
+    def set_device(self, d):
+        pass
+
+
+class _TorchProxy(object):
+    """`torch` as seen by cdnet_b200's host layer under emulation: no pinning, no CUDA streams"""
+
+    def __init__(self, torch):
+        self._t = torch
+        self.cuda = _CudaProxy()
+
+    def __getattr__(self, name):
+        return getattr(self._t, name)
+
+    def device(self, kind, index=None):
+        return self._t.device("cpu")
+
+    def empty(self, *a, **k):
+        k.pop("pin_memory", None)
+        return self._t.empty(*a, **k)
+
+    def zeros(self, *a, **k):
+        k.pop("pin_memory", None)
+        return self._t.zeros(*a, **k)
+
+
+@contextlib.contextmanager
+def emulated_api():
+    import torch
+    from cdnet_b200 import _cabi, api, metrics, sharded
+    L = load()
+    cpu = torch.device("cpu")
+    proxy = _TorchProxy(torch)
+    mods = [api, metrics]
+    saved = [(_cabi, "_lib", _cabi._lib), (api, "_device", api._device), (metrics, "_device", metrics._device),
+             (torch.Tensor, "record_stream", torch.Tensor.record_stream),
+             (sharded.CudaBackend, "_st", sharded.CudaBackend._st)]
+    saved += [(m, "torch", m.torch) for m in mods if hasattr(m, "torch")]
+    plans = dict(getattr(api, "_plans", {}))
+    try:
+        _cabi._lib = L
+        api._device = metrics._device = lambda device=None: cpu
+        sharded.CudaBackend._st = lambda self: None
+        torch.Tensor.record_stream = lambda self, s: None
+        for m in mods:
+            if hasattr(m, "torch"):
+                m.torch = proxy
+        api._plans.clear()
+        api._ws_cache.clear()
+        yield api
+    finally:
+        for obj, name, val in saved:
+            setattr(obj, name, val)
+        api._plans.clear()
+        api._plans.update(plans)
+        api._ws_cache.clear()

@@ -43,6 +43,8 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+                # the SIMT emulator (tests/simt) is test infrastructure too: the product must not load it
+                assert "import simt" not in txt and "from simt" not in txt and "_simt.so" not in txt, f
 
 
 def test_no_cpu_fallback_without_cuda():

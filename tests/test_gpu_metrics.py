@@ -6,18 +6,12 @@ import io
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import load_golden, to_dev
 from metrics_numpy_pairs import pair_arrays
 from test_metrics_host import cases, inputs, check_against_golden, same, _edge_inputs, _outcome, _same_outcome
 
-pytestmark = pytest.mark.gpu
-
-
-@pytest.fixture(scope="module")
-def M():
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
+@pytest.fixture
+def M(kernel_api):
     from cdnet_b200 import metrics
     return metrics
 
@@ -33,8 +27,8 @@ def test_pair_table_vs_numpy(M, H, W, n, dtype):
     import torch
     from cdnet_b200 import synth
     true, pred = synth.metric_pair(500 + H, H, W, n, 1)
-    t = torch.from_numpy(true.astype(dtype))[None].cuda()
-    p = torch.from_numpy(pred.astype(dtype))[None].cuda()
+    t = to_dev(M, torch.from_numpy(true.astype(dtype))[None])
+    p = to_dev(M, torch.from_numpy(pred.astype(dtype))[None])
     T = M.label_pairs_cuda(t, p)[0]
     rk, rc = _sorted_pairs(*pair_arrays(true, pred))
     got = (T.t.astype(np.uint64) << np.uint64(32)) | T.q.astype(np.uint64)
@@ -47,8 +41,8 @@ def test_pair_table_batch_and_small_cap(M):
     import torch
     from cdnet_b200 import synth
     pairs = [synth.metric_pair(600 + i, 120, 136, 15, i % 2) for i in range(5)]
-    t = torch.from_numpy(np.stack([a for a, _ in pairs])).cuda()
-    p = torch.from_numpy(np.stack([b for _, b in pairs])).cuda()
+    t = to_dev(M, torch.from_numpy(np.stack([a for a, _ in pairs])))
+    p = to_dev(M, torch.from_numpy(np.stack([b for _, b in pairs])))
     for cap in (None, 3):
         tabs = M.label_pairs_cuda(t, p, cap=cap)
         for (a, b), T in zip(pairs, tabs):
@@ -118,7 +112,7 @@ def test_metrics_after_postprocessing(M, cuda_api):
     pred = M.remap_label(lab)
     ref_pred = O.remap_label(z["dam_pp0_labels"])
     assert np.array_equal(pred, ref_pred)
-    res = M.instance_metrics_cuda(torch.from_numpy(gt)[None].cuda(), torch.from_numpy(pred)[None].cuda())[0]
+    res = M.instance_metrics_cuda(to_dev(M, torch.from_numpy(gt)[None]), to_dev(M, torch.from_numpy(pred)[None]))[0]
     with contextlib.redirect_stdout(io.StringIO()):
         ref_aji = O.get_fast_aji(gt, ref_pred)
     assert same([res["aji"], res["ana_FP"], res["ana_FN"], res["ana_less"], res["ana_more"]], list(ref_aji))

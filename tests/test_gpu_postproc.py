@@ -3,9 +3,7 @@ vectors generated from the verbatim reference, and vs the oracle restatement on 
 import numpy as np
 import pytest
 
-from conftest import load_golden
-
-pytestmark = pytest.mark.gpu
+from conftest import load_golden, to_dev
 
 
 def _inputs(meta):
@@ -15,30 +13,30 @@ def _inputs(meta):
     return d
 
 
-def test_ddm_golden(cuda_api):
+def test_ddm_golden(kernel_api):
     z, meta = load_golden("ddm")
     for key, cls in meta["cases"]:
-        out = cuda_api.generate_dd_map(z[key + "_in"], cls)
+        out = kernel_api.generate_dd_map(z[key + "_in"], cls)
         ref = z[key + "_out"]
         assert out.dtype == np.float32 and out.shape == ref.shape
         assert np.array_equal(out, ref, equal_nan=True), key
 
 
-def test_circshift_golden(cuda_api):
+def test_circshift_golden(kernel_api):
     z, meta = load_golden("ddm")
     for i, (d, s1, s2) in enumerate(meta["circshift"]):
-        out = cuda_api.circshift(z["cs_in"], d, s1, s2)
+        out = kernel_api.circshift(z["cs_in"], d, s1, s2)
         assert out.dtype == z["cs_in"].dtype
         assert np.array_equal(out, z["cs_%d" % i]), (d, s1, s2)
 
 
 @pytest.mark.parametrize("name", ["p_96x128", "p_200x150", "p_256", "p_333x517", "p_1000"])
 @pytest.mark.parametrize("postproc", [0, 1])
-def test_dam_postprocess_golden(cuda_api, name, postproc):
+def test_dam_postprocess_golden(kernel_api, name, postproc):
     z, meta = load_golden(name)
     d = _inputs(meta)
     prob = d["prob"].copy()
-    lab = cuda_api.dam_postprocess(prob, d["point"], d["dcm"], meta["direction_classes"], meta["min_area"],
+    lab = kernel_api.dam_postprocess(prob, d["point"], d["dcm"], meta["direction_classes"], meta["min_area"],
                                    meta["radius"], postproc)
     ref = z["dam_pp%d_labels" % postproc]
     assert str(lab.dtype) == str(z["dam_pp%d_dtype" % postproc])
@@ -48,50 +46,50 @@ def test_dam_postprocess_golden(cuda_api, name, postproc):
 
 @pytest.mark.parametrize("name", ["p_96x128", "p_256", "p_333x517"])
 @pytest.mark.parametrize("postproc", [0, 1])
-def test_plain_postprocess_golden(cuda_api, name, postproc):
+def test_plain_postprocess_golden(kernel_api, name, postproc):
     z, meta = load_golden(name)
     d = _inputs(meta)
-    lab = cuda_api.plain_postprocess(d["prob"].copy(), meta["min_area"], meta["radius"], postproc)
+    lab = kernel_api.plain_postprocess(d["prob"].copy(), meta["min_area"], meta["radius"], postproc)
     ref = z["plain_pp%d_labels" % postproc]
     assert str(lab.dtype) == str(z["plain_pp%d_dtype" % postproc])
     assert np.array_equal(lab, ref), "%d differing pixels" % int((lab != ref).sum())
 
 
-def test_process_golden(cuda_api):
+def test_process_golden(kernel_api):
     z, meta = load_golden("process")
     for key, shape in meta["cases"]:
         mask = np.unpackbits(z[key + "_in"])[:shape[0] * shape[1]].reshape(shape).astype(bool)
         for ms in (5, 10):
             src = mask.astype(np.uint8) * 255
-            out = cuda_api.process(src, "modelName", min_size=ms)
+            out = kernel_api.process(src, "modelName", min_size=ms)
             assert out.dtype == np.int32
             assert set(np.unique(src)) <= {0, 1}, "process() must binarise its input in place"
             assert np.array_equal(out, z["%s_ms%d" % (key, ms)]), (key, ms)
-        out = cuda_api.process(mask.astype(np.uint8) * 255, "unet", min_size=10)
+        out = kernel_api.process(mask.astype(np.uint8) * 255, "unet", min_size=10)
         assert np.array_equal(out, z["%s_unet" % key]), key
 
 
-def test_dam_mutates_prob_like_reference(cuda_api):
+def test_dam_mutates_prob_like_reference(kernel_api):
     from oracle import restate as O
     from cdnet_b200 import synth
     d = synth.postproc_inputs(3, 120, 90, 10)
     p_ref = d["prob"].copy()
     O.dam_postprocess(p_ref, d["point"], d["dcm"], 9, 20, 2, 0)
     p_gpu = d["prob"].copy()
-    cuda_api.dam_postprocess(p_gpu, d["point"], d["dcm"], 9, 20, 2, 0)
+    kernel_api.dam_postprocess(p_gpu, d["point"], d["dcm"], 9, 20, 2, 0)
     assert np.array_equal(p_ref.view(np.uint32), p_gpu.view(np.uint32))
 
 
-def test_dam_constant_direction_map_asserts(cuda_api):
+def test_dam_constant_direction_map_asserts(kernel_api):
     from cdnet_b200 import synth
     d = synth.postproc_inputs(3, 64, 64, 4)
     d["dcm"][3] = 0  # constant map -> NaN DDM -> the reference's assert fires (test_dam.py:535)
     with pytest.raises(AssertionError):
-        cuda_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 0)
+        kernel_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 0)
 
 
 @pytest.mark.parametrize("seed,H,W,n", [(201, 77, 131, 12), (202, 301, 299, 70), (203, 512, 384, 140)])
-def test_dam_postprocess_vs_oracle(cuda_api, seed, H, W, n):
+def test_dam_postprocess_vs_oracle(kernel_api, seed, H, W, n):
     """fresh seeds / ragged sizes: CUDA vs the oracle restatement run on the box's host"""
     from oracle import restate as O
     from cdnet_b200 import synth
@@ -99,11 +97,11 @@ def test_dam_postprocess_vs_oracle(cuda_api, seed, H, W, n):
     for cls in (9,):
         for pp in (0, 1):
             ref = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], cls, 20, 2, pp, literal=False)
-            lab = cuda_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], cls, 20, 2, pp)
+            lab = kernel_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], cls, 20, 2, pp)
             assert np.array_equal(lab, ref["pred_labeled"]), (seed, pp, int((lab != ref["pred_labeled"]).sum()))
 
 
-def test_primitives_vs_scipy(cuda_api):
+def test_primitives_vs_scipy(kernel_api):
     from scipy import ndimage as ndi
     from oracle import restate as O
     rng = np.random.default_rng(5)
@@ -113,34 +111,34 @@ def test_primitives_vs_scipy(cuda_api):
                     (64, 64, 0.0), (31, 33, 1.0), (7, 8, 0.6), (3, 12, 0.7), (50, 64, 0.58), (5, 2052, 0.6),
                     (9, 4100, 0.62), (4, 16500, 0.6), (3, 17001, 0.6)):
         m = rng.random((H, W)) < p
-        assert np.array_equal(cuda_api.label(m, connectivity=1), ndi.label(m)[0]), (H, W, "label4")
-        assert np.array_equal(cuda_api.label(m), O.label8(m)), (H, W, "label8")
-        assert np.array_equal(cuda_api.binary_fill_holes(m), ndi.binary_fill_holes(m)), (H, W, "fill")
-        assert np.array_equal(cuda_api.remove_small_objects(m, 7), O.remove_small_objects(m, 7)), (H, W, "rso")
+        assert np.array_equal(kernel_api.label(m, connectivity=1), ndi.label(m)[0]), (H, W, "label4")
+        assert np.array_equal(kernel_api.label(m), O.label8(m)), (H, W, "label8")
+        assert np.array_equal(kernel_api.binary_fill_holes(m), ndi.binary_fill_holes(m)), (H, W, "fill")
+        assert np.array_equal(kernel_api.remove_small_objects(m, 7), O.remove_small_objects(m, 7)), (H, W, "rso")
         if not m.all():
-            assert np.array_equal(cuda_api.distance_transform_edt(m), ndi.distance_transform_edt(m)), (H, W, "edt")
+            assert np.array_equal(kernel_api.distance_transform_edt(m), ndi.distance_transform_edt(m)), (H, W, "edt")
         lab = ndi.label(m)[0]
         for r in (1, 2):
-            assert np.array_equal(cuda_api.dilation(lab, radius=r), O.dilate(lab, O.disk(r))), (H, W, "dil", r)
-        assert np.array_equal(cuda_api.remove_small_objects(lab, 5), O.remove_small_objects(lab, 5))
+            assert np.array_equal(kernel_api.dilation(lab, radius=r), O.dilate(lab, O.disk(r))), (H, W, "dil", r)
+        assert np.array_equal(kernel_api.remove_small_objects(lab, 5), O.remove_small_objects(lab, 5))
 
 
-def test_batched_equals_single(cuda_api):
+def test_batched_equals_single(kernel_api):
     import torch
     from cdnet_b200 import synth
     tiles = [synth.postproc_inputs(300 + i, 96, 160, 12) for i in range(3)]
-    dcm = torch.from_numpy(np.stack([t["dcm"] for t in tiles])).cuda()
-    prob = torch.from_numpy(np.stack([t["prob"] for t in tiles])).cuda()
-    point = torch.from_numpy(np.stack([t["point"] for t in tiles])).cuda()
+    dcm = to_dev(kernel_api, torch.from_numpy(np.stack([t["dcm"] for t in tiles])))
+    prob = to_dev(kernel_api, torch.from_numpy(np.stack([t["prob"] for t in tiles])))
+    point = to_dev(kernel_api, torch.from_numpy(np.stack([t["point"] for t in tiles])))
     for pp in (0, 1):
-        out, status = cuda_api.dam_postprocess_cuda(dcm, prob.clone(), point, 9, 20, 2, pp)
+        out, status = kernel_api.dam_postprocess_cuda(dcm, prob.clone(), point, 9, 20, 2, pp)
         assert int(status.abs().sum()) == 0
         for i, t in enumerate(tiles):
-            single = cuda_api.dam_postprocess(t["prob"].copy(), t["point"], t["dcm"], 9, 20, 2, pp)
+            single = kernel_api.dam_postprocess(t["prob"].copy(), t["point"], t["dcm"], 9, 20, 2, pp)
             assert np.array_equal(out[i].cpu().numpy(), single)
 
 
-def test_wide_tile_pipeline_vs_oracle(cuda_api):
+def test_wide_tile_pipeline_vs_oracle(kernel_api):
     """W > 16384: the whole-slide fallback path (row-chunk init + row-tree merge) through the full pipeline"""
     from oracle import restate as O
     from cdnet_b200 import synth
@@ -150,28 +148,28 @@ def test_wide_tile_pipeline_vs_oracle(cuda_api):
     assert d["dcm"].shape[-1] == 17600
     for pp in (0, 1):
         ref = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp, literal=False)["pred_labeled"]
-        got = cuda_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
+        got = kernel_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
         assert np.array_equal(got, ref), (pp, int((got != ref).sum()))
 
 
-def test_dcm_voting2_vs_oracle(cuda_api):
+def test_dcm_voting2_vs_oracle(kernel_api):
     from oracle import restate as O
     rng = np.random.default_rng(11)
     dm = rng.integers(0, 9, size=(57, 83, 8)).astype(np.uint8)
-    got = cuda_api.DcmVoting2(dm)
+    got = kernel_api.DcmVoting2(dm)
     assert got.dtype == np.int64 and np.array_equal(got, O.dcm_voting2(dm))
 
 
-def test_direction_argmax_handoff(cuda_api):
+def test_direction_argmax_handoff(kernel_api):
     """device-resident hand-off == the reference's softmax / argmax done by torch (test_dam.py:984-1013)"""
     import torch
     g = torch.Generator(device="cpu").manual_seed(3)
     mask_logits = torch.randn((2, 3, 40, 48), generator=g)
     dir_logits = torch.randn((2, 9, 40, 48), generator=g)
-    prob, cls = cuda_api.direction_argmax_cuda(mask_logits.cuda(), dir_logits.cuda())
+    prob, cls = kernel_api.direction_argmax_cuda(to_dev(kernel_api, mask_logits), to_dev(kernel_api, dir_logits))
     for i in range(2):
-        p = torch.softmax(mask_logits[i].cuda(), dim=0)
-        d = torch.softmax(dir_logits[i].cuda(), dim=0)
+        p = torch.softmax(to_dev(kernel_api, mask_logits[i]), dim=0)
+        d = torch.softmax(to_dev(kernel_api, dir_logits[i]), dim=0)
         d[0] = d[0] * p[0]
         top2 = torch.topk(d, 2, dim=0).values
         clear = (top2[0] - top2[1]) > 1e-6   # an exact tie-break is a property of torch's kernels, not ours

@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+from conftest import to_dev
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
@@ -18,13 +18,13 @@ def _slide(seed, H, W, n, n_maps):
 
 @pytest.mark.parametrize("G", [2, 3, 4, 7])
 @pytest.mark.parametrize("n_maps", [8, 1])
-def test_sharded_equals_single_gpu(cuda_api, G, n_maps):
+def test_sharded_equals_single_gpu(kernel_api, G, n_maps):
     import torch
     from cdnet_b200 import sharded
     H, W = 612, 524
     dcm, prob, point = _slide(41, H, W, 230, n_maps)
-    single, status = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(prob)[None].cuda(),
-                                                   torch.from_numpy(point)[None].cuda(), 9, 20, 2, 0)
+    single, status = kernel_api.dam_postprocess_cuda(to_dev(kernel_api, torch.from_numpy(dcm)[None]), to_dev(kernel_api, torch.from_numpy(prob)[None]),
+                                                   to_dev(kernel_api, torch.from_numpy(point)[None]), 9, 20, 2, 0)
     assert int(status.sum()) == 0
     single = single[0].cpu().numpy()
     parts = sharded.row_partition(H, G)
@@ -36,7 +36,7 @@ def test_sharded_equals_single_gpu(cuda_api, G, n_maps):
     assert np.array_equal(got, single), int((got != single).sum())
 
 
-def test_sharded_equals_oracle(cuda_api):
+def test_sharded_equals_oracle(kernel_api):
     from cdnet_b200 import sharded
     from oracle import restate as O
     H, W = 300, 280
@@ -49,7 +49,7 @@ def test_sharded_equals_oracle(cuda_api):
     assert np.array_equal(got, ref)
 
 
-def test_single_map_variant_vs_oracle(cuda_api):
+def test_single_map_variant_vs_oracle(kernel_api):
     """n_maps = 1 (test_dam.py:499-502) through the unsharded C ABI"""
     import torch
     from oracle import restate as O
@@ -57,12 +57,12 @@ def test_single_map_variant_vs_oracle(cuda_api):
     d = synth.postproc_inputs(43, 200, 240, 30)
     dcm = d["dcm"][:1].copy()
     ref = O.dam_postprocess(d["prob"].copy(), d["point"], dcm, 9, 20, 2, 0, literal=False)["pred_labeled"]
-    out, _ = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(d["prob"])[None].cuda(),
-                                           torch.from_numpy(d["point"])[None].cuda(), 9, 20, 2, 0)
+    out, _ = kernel_api.dam_postprocess_cuda(to_dev(kernel_api, torch.from_numpy(dcm)[None]), to_dev(kernel_api, torch.from_numpy(d["prob"])[None]),
+                                           to_dev(kernel_api, torch.from_numpy(d["point"])[None]), 9, 20, 2, 0)
     assert np.array_equal(out[0].cpu().numpy(), ref)
 
 
-def test_sharded_wide_slide(cuda_api):
+def test_sharded_wide_slide(kernel_api):
     """W > 16384 (what a 40 000-wide slide uses): shards == single GPU"""
     import torch
     from cdnet_b200 import sharded, synth
@@ -70,8 +70,8 @@ def test_sharded_wide_slide(cuda_api):
     d = {k: np.ascontiguousarray(np.concatenate([base[k]] * 16, axis=-1)) for k in ("dcm", "prob", "point")}
     H, W = 30, d["dcm"].shape[-1]
     dcm = d["dcm"][:1].copy()
-    single, _ = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(d["prob"])[None].cuda(),
-                                              torch.from_numpy(d["point"])[None].cuda(), 9, 20, 2, 0)
+    single, _ = kernel_api.dam_postprocess_cuda(to_dev(kernel_api, torch.from_numpy(dcm)[None]), to_dev(kernel_api, torch.from_numpy(d["prob"])[None]),
+                                              to_dev(kernel_api, torch.from_numpy(d["point"])[None]), 9, 20, 2, 0)
     parts = sharded.row_partition(H, 3)
     shards = [dict(dcm=dcm[:, a:b].copy(), prob=d["prob"][:, a:b].copy(), point=d["point"][:, a:b].copy()) for a, b in parts]
     outs = sharded.postprocess_slide(shards, sharded.SimComm(3), H, W, sharded.CudaBackend(), 9, 20, 2)
@@ -80,7 +80,7 @@ def test_sharded_wide_slide(cuda_api):
 
 
 @pytest.mark.parametrize("seed,H,W,G", [(51, 64, 40, 8), (52, 97, 132, 6), (54, 120, 64, 7)])
-def test_sharded_thin_shards(cuda_api, seed, H, W, G):
+def test_sharded_thin_shards(kernel_api, seed, H, W, G):
     """thin shards: components and holes that cross several seams (device-side seam rounds)"""
     import torch
     from cdnet_b200 import sharded
@@ -91,8 +91,8 @@ def test_sharded_thin_shards(cuda_api, seed, H, W, G):
     snake = ((yy // 3) % 2 == 0) & (xx > 2) & (xx < W - 3)
     link = ((yy % 6) == 3) & (xx >= W - 6) & (xx < W - 3) | ((yy % 6) == 0) & (xx > 2) & (xx <= 5) & (yy > 0)
     prob[1][(snake | link) & (rng.random((H, W)) < 0.97)] += np.float32(3.0)
-    single, _ = cuda_api.dam_postprocess_cuda(torch.from_numpy(dcm)[None].cuda(), torch.from_numpy(prob)[None].cuda(),
-                                              torch.from_numpy(point)[None].cuda(), 9, 20, 2, 0)
+    single, _ = kernel_api.dam_postprocess_cuda(to_dev(kernel_api, torch.from_numpy(dcm)[None]), to_dev(kernel_api, torch.from_numpy(prob)[None]),
+                                              to_dev(kernel_api, torch.from_numpy(point)[None]), 9, 20, 2, 0)
     parts = sharded.row_partition(H, G)
     shards = [dict(dcm=dcm[:, a:b].copy(), prob=prob[:, a:b].copy(), point=point[:, a:b].copy()) for a, b in parts]
     outs = sharded.postprocess_slide(shards, sharded.SimComm(G), H, W, sharded.CudaBackend(), 9, 20, 2)

@@ -3,9 +3,7 @@ ABI vs goldens generated from the verbatim reference and vs the oracle restateme
 import numpy as np
 import pytest
 
-from conftest import load_golden
-
-pytestmark = pytest.mark.gpu
+from conftest import load_golden, to_dev
 
 # The reference's float32 angle goes through the host libm / SVML atan2f, which is not correctly
 # rounded and differs between hosts by a few ulp; the direction CLASS can therefore legitimately
@@ -41,13 +39,13 @@ def _check_direction(got, ref, lab, n, name):
 
 @pytest.mark.parametrize("name", ["t_64_single", "t_128", "t_256", "t_250x300_dense", "t_500", "t_1000",
                                   "t_128x160_threeclass", "t_128_d16", "t_256_d16"])
-def test_label_encoding_golden(cuda_api, name):
+def test_label_encoding_golden(kernel_api, name):
     try:
         z, meta = load_golden(name)
     except FileNotFoundError:
         pytest.skip("golden %s not generated" % name)
     lab = _labels(meta, three_class="threeclass" in name)
-    enc = cuda_api.LabelEncoding(3, 1, 1, num_classes=meta["num_classes"])
+    enc = kernel_api.LabelEncoding(3, 1, 1, num_classes=meta["num_classes"])
     res = enc((None, None, lab))
     assert len(res) == 5
     tern = np.asarray(res[2])
@@ -60,26 +58,26 @@ def test_label_encoding_golden(cuda_api, name):
     _check_direction(res[4], z["direction"].astype(np.int64), lab, meta["num_classes"], name)
 
 
-def test_centre_points_golden(cuda_api):
+def test_centre_points_golden(kernel_api):
     import torch
     z, meta = load_golden("centre")
     ids = z["ids"]
-    c = cuda_api.center_points_cuda(torch.from_numpy(ids)[None].cuda(), int(ids.max()))[0].cpu().numpy()
+    c = kernel_api.center_points_cuda(to_dev(kernel_api, torch.from_numpy(ids)[None]), int(ids.max()))[0].cpu().numpy()
     for k in range(1, meta["n"] + 1):
         assert list(c[k]) == list(z["c_%d" % k]), k
         m = (ids == k).astype(np.int64)
-        assert cuda_api.get_centerpoint2(m, m.shape[0], m.shape[1]) == list(z["c_%d" % k])
+        assert kernel_api.get_centerpoint2(m, m.shape[0], m.shape[1]) == list(z["c_%d" % k])
 
 
 @pytest.mark.parametrize("seed,H,W,n,classes", [(401, 97, 143, 14, 8), (402, 256, 200, 60, 8), (403, 180, 180, 30, 16)])
-def test_label_encoding_vs_oracle(cuda_api, seed, H, W, n, classes):
+def test_label_encoding_vs_oracle(kernel_api, seed, H, W, n, classes):
     import torch
     from oracle import restate as O
     from cdnet_b200 import synth
     ids = synth.instance_map(seed, H, W, n)
     lab = synth.as_uint8_label(ids)
     tern, point, direction, parts = O.label_encoding(lab, num_classes=classes, literal=False, return_parts=True)
-    g = cuda_api.encode_targets_cuda(torch.from_numpy(lab[:, :, 0].copy())[None].cuda(), True, classes,
+    g = kernel_api.encode_targets_cuda(to_dev(kernel_api, torch.from_numpy(lab[:, :, 0].copy())[None]), True, classes,
                                      want_inst=True, want_dir=True)
     assert np.array_equal(g[0][0].cpu().numpy(), tern)
     assert np.array_equal(g[3][0].cpu().numpy(), parts["inst"])
@@ -88,7 +86,7 @@ def test_label_encoding_vs_oracle(cuda_api, seed, H, W, n, classes):
     _check_direction(g[2][0].cpu().numpy(), direction, lab, classes, "seed%d" % seed)
 
 
-def test_label_encoding_edge_cases(cuda_api):
+def test_label_encoding_edge_cases(kernel_api):
     from oracle import restate as O
     # empty tile, tiny nucleus (< 5 px), nucleus on the frame
     H, W = 48, 56
@@ -101,32 +99,32 @@ def test_label_encoding_edge_cases(cuda_api):
     for name, ids in cases.items():
         lab = np.repeat(ids[:, :, None], 3, axis=2)
         ref = O.label_encoding(lab, literal=False)
-        res = cuda_api.LabelEncoding(3, 1, 1, num_classes=8)((None, None, lab))
+        res = kernel_api.LabelEncoding(3, 1, 1, num_classes=8)((None, None, lab))
         assert np.array_equal(np.asarray(res[2]), ref[0]), name
         assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), name
         assert np.array_equal(res[4], ref[2]), name
 
 
-def test_encode_targets_plan_host_buffers(cuda_api):
+def test_encode_targets_plan_host_buffers(kernel_api):
     """The pinned host-buffer plan (chunked copy/compute overlap) returns what the one-shot call returns."""
     import torch
     from cdnet_b200 import synth
     B, H, W = 5, 120, 136
     ids = np.stack([synth.as_uint8_label(synth.instance_map(700 + i, H, W, 12))[:, :, 0] for i in range(B)])
-    ref = [t.cpu().numpy() for t in cuda_api.encode_targets_cuda(torch.from_numpy(ids).cuda(), True, 8)]
-    plan = cuda_api.EncodeTargetsPlan(B, H, W, 8)
+    ref = [t.cpu().numpy() for t in kernel_api.encode_targets_cuda(to_dev(kernel_api, torch.from_numpy(ids)), True, 8)]
+    plan = kernel_api.EncodeTargetsPlan(B, H, W, 8)
     for chunk in (2, 32):
         plan.h_ids[:] = ids
         plan.h_ternary[:] = 7
         plan.launch(chunk=chunk)
-        torch.cuda.synchronize()
+        kernel_api.torch.cuda.synchronize()
         assert np.array_equal(plan.h_ternary, ref[0])
         assert np.array_equal(plan.h_point.view(np.uint16), ref[1].view(np.uint16))
         assert np.array_equal(plan.h_direction, ref[2])
     # golden anchor for one tile through the plan
     z, meta = load_golden("t_128")
     lab = _labels(meta)
-    p1 = cuda_api.EncodeTargetsPlan(1, meta["H"], meta["W"], meta["num_classes"])
+    p1 = kernel_api.EncodeTargetsPlan(1, meta["H"], meta["W"], meta["num_classes"])
     p1.h_ids[0] = lab[:, :, 0]
     tern, point, direction = p1.run()
     assert np.array_equal(tern[0], z["ternary"])
