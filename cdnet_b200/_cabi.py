@@ -75,7 +75,7 @@ SIGNATURES = {
 }
 
 E_BADARG, E_WORKSPACE = 1, 2
-S_DDM_CONSTANT, S_WS_OVERFLOW = 1, 2
+S_DDM_CONSTANT, S_WS_OVERFLOW, S_NO_BACKGROUND = 1, 2, 16
 
 _lib = None
 

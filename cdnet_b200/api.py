@@ -160,8 +160,12 @@ def edt_cuda(mask, return_squared=False):
     return (dist, d2) if return_squared else dist
 
 
-def process_cuda(pred01, min_size=10, ws=True):
-    """pred01 uint8 [B,H,W] already binarised -> int32 labels (postproc_other.process)."""
+_NO_BACKGROUND_MSG = "list.remove(x): x not in list"  # what postproc_other.py:19 raises on a mask without background
+
+
+def process_cuda(pred01, min_size=10, ws=True, return_status=False):
+    """pred01 uint8 [B,H,W] already binarised -> int32 labels (postproc_other.process).  With ws=True a tile
+    without any background pixel sets CDNET_S_NO_BACKGROUND in status[b] (the reference raises ValueError)."""
     L = _cabi.lib()
     dev = _device(pred01.device)
     m = _cu8(pred01)
@@ -172,7 +176,7 @@ def process_cuda(pred01, min_size=10, ws=True):
     wsb = _workspace(nb, dev)
     check(L.cdnet_ws_postproc(_ptr(m), _ptr(out), _ptr(status), B, H, W, int(min_size), 1 if ws else 0, _ptr(wsb),
                               wsb.numel(), _stream()), "cdnet_ws_postproc")
-    return out
+    return (out, status) if return_status else out
 
 
 def dam_postprocess_cuda(dcm, prob, point, direction_classes=9, min_area=20, radius=2, postproc=0,
@@ -321,6 +325,8 @@ def process(pred, model_mode, min_size=10, ws=True):
     pred[~hi] = 0
     if model_mode == "unet":
         ws = False
+    if ws and hi.all():
+        raise ValueError(_NO_BACKGROUND_MSG)  # gen_inst_dst_map: `nuc_list.remove(0)` (postproc_other.py:18-19)
     return process_cuda(_h2d(hi.astype(np.uint8))[None], min_size, ws)[0].cpu().numpy()
 
 
@@ -400,6 +406,8 @@ class DamPostprocessPlan(object):
         if (self.h_status & _cabi.S_DDM_CONSTANT).any():
             # the reference: NaN direction-difference map -> `assert(np.min(enhanced_boundary) >= 0)` fails
             raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
+        if (self.h_status & _cabi.S_NO_BACKGROUND).any():
+            raise ValueError(_NO_BACKGROUND_MSG)  # process() on an all-inside tile (postproc_other.py:18-19)
         return self.h_labels
 
 
@@ -443,7 +451,9 @@ def plain_postprocess(prob_maps, min_area=20, radius=2, postproc=0, model_name="
     if model_name in ("unet", "micronet", "dcan") and int(postproc) == 1:
         raise NotImplementedError("postproc=1 with model_mode %r is out of scope" % model_name)
     prob = _h2d(np.asarray(prob_maps), np.float32)[None]
-    out, _ = plain_postprocess_cuda(prob, min_area, radius, postproc, multi_class)
+    out, status = plain_postprocess_cuda(prob, min_area, radius, postproc, multi_class)
+    if int(status[0]) & _cabi.S_NO_BACKGROUND:
+        raise ValueError(_NO_BACKGROUND_MSG)  # process() on an all-inside tile (postproc_other.py:18-19)
     return out[0].cpu().numpy()
 
 

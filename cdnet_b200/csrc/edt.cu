@@ -14,7 +14,7 @@
 
 namespace cdnet {
 
-constexpr int kInf = 1 << 30;
+constexpr int kInf = kEdtInf;
 
 __global__ void __launch_bounds__(256) k_edt_cols(const uint8_t* __restrict__ mask, int* __restrict__ g2, int H, int W) {
     const int x = blockIdx.x * 64 + threadIdx.x;

@@ -35,5 +35,7 @@ size_t ws_process_workspace(int B, int H, int W);
 int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W, int min_size,
                       int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st);
 int edt_launch(const uint8_t* mask, int32_t* d2, int32_t* g2, int B, int H, int W, cudaStream_t st);
+// squared distance reported where a tile has no background pixel at all (edt.cu)
+constexpr int kEdtInf = 1 << 30;
 
 }  // namespace cdnet

@@ -33,10 +33,12 @@ static inline dim3 px_block() { return dim3(kBX, kBY); }
     const int lane = threadIdx.x & 31;                         \
     (void)lane; (void)p; (void)tile; (void)inb;
 
-// L <- roots of pred's 4-conn components; maxd2[root] = max d2 over the component
+// L <- roots of pred's 4-conn components; maxd2[root] = max d2 over the component.  A squared distance of
+// kEdtInf means the tile has no background pixel: the reference's gen_inst_dst_map raises there
+// (postproc_other.py:18-19), reported as CDNET_S_NO_BACKGROUND.
 __global__ void __launch_bounds__(kBX* kBY) k_comp_stats(const uint8_t* __restrict__ pred, int* __restrict__ L,
                                                          const int* __restrict__ d2, int* __restrict__ maxd2,
-                                                         int H, int W) {
+                                                         int32_t* __restrict__ status, int H, int W) {
     PX_COORDS
     int r = -1, d = 0;
     if (inb && pred[tile + p]) {
@@ -45,7 +47,11 @@ __global__ void __launch_bounds__(kBX* kBY) k_comp_stats(const uint8_t* __restri
         Lt[p] = r;
         d = d2[tile + p];
     }
-    if (r >= 0) atomicMax(maxd2 + tile + r, d);
+    if (r >= 0) {
+        atomicMax(maxd2 + tile + r, d);
+        if (d >= kEdtInf && status && !(__ldcg(status + b) & CDNET_S_NO_BACKGROUND))
+            atomicOr(status + b, CDNET_S_NO_BACKGROUND);
+    }
 }
 
 // dist = uint8(255 * (sqrt(d2) / sqrt(max d2)))  (postproc_other.py:24-26, f64, truncating);
@@ -377,7 +383,6 @@ __global__ void k_state_mask(const uint8_t* __restrict__ state, uint8_t* __restr
 
 int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W, int min_size,
                       int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st) {
-    (void)status;
     const size_t n = (size_t)B * H * W;
     if (n >= 4294967296ull) return CDNET_E_BADARG;  // root list holds 32-bit batch-global pixel indices
     Arena ar(ws, ws_bytes);
@@ -409,7 +414,7 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     rc = edt_launch(pred01, C, Bp, B, H, W, st);
     if (rc) return rc;
     CDNET_CUDA_OK(cudaMemsetAsync(D, 0, n * 4, st));
-    CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, H, W);
+    CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, status, H, W);
     // 2. uint8 distance, its negation, markers (:25-26, :39-41, :47)
     CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, H, W);
     // 3. fill holes, cross erosion, label, remove small (:42-46)

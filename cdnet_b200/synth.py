@@ -195,6 +195,37 @@ def postproc_inputs(seed, H, W, n_target=None, n_dir=8, flip_frac=0.02):
             "ids": ids}
 
 
+def postproc_edge_cases():
+    """(name, dict(dcm, prob, point)) degenerate post-processing inputs: point map
+    without a positive maximum, no foreground, only foreground, unknown class ids, exact probability ties,
+    tiles down to 1 x 1, a single nucleus."""
+    base = postproc_inputs(901, 72, 88, 8)
+
+    def cp():
+        return {k: base[k].copy() for k in ("dcm", "prob", "point")}
+    c = cp(); c["point"][:] = 0
+    yield "point_all_zero", c
+    c = cp(); c["point"][:] = -1.5
+    yield "point_all_negative", c
+    c = cp(); c["point"] = -np.abs(c["point"]) - np.float32(0.25)
+    yield "point_negative_varied", c
+    c = cp(); c["point"][:] = 3.0
+    yield "point_constant_positive", c
+    c = cp(); c["prob"][0] = 5; c["prob"][1] = 0; c["prob"][2] = 0
+    yield "all_background", c
+    c = cp(); c["prob"][0] = 0; c["prob"][1] = 5; c["prob"][2] = 0
+    yield "all_inside", c
+    c = cp(); c["dcm"][:, 10:30, 10:40] = 200
+    yield "unknown_class_ids", c
+    c = cp(); c["prob"][:, :, :] = 0.25
+    yield "prob_ties", c
+    for H, W in ((1, 1), (1, 37), (41, 1), (2, 2), (3, 5), (8, 4)):
+        d = postproc_inputs(902, max(H, 24), max(W, 24), 3)
+        yield "tiny_%dx%d" % (H, W), {k: np.ascontiguousarray(d[k][..., :H, :W]) for k in ("dcm", "prob", "point")}
+    d = postproc_inputs(903, 64, 64, 1)
+    yield "single_nucleus", {k: d[k] for k in ("dcm", "prob", "point")}
+
+
 def contiguous_ids(ids):
     """ids renumbered 1..N in ascending order of the old id (what stats_utils.remap_label does), int32."""
     u = np.unique(ids)

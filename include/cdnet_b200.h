@@ -34,6 +34,9 @@ extern "C" {
 #define CDNET_S_WS_OVERFLOW 2  /* watershed queue overflow (cannot happen with the sizes from
                                   *_workspace_bytes; kept as a guard) */
 
+#define CDNET_S_NO_BACKGROUND 16 /* watershed path: the mask has no background pixel; the reference's
+                                  * gen_inst_dst_map raises ValueError there (`nuc_list.remove(0)`,
+                                  * postproc_other.py:18-19) */
 #define CDNET_S_PAIR_OVERFLOW 4 /* cdnet_label_pairs: more distinct (true, pred) pairs than `cap` */
 #define CDNET_S_PAIR_RANGE 8    /* cdnet_label_pairs: a label id is negative or above INT32_MAX */
 

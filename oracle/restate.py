@@ -264,6 +264,10 @@ def process(pred, model_mode="modelName", min_size=10, ws=True, literal=True, or
             raise NotImplementedError("micronet tail (postproc_other.py:56-68) is out of scope")
         return out
     comps = label4(pred)
+    if comps.size == 0 or comps.min() != 0:
+        # postproc_other.py:18-19: `nuc_list = list(np.unique(ann)); nuc_list.remove(0)` -- a mask without
+        # any background pixel makes list.remove raise
+        raise ValueError("list.remove(x): x not in list")
     dist = inst_dist_map(comps, literal=literal)
     marker = dist > 125
     marker = ndi.binary_fill_holes(marker)

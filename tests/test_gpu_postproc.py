@@ -101,6 +101,48 @@ def test_dam_postprocess_vs_oracle(kernel_api, seed, H, W, n):
             assert np.array_equal(lab, ref["pred_labeled"]), (seed, pp, int((lab != ref["pred_labeled"]).sum()))
 
 
+def _outcome(fn):
+    try:
+        return ("ok", fn())
+    except (AssertionError, ValueError) as e:
+        return (type(e).__name__, None)
+
+
+def test_dam_postprocess_edge_cases(kernel_api):
+    """degenerate tiles (synth.postproc_edge_cases; the oracle is pinned to the verbatim reference on the same
+    cases in tests/test_oracle_vs_reference.py): same labels, or the same exception type as the reference"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    for name, c in synth.postproc_edge_cases():
+        for pp in (0, 1):
+            ref = _outcome(lambda: O.dam_postprocess(c["prob"].copy(), c["point"], c["dcm"], 9, 20, 2, pp,
+                                                     literal=False)["pred_labeled"])
+            got = _outcome(lambda: kernel_api.dam_postprocess(c["prob"].copy(), c["point"], c["dcm"], 9, 20, 2, pp))
+            assert got[0] == ref[0], (name, pp, got[0], ref[0])
+            if ref[1] is not None:
+                assert got[1].dtype == ref[1].dtype and np.array_equal(got[1], ref[1]), (name, pp)
+            ref = _outcome(lambda: O.plain_postprocess(c["prob"].copy(), 20, 2, pp, literal=False)["pred_labeled"])
+            got = _outcome(lambda: kernel_api.plain_postprocess(c["prob"].copy(), 20, 2, pp))
+            assert got[0] == ref[0], (name, pp, "plain", got[0], ref[0])
+            if ref[1] is not None:
+                assert got[1].dtype == ref[1].dtype and np.array_equal(got[1], ref[1]), (name, pp, "plain")
+
+
+def test_process_all_foreground_raises(kernel_api):
+    """postproc_other.py:18-19: `nuc_list.remove(0)` raises ValueError when the mask has no background pixel"""
+    import torch
+    full = np.full((24, 40), 255, np.uint8)
+    with pytest.raises(ValueError):
+        kernel_api.process(full.copy(), "modelName")
+    assert kernel_api.process(full.copy(), "unet").max() == 1  # the no-watershed head has no such list
+    # device-resident batch: the status bit marks exactly the tile without background
+    m = np.ones((3, 24, 40), np.uint8)
+    m[0, 3, 4] = 0
+    m[2, :, 20:] = 0
+    _, st = kernel_api.process_cuda(to_dev(kernel_api, torch.from_numpy(m)), 10, True, return_status=True)
+    assert [int(v) & 16 for v in st.cpu().numpy()] == [0, 16, 0]
+
+
 def test_primitives_vs_scipy(kernel_api):
     from scipy import ndimage as ndi
     from oracle import restate as O

@@ -49,6 +49,36 @@ def test_postprocess_and_process(ref):
     assert np.array_equal(ref.process(m.copy(), "modelName", min_size=5), O.process(m.copy(), "modelName", min_size=5))
 
 
+def _outcome(fn):
+    try:
+        return ("ok", fn())
+    except (AssertionError, ValueError) as e:
+        return (type(e).__name__, None)
+
+
+def test_postprocess_edge_cases(ref):
+    """degenerate tiles: the restatement returns what the verbatim reference returns, or raises the same
+    exception type (AssertionError test_dam.py:535, ValueError postproc_other.py:19)"""
+    import warnings
+    for name, c in synth.postproc_edge_cases():
+        for pp in (0, 1):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                r = _outcome(lambda: ref.dam_postprocess(c["prob"].copy(), c["point"], c["dcm"], 9, 20, 2, pp)["pred_labeled"])
+                o = _outcome(lambda: O.dam_postprocess(c["prob"].copy(), c["point"], c["dcm"], 9, 20, 2, pp)["pred_labeled"])
+                o2 = _outcome(lambda: O.dam_postprocess(c["prob"].copy(), c["point"], c["dcm"], 9, 20, 2, pp,
+                                                        literal=False)["pred_labeled"])
+            for got in (o, o2):
+                assert got[0] == r[0], (name, pp, got[0], r[0])
+                if r[1] is not None:
+                    assert got[1].dtype == r[1].dtype and np.array_equal(got[1], r[1]), (name, pp)
+            r = _outcome(lambda: ref.plain_postprocess(c["prob"].copy(), 20, 2, pp)["pred_labeled"])
+            o = _outcome(lambda: O.plain_postprocess(c["prob"].copy(), 20, 2, pp, literal=False)["pred_labeled"])
+            assert o[0] == r[0], (name, pp, "plain", o[0], r[0])
+            if r[1] is not None:
+                assert o[1].dtype == r[1].dtype and np.array_equal(o[1], r[1]), (name, pp, "plain")
+
+
 def test_label_encoding(ref):
     lab = synth.as_uint8_label(synth.instance_map(779, 110, 130, 12))
     res = ref.LabelEncoding(3, 1, 1)((None, None, lab))
