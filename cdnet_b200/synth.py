@@ -226,6 +226,43 @@ def postproc_edge_cases():
     yield "single_nucleus", {k: d[k] for k in ("dcm", "prob", "point")}
 
 
+def label_edge_cases(H=48, W=56):
+    """(name, uint8 [H,W] id plane) degenerate inputs of the target transform: empty, one id everywhere, binary
+    masks (three-class branch), nuclei below the 5-pixel limit, touching / diagonal pairs, 1- and 3-pixel lines,
+    nuclei on the frame, holes, nesting, one id on two blobs, a tile without background, salt-and-pepper ids."""
+    z = np.zeros((H, W), np.uint8)
+    yield "empty", z.copy()
+    a = z.copy(); a[:] = 9
+    yield "one_id_everywhere", a
+    a = z.copy(); a[10:30, 10:30] = 255
+    yield "binary_255", a
+    a = z.copy(); a[10:30, 10:30] = 100
+    yield "binary_100", a
+    a = z.copy(); a[10:12, 10:12] = 7
+    yield "tiny", a
+    a = z.copy(); a[10:12, 10:12] = 7; a[30:32, 30:33] = 9
+    yield "two_tiny", a
+    a = z.copy(); a[5:25, 5:25] = 3; a[5:25, 25:45] = 4
+    yield "touching_pair", a
+    a = z.copy(); a[5:25, 5:25] = 3; a[25:45, 25:45] = 4
+    yield "diagonal_pair", a
+    a = z.copy(); a[20, 5:50] = 3; a[30:40, 10:30] = 8
+    yield "line_1px", a
+    a = z.copy(); a[20:23, 5:50] = 3; a[30:40, 10:30] = 8
+    yield "line_3px", a
+    a = z.copy(); a[0:14, 0:17] = 3; a[30:48, 40:56] = 9; a[20:30, 20:33] = 200
+    yield "frame", a
+    a = z.copy(); a[8:40, 8:48] = 5; a[18:28, 20:34] = 0; a[2:6, 2:6] = 6
+    yield "ring_with_hole", a
+    a = z.copy(); a[8:40, 8:48] = 5; a[18:28, 20:34] = 7
+    yield "nested", a
+    a = z.copy(); a[4:20, 4:20] = 5; a[28:44, 30:50] = 5; a[24:27, 4:10] = 6
+    yield "same_id_two_blobs", a
+    yield "no_background_stripes", (np.arange(H * W).reshape(H, W) % 7 + 1).astype(np.uint8)
+    rng = np.random.default_rng(1)
+    yield "noise", (rng.random((H, W)) < 0.5).astype(np.uint8) * rng.integers(1, 5, (H, W)).astype(np.uint8)
+
+
 def contiguous_ids(ids):
     """ids renumbered 1..N in ascending order of the old id (what stats_utils.remap_label does), int32."""
     u = np.unique(ids)

@@ -90,6 +90,19 @@ def test_label_encoding(ref):
         assert np.array_equal(res[4], direction)
 
 
+def test_label_encoding_edge_cases(ref):
+    """degenerate label images, [H,W,3] and [H,W]: verbatim reference == restatement (both forms)"""
+    n = ref.DTOffsetConfig.num_classes
+    for name, ids in synth.label_edge_cases():
+        for lab in (np.repeat(ids[:, :, None], 3, axis=2), ids):
+            res = ref.LabelEncoding(3, 1, 1)((None, None, lab.copy()))
+            for literal in (True, False):
+                tern, point, direction = O.label_encoding(lab.copy(), num_classes=n, literal=literal)
+                assert np.array_equal(np.asarray(res[2]), tern), (name, lab.ndim, literal)
+                assert np.array_equal(res[3].view(np.uint16), point.view(np.uint16)), (name, lab.ndim, literal)
+                assert np.array_equal(res[4], direction), (name, lab.ndim, literal)
+
+
 def test_dcm_voting2(ref):
     rng = np.random.default_rng(3)
     dm = rng.integers(0, 9, size=(33, 47, 8)).astype(np.uint8)
