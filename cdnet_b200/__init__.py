@@ -1,7 +1,10 @@
 """cdnet_b200 -- B200-native (sm_100a) implementation of CDNet's geometry hot path.
 
-Drop-in callables with the reference's signatures live in `cdnet_b200.api` (re-exported here);
-they call hand-written CUDA kernels through the C ABI of libcdnet_b200.so.  There is no CPU
+Drop-in callables with the reference's signatures live in `cdnet_b200.api` (re-exported here; inference
+post-processing and the direction-aware target transform), `cdnet_b200.training` (DTOffsetHelper, the
+direction one-hot block, my_transforms.LabelEncoding), `cdnet_b200.metrics` (stats_utils.py) and
+`cdnet_b200.sharded` (whole-slide row partition); they call hand-written CUDA kernels through the C ABI of
+libcdnet_b200.so.  There is no CPU
 fallback: without the library or without a Blackwell GPU the calls raise.
 """
 from ._cabi import CdnetError  # noqa: F401

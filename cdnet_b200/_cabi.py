@@ -45,6 +45,14 @@ SIGNATURES = {
     "cdnet_label_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cdnet_encode_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdnet_label_to_vector": (c_int, [c_void_p, c_int, c_void_p, c_int, c_size_t, c_int, c_void_p]),
+    "cdnet_align_angle": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "cdnet_angle_to_vector": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "cdnet_vector_to_label": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "cdnet_direction_one_hot_workspace_bytes": (c_size_t, [c_int]),
+    "cdnet_direction_one_hot": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_size_t,
+                                        c_void_p, c_size_t, c_void_p]),
+    "cdnet_ternary_label": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cdnet_shard_ddm_codes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cdnet_shard_point_max": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdnet_shard_boost": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -75,7 +83,7 @@ SIGNATURES = {
 }
 
 E_BADARG, E_WORKSPACE = 1, 2
-S_DDM_CONSTANT, S_WS_OVERFLOW, S_NO_BACKGROUND = 1, 2, 16
+S_DDM_CONSTANT, S_WS_OVERFLOW, S_NO_BACKGROUND, S_CLASS_RANGE = 1, 2, 16, 32
 
 _lib = None
 

@@ -263,6 +263,29 @@ def label_edge_cases(H=48, W=56):
     yield "noise", (rng.random((H, W)) < 0.5).astype(np.uint8) * rng.integers(1, 5, (H, W)).astype(np.uint8)
 
 
+def training_inputs(seed=31):
+    """Seeded inputs of the training-side operators (quantiser, one-hot, label image): dict of arrays."""
+    rng = np.random.default_rng(seed)
+    special = [22.5, 22.500002, 67.5, -157.5, 157.5, 180.0, -180.0, 0.0, -0.0, 11.25, -168.75, 168.75,
+               np.nan, np.inf, -np.inf, 1e30, -1e30]
+    ang = np.concatenate([np.linspace(-180, 180, 1441), special, rng.uniform(-200, 200, 470)])
+    vec = rng.standard_normal((40, 56, 2))
+    vec[0, :8] = [[0, 0], [0, 1], [1, 0], [0, -1], [-1, 0], [1, 1], [-1, -1], [1e-30, -1]]
+    out = {"angle64": ang.reshape(8, -1).astype(np.float64), "angle32": ang.reshape(8, -1).astype(np.float32),
+           "vec64": vec.astype(np.float64), "vec32": vec.astype(np.float32)}
+    B, H, W = 4, 40, 52
+    ids = np.stack([instance_map(seed + 1 + i, H, W, 7) for i in range(B)])
+    cls = np.stack([centripetal_classes(*instance_map(seed + 1 + i, H, W, 7, return_centres=True), n_dir=8)
+                    for i in range(B)]).astype(np.int64)
+    tern = np.where(ids > 0, 1, 0).astype(np.int64)
+    tern[:, ::7, :] = np.where(ids[:, ::7, :] > 0, 2, 0)
+    cls[2] = 5        # a tile with ONE distinct direction value (train_util_dam.py:141)
+    cls[3] = 0        # an all-background tile
+    out.update(onehot_dir=cls, onehot_target=tern)
+    out["labels17"] = rng.integers(0, 19, size=(2, 21, 33)).astype(np.int64)
+    return out
+
+
 def contiguous_ids(ids):
     """ids renumbered 1..N in ascending order of the old id (what stats_utils.remap_label does), int32."""
     u = np.unique(ids)

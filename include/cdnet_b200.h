@@ -37,6 +37,8 @@ extern "C" {
 #define CDNET_S_NO_BACKGROUND 16 /* watershed path: the mask has no background pixel; the reference's
                                   * gen_inst_dst_map raises ValueError there (`nuc_list.remove(0)`,
                                   * postproc_other.py:18-19) */
+#define CDNET_S_CLASS_RANGE 32   /* cdnet_direction_one_hot: a class id outside [0, C); the reference's
+                                  * `target_direction_temp[j, k]` raises IndexError (train_util_dam.py:138) */
 #define CDNET_S_PAIR_OVERFLOW 4 /* cdnet_label_pairs: more distinct (true, pred) pairs than `cap` */
 #define CDNET_S_PAIR_RANGE 8    /* cdnet_label_pairs: a label id is negative or above INT32_MAX */
 
@@ -171,6 +173,46 @@ int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternar
                          int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status,
                          int B, int H, int W, int num_classes, const double* gauss_w, void* ws,
                          size_t ws_bytes, void* stream);
+
+/* ---- the direction quantiser as stand-alone operators --------------------------------------------
+ * DTOffsetHelper static methods of data_prepare/SegFix_offset_helper.py; `n` counts elements.
+ *
+ * cdnet_label_to_vector  (:246-261, table :50-89): labels [N, plane] (uint8 / int32 / int64 by
+ *   elem_bytes) -> int64 [N, 2, plane] = (dh, dw); ids the table does not hold give (0, 0).
+ *   num_classes in {4, 5, 8, 9, 16, 17, 32} (c4_align_axis unset).
+ * cdnet_align_angle      (:311-341; num_classes 4 -> align_angle_c4 :286-309): angle (float32 / float64 by
+ *   in_elem_bytes) -> snapped angle (float64 on the reference's numpy path, float32 on its torch path and
+ *   for 4 classes; may be NULL) and int64 bin index (may be NULL).  num_classes in {4, 8, 16, 32}.
+ * cdnet_angle_to_vector  (:423-450): angle -> snapped angle -> (sin, cos) [n, 2].  `table` is a HOST pointer to
+ *   (num_classes + 1) x 2 float64: (sin, cos) of every bin centre as the caller's numpy / torch evaluates
+ *   them, then (sin 0, cos 0) for angles no bin matches (NaN).
+ * cdnet_vector_to_label  (:486-506): (v0, v1) [n, 2] float32 / float64 -> int64 bin index of
+ *   degrees(atan2(v0, v1)). */
+int cdnet_label_to_vector(const void* labels, int elem_bytes, int64_t* out, int N, size_t plane,
+                          int num_classes, void* stream);
+int cdnet_align_angle(const void* angle, int in_elem_bytes, void* snapped, int out_elem_bytes,
+                      int64_t* index, size_t n, int num_classes, void* stream);
+int cdnet_angle_to_vector(const void* angle, int in_elem_bytes, void* vec, int out_elem_bytes,
+                          const double* table, size_t n, int num_classes, void* stream);
+int cdnet_vector_to_label(const void* vec, int elem_bytes, int64_t* label, size_t n, int num_classes,
+                          void* stream);
+
+/* ---- training-side consumers of the targets ------------------------
+ * cdnet_direction_one_hot: train_util_dam.py:123-142.  direction int64 [B, plane] class ids; target0: the
+ *   ternary target {0,1,2} of TILE 0 [plane] (uint8 or int64 by target_elem_bytes) -- the reference masks every
+ *   tile of the batch with `target[0]` (:139); out float32 [B, C, plane]: channel k = 1 where direction == k on
+ *   foreground; a tile with one distinct direction value gets channel 0 = 1 everywhere (:141).
+ *   status (may be NULL): CDNET_S_CLASS_RANGE.
+ * cdnet_ternary_label: my_transforms.py:661-761, LabelEncoding without direction.  ch0 / ch1 (ch1 only for
+ *   mode 3, may be NULL): uint8 [B,H,W] label channels; out uint8 [B,H,W] in {0,127,255}.
+ *   mode 0: out_c == 3, instance ids (:713-727); 1: out_c == 3, {0,255} label (:728-742);
+ *   mode 2: out_c != 3, instance ids (:690-699); 3: out_c != 3, {0,255} label (:700-708). */
+size_t cdnet_direction_one_hot_workspace_bytes(int B);
+int cdnet_direction_one_hot(const int64_t* direction, const void* target0, int target_elem_bytes,
+                            float* out, int32_t* status, int B, int C, size_t plane, void* ws,
+                            size_t ws_bytes, void* stream);
+int cdnet_ternary_label(const uint8_t* ch0, const uint8_t* ch1, int mode, uint8_t* out, int B, int H,
+                        int W, void* stream);
 
 /* ---- whole-slide row shards ---------------------------------------------
  * One EXTENDED tile per call: the shard's own rows plus one ghost row of the neighbouring shard on

@@ -231,6 +231,38 @@ def gold_metrics():
     _save("metrics", meta, **out)
 
 
+def gold_training(ns):
+    """Quantiser operators (DTOffsetHelper), the direction one-hot block (train_util_dam.py:123-142) and
+    my_transforms.LabelEncoding without direction, all executed verbatim (8 direction classes)."""
+    import torch
+    H = ns.DTOffsetHelper
+    d = synth.training_inputs()
+    out, meta = {}, {"digest": synth.digest(*[d[k] for k in sorted(d)]), "plain": []}
+    for tag in ("32", "64"):
+        a = d["angle" + tag]
+        for n in (8, 4):
+            s, i = H.align_angle(a.copy(), num_classes=n)
+            out["align%d_np%s_s" % (n, tag)], out["align%d_np%s_i" % (n, tag)] = s, i
+            s, i = H.align_angle(torch.from_numpy(a.copy()), num_classes=n, return_tensor=True)
+            out["align%d_pt%s_s" % (n, tag)], out["align%d_pt%s_i" % (n, tag)] = s.numpy(), i.numpy()
+            out["a2v%d_np%s" % (n, tag)] = H.angle_to_vector(a.copy(), num_classes=n)
+            out["a2v%d_pt%s" % (n, tag)] = H.angle_to_vector(torch.from_numpy(a.copy()), num_classes=n,
+                                                             return_tensor=True).numpy()
+        out["v2l8_np" + tag] = H.vector_to_label(d["vec" + tag].copy(), num_classes=8)
+        out["v2l8_roundtrip" + tag] = H.vector_to_label(out["a2v8_np" + tag].copy(), num_classes=8)
+    for C in (4, 5, 8, 9, 16, 17, 32):
+        out["l2v%d" % C] = H.label_to_vector(torch.from_numpy(d["labels17"].copy()), num_classes=C).numpy()
+    out["onehot9"] = ns.direction_one_hot(torch.from_numpy(d["onehot_dir"].copy()),
+                                          torch.from_numpy(d["onehot_target"].copy()), 9).numpy()
+    for name, ids in synth.label_edge_cases():
+        lab = np.repeat(ids[:, :, None], 3, axis=2)
+        lab[:, :, 1] = np.where(ids > 0, 0, 255)[..., ::-1]  # a second channel that matters for out_c != 3
+        for out_c in (3, 1):
+            out["plain_%s_c%d" % (name, out_c)] = np.asarray(ns.LabelEncodingPlain(out_c, 1, 0)((None, None, lab.copy()))[2])
+        meta["plain"].append(name)
+    _save("training", meta, **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -248,7 +280,7 @@ def main():
         return
     ns = ref_loader.load()
     assert ns.DTOffsetConfig.num_classes == 8
-    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16", "metrics"]
+    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16", "metrics", "training"]
     if "ddm" in todo:
         gold_ddm(ns)
     if "process" in todo:
@@ -261,6 +293,8 @@ def main():
         gold_targets(ns, a.quick, 8)
     if "metrics" in todo:
         gold_metrics()
+    if "training" in todo:
+        gold_training(ns)
     if "t16" in todo:
         env = dict(os.environ, dt_num_classes="16")
         subprocess.check_call([sys.executable, "-m", "oracle.make_goldens", "--child16"], env=env,

@@ -75,6 +75,8 @@ def load():
     ns.dam_postprocess = lambda *a, **k: _dam_postprocess(ns, *a, **k)
     ns.plain_postprocess = lambda *a, **k: _plain_postprocess(ns, *a, **k)
     ns.DcmVoting2 = _load_function(root, "utils.py", "DcmVoting2")
+    ns.LabelEncodingPlain = importlib.import_module("my_transforms").LabelEncoding  # my_transforms.py:661-837
+    ns.direction_one_hot = lambda *a, **k: _direction_one_hot(ns, *a, **k)
     _ns = ns
     return ns
 
@@ -142,6 +144,18 @@ def _dam_postprocess(ns, prob_maps, point_maps, dcm_tta, direction_classes=9, mi
     exec(compile(code, "test_dam.py:455-563", "exec"), g)
     return {"pred_labeled": g["pred_labeled"], "pred_inside": g["pred_inside"],
             "pred2": g["pred2"], "prob_direction_maps": g["prob_direction_maps"]}
+
+
+def _direction_one_hot(ns, target_direction0, target, direction_classes):
+    """Runs train_util_dam.py:123-142 verbatim (torch CPU tensors in, float tensor [B,C,H,W] out)."""
+    import copy
+    import torch
+    opt = types.SimpleNamespace(model={"direction": 1}, direction_classes=direction_classes)
+    g = {"np": np, "torch": torch, "copy": copy, "opt": opt, "direction_label": True,
+         "target_direction0": target_direction0, "target": target}
+    code = _read_block(ns.root, "train_util_dam.py", 123, 142)
+    exec(compile(code, "train_util_dam.py:123-142", "exec"), g)
+    return g["target_direction0"]
 
 
 def _plain_postprocess(ns, prob_maps, min_area=20, radius=2, postproc=0, model_name="modelName",

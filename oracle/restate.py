@@ -515,3 +515,73 @@ def label_encoding(label, out_c=3, radius=1, do_direction=1, num_classes=8, lite
                                            "centres": np.asarray(centres, dtype=np.int64),
                                            "dc": dc_sum, "angle": angle, "new_label": new_label}
     return ternary, point, direction
+
+
+# --------------------------------------------------------------------------------------------
+# training-side consumers
+# --------------------------------------------------------------------------------------------
+def direction_one_hot(target_direction0, target, direction_classes):
+    """train_util_dam.py:123-142.  target_direction0 int [B,H,W], target ternary [B,H,W] ->
+    float32 [B,C,H,W].  The foreground mask of every tile is target[0] (:139, sic); a tile with a
+    single distinct direction value gets channel 0 = 1 everywhere (:141)."""
+    d = np.asarray(target_direction0)
+    t = np.asarray(target)
+    B, H, W = d.shape
+    out = np.zeros((B, int(direction_classes), H, W), dtype=np.float32)
+    fg0 = (t[0] == 1) | (t[0] == 2)
+    for j in range(B):
+        uniq = np.unique(d[j])
+        if len(uniq) > 1:
+            for k in uniq:
+                if k < 0 or k >= direction_classes:
+                    raise IndexError("index %d is out of bounds for dimension 1 with size %d" % (k, direction_classes))
+                out[j, k][d[j] == k] = 1
+                out[j, k][~fg0] = 0
+        else:
+            out[j, 0] = 1
+    return out
+
+
+def label_encoding_plain(label, out_c=3):
+    """my_transforms.LabelEncoding with do_direction=0 (my_transforms.py:661-761): the ternary /
+    binary label image uint8 {0,127,255}."""
+    label = np.asarray(label)
+    inside = label if label.ndim == 2 else label[:, :, 0]
+    instance_level = len(np.unique(inside)) > 2
+    new_label = np.zeros(label.shape[:2], dtype=np.uint8)
+    if out_c != 3:
+        if instance_level:
+            new_label[label[:, :, 0] > 0] = 2  # measure.label(label)[:, :, 0] > 0  (:690-696)
+        else:
+            new_label[label[:, :, 0] > 127.5] = 2
+            new_label[label[:, :, 1] > 127.5] = 2
+            new_label = erode(new_label, disk(1))  # :703
+    elif instance_level:
+        inst = label8_values(inside)
+        new_label[inst > 0] = 1
+        boun = dilate(inst) & (~erode(inst, disk(1)))  # :725
+        new_label[boun > 0] = 2
+    else:
+        new_label[inside > 127.5] = 1
+        boun = dilate(new_label) & (~erode(new_label, disk(1)))  # :735
+        new_label[boun > 0] = 2
+    return (new_label / 2 * 255).astype(np.uint8)
+
+
+def label8_values(x):
+    """skimage.measure.label(x) for a multi-valued image: 8-connected components of EQUAL value,
+    background 0, ids in raster order of each component's first pixel."""
+    x = np.asarray(x)
+    prov = np.zeros(x.shape, dtype=np.int64)
+    nxt = 0
+    for v in np.unique(x):
+        if v == 0:
+            continue
+        lab, n = ndi.label(x == v, structure=FULL3)
+        prov[lab > 0] = lab[lab > 0] + nxt
+        nxt += n
+    ids, first = np.unique(prov.ravel(), return_index=True)  # first raster pixel of every provisional id
+    rank = np.zeros(nxt + 1, dtype=np.int64)
+    fg = ids > 0
+    rank[ids[fg][np.argsort(first[fg])]] = np.arange(1, int(fg.sum()) + 1)
+    return rank[prov]

@@ -107,19 +107,20 @@ class _TorchProxy(object):
 @contextlib.contextmanager
 def emulated_api():
     import torch
-    from cdnet_b200 import _cabi, api, metrics, sharded
+    from cdnet_b200 import _cabi, api, metrics, sharded, training
     L = load()
     cpu = torch.device("cpu")
     proxy = _TorchProxy(torch)
-    mods = [api, metrics]
+    mods = [api, metrics, training]
     saved = [(_cabi, "_lib", _cabi._lib), (api, "_device", api._device), (metrics, "_device", metrics._device),
+             (training, "_device", training._device),
              (torch.Tensor, "record_stream", torch.Tensor.record_stream),
              (sharded.CudaBackend, "_st", sharded.CudaBackend._st)]
     saved += [(m, "torch", m.torch) for m in mods if hasattr(m, "torch")]
     plans = dict(getattr(api, "_plans", {}))
     try:
         _cabi._lib = L
-        api._device = metrics._device = lambda device=None: cpu
+        api._device = metrics._device = training._device = lambda device=None: cpu
         sharded.CudaBackend._st = lambda self: None
         torch.Tensor.record_stream = lambda self, s: None
         for m in mods:

@@ -107,3 +107,22 @@ def test_dcm_voting2(ref):
     rng = np.random.default_rng(3)
     dm = rng.integers(0, 9, size=(33, 47, 8)).astype(np.uint8)
     assert np.array_equal(ref.DcmVoting2(dm), O.dcm_voting2(dm))
+
+
+def test_training_consumers(ref):
+    """train_util_dam.py:123-142 and my_transforms.LabelEncoding (no direction), verbatim vs restatement"""
+    import torch
+    rng = np.random.default_rng(17)
+    for B, H, W, C in ((2, 19, 23, 9), (3, 8, 8, 17)):
+        d = rng.integers(0, C, size=(B, H, W)).astype(np.int64)
+        t = rng.integers(0, 3, size=(B, H, W)).astype(np.int64)
+        d[B - 1] = 3
+        r = ref.direction_one_hot(torch.from_numpy(d.copy()), torch.from_numpy(t.copy()), C).numpy()
+        o = O.direction_one_hot(d, t, C)
+        assert r.dtype == o.dtype and np.array_equal(r, o)
+    lab = synth.as_uint8_label(synth.instance_map(781, 90, 110, 14))
+    binary = np.repeat(((lab[:, :, 0] > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    for img in (lab, binary, lab[:, :, 0].copy()):
+        for out_c in ((3, 1) if img.ndim == 3 else (3,)):
+            r = np.asarray(ref.LabelEncodingPlain(out_c, 1, 0)((None, None, img.copy()))[2])
+            assert np.array_equal(r, O.label_encoding_plain(img.copy(), out_c)), (img.shape, out_c)
