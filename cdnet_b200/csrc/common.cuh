@@ -41,18 +41,28 @@ static inline int last_error() {
     return e == cudaSuccess ? 0 : -(int)e;
 }
 
+// AddressSanitizer builds of the emulated test library (tests/simt/build.py --asan) put a poisoned gap after
+// every workspace slice, so a kernel that runs over the end of its slice is caught; no-ops everywhere else.
+#ifndef CDNET_ARENA_GAP
+#define CDNET_ARENA_GAP 0
+#define CDNET_ARENA_RESET(p, n) ((void)0)
+#define CDNET_ARENA_POISON(p, n) ((void)0)
+#endif
+
 // bump allocator over the caller's workspace (256-byte aligned slices)
 struct Arena {
     char* base;
     size_t size, off;
     bool ok;
-    Arena(void* p, size_t n) : base((char*)p), size(n), off(0), ok(true) {}
+    Arena(void* p, size_t n) : base((char*)p), size(n), off(0), ok(true) { CDNET_ARENA_RESET(p, n); }
     template <typename T>
     T* take(size_t count) {
         size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
         if (base == nullptr || off + bytes > size) { ok = false; off += bytes; return nullptr; }
         T* r = (T*)(base + off);
-        off += bytes;
+        const size_t gap = (CDNET_ARENA_GAP && off + bytes + CDNET_ARENA_GAP <= size) ? CDNET_ARENA_GAP : 0;
+        CDNET_ARENA_POISON(base + off + count * sizeof(T), bytes - count * sizeof(T) + gap);
+        off += bytes + gap;
         return r;
     }
 };

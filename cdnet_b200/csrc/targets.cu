@@ -614,7 +614,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     uint8_t* cflag = ar.take<uint8_t>(n);
     int32_t* fg = ar.take<int32_t>(B);
     int32_t* pres = ar.take<int32_t>((size_t)B * 256);
-    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
+    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H < 2 ? 2 : (size_t)B * H);  // [0], [1] double as list count / cursor
     if (!ar.ok) return CDNET_E_WORKSPACE;
     void* sub_ws = (char*)ws + ar.off;
     const size_t sub_bytes = ws_bytes - ar.off;

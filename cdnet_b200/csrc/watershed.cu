@@ -395,7 +395,7 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     uint8_t* val = ar.take<uint8_t>(n);
     uint8_t* mk = ar.take<uint8_t>(n);
     uint8_t* state = ar.take<uint8_t>(n);
-    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
+    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H < 2 ? 2 : (size_t)B * H);  // [0], [1] double as list count / cursor
     if (!ar.ok) return CDNET_E_WORKSPACE;
     int rc;
     if (!ws_flag) {

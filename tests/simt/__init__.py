@@ -12,6 +12,7 @@ The product never does any of this: cdnet_b200 has no CPU path and raises CdnetE
 """
 import contextlib
 import ctypes
+import os
 
 _lib = None
 
@@ -21,7 +22,9 @@ def load():
     if _lib is None:
         from . import build as _build
         from cdnet_b200 import _cabi
-        L = ctypes.CDLL(_build.build())
+        # CDNET_SIMT_LIB: an alternative build of the emulated library (e.g. one compiled with -fsanitize=address,
+        # run under LD_PRELOAD=libasan.so, to catch out-of-bounds accesses of the kernels)
+        L = ctypes.CDLL(os.environ.get("CDNET_SIMT_LIB") or _build.build())
         for name, (res, args) in _cabi.SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res
@@ -128,6 +131,19 @@ def emulated_api():
                 m.torch = proxy
         api._plans.clear()
         api._ws_cache.clear()
+        if os.environ.get("CDNET_SIMT_LIB"):
+            # sanitizer builds may put guard gaps between the workspace slices: leave room for them
+            real_ws = api._workspace
+            saved.append((api, "_workspace", real_ws))
+            api._workspace = lambda nbytes, dev: real_ws(nbytes + (1 << 16), dev)
+            for m in (metrics, training):
+                saved.append((m, "_workspace", m._workspace))
+                m._workspace = api._workspace
+            real_empty = sharded.CudaBackend.empty
+            saved.append((sharded.CudaBackend, "empty", real_empty))
+            sharded.CudaBackend.empty = lambda self, shape, dtype: (
+                real_empty(self, (shape[0] + (1 << 16),), dtype) if dtype == "uint8" and len(shape) == 1
+                else real_empty(self, shape, dtype))
         yield api
     finally:
         for obj, name, val in saved:

@@ -1,6 +1,9 @@
 """Builds the SIMT-emulated test double of libcdnet_b200.so with g++ (TEST INFRASTRUCTURE ONLY).
 
-    python tests/simt/build.py [--force]
+    python tests/simt/build.py [--force] [--asan]
+
+--asan builds tests/simt/_build/asan/libcdnet_b200_simt_asan.so with -fsanitize=address and poisoned gaps
+between the workspace slices; tests/simt/run_asan.sh runs the emulated kernel tests against it.
 
 The kernel sources cdnet_b200/csrc/*.cu are compiled UNMODIFIED as C++ against tests/simt/include
 (shims of cuda_runtime.h / cuda_fp16.h) and linked with tests/simt/simt_runtime.cpp into
@@ -28,7 +31,13 @@ def _deps():
             [os.path.join(HERE, "simt_runtime.cpp"), os.path.join(REPO, "include", "cdnet_b200.h"), __file__])
 
 
-def build(force=False):
+def build(force=False, asan=False):
+    OUT = os.path.join(HERE, "_build", "asan") if asan else os.path.join(HERE, "_build")
+    LIB = os.path.join(OUT, "libcdnet_b200_simt_asan.so" if asan else "libcdnet_b200_simt.so")
+    FLAGS = globals()["FLAGS"] + (["-fsanitize=address", "-fno-omit-frame-pointer", "-DCDNET_SIMT_ASAN"] if asan else [])
+    CXX = globals()["CXX"]
+    if asan and subprocess.run([CXX, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip() == "libasan.so":
+        CXX = "/usr/bin/g++"  # a compiler wrapper that cannot locate the sanitizer runtime: use the system one
     if (not force and os.path.exists(LIB)
             and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in _deps())):
         return LIB
@@ -45,10 +54,10 @@ def build(force=False):
         if pr.returncode != 0:
             raise RuntimeError("g++ failed: %s\n%s" % (" ".join(cmd), out[-6000:]))
     tmp = LIB + ".tmp%d" % os.getpid()
-    subprocess.check_call([CXX, "-shared", "-pthread", "-o", tmp] + objs)
+    subprocess.check_call([CXX, "-shared", "-pthread", "-o", tmp] + objs + (["-fsanitize=address"] if asan else []))
     os.replace(tmp, LIB)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))

@@ -121,6 +121,13 @@ int lane_id();
         ::simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); }, #kernel); \
         ++::cdnet::g_launches;                                                                        \
     } while (0)
+#ifdef CDNET_SIMT_ASAN  // tests/simt/build.py --asan: poisoned gaps between the workspace slices (common.cuh Arena)
+extern "C" void __asan_poison_memory_region(void const volatile*, size_t);
+extern "C" void __asan_unpoison_memory_region(void const volatile*, size_t);
+#define CDNET_ARENA_GAP 256
+#define CDNET_ARENA_RESET(p, n) do { if (p) __asan_unpoison_memory_region((p), (n)); } while (0)
+#define CDNET_ARENA_POISON(p, n) __asan_poison_memory_region((p), (n))
+#endif
 #define CDNET_DYN_SHARED(type, name) type* name = (type*)::simt::dyn_smem()
 #define CDNET_KEEP_IN_REG64(x) ((void)0)
 
