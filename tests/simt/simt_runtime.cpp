@@ -60,9 +60,12 @@ struct BlockExec {  // one per pool thread
     int b_arrived = 0, b_or = 0, b_or_result = 0;
     const std::function<void()>* body = nullptr;
     const char* name = "";
+    int order[kMaxThreads];
+    unsigned long long rng = 0x9e3779b97f4a7c15ull;
 };
 
 thread_local BlockExec* t_exec = nullptr;
+int g_schedule = 0;  // 0 in thread order, 1 reversed, 2 shuffled before every scheduling round
 
 struct Pool {
     std::mutex mu;
@@ -146,9 +149,20 @@ void run_block(BlockExec* e, unsigned bx, unsigned by, unsigned bz) {
         f.ctx.uc_link = nullptr;
         makecontext(&f.ctx, fiber_main, 0);
     }
+    // SIMT_SCHEDULE=reverse | random[:seed] changes the order in which runnable threads are resumed: a kernel
+    // whose result depends on that order has a missing barrier (or relies on warp-synchronous execution)
+    int* order = e->order;
+    for (int i = 0; i < n; ++i) order[i] = g_schedule == 1 ? n - 1 - i : i;
     while (e->alive > 0) {
         bool progressed = false;
-        for (int i = 0; i < n; ++i) {
+        if (g_schedule == 2)
+            for (int i = n - 1; i > 0; --i) {
+                e->rng = e->rng * 6364136223846793005ull + 1442695040888963407ull;
+                const int j = (int)((e->rng >> 33) % (unsigned long long)(i + 1));
+                const int t = order[i]; order[i] = order[j]; order[j] = t;
+            }
+        for (int oi = 0; oi < n; ++oi) {
+            const int i = order[oi];
             Fiber& f = e->fibers[i];
             if (f.state != kRunnable) continue;
             progressed = true;
@@ -179,7 +193,9 @@ void worker_main(int wid) {
     if (e->stacks == (char*)MAP_FAILED) { perror("simt: mmap"); abort(); }
     t_exec = e;
     unsigned long long seen = 0;
-    (void)wid;
+    if (const char* sch = getenv("SIMT_SCHEDULE"))
+        if (!strncmp(sch, "random:", 7)) e->rng ^= strtoull(sch + 7, nullptr, 10) * 0x2545f4914f6cdd1dull;
+    e->rng += (unsigned long long)wid * 0x632be59bd9b4e019ull;
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(g.mu);
@@ -278,6 +294,10 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
     static std::mutex launch_mu;  // launches are serialised, like work on one stream
     std::lock_guard<std::mutex> guard(launch_mu);
     if (g.workers.empty()) {
+        if (const char* sch = getenv("SIMT_SCHEDULE")) {
+            if (!strncmp(sch, "reverse", 7)) g_schedule = 1;
+            else if (!strncmp(sch, "random", 6)) g_schedule = 2;
+        }
         unsigned hw = std::thread::hardware_concurrency();
         const char* env = getenv("SIMT_WORKERS");
         int nw = env ? atoi(env) : (int)(hw ? (hw > 8 ? 8 : hw) : 4);
