@@ -489,6 +489,43 @@ def direction_argmax_cuda(mask_logits, direction_logits):
     return prob.contiguous(), torch.argmax(dprob, dim=1).to(torch.uint8).contiguous()
 
 
+TTA_VARIANTS = ("id", "hf", "vf", "hvf", "r90", "r90_hf", "r90_vf", "r90_hvf")
+
+
+def tta_merge_cuda(mask_logits, point, dir_logits):
+    """Device-resident hand-off for test-time augmentation (test_dam.py:299-450 and get_probmaps :983-1013) in ONE
+    kernel.  Each argument is a sequence of 8 CUDA float32 tensors, the raw network outputs of the variants in the
+    order TTA_VARIANTS, in the variant's own frame: [B,3,h,w], [B,1,h,w], [B,C,h,w] (h,w = H,W for the flips,
+    W,H for the rotated ones).  Returns (prob float32 [B,3,H,W], point float32 [B,1,H,W], dcm uint8 [B,8,H,W]) in
+    the original frame: exactly the inputs of dam_postprocess_cuda."""
+    import ctypes
+    L = _cabi.lib()
+    assert len(mask_logits) == 8 and len(point) == 8 and len(dir_logits) == 8
+    dev = _device(mask_logits[0].device)
+    B, three, H, W = mask_logits[0].shape
+    C = dir_logits[0].shape[1]
+    assert three == 3
+    keep = []
+    arrays = []
+    for seq, ch in ((mask_logits, 3), (point, 1), (dir_logits, C)):
+        ptrs = (ctypes.c_void_p * 8)()
+        for v, t in enumerate(seq):
+            shape = (B, ch, H, W) if v < 4 else (B, ch, W, H)
+            if t.dim() == 3 and ch == 1:
+                t = t[:, None]
+            assert t.dtype == torch.float32 and tuple(t.shape) == shape, (TTA_VARIANTS[v], tuple(t.shape), shape)
+            t = t.contiguous()
+            keep.append(t)
+            ptrs[v] = t.data_ptr()
+        arrays.append(ptrs)
+    prob = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    pt = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    dcm = torch.empty((B, 8, H, W), dtype=torch.uint8, device=dev)
+    check(L.cdnet_tta_merge(arrays[0], arrays[1], arrays[2], _ptr(prob), _ptr(pt), _ptr(dcm), B, H, W, int(C),
+                            _stream()), "cdnet_tta_merge")
+    return prob, pt, dcm
+
+
 # =====================================================================================================
 # target transform (my_transforms_direction.py:651-885)
 # =====================================================================================================

@@ -1,0 +1,186 @@
+// handoff.cu -- device-resident hand-off from the CNN to the post-processing.
+//
+// Replaces, in ONE kernel over the raw network outputs of the 8 test-time-augmentation variants,
+//   get_probmaps            test_dam.py:983-1013   softmax of the 3-class head, softmax of the direction head,
+//                                                  direction[0] *= mask[0], first-maximum argmax
+//   un-flip / un-rotate     test_dam.py:357-367, 426-441   np.flip / np.rot90(k=3) back to the original frame
+//   averaging               test_dam.py:445-450    ((((((p0 + hf) + vf) + hvf) + r90) + r90_hf) + r90_vf) + r90_hvf) / 8
+// which the reference runs as torch softmax on the GPU, .cpu().numpy(), eight numpy flips / rotations and seven
+// array additions per map.  Output is exactly what cdnet_dam_postproc consumes: prob float32 [B,3,H,W],
+// point float32 [B,1,H,W], dcm uint8 [B,8,H,W] -- nothing leaves the device in between.
+//
+// Roofline: HBM.  Algorithmic bytes per output pixel = 8 variants x (3 + 1 + C) float32 read + 16 + 8 written
+// (C = 9: 440 B/px).  Each logit is read once, coalesced: the four rotated variants are read along THEIR rows
+// (the original frame's columns) and transposed through a padded shared-memory tile.
+#include <math.h>
+
+#include "internal.h"
+
+namespace cdnet {
+
+struct TtaPtrs {
+    const float* mask[8];   // [B,3,h_v,w_v]
+    const float* point[8];  // [B,1,h_v,w_v]
+    const float* dir[8];    // [B,C,h_v,w_v]
+};
+
+constexpr int kTile = 32, kRowsPerPass = 8, kPasses = kTile / kRowsPerPass;
+
+struct PixelOut {
+    float p0, p1, p2, pt;
+    int cls;
+};
+
+// one pixel of one variant: softmax as torch's spatial soft-max kernel does it in float32 (channel maximum,
+// channels summed in order, exp(x - max) / sum), then the reference's numpy steps
+template <int C>
+__device__ __forceinline__ PixelOut eval_pixel(const float* __restrict__ mask, const float* __restrict__ point,
+                                               const float* __restrict__ dir, size_t plane, size_t off) {
+    PixelOut o;
+    const float m0 = __ldg(mask + off), m1 = __ldg(mask + plane + off), m2 = __ldg(mask + 2 * plane + off);
+    const float mx = fmaxf(fmaxf(m0, m1), m2);
+    const float e0 = expf(m0 - mx), e1 = expf(m1 - mx), e2 = expf(m2 - mx);
+    const float s = __fadd_rn(__fadd_rn(e0, e1), e2);
+    o.p0 = __fdiv_rn(e0, s);
+    o.p1 = __fdiv_rn(e1, s);
+    o.p2 = __fdiv_rn(e2, s);
+    o.pt = __ldg(point + off);
+    float d[C];
+    float dmx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        d[c] = __ldg(dir + (size_t)c * plane + off);
+        dmx = fmaxf(dmx, d[c]);
+    }
+    float ds = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        d[c] = expf(d[c] - dmx);
+        ds = __fadd_rn(ds, d[c]);
+    }
+    float best = __fmul_rn(__fdiv_rn(d[0], ds), o.p0);  // prob_maps_direction[0] *= prob_maps[0]  (:1010)
+    int arg = 0;
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+        const float q = __fdiv_rn(d[c], ds);
+        if (q > best) { best = q; arg = c; }  // np.argmax: the first maximum wins
+    }
+    o.cls = arg;
+    return o;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTile* kRowsPerPass) k_tta_merge(TtaPtrs P, float* __restrict__ prob_out,
+                                                                    float* __restrict__ point_out,
+                                                                    uint8_t* __restrict__ dcm_out, int H, int W) {
+    // staging tile of the rotated variants, [local y][local x]: filled by lanes that walk y (row stride
+    // kTile + 1 words: conflict-free), consumed by lanes that walk x
+    __shared__ float s_val[4][kTile][kTile + 1];
+    __shared__ int s_cls[kTile][kTile + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const size_t plane = (size_t)H * W;
+    float acc[kPasses][4];
+    const int x = x0 + tx;
+
+    // ---- variants 0..3: flips only, read in place (a reversed row is still one coalesced segment) ----
+#pragma unroll 1
+    for (int v = 0; v < 4; ++v) {
+        const float* mask = P.mask[v] + (size_t)b * 3 * plane;
+        const float* point = P.point[v] + (size_t)b * plane;
+        const float* dir = P.dir[v] + (size_t)b * C * plane;
+#pragma unroll
+        for (int r = 0; r < kPasses; ++r) {
+            const int y = y0 + ty + r * kRowsPerPass;
+            if (x < W && y < H) {
+                const int sy = (v & 2) ? H - 1 - y : y, sx = (v & 1) ? W - 1 - x : x;
+                const PixelOut o = eval_pixel<C>(mask, point, dir, plane, (size_t)sy * W + sx);
+                if (v == 0) { acc[r][0] = o.p0; acc[r][1] = o.p1; acc[r][2] = o.p2; acc[r][3] = o.pt; }
+                else {
+                    acc[r][0] = __fadd_rn(acc[r][0], o.p0);
+                    acc[r][1] = __fadd_rn(acc[r][1], o.p1);
+                    acc[r][2] = __fadd_rn(acc[r][2], o.p2);
+                    acc[r][3] = __fadd_rn(acc[r][3], o.pt);
+                }
+                dcm_out[((size_t)b * 8 + v) * plane + (size_t)y * W + x] = (uint8_t)o.cls;
+            }
+        }
+    }
+
+    // ---- variants 4..7: rotated by 90 degrees; their frame is [W rows, H cols] --------------------------
+    // original (y, x) <- variant (row, col) = (v&2 ? x : W-1-x,  v&1 ? H-1-y : y): consecutive lanes walk the
+    // variant's columns, i.e. the original frame's rows y; results are transposed through shared memory
+#pragma unroll 1
+    for (int v = 4; v < 8; ++v) {
+        const float* mask = P.mask[v] + (size_t)b * 3 * plane;
+        const float* point = P.point[v] + (size_t)b * plane;
+        const float* dir = P.dir[v] + (size_t)b * C * plane;
+        __syncthreads();  // the previous variant's tile has been consumed
+#pragma unroll
+        for (int r = 0; r < kPasses; ++r) {
+            const int lx = ty + r * kRowsPerPass;  // local x of the original frame
+            const int oy = y0 + tx, ox = x0 + lx;  // lanes walk y
+            if (oy < H && ox < W) {
+                const int row = (v & 2) ? ox : W - 1 - ox, col = (v & 1) ? H - 1 - oy : oy;
+                const PixelOut o = eval_pixel<C>(mask, point, dir, plane, (size_t)row * H + col);
+                s_val[0][tx][lx] = o.p0;
+                s_val[1][tx][lx] = o.p1;
+                s_val[2][tx][lx] = o.p2;
+                s_val[3][tx][lx] = o.pt;
+                s_cls[tx][lx] = o.cls;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kPasses; ++r) {
+            const int ly = ty + r * kRowsPerPass;
+            const int y = y0 + ly;
+            if (x < W && y < H) {
+                acc[r][0] = __fadd_rn(acc[r][0], s_val[0][ly][tx]);
+                acc[r][1] = __fadd_rn(acc[r][1], s_val[1][ly][tx]);
+                acc[r][2] = __fadd_rn(acc[r][2], s_val[2][ly][tx]);
+                acc[r][3] = __fadd_rn(acc[r][3], s_val[3][ly][tx]);
+                dcm_out[((size_t)b * 8 + v) * plane + (size_t)y * W + x] = (uint8_t)s_cls[ly][tx];
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < kPasses; ++r) {
+        const int y = y0 + ty + r * kRowsPerPass;
+        if (x < W && y < H) {
+            const size_t p = (size_t)y * W + x;
+            prob_out[((size_t)b * 3 + 0) * plane + p] = __fmul_rn(acc[r][0], 0.125f);  // / 8 is exact
+            prob_out[((size_t)b * 3 + 1) * plane + p] = __fmul_rn(acc[r][1], 0.125f);
+            prob_out[((size_t)b * 3 + 2) * plane + p] = __fmul_rn(acc[r][2], 0.125f);
+            point_out[(size_t)b * plane + p] = __fmul_rn(acc[r][3], 0.125f);
+        }
+    }
+}
+
+}  // namespace cdnet
+
+using namespace cdnet;
+
+extern "C" int cdnet_tta_merge(const float* const* mask_logits, const float* const* point, const float* const* dir_logits,
+                               float* prob_out, float* point_out, uint8_t* dcm_out, int B, int H, int W, int dir_classes,
+                               void* stream) {
+    if (!mask_logits || !point || !dir_logits || !prob_out || !point_out || !dcm_out) return CDNET_E_BADARG;
+    if (B <= 0 || B > 65535 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0) return CDNET_E_BADARG;
+    TtaPtrs P;
+    for (int v = 0; v < 8; ++v) {
+        if (!mask_logits[v] || !point[v] || !dir_logits[v]) return CDNET_E_BADARG;
+        P.mask[v] = mask_logits[v];
+        P.point[v] = point[v];
+        P.dir[v] = dir_logits[v];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(ceil_div(W, kTile), ceil_div(H, kTile), B), block(kTile, kRowsPerPass);
+    if (ceil_div(H, kTile) > 65535) return CDNET_E_BADARG;
+    if (dir_classes == 5) CDNET_LAUNCH(k_tta_merge<5>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W);
+    else if (dir_classes == 9) CDNET_LAUNCH(k_tta_merge<9>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W);
+    else if (dir_classes == 17) CDNET_LAUNCH(k_tta_merge<17>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W);
+    else return CDNET_E_BADARG;
+    return last_error();
+}

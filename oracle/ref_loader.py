@@ -77,6 +77,7 @@ def load():
     ns.DcmVoting2 = _load_function(root, "utils.py", "DcmVoting2")
     ns.LabelEncodingPlain = importlib.import_module("my_transforms").LabelEncoding  # my_transforms.py:661-837
     ns.direction_one_hot = lambda *a, **k: _direction_one_hot(ns, *a, **k)
+    ns.tta_merge = lambda *a, **k: _tta_merge(ns, *a, **k)
     _ns = ns
     return ns
 
@@ -95,7 +96,7 @@ def _read_block(root, fname, first, last):
     return textwrap.dedent("".join(lines[first - 1:last]))
 
 
-def _load_function(root, fname, name):
+def _load_function(root, fname, name, extra=None):
     """exec one top-level function of a reference file that cannot be imported as a module."""
     with open(os.path.join(root, fname), "r", encoding="utf-8") as f:
         lines = f.readlines()
@@ -104,6 +105,7 @@ def _load_function(root, fname, name):
     while end < len(lines) and (lines[end].strip() == "" or lines[end][0] in " \t"):
         end += 1
     g = {"np": np}
+    g.update(extra or {})
     exec(compile("".join(lines[start:end]), fname, "exec"), g)
     return g[name]
 
@@ -144,6 +146,59 @@ def _dam_postprocess(ns, prob_maps, point_maps, dcm_tta, direction_classes=9, mi
     exec(compile(code, "test_dam.py:455-563", "exec"), g)
     return {"pred_labeled": g["pred_labeled"], "pred_inside": g["pred_inside"],
             "pred2": g["pred2"], "prob_direction_maps": g["prob_direction_maps"]}
+
+
+class _Tok(object):
+    """stands in for the PIL image / input tensor of one TTA variant inside the verbatim TTA block"""
+
+    def __init__(self, key=()):
+        self.key = key
+
+    def rotate(self, angle, expand=False):
+        assert angle == 90 and expand
+        return _Tok(self.key + ("r90",))
+
+    def transpose(self, how):
+        return _Tok(self.key + (int(how),))
+
+    def unsqueeze(self, dim):
+        return self
+
+    def cuda(self):
+        return self
+
+
+def _tta_merge(ns, mask_logits, point, dir_logits):
+    """Runs the reference's test-time augmentation verbatim: `get_probmaps` (test_dam.py:930-1034: softmax,
+    direction[0] *= mask[0], argmax) for each of the 8 variants and the un-flip / un-rotate / average block
+    (test_dam.py:314-450).  Variant order: id, hf, vf, hvf, r90, r90_hf, r90_vf, r90_hvf; mask_logits[v] torch
+    float32 [3,h,w], point[v] [1,h,w], dir_logits[v] [C,h,w] in the variant's own frame (the model's outputs).
+    Returns (prob_maps f32 [3,H,W], point_maps f32 [1,H,W], the 8 un-flipped direction-class maps [8,H,W])."""
+    import copy
+    import torch
+    import torch.nn.functional as F
+    from PIL import Image
+    LR, TB = int(Image.FLIP_LEFT_RIGHT), int(Image.FLIP_TOP_BOTTOM)
+    keys = [(), (LR,), (TB,), (LR, TB), ("r90",), ("r90", LR), ("r90", TB), ("r90", LR, TB)]
+    index = {k: i for i, k in enumerate(keys)}
+    opt = types.SimpleNamespace(model={"modelName": "CDNet", "mseloss": 1, "direction": 1, "multi_class": True},
+                                test={"patch_size": 0, "overlap": 0})
+    get_probmaps = _load_function(ns.root, "test_dam.py", "get_probmaps",
+                                  extra={"torch": torch, "F": F, "copy": copy, "all_img_test": 1, "utils": None,
+                                         "DTOffsetHelper": ns.DTOffsetHelper, "print": lambda *a, **k: None})
+
+    def model(tok):
+        v = index[tok.key]
+        return (mask_logits[v][None], point[v][None], dir_logits[v][None])
+    times = [0]
+    base = get_probmaps(_Tok(), model, opt, "tile", times)
+    g = {"np": np, "Image": Image, "img": _Tok(), "test_transform": lambda t: (t[0],), "get_probmaps": get_probmaps,
+         "model": model, "opt": opt, "name": "tile", "times": times, "print": lambda *a, **k: None,
+         "prob_maps": base[0], "point_maps": base[1], "prob_dcm": base[2]}
+    exec(compile(_read_block(ns.root, "test_dam.py", 314, 450), "test_dam.py:314-450", "exec"), g)
+    dcm = np.stack([np.asarray(g[n])[0] for n in ("prob_dcm", "prob_dcm_hf", "prob_dcm_vf", "prob_dcm_hvf", "prob_dcm_r90",
+                                                  "prob_dcm_r90_hf", "prob_dcm_r90_vf", "prob_dcm_r90_hvf")])
+    return g["prob_maps"], g["point_maps"], dcm
 
 
 def _direction_one_hot(ns, target_direction0, target, direction_classes):

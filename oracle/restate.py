@@ -585,3 +585,58 @@ def label8_values(x):
     fg = ids > 0
     rank[ids[fg][np.argsort(first[fg])]] = np.arange(1, int(fg.sum()) + 1)
     return rank[prov]
+
+
+# --------------------------------------------------------------------------------------------
+# test-time augmentation hand-off
+# --------------------------------------------------------------------------------------------
+def tta_variant_to_original(a, v):
+    """test_dam.py:357-367, 426-441 (averaging :445-450): bring the [C,h,w] output of TTA variant v (0 id, 1 hf, 2 vf,
+    3 hvf, 4 r90, 5 r90_hf, 6 r90_vf, 7 r90_hvf) back into the frame of the original image."""
+    a = np.asarray(a)
+    if v & 1:
+        a = np.flip(a, 2)
+    if v & 2:
+        a = np.flip(a, 1)
+    if v & 4:
+        a = np.rot90(a, k=3, axes=(1, 2))
+    return a
+
+
+def tta_source_index(v, y, x, H, W):
+    """closed form of the above: (row, col) in variant v's own frame of original-frame pixel (y, x)"""
+    if v < 4:
+        return (H - 1 - y if v & 2 else y), (W - 1 - x if v & 1 else x)
+    return (x if v & 2 else W - 1 - x), (H - 1 - y if v & 1 else y)
+
+
+def variant_probmaps(mask_logits, point, dir_logits):
+    """get_probmaps, test_dam.py:983-1013 with direction_label=True: float32 softmax over channels
+    (max-shifted, channels summed in order), direction[0] *= mask[0], first-maximum argmax."""
+    def softmax(z):
+        z = np.asarray(z, dtype=np.float32)
+        e = np.exp(z - z.max(axis=0, keepdims=True), dtype=np.float32)
+        s = np.zeros(e.shape[1:], dtype=np.float32)
+        for c in range(e.shape[0]):
+            s = s + e[c]
+        return e / s
+    prob = softmax(mask_logits)
+    d = softmax(dir_logits)
+    d[0] = d[0] * prob[0]
+    return prob, np.asarray(point, dtype=np.float32), np.argmax(d, axis=0)[None]
+
+
+def tta_merge(mask_logits, point, dir_logits):
+    """test_dam.py:299-450: 8 variants -> (prob f32 [3,H,W], point f32 [1,H,W], dcm int64 [8,H,W]);
+    probabilities and point maps are summed in variant order and divided by 8 in float32."""
+    probs, points, dcms = [], [], []
+    for v in range(8):
+        p, q, c = variant_probmaps(mask_logits[v], point[v], dir_logits[v])
+        probs.append(tta_variant_to_original(p, v))
+        points.append(tta_variant_to_original(q, v))
+        dcms.append(tta_variant_to_original(c, v)[0])
+    prob, pt = probs[0], points[0]
+    for v in range(1, 8):
+        prob = prob + probs[v]
+        pt = pt + points[v]
+    return prob / 8, pt / 8, np.stack(dcms)

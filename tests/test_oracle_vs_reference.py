@@ -126,3 +126,29 @@ def test_training_consumers(ref):
         for out_c in ((3, 1) if img.ndim == 3 else (3,)):
             r = np.asarray(ref.LabelEncodingPlain(out_c, 1, 0)((None, None, img.copy()))[2])
             assert np.array_equal(r, O.label_encoding_plain(img.copy(), out_c)), (img.shape, out_c)
+
+
+def test_tta_merge(ref):
+    """the TTA block (test_dam.py:314-450) and get_probmaps (:930-1034) executed verbatim with stand-in model /
+    image objects vs the restatement: point maps and direction classes exact, probabilities to float32 rounding
+    (torch's CPU softmax vs numpy's exp)"""
+    import torch
+    g = torch.Generator().manual_seed(5)
+    for H, W, C in ((21, 34, 9), (16, 16, 17)):
+        shapes = [(H, W)] * 4 + [(W, H)] * 4
+        ml = [torch.randn((3,) + s, generator=g) * 3 for s in shapes]
+        pt = [torch.randn((1,) + s, generator=g) for s in shapes]
+        dl = [torch.randn((C,) + s, generator=g) * 3 for s in shapes]
+        rp, rq, rd = ref.tta_merge(ml, pt, dl)
+        op, oq, od = O.tta_merge([m.numpy() for m in ml], [p.numpy() for p in pt], [d.numpy() for d in dl])
+        assert rp.dtype == op.dtype == np.float32 and rp.shape == op.shape
+        assert np.allclose(rp, op, rtol=1e-6, atol=1e-7)
+        assert np.array_equal(rq.view(np.uint32), oq.view(np.uint32))
+        assert (rd != od).mean() < 1e-3  # exact float ties aside
+        for v in range(8):  # closed-form index maps used by the kernel
+            a = np.arange(shapes[v][0] * shapes[v][1]).reshape((1,) + shapes[v])
+            b = O.tta_variant_to_original(a, v)[0]
+            yy, xx = np.mgrid[0:H, 0:W]
+            for y, x in ((0, 0), (H - 1, 0), (0, W - 1), (H - 1, W - 1), (3, 7), (11, 2)):
+                r, c = O.tta_source_index(v, y, x, H, W)
+                assert b[y, x] == a[0, r, c]
