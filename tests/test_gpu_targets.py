@@ -105,21 +105,6 @@ def test_label_encoding_edge_cases(kernel_api):
         assert np.array_equal(res[4], ref[2]), name
 
 
-def test_label_encoding_degenerate_sweep(kernel_api):
-    """synth.label_edge_cases (pinned reference -> oracle in tests/test_oracle_vs_reference.py), as [H,W,3] and
-    [H,W] label images, 8 and 16 direction classes"""
-    from oracle import restate as O
-    from cdnet_b200 import synth
-    for name, ids in synth.label_edge_cases():
-        for lab in (np.repeat(ids[:, :, None], 3, axis=2), ids):
-            for n in (8, 16):
-                ref = O.label_encoding(lab.copy(), num_classes=n, literal=False)
-                res = kernel_api.LabelEncoding(3, 1, 1, num_classes=n)((None, None, lab.copy()))
-                assert np.array_equal(np.asarray(res[2]), ref[0]), (name, lab.ndim, n)
-                assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), (name, lab.ndim, n)
-                _check_direction(res[4], ref[2], lab if lab.ndim == 3 else np.repeat(lab[:, :, None], 3, axis=2), n, name)
-
-
 def test_encode_targets_plan_host_buffers(kernel_api):
     """The pinned host-buffer plan (chunked copy/compute overlap) returns what the one-shot call returns."""
     import torch

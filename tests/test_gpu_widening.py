@@ -1,0 +1,139 @@
+"""Kernel parity tests added while widening round 1 (degenerate-input sweeps, the all-foreground error path, the
+fused TTA hand-off): same two backends as the other kernel tests -- [cuda] on the B200 through the C ABI, [simt] on
+the host under the SIMT emulator.  Kept in a file that sorts after the others so that `pytest -x` reaches the long
+established parity tests first."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, to_dev
+from test_gpu_targets import _check_direction
+
+
+def _outcome(fn):
+    try:
+        return ("ok", fn())
+    except (AssertionError, ValueError) as e:
+        return (type(e).__name__, None)
+
+
+def test_dam_postprocess_edge_cases(kernel_api):
+    """degenerate tiles (synth.postproc_edge_cases; the oracle is pinned to the verbatim reference on the same
+    cases in tests/test_oracle_vs_reference.py): same labels, or the same exception type as the reference"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    for name, c in synth.postproc_edge_cases():
+        for pp in (0, 1):
+            ref = _outcome(lambda: O.dam_postprocess(c["prob"].copy(), c["point"], c["dcm"], 9, 20, 2, pp,
+                                                     literal=False)["pred_labeled"])
+            got = _outcome(lambda: kernel_api.dam_postprocess(c["prob"].copy(), c["point"], c["dcm"], 9, 20, 2, pp))
+            assert got[0] == ref[0], (name, pp, got[0], ref[0])
+            if ref[1] is not None:
+                assert got[1].dtype == ref[1].dtype and np.array_equal(got[1], ref[1]), (name, pp)
+            ref = _outcome(lambda: O.plain_postprocess(c["prob"].copy(), 20, 2, pp, literal=False)["pred_labeled"])
+            got = _outcome(lambda: kernel_api.plain_postprocess(c["prob"].copy(), 20, 2, pp))
+            assert got[0] == ref[0], (name, pp, "plain", got[0], ref[0])
+            if ref[1] is not None:
+                assert got[1].dtype == ref[1].dtype and np.array_equal(got[1], ref[1]), (name, pp, "plain")
+
+
+def test_process_all_foreground_raises(kernel_api):
+    """postproc_other.py:18-19: `nuc_list.remove(0)` raises ValueError when the mask has no background pixel"""
+    import torch
+    full = np.full((24, 40), 255, np.uint8)
+    with pytest.raises(ValueError):
+        kernel_api.process(full.copy(), "modelName")
+    assert kernel_api.process(full.copy(), "unet").max() == 1  # the no-watershed head has no such list
+    # device-resident batch: the status bit marks exactly the tile without background
+    m = np.ones((3, 24, 40), np.uint8)
+    m[0, 3, 4] = 0
+    m[2, :, 20:] = 0
+    _, st = kernel_api.process_cuda(to_dev(kernel_api, torch.from_numpy(m)), 10, True, return_status=True)
+    assert [int(v) & 16 for v in st.cpu().numpy()] == [0, 16, 0]
+
+
+def test_label_encoding_degenerate_sweep(kernel_api):
+    """synth.label_edge_cases (pinned reference -> oracle in tests/test_oracle_vs_reference.py), as [H,W,3] and
+    [H,W] label images, 8 and 16 direction classes"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    for name, ids in synth.label_edge_cases():
+        for lab in (np.repeat(ids[:, :, None], 3, axis=2), ids):
+            for n in (8, 16):
+                ref = O.label_encoding(lab.copy(), num_classes=n, literal=False)
+                res = kernel_api.LabelEncoding(3, 1, 1, num_classes=n)((None, None, lab.copy()))
+                assert np.array_equal(np.asarray(res[2]), ref[0]), (name, lab.ndim, n)
+                assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), (name, lab.ndim, n)
+                _check_direction(res[4], ref[2], lab if lab.ndim == 3 else np.repeat(lab[:, :, None], 3, axis=2), n, name)
+
+
+def _tta_inputs(seed, B, H, W, C):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(H, W)] * 4 + [(W, H)] * 4
+    ml = [torch.randn((B, 3) + s, generator=g) * 3 for s in shapes]
+    pt = [torch.randn((B, 1) + s, generator=g) for s in shapes]
+    dl = [torch.randn((B, C) + s, generator=g) * 3 for s in shapes]
+    return ml, pt, dl
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 21, 34, 9), (2, 64, 96, 9), (1, 33, 31, 17), (1, 1, 1, 5), (1, 70, 5, 9)])
+def test_tta_merge_vs_oracle(kernel_api, B, H, W, C):
+    """fused TTA hand-off (test_dam.py:299-450, :983-1013) vs the restatement (pinned to the verbatim reference in
+    tests/test_oracle_vs_reference.py).  Probabilities: 1e-5 relative (the softmax's expf is the device's, the
+    reference's is torch's); point map: bit-exact; direction classes: exact wherever the top-2 margin exceeds
+    the float noise."""
+    from oracle import restate as O
+    ml, pt, dl = _tta_inputs(B * 100 + H, B, H, W, C)
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t) for t in ml], [to_dev(kernel_api, t) for t in pt],
+                                                 [to_dev(kernel_api, t) for t in dl])
+    assert prob.dtype == kernel_api.torch.float32 and dcm.dtype == kernel_api.torch.uint8
+    assert tuple(prob.shape) == (B, 3, H, W) and tuple(point.shape) == (B, 1, H, W) and tuple(dcm.shape) == (B, 8, H, W)
+    for b in range(B):
+        rp, rq, rd = O.tta_merge([t[b].numpy() for t in ml], [t[b].numpy() for t in pt], [t[b].numpy() for t in dl])
+        assert np.allclose(prob[b].cpu().numpy(), rp, rtol=1e-5, atol=1e-7)
+        assert np.array_equal(point[b].cpu().numpy().view(np.uint32), rq.view(np.uint32))
+        got = dcm[b].cpu().numpy().astype(np.int64)
+        for v in range(8):
+            p, _, _ = O.variant_probmaps(ml[v][b].numpy(), pt[v][b].numpy(), dl[v][b].numpy())
+            z = dl[v][b].numpy().astype(np.float64)
+            q = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
+            q[0] *= p[0]
+            top = np.sort(q, axis=0)
+            clear = O.tta_variant_to_original(((top[-1] - top[-2]) > 1e-6)[None], v)[0]
+            assert np.array_equal(got[v][clear], rd[v][clear]), (b, v)
+            assert clear.mean() > 0.99
+
+
+def test_tta_merge_feeds_postprocess(kernel_api):
+    """hand-off -> dam_postprocess_cuda without leaving the device == the same two steps through the oracle"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    torch = kernel_api.torch
+    d = synth.postproc_inputs(88, 96, 80, 9)
+    H, W = 96, 80
+    # logits whose softmax / argmax reproduce the synthetic tile in every variant's frame
+    def to_variant(a, v):
+        a = np.asarray(a)
+        if v & 4:
+            a = np.rot90(a, k=1, axes=(1, 2))
+        if v & 2:
+            a = np.flip(a, 1)
+        if v & 1:
+            a = np.flip(a, 2)
+        return np.ascontiguousarray(a)
+    ml, pt, dl = [], [], []
+    for v in range(8):
+        ml.append(torch.from_numpy(to_variant(np.log(d["prob"] + 1e-6), v))[None])
+        pt.append(torch.from_numpy(to_variant(d["point"], v))[None])
+        onehot = (np.arange(9)[:, None, None] == d["dcm"][v][None]).astype(np.float32) * 12.0
+        dl.append(torch.from_numpy(to_variant(onehot, v))[None])
+    for v in range(8):  # to_variant inverts tta_variant_to_original
+        assert np.array_equal(O.tta_variant_to_original(to_variant(d["point"], v), v), d["point"])
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t) for t in ml], [to_dev(kernel_api, t) for t in pt],
+                                                 [to_dev(kernel_api, t) for t in dl])
+    assert np.array_equal(dcm[0].cpu().numpy(), d["dcm"])
+    lab, status = kernel_api.dam_postprocess_cuda(dcm, prob, point, 9, 20, 2, 0)
+    assert int(status[0]) == 0
+    ref = O.dam_postprocess(prob[0].cpu().numpy().copy(), point[0].cpu().numpy(), dcm[0].cpu().numpy(), 9, 20, 2, 0,
+                            literal=False)["pred_labeled"]
+    assert np.array_equal(lab[0].cpu().numpy(), ref)
