@@ -31,13 +31,19 @@ struct PixelOut {
     int cls;
 };
 
-// one pixel of one variant: softmax as torch's spatial soft-max kernel does it in float32 (channel maximum,
-// channels summed in order, exp(x - max) / sum), then the reference's numpy steps
+// one pixel of one variant: the 3-class soft-max as torch's spatial soft-max kernel does it in float32 (channel
+// maximum, channels summed in order, exp(x - max) / sum), then the reference's numpy steps
 template <int C>
 __device__ __forceinline__ PixelOut eval_pixel(const float* __restrict__ mask, const float* __restrict__ point,
                                                const float* __restrict__ dir, size_t plane, size_t off) {
     PixelOut o;
-    const float m0 = __ldg(mask + off), m1 = __ldg(mask + plane + off), m2 = __ldg(mask + 2 * plane + off);
+    // channel c of this pixel lives at base + off + c * plane: walk a pointer
+    const float* pm = mask + off;
+    const float m0 = __ldg(pm);
+    pm += plane;
+    const float m1 = __ldg(pm);
+    pm += plane;
+    const float m2 = __ldg(pm);
     const float mx = fmaxf(fmaxf(m0, m1), m2);
     const float e0 = expf(m0 - mx), e1 = expf(m1 - mx), e2 = expf(m2 - mx);
     const float s = __fadd_rn(__fadd_rn(e0, e1), e2);
@@ -45,26 +51,28 @@ __device__ __forceinline__ PixelOut eval_pixel(const float* __restrict__ mask, c
     o.p1 = __fdiv_rn(e1, s);
     o.p2 = __fdiv_rn(e2, s);
     o.pt = __ldg(point + off);
-    float d[C];
-    float dmx = -INFINITY;
+    // Direction head (:1008-1011): arg max_c q_c, q = softmax(dir), q_0 scaled by p0.  The soft-max's common
+    // positive factor 1/sum cannot change the winner, so no sum and no division: among the classes >= 1 the
+    // largest logit wins (the first one on ties, like np.argmax), and class 0 keeps the pixel unless
+    // exp(l* - max) > exp(l0 - max) * p0 -- two exponentials instead of C exponentials and C IEEE divisions
+    // (406 -> ~150 thread instructions per (pixel, variant), profiles/r01_widening.md).  Results can differ from
+    // the reference's only where two scaled probabilities agree to float rounding.
+    const float* pd = dir + off;
+    float l[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        d[c] = __ldg(dir + (size_t)c * plane + off);
-        dmx = fmaxf(dmx, d[c]);
+    for (int c = 0; c < C; ++c) {  // all loads first, then the compare chain
+        l[c] = __ldg(pd);
+        pd += plane;
     }
-    float ds = 0.0f;
+    const float l0 = l[0];
+    float ls = l[1];
+    int arg = 1;
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        d[c] = expf(d[c] - dmx);
-        ds = __fadd_rn(ds, d[c]);
-    }
-    float best = __fmul_rn(__fdiv_rn(d[0], ds), o.p0);  // prob_maps_direction[0] *= prob_maps[0]  (:1010)
-    int arg = 0;
-#pragma unroll
-    for (int c = 1; c < C; ++c) {
-        const float q = __fdiv_rn(d[c], ds);
-        if (q > best) { best = q; arg = c; }  // np.argmax: the first maximum wins
-    }
+    for (int c = 2; c < C; ++c)
+        if (l[c] > ls) { ls = l[c]; arg = c; }
+    const float dmx = fmaxf(l0, ls);
+    const float w0 = __fmul_rn(expf(l0 - dmx), o.p0);
+    if (!(expf(ls - dmx) > w0)) arg = 0;
     o.cls = arg;
     return o;
 }
