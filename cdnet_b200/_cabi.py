@@ -45,8 +45,8 @@ SIGNATURES = {
     "cdnet_label_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cdnet_encode_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "cdnet_tta_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                c_void_p]),
+    "cdnet_tta_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_void_p]),
     "cdnet_label_to_vector": (c_int, [c_void_p, c_int, c_void_p, c_int, c_size_t, c_int, c_void_p]),
     "cdnet_align_angle": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "cdnet_angle_to_vector": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),

@@ -496,11 +496,13 @@ def tta_merge_cuda(mask_logits, point, dir_logits):
     """Device-resident hand-off for test-time augmentation (test_dam.py:299-450 and get_probmaps :983-1013) in ONE
     kernel.  Each argument is a sequence of 8 CUDA float32 tensors, the raw network outputs of the variants in the
     order TTA_VARIANTS, in the variant's own frame: [B,3,h,w], [B,1,h,w], [B,C,h,w] (h,w = H,W for the flips,
-    W,H for the rotated ones).  Returns (prob float32 [B,3,H,W], point float32 [B,1,H,W], dcm uint8 [B,8,H,W]) in
-    the original frame: exactly the inputs of dam_postprocess_cuda."""
+    W,H for the rotated ones) -- or sequences of ONE tensor each when test-time augmentation is off.  Returns
+    (prob float32 [B,3,H,W], point float32 [B,1,H,W], dcm uint8 [B,n,H,W]) in the original frame: exactly the
+    inputs of dam_postprocess_cuda."""
     import ctypes
     L = _cabi.lib()
-    assert len(mask_logits) == 8 and len(point) == 8 and len(dir_logits) == 8
+    nv = len(mask_logits)
+    assert nv in (1, 8) and len(point) == nv and len(dir_logits) == nv
     dev = _device(mask_logits[0].device)
     B, three, H, W = mask_logits[0].shape
     C = dir_logits[0].shape[1]
@@ -508,7 +510,7 @@ def tta_merge_cuda(mask_logits, point, dir_logits):
     keep = []
     arrays = []
     for seq, ch in ((mask_logits, 3), (point, 1), (dir_logits, C)):
-        ptrs = (ctypes.c_void_p * 8)()
+        ptrs = (ctypes.c_void_p * nv)()
         for v, t in enumerate(seq):
             shape = (B, ch, H, W) if v < 4 else (B, ch, W, H)
             if t.dim() == 3 and ch == 1:
@@ -520,8 +522,8 @@ def tta_merge_cuda(mask_logits, point, dir_logits):
         arrays.append(ptrs)
     prob = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
     pt = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
-    dcm = torch.empty((B, 8, H, W), dtype=torch.uint8, device=dev)
-    check(L.cdnet_tta_merge(arrays[0], arrays[1], arrays[2], _ptr(prob), _ptr(pt), _ptr(dcm), B, H, W, int(C),
+    dcm = torch.empty((B, nv, H, W), dtype=torch.uint8, device=dev)
+    check(L.cdnet_tta_merge(arrays[0], arrays[1], arrays[2], nv, _ptr(prob), _ptr(pt), _ptr(dcm), B, H, W, int(C),
                             _stream()), "cdnet_tta_merge")
     return prob, pt, dcm
 

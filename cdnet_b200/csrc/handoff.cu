@@ -80,7 +80,8 @@ __device__ __forceinline__ PixelOut eval_pixel(const float* __restrict__ mask, c
 template <int C>
 __global__ void __launch_bounds__(kTile* kRowsPerPass) k_tta_merge(TtaPtrs P, float* __restrict__ prob_out,
                                                                     float* __restrict__ point_out,
-                                                                    uint8_t* __restrict__ dcm_out, int H, int W) {
+                                                                    uint8_t* __restrict__ dcm_out, int H, int W,
+                                                                    int n_var) {
     // staging tile of the rotated variants, [local y][local x]: filled by lanes that walk y (row stride
     // kTile + 1 words: conflict-free), consumed by lanes that walk x
     __shared__ float s_val[4][kTile][kTile + 1];
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kTile* kRowsPerPass) k_tta_merge(TtaPtrs P, fl
 
     // ---- variants 0..3: flips only, read in place (a reversed row is still one coalesced segment) ----
 #pragma unroll 1
-    for (int v = 0; v < 4; ++v) {
+    for (int v = 0; v < (n_var < 4 ? n_var : 4); ++v) {
         const float* mask = P.mask[v] + (size_t)b * 3 * plane;
         const float* point = P.point[v] + (size_t)b * plane;
         const float* dir = P.dir[v] + (size_t)b * C * plane;
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kTile* kRowsPerPass) k_tta_merge(TtaPtrs P, fl
                     acc[r][2] = __fadd_rn(acc[r][2], o.p2);
                     acc[r][3] = __fadd_rn(acc[r][3], o.pt);
                 }
-                dcm_out[((size_t)b * 8 + v) * plane + (size_t)y * W + x] = (uint8_t)o.cls;
+                dcm_out[((size_t)b * n_var + v) * plane + (size_t)y * W + x] = (uint8_t)o.cls;
             }
         }
     }
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kTile* kRowsPerPass) k_tta_merge(TtaPtrs P, fl
     // original (y, x) <- variant (row, col) = (v&2 ? x : W-1-x,  v&1 ? H-1-y : y): consecutive lanes walk the
     // variant's columns, i.e. the original frame's rows y; results are transposed through shared memory
 #pragma unroll 1
-    for (int v = 4; v < 8; ++v) {
+    for (int v = 4; v < n_var; ++v) {
         const float* mask = P.mask[v] + (size_t)b * 3 * plane;
         const float* point = P.point[v] + (size_t)b * plane;
         const float* dir = P.dir[v] + (size_t)b * C * plane;
@@ -149,20 +150,21 @@ __global__ void __launch_bounds__(kTile* kRowsPerPass) k_tta_merge(TtaPtrs P, fl
                 acc[r][1] = __fadd_rn(acc[r][1], s_val[1][ly][tx]);
                 acc[r][2] = __fadd_rn(acc[r][2], s_val[2][ly][tx]);
                 acc[r][3] = __fadd_rn(acc[r][3], s_val[3][ly][tx]);
-                dcm_out[((size_t)b * 8 + v) * plane + (size_t)y * W + x] = (uint8_t)s_cls[ly][tx];
+                dcm_out[((size_t)b * n_var + v) * plane + (size_t)y * W + x] = (uint8_t)s_cls[ly][tx];
             }
         }
     }
 
+    const float scale = n_var == 8 ? 0.125f : 1.0f;  // "/ 8" (:446,450) is exact; without TTA nothing is averaged
 #pragma unroll
     for (int r = 0; r < kPasses; ++r) {
         const int y = y0 + ty + r * kRowsPerPass;
         if (x < W && y < H) {
             const size_t p = (size_t)y * W + x;
-            prob_out[((size_t)b * 3 + 0) * plane + p] = __fmul_rn(acc[r][0], 0.125f);  // / 8 is exact
-            prob_out[((size_t)b * 3 + 1) * plane + p] = __fmul_rn(acc[r][1], 0.125f);
-            prob_out[((size_t)b * 3 + 2) * plane + p] = __fmul_rn(acc[r][2], 0.125f);
-            point_out[(size_t)b * plane + p] = __fmul_rn(acc[r][3], 0.125f);
+            prob_out[((size_t)b * 3 + 0) * plane + p] = __fmul_rn(acc[r][0], scale);
+            prob_out[((size_t)b * 3 + 1) * plane + p] = __fmul_rn(acc[r][1], scale);
+            prob_out[((size_t)b * 3 + 2) * plane + p] = __fmul_rn(acc[r][2], scale);
+            point_out[(size_t)b * plane + p] = __fmul_rn(acc[r][3], scale);
         }
     }
 }
@@ -172,23 +174,25 @@ __global__ void __launch_bounds__(kTile* kRowsPerPass) k_tta_merge(TtaPtrs P, fl
 using namespace cdnet;
 
 extern "C" int cdnet_tta_merge(const float* const* mask_logits, const float* const* point, const float* const* dir_logits,
-                               float* prob_out, float* point_out, uint8_t* dcm_out, int B, int H, int W, int dir_classes,
-                               void* stream) {
+                               int n_variants, float* prob_out, float* point_out, uint8_t* dcm_out, int B, int H, int W,
+                               int dir_classes, void* stream) {
     if (!mask_logits || !point || !dir_logits || !prob_out || !point_out || !dcm_out) return CDNET_E_BADARG;
     if (B <= 0 || B > 65535 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0) return CDNET_E_BADARG;
+    if (n_variants != 1 && n_variants != 8) return CDNET_E_BADARG;
     TtaPtrs P;
     for (int v = 0; v < 8; ++v) {
-        if (!mask_logits[v] || !point[v] || !dir_logits[v]) return CDNET_E_BADARG;
-        P.mask[v] = mask_logits[v];
-        P.point[v] = point[v];
-        P.dir[v] = dir_logits[v];
+        const int u = v < n_variants ? v : 0;
+        if (!mask_logits[u] || !point[u] || !dir_logits[u]) return CDNET_E_BADARG;
+        P.mask[v] = mask_logits[u];
+        P.point[v] = point[u];
+        P.dir[v] = dir_logits[u];
     }
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid(ceil_div(W, kTile), ceil_div(H, kTile), B), block(kTile, kRowsPerPass);
     if (ceil_div(H, kTile) > 65535) return CDNET_E_BADARG;
-    if (dir_classes == 5) CDNET_LAUNCH(k_tta_merge<5>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W);
-    else if (dir_classes == 9) CDNET_LAUNCH(k_tta_merge<9>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W);
-    else if (dir_classes == 17) CDNET_LAUNCH(k_tta_merge<17>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W);
+    if (dir_classes == 5) CDNET_LAUNCH(k_tta_merge<5>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W, n_variants);
+    else if (dir_classes == 9) CDNET_LAUNCH(k_tta_merge<9>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W, n_variants);
+    else if (dir_classes == 17) CDNET_LAUNCH(k_tta_merge<17>, grid, block, 0, st, P, prob_out, point_out, dcm_out, H, W, n_variants);
     else return CDNET_E_BADARG;
     return last_error();
 }

@@ -180,12 +180,13 @@ int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternar
  * float32 softmax of the 3-class head, float32 softmax of the direction head, direction[0] *= mask[0],
  * first-maximum argmax; np.flip / np.rot90(k=3) back to the original frame; probabilities and point maps summed
  * in variant order and divided by 8.
- * mask_logits / point / dir_logits: HOST arrays of 8 DEVICE pointers: float32 [B,3,h_v,w_v], [B,1,h_v,w_v],
- * [B,dir_classes,h_v,w_v]; prob_out float32 [B,3,H,W]; point_out float32 [B,1,H,W]; dcm_out uint8 [B,8,H,W]
- * -- the three inputs of cdnet_dam_postproc.  dir_classes in {5, 9, 17}. */
+ * mask_logits / point / dir_logits: HOST arrays of n_variants DEVICE pointers: float32 [B,3,h_v,w_v],
+ * [B,1,h_v,w_v], [B,dir_classes,h_v,w_v]; prob_out float32 [B,3,H,W]; point_out float32 [B,1,H,W]; dcm_out
+ * uint8 [B,n_variants,H,W] -- the three inputs of cdnet_dam_postproc.  n_variants 8, or 1 = no augmentation
+ * (`tta` off, test_dam.py:313: the identity variant alone, nothing averaged).  dir_classes in {5, 9, 17}. */
 int cdnet_tta_merge(const float* const* mask_logits, const float* const* point,
-                    const float* const* dir_logits, float* prob_out, float* point_out, uint8_t* dcm_out,
-                    int B, int H, int W, int dir_classes, void* stream);
+                    const float* const* dir_logits, int n_variants, float* prob_out, float* point_out,
+                    uint8_t* dcm_out, int B, int H, int W, int dir_classes, void* stream);
 
 /* ---- the direction quantiser as stand-alone operators --------------------------------------------
  * DTOffsetHelper static methods of data_prepare/SegFix_offset_helper.py; `n` counts elements.

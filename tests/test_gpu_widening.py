@@ -104,6 +104,25 @@ def test_tta_merge_vs_oracle(kernel_api, B, H, W, C):
             assert clear.mean() > 0.99
 
 
+def test_hand_off_without_tta(kernel_api):
+    """one variant (tta off): soft-max / argmax only, nothing averaged; dcm has one map (test_dam.py:499-502)"""
+    from oracle import restate as O
+    ml, pt, dl = _tta_inputs(7, 2, 40, 56, 9)
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, ml[0])], [to_dev(kernel_api, pt[0])],
+                                                 [to_dev(kernel_api, dl[0])])
+    assert tuple(dcm.shape) == (2, 1, 40, 56)
+    for b in range(2):
+        p, q, c = O.variant_probmaps(ml[0][b].numpy(), pt[0][b].numpy(), dl[0][b].numpy())
+        assert np.allclose(prob[b].cpu().numpy(), p, rtol=1e-5, atol=1e-7)
+        assert np.array_equal(point[b].cpu().numpy(), q)
+        z = dl[0][b].numpy().astype(np.float64)
+        qq = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
+        qq[0] *= p[0]
+        top = np.sort(qq, axis=0)
+        clear = (top[-1] - top[-2]) > 1e-6
+        assert np.array_equal(dcm[b, 0].cpu().numpy().astype(np.int64)[clear], c[0][clear]) and clear.mean() > 0.99
+
+
 def test_tta_merge_feeds_postprocess(kernel_api):
     """hand-off -> dam_postprocess_cuda without leaving the device == the same two steps through the oracle"""
     from oracle import restate as O
