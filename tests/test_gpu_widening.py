@@ -76,7 +76,9 @@ def _tta_inputs(seed, B, H, W, C):
     return ml, pt, dl
 
 
-@pytest.mark.parametrize("B,H,W,C", [(1, 21, 34, 9), (2, 64, 96, 9), (1, 33, 31, 17), (1, 1, 1, 5), (1, 70, 5, 9)])
+# H % 4 == W % 4 == 0 takes the 4-pixel (128-bit) kernel, everything else the scalar one
+@pytest.mark.parametrize("B,H,W,C", [(1, 21, 34, 9), (2, 64, 96, 9), (1, 33, 31, 17), (1, 1, 1, 5), (1, 70, 5, 9),
+                                     (1, 36, 100, 17), (2, 100, 36, 5), (1, 4, 4, 9), (1, 8, 132, 9)])
 def test_tta_merge_vs_oracle(kernel_api, B, H, W, C):
     """fused TTA hand-off (test_dam.py:299-450, :983-1013) vs the restatement (pinned to the verbatim reference in
     tests/test_oracle_vs_reference.py).  Probabilities: 1e-5 relative (the softmax's expf is the device's, the
