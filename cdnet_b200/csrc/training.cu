@@ -74,102 +74,186 @@ __global__ void __launch_bounds__(256) k_label_to_vector(const T* __restrict__ l
     }
 }
 
-// ---- align_angle --------------------------------------------------------------------------------------
-// index of the (upper-inclusive) bin of `a`; all thresholds -180 + step*(i +- 1/2) are exact in f32 and f64
-// for the supported n (8, 16, 32), so comparing the f64-promoted angle is what numpy / torch compute.
-// NaN matches no bin: the reference leaves its zero-initialised outputs (index 0, angle 0.0).
-__device__ __forceinline__ int align_bin(double a, int n, bool* matched) {
-    const double step = 360.0 / (double)n, half = step * 0.5;
-    *matched = true;
-    if (a <= -180.0 + half || a > 180.0 - half) return 0;
-    for (int i = 1; i < n; ++i) {
-        const double mid = -180.0 + step * (double)i;
-        if (a > mid - half && a <= mid + half) return i;
-    }
-    *matched = false;
-    return 0;
+// ---- 128-bit accesses: four consecutive elements from a 16-byte aligned address -------------------------------------
+template <typename T>
+struct Quad {
+    T v[4];
+};
+__device__ __forceinline__ Quad<float> ld_quad(const float* p) {
+    const float4 t = __ldg((const float4*)p);
+    Quad<float> q;
+    q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+    return q;
 }
+__device__ __forceinline__ Quad<double> ld_quad(const double* p) {
+    const double2 a = __ldg((const double2*)p), b = __ldg((const double2*)p + 1);
+    Quad<double> q;
+    q.v[0] = a.x; q.v[1] = a.y; q.v[2] = b.x; q.v[3] = b.y;
+    return q;
+}
+__device__ __forceinline__ void st_quad(float* p, const Quad<float>& q) {
+    *(float4*)p = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+}
+__device__ __forceinline__ void st_quad(double* p, const Quad<double>& q) {
+    *(double2*)p = make_double2(q.v[0], q.v[1]);
+    *((double2*)p + 1) = make_double2(q.v[2], q.v[3]);
+}
+__device__ __forceinline__ void st_quad(long long* p, const Quad<long long>& q) {
+    *(longlong2*)p = make_longlong2(q.v[0], q.v[1]);
+    *((longlong2*)p + 1) = make_longlong2(q.v[2], q.v[3]);
+}
+
+// ---- align_angle --------------------------------------------------------------------------------------
+// Index of the (upper-inclusive) bin of `a`.  The bin edges T_j = -180 + step * (j + 1/2), j = 0..n-1, are exact in
+// f32 and f64 for the supported n (8, 16, 32), so comparing the f64-promoted angle is what numpy / torch compute;
+// the reference's mask loop (:323-339) assigns bin #{j : T_j < a}, the count n wrapping to bin 0 -- found here
+// by bisection (n is a power of two).  NaN matches no bin: the reference leaves its zero-initialised outputs
+// (index 0, angle 0.0).
+__device__ __forceinline__ int align_bin(double a, int n, bool* matched) {
+    const double step = 360.0 / (double)n, t0 = -180.0 + 0.5 * step;
+    *matched = (a == a);
+    int c = 0;
+    for (int s = n >> 1; s >= 1; s >>= 1)
+        if (t0 + step * (double)(c + s - 1) < a) c += s;
+    if (t0 + step * (double)c < a) c += 1;
+    return c == n ? 0 : c;
+}
+
+// align_angle_c4 (:286-309): trunc((a + 180) / 90) in the angle's own precision, clamped to 0..3.
+// torch.trunc(..).long(): NaN / out-of-range conversions are implementation-defined on the host (x86: INT64_MIN);
+// the clamp makes every such value 0, +inf included (it is INT64_MIN there too)
+template <typename TI>
+__device__ __forceinline__ int align_bin_c4(TI a) {
+    const TI q = (a + (TI)180) / (TI)90;
+    long long k = 0;
+    if (q == q && q > (TI)-9.0e18 && q < (TI)9.0e18) k = (long long)q;  // the C cast truncates toward zero
+    return (int)(k < 0 ? 0 : (k > 3 ? 3 : k));
+}
+
+// Every kernel below is a stream over n elements: quads first (`vec` = every base pointer is 16-byte aligned),
+// then the ragged tail element by element.
+#define CDNET_STREAM_QUADS(n, vec)                                                        \
+    const size_t nq = (vec) ? (n) / 4 : 0;                                                \
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x
 
 // TI: input angle type; TO: type of the snapped angle (numpy path f64, torch path f32)
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) k_align_angle(const TI* __restrict__ angle, TO* __restrict__ snapped,
-                                                     long long* __restrict__ index, size_t n, int classes) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+                                                     long long* __restrict__ index, size_t n, int classes, int vec) {
+    CDNET_STREAM_QUADS(n, vec);
+    const double step = 360.0 / (double)classes;
+    for (size_t q = tid; q < nq; q += nth) {
+        const Quad<TI> a = ld_quad(angle + 4 * q);
+        Quad<TO> s;
+        Quad<long long> k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bool hit;
+            const int bin = align_bin((double)a.v[j], classes, &hit);
+            s.v[j] = hit ? (TO)(-180.0 + step * (double)bin) : (TO)0.0;
+            k.v[j] = bin;
+        }
+        if (snapped) st_quad(snapped + 4 * q, s);
+        if (index) st_quad(index + 4 * q, k);
+    }
+    for (size_t i = nq * 4 + tid; i < n; i += nth) {
         bool hit;
-        const int k = align_bin((double)angle[i], classes, &hit);
-        if (snapped) snapped[i] = hit ? (TO)(-180.0 + (360.0 / (double)classes) * (double)k) : (TO)0.0;
-        if (index) index[i] = k;
+        const int bin = align_bin((double)angle[i], classes, &hit);
+        if (snapped) snapped[i] = hit ? (TO)(-180.0 + step * (double)bin) : (TO)0.0;
+        if (index) index[i] = bin;
     }
 }
 
-// align_angle_c4 (:286-309): trunc((a + 180) / 90) in the angle's own precision, clamped to 0..3; the
-// snapped angle is float32 on both of the reference's paths
+// the snapped angle of align_angle_c4 is float32 on both of the reference's paths
 template <typename TI>
 __global__ void __launch_bounds__(256) k_align_angle_c4(const TI* __restrict__ angle, float* __restrict__ snapped,
-                                                        long long* __restrict__ index, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const TI q = (angle[i] + (TI)180) / (TI)90;
-        // torch.trunc(..).long(): NaN / out-of-range conversions are implementation-defined on the host
-        // (x86: INT64_MIN); the clamp makes every such value 0, +inf included (it is INT64_MIN there too)
-        long long k = 0;
-        if (q == q && q > (TI)-9.0e18 && q < (TI)9.0e18) k = (long long)q;  // C cast truncates toward zero
-        k = k < 0 ? 0 : (k > 3 ? 3 : k);
-        if (snapped) snapped[i] = (float)(k * 90 - 135);
-        if (index) index[i] = k;
+                                                        long long* __restrict__ index, size_t n, int vec) {
+    CDNET_STREAM_QUADS(n, vec);
+    for (size_t q = tid; q < nq; q += nth) {
+        const Quad<TI> a = ld_quad(angle + 4 * q);
+        Quad<float> s;
+        Quad<long long> k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int bin = align_bin_c4<TI>(a.v[j]);
+            s.v[j] = (float)(bin * 90 - 135);
+            k.v[j] = bin;
+        }
+        if (snapped) st_quad(snapped + 4 * q, s);
+        if (index) st_quad(index + 4 * q, k);
+    }
+    for (size_t i = nq * 4 + tid; i < n; i += nth) {
+        const int bin = align_bin_c4<TI>(angle[i]);
+        if (snapped) snapped[i] = (float)(bin * 90 - 135);
+        if (index) index[i] = bin;
     }
 }
 
 // ---- angle_to_vector: snap, then (sin, cos) of the bin centre from a host-computed table ------------------
 struct SinCosTable {
-    double s[32], c[32];
+    double s[33], c[33];  // [classes] = the row for angles no bin matches (NaN keeps the snapped angle 0.0)
 };
+template <typename TI>
+__device__ __forceinline__ int sincos_row(TI a, int classes, int c4) {
+    if (c4) return align_bin_c4<TI>(a);
+    bool hit;
+    const int bin = align_bin((double)a, classes, &hit);
+    return hit ? bin : classes;
+}
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) k_angle_to_vector(const TI* __restrict__ angle, TO* __restrict__ vec, size_t n,
-                                                         int classes, int c4, SinCosTable tab, double s0, double c0) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        double s, c;
-        if (c4) {
-            const TI q = (angle[i] + (TI)180) / (TI)90;
-            long long k = 0;
-            if (q == q && q > (TI)-9.0e18 && q < (TI)9.0e18) k = (long long)q;
-            k = k < 0 ? 0 : (k > 3 ? 3 : k);
-            s = tab.s[k];
-            c = tab.c[k];
-        } else {
-            bool hit;
-            const int k = align_bin((double)angle[i], classes, &hit);
-            s = hit ? tab.s[k] : s0;  // unmatched (NaN) angles keep the snapped angle 0.0: (sin 0, cos 0)
-            c = hit ? tab.c[k] : c0;
+                                                         int classes, int c4, SinCosTable tab, int vecq) {
+    CDNET_STREAM_QUADS(n, vecq);
+    for (size_t q = tid; q < nq; q += nth) {
+        const Quad<TI> a = ld_quad(angle + 4 * q);
+        Quad<TO> lo, hi;  // (s0, c0, s1, c1), (s2, c2, s3, c3)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = sincos_row<TI>(a.v[j], classes, c4);
+            Quad<TO>& d = j < 2 ? lo : hi;
+            d.v[2 * (j & 1)] = (TO)tab.s[r];
+            d.v[2 * (j & 1) + 1] = (TO)tab.c[r];
         }
-        vec[2 * i] = (TO)s;
-        vec[2 * i + 1] = (TO)c;
+        st_quad(vec + 8 * q, lo);
+        st_quad(vec + 8 * q + 4, hi);
+    }
+    for (size_t i = nq * 4 + tid; i < n; i += nth) {
+        const int r = sincos_row<TI>(angle[i], classes, c4);
+        vec[2 * i] = (TO)tab.s[r];
+        vec[2 * i + 1] = (TO)tab.c[r];
     }
 }
 
 // ---- vector_to_label: atan2 -> degrees -> bin index (no ignore mask: seg_label_map is None at :503-505) ----
+// np.arctan2 in the vector's precision, np.rad2deg = x * (180 / pi) in the same precision
+template <typename TI>
+__device__ __forceinline__ long long vector_bin(TI v0, TI v1, int classes, int c4) {
+    double deg;
+    if (sizeof(TI) == 4) {
+        const float a = (float)atan2((double)v0, (double)v1);
+        deg = (double)__fmul_rn(a, 57.295779513082320876798154814105f);
+        if (c4) return align_bin_c4<float>((float)deg);
+    } else {
+        deg = __dmul_rn(atan2((double)v0, (double)v1), 57.295779513082320876798154814105);
+        if (c4) return align_bin_c4<double>(deg);
+    }
+    bool hit;
+    return align_bin(deg, classes, &hit);
+}
 template <typename TI>
 __global__ void __launch_bounds__(256) k_vector_to_label(const TI* __restrict__ vec, long long* __restrict__ label,
-                                                         size_t n, int classes, int c4) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        // np.arctan2 in the vector's precision, np.rad2deg = x * (180 / pi) in the same precision
-        double deg;
-        if (sizeof(TI) == 4) {
-            const float a = (float)atan2((double)vec[2 * i], (double)vec[2 * i + 1]);
-            deg = (double)__fmul_rn(a, 57.295779513082320876798154814105f);
-        } else {
-            deg = __dmul_rn(atan2((double)vec[2 * i], (double)vec[2 * i + 1]), 57.295779513082320876798154814105);
-        }
-        long long k;
-        if (c4) {
-            double q = (sizeof(TI) == 4) ? (double)(((float)deg + 180.0f) / 90.0f) : (deg + 180.0) / 90.0;
-            k = (q == q) ? (long long)q : 0;
-            k = k < 0 ? 0 : (k > 3 ? 3 : k);
-        } else {
-            bool hit;
-            k = align_bin(deg, classes, &hit);
-        }
-        label[i] = k;
+                                                         size_t n, int classes, int c4, int vecq) {
+    CDNET_STREAM_QUADS(n, vecq);
+    for (size_t q = tid; q < nq; q += nth) {
+        const Quad<TI> lo = ld_quad(vec + 8 * q), hi = ld_quad(vec + 8 * q + 4);
+        Quad<long long> k;
+        k.v[0] = vector_bin<TI>(lo.v[0], lo.v[1], classes, c4);
+        k.v[1] = vector_bin<TI>(lo.v[2], lo.v[3], classes, c4);
+        k.v[2] = vector_bin<TI>(hi.v[0], hi.v[1], classes, c4);
+        k.v[3] = vector_bin<TI>(hi.v[2], hi.v[3], classes, c4);
+        st_quad(label + 4 * q, k);
     }
+    for (size_t i = nq * 4 + tid; i < n; i += nth) label[i] = vector_bin<TI>(vec[2 * i], vec[2 * i + 1], classes, c4);
 }
 
 // ---- direction one-hot + foreground mask (train_util_dam.py:123-142) ------------------------------------------
@@ -281,6 +365,42 @@ __global__ void __launch_bounds__(256) k_ternary_label(const uint8_t* __restrict
     out[tile + p] = nl == 0 ? 0 : (nl == 1 ? 127 : 255);
 }
 
+// four pixels per thread for modes 0-2 (W % 4 == 0, 4-byte aligned planes): the rows above / below and the centre
+// row arrive as 32-bit words, the two horizontal neighbours outside the word as single bytes
+__global__ void __launch_bounds__(256) k_ternary_label4(const uint8_t* __restrict__ ch0, int mode,
+                                                        uint8_t* __restrict__ out, int H, int W) {
+    const int x = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const size_t tile = (size_t)b * H * W;
+    const uint8_t* A = ch0 + tile + (size_t)y * W + x;
+    auto val = [&](unsigned v) -> int { return mode == 0 ? (int)v : (mode == 1 ? (v > 127u ? 1 : 0) : (v > 0u ? 2 : 0)); };
+    const unsigned wc = __ldg((const unsigned*)A);
+    unsigned res = 0;
+    if (mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res |= (((wc >> (8 * j)) & 0xffu) ? 255u : 0u) << (8 * j);
+    } else {
+        // a missing neighbour (outside the image) is replaced by the centre pixel: it changes neither max nor min
+        const unsigned wu = y > 0 ? __ldg((const unsigned*)(A - W)) : wc;
+        const unsigned wd = y + 1 < H ? __ldg((const unsigned*)(A + W)) : wc;
+        const unsigned left = x > 0 ? (unsigned)__ldg(A - 1) : (wc & 0xffu);
+        const unsigned right = x + 4 < W ? (unsigned)__ldg(A + 4) : (wc >> 24);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = val((wc >> (8 * j)) & 0xffu);
+            const int u = val((wu >> (8 * j)) & 0xffu), d = val((wd >> (8 * j)) & 0xffu);
+            const int l = val(j == 0 ? left : (wc >> (8 * (j - 1))) & 0xffu);
+            const int r = val(j == 3 ? right : (wc >> (8 * (j + 1))) & 0xffu);
+            const int mx = max(max(max(v, u), max(d, l)), r), mn = min(min(min(v, u), min(d, l)), r);
+            const unsigned nl = (mx != mn) ? 255u : (v > 0 ? 127u : 0u);
+            res |= nl << (8 * j);
+        }
+    }
+    *(unsigned*)(out + tile + (size_t)y * W + x) = res;
+}
+
 static inline unsigned stream_grid(size_t n, int per_block) {
     size_t g = (n + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -305,6 +425,9 @@ extern "C" int cdnet_label_to_vector(const void* labels, int elem_bytes, int64_t
 }
 
 static bool align_classes_ok(int n) { return n == 4 || n == 8 || n == 16 || n == 32; }
+static int aligned16(const void* a, const void* b, const void* c) {
+    return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) == 0;  // NULL counts as aligned
+}
 
 extern "C" int cdnet_align_angle(const void* angle, int in_elem_bytes, void* snapped, int out_elem_bytes, int64_t* index,
                                  size_t n, int num_classes, void* stream) {
@@ -313,18 +436,19 @@ extern "C" int cdnet_align_angle(const void* angle, int in_elem_bytes, void* sna
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = stream_grid(n, 256 * 4);
     long long* idx = (long long*)index;
+    const int vec = aligned16(angle, snapped, index);
     if (num_classes == 4) {
         if (snapped && out_elem_bytes != 4) return CDNET_E_BADARG;  // align_angle_c4 returns float32
-        if (in_elem_bytes == 4) CDNET_LAUNCH(k_align_angle_c4<float>, grid, 256, 0, st, (const float*)angle, (float*)snapped, idx, n);
-        else CDNET_LAUNCH(k_align_angle_c4<double>, grid, 256, 0, st, (const double*)angle, (float*)snapped, idx, n);
+        if (in_elem_bytes == 4) CDNET_LAUNCH(k_align_angle_c4<float>, grid, 256, 0, st, (const float*)angle, (float*)snapped, idx, n, vec);
+        else CDNET_LAUNCH(k_align_angle_c4<double>, grid, 256, 0, st, (const double*)angle, (float*)snapped, idx, n, vec);
         return last_error();
     }
     if (in_elem_bytes == 4) {
-        if (!snapped || out_elem_bytes == 8) CDNET_LAUNCH((k_align_angle<float, double>), grid, 256, 0, st, (const float*)angle, (double*)snapped, idx, n, num_classes);
-        else CDNET_LAUNCH((k_align_angle<float, float>), grid, 256, 0, st, (const float*)angle, (float*)snapped, idx, n, num_classes);
+        if (!snapped || out_elem_bytes == 8) CDNET_LAUNCH((k_align_angle<float, double>), grid, 256, 0, st, (const float*)angle, (double*)snapped, idx, n, num_classes, vec);
+        else CDNET_LAUNCH((k_align_angle<float, float>), grid, 256, 0, st, (const float*)angle, (float*)snapped, idx, n, num_classes, vec);
     } else {
-        if (!snapped || out_elem_bytes == 8) CDNET_LAUNCH((k_align_angle<double, double>), grid, 256, 0, st, (const double*)angle, (double*)snapped, idx, n, num_classes);
-        else CDNET_LAUNCH((k_align_angle<double, float>), grid, 256, 0, st, (const double*)angle, (float*)snapped, idx, n, num_classes);
+        if (!snapped || out_elem_bytes == 8) CDNET_LAUNCH((k_align_angle<double, double>), grid, 256, 0, st, (const double*)angle, (double*)snapped, idx, n, num_classes, vec);
+        else CDNET_LAUNCH((k_align_angle<double, float>), grid, 256, 0, st, (const double*)angle, (float*)snapped, idx, n, num_classes, vec);
     }
     return last_error();
 }
@@ -334,16 +458,16 @@ extern "C" int cdnet_angle_to_vector(const void* angle, int in_elem_bytes, void*
     if (!angle || !vec || !table || n == 0 || !align_classes_ok(num_classes)) return CDNET_E_BADARG;
     if ((in_elem_bytes != 4 && in_elem_bytes != 8) || (out_elem_bytes != 4 && out_elem_bytes != 8)) return CDNET_E_BADARG;
     SinCosTable tab;
-    for (int i = 0; i < 32; ++i) { tab.s[i] = 0.0; tab.c[i] = 0.0; }
-    for (int i = 0; i < num_classes; ++i) { tab.s[i] = table[2 * i]; tab.c[i] = table[2 * i + 1]; }
-    const double s0 = table[2 * num_classes], c0 = table[2 * num_classes + 1];
+    for (int i = 0; i < 33; ++i) { tab.s[i] = 0.0; tab.c[i] = 0.0; }
+    for (int i = 0; i <= num_classes; ++i) { tab.s[i] = table[2 * i]; tab.c[i] = table[2 * i + 1]; }
     const int c4 = num_classes == 4;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = stream_grid(n, 256 * 4);
-    if (in_elem_bytes == 4 && out_elem_bytes == 8) CDNET_LAUNCH((k_angle_to_vector<float, double>), grid, 256, 0, st, (const float*)angle, (double*)vec, n, num_classes, c4, tab, s0, c0);
-    else if (in_elem_bytes == 4) CDNET_LAUNCH((k_angle_to_vector<float, float>), grid, 256, 0, st, (const float*)angle, (float*)vec, n, num_classes, c4, tab, s0, c0);
-    else if (out_elem_bytes == 8) CDNET_LAUNCH((k_angle_to_vector<double, double>), grid, 256, 0, st, (const double*)angle, (double*)vec, n, num_classes, c4, tab, s0, c0);
-    else CDNET_LAUNCH((k_angle_to_vector<double, float>), grid, 256, 0, st, (const double*)angle, (float*)vec, n, num_classes, c4, tab, s0, c0);
+    const int vq = aligned16(angle, vec, nullptr);
+    if (in_elem_bytes == 4 && out_elem_bytes == 8) CDNET_LAUNCH((k_angle_to_vector<float, double>), grid, 256, 0, st, (const float*)angle, (double*)vec, n, num_classes, c4, tab, vq);
+    else if (in_elem_bytes == 4) CDNET_LAUNCH((k_angle_to_vector<float, float>), grid, 256, 0, st, (const float*)angle, (float*)vec, n, num_classes, c4, tab, vq);
+    else if (out_elem_bytes == 8) CDNET_LAUNCH((k_angle_to_vector<double, double>), grid, 256, 0, st, (const double*)angle, (double*)vec, n, num_classes, c4, tab, vq);
+    else CDNET_LAUNCH((k_angle_to_vector<double, float>), grid, 256, 0, st, (const double*)angle, (float*)vec, n, num_classes, c4, tab, vq);
     return last_error();
 }
 
@@ -353,8 +477,9 @@ extern "C" int cdnet_vector_to_label(const void* vec, int elem_bytes, int64_t* l
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = stream_grid(n, 256 * 4);
     const int c4 = num_classes == 4;
-    if (elem_bytes == 4) CDNET_LAUNCH(k_vector_to_label<float>, grid, 256, 0, st, (const float*)vec, (long long*)label, n, num_classes, c4);
-    else CDNET_LAUNCH(k_vector_to_label<double>, grid, 256, 0, st, (const double*)vec, (long long*)label, n, num_classes, c4);
+    const int vq = aligned16(vec, label, nullptr);
+    if (elem_bytes == 4) CDNET_LAUNCH(k_vector_to_label<float>, grid, 256, 0, st, (const float*)vec, (long long*)label, n, num_classes, c4, vq);
+    else CDNET_LAUNCH(k_vector_to_label<double>, grid, 256, 0, st, (const double*)vec, (long long*)label, n, num_classes, c4, vq);
     return last_error();
 }
 
@@ -391,6 +516,9 @@ extern "C" int cdnet_ternary_label(const uint8_t* ch0, const uint8_t* ch1, int m
     if (!ch0 || !out || B <= 0 || B > 65535 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0 || mode < 0 || mode > 3)
         return CDNET_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    CDNET_LAUNCH(k_ternary_label, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, ch0, ch1, mode, out, H, W);
+    if (mode != 3 && W % 4 == 0 && (((uintptr_t)ch0 | (uintptr_t)out) & 3u) == 0)
+        CDNET_LAUNCH(k_ternary_label4, dim3(ceil_div(W, 256), ceil_div(H, 4), B), dim3(64, 4), 0, st, ch0, mode, out, H, W);
+    else
+        CDNET_LAUNCH(k_ternary_label, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, ch0, ch1, mode, out, H, W);
     return last_error();
 }

@@ -65,6 +65,29 @@ def test_quantiser_16_and_32_vs_oracle(T):
             assert _same(T.DTOffsetHelper.angle_to_vector(a.copy(), num_classes=n), O.angle_to_vector(a.copy(), n))
 
 
+def test_quantiser_ragged_and_unaligned(T):
+    """n % 4 != 0 (scalar tail after the 128-bit quads) and a base pointer that is not 16-byte aligned"""
+    from oracle import restate as O
+    d = synth.training_inputs()
+    flat = d["angle32"].reshape(-1)
+    for a in (flat[:1001], flat[:3], flat[1:1002], flat[3:]):
+        t = torch.from_numpy(a.copy())
+        if a is not flat[:1001] and a is not flat[:3]:
+            t = torch.from_numpy(flat.copy())[flat.size - a.size:]  # a view: data pointer offset by 4 or 12 bytes
+            a = t.numpy()
+        so, io = O.align_angle(a.copy(), 8)
+        s, i = T.DTOffsetHelper.align_angle(a.copy(), num_classes=8)
+        assert _same(s, so) and _same(i, io)
+        st, it = T.DTOffsetHelper.align_angle(t, num_classes=8, return_tensor=True)
+        assert _same(it.numpy(), io) and _same(st.numpy(), so.astype(np.float32))
+        assert _same(T.DTOffsetHelper.angle_to_vector(a.copy(), num_classes=8), O.angle_to_vector(a.copy(), 8))
+        v = O.angle_to_vector(a.copy(), 8)
+        assert _same(T.DTOffsetHelper.vector_to_label(v.copy(), num_classes=8), O.vector_to_label(v.copy(), 8))
+        vt = torch.from_numpy(np.concatenate([np.zeros((1, 2)), v]).astype(np.float32))[1:]  # offset by 8 bytes
+        assert _same(T.DTOffsetHelper.vector_to_label(vt, num_classes=8, return_tensor=True).numpy(),
+                     O.vector_to_label(v.copy(), 8))
+
+
 def test_label_to_vector_golden(T):
     z, meta, d = _inputs()
     lab = torch.from_numpy(d["labels17"])
