@@ -5,7 +5,8 @@
   torch.distributed with the gloo backend -- both must reproduce the UNSHARDED oracle bit for bit
   (labels incl. raster-order numbering, hole filling and small-object removal across seams).
 The per-rank device ops are a numpy stand-in (tests/sharded_numpy_backend.py); the CUDA backend is
-checked against the same property on the GPU box (tests/test_gpu_sharded.py)."""
+checked against the same property on the GPU box (tests/test_gpu_sharded.py) and, here, in 2 and 3 gloo
+processes with its kernels running under the SIMT emulator (tests/simt)."""
 import os
 import sys
 
@@ -90,6 +91,46 @@ def test_slide_two_processes_gloo():
     ref = O.dam_postprocess(prob.copy(), point, dcm, 9, 20, 2, 0, literal=False)["pred_labeled"]
     got = np.concatenate([res[r] for r in range(world)], axis=0)
     assert np.array_equal(got, ref)
+
+
+def _worker_kernels(rank, world, port, H, W, n_maps, q):
+    """like _worker, but with the product's CudaBackend: its kernels run under the SIMT emulator (tests/simt), its
+    exchanges over gloo -- the orchestration, the C-ABI calls and the kernels are all the shipped code"""
+    import torch.distributed as dist
+    from simt import emulated_api
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        with emulated_api():
+            dcm, prob, point = _slide(34, H, W, 30, n_maps)
+            mine = _split(dcm, prob, point, H, world)[rank]
+            be = sharded.CudaBackend()
+            out = sharded.postprocess_slide([mine], sharded.DistComm(), H, W, be, 9, 20, 2)[0]
+            q.put((rank, be.to_host(out)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.simt
+@pytest.mark.parametrize("world,n_maps", [(2, 8), (3, 1)])
+def test_slide_processes_gloo_with_emulated_kernels(world, n_maps):
+    import torch.multiprocessing as mp
+    H, W = 132, 140
+    port = 31500 + (os.getpid() % 2000) + world
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_kernels, args=(r, world, port, H, W, n_maps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    dcm, prob, point = _slide(34, H, W, 30, n_maps)
+    ref = O.dam_postprocess(prob.copy(), point, dcm, 9, 20, 2, 0, literal=False)["pred_labeled"]
+    got = np.concatenate([res[r] for r in range(world)], axis=0)
+    assert got.dtype == ref.dtype and np.array_equal(got, ref), int((got != ref).sum())
 
 
 def test_constant_direction_map_asserts():
