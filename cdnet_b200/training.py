@@ -1,6 +1,7 @@
 """Training-side drop-ins (SURVEY.md section 8a rows A3/A4 as stand-alone operators, section 8f row 4).
 
     DTOffsetConfig, DTOffsetHelper      data_prepare/SegFix_offset_helper.py:21-46, 246-261, 286-341, 423-506
+    Sobel                               data_prepare/SegFix_offset_helper.py:97-132 (constant stencil table)
     direction_one_hot                   train_util_dam.py:123-142 (inline block, wrapped)
     LabelEncoding                       my_transforms.py:661-837, the transform WITHOUT direction targets
                                         (cdnet_b200.api.LabelEncoding is my_transforms_direction's)
@@ -72,6 +73,37 @@ def _result(t, like, return_tensor):
     if return_tensor:
         return t.to(like.device) if isinstance(like, torch.Tensor) else t
     return t.cpu().numpy()
+
+
+class Sobel(object):
+    """data_prepare/SegFix_offset_helper.py:97-132: the 11 x 11 (ksize x ksize) gradient stencil of the direction
+    targets as a torch tensor [2,1,k,k], channel 0 = d/dy (row offset / r^2), channel 1 = d/dx, cached per ksize.
+    A table of constants (the kernels of csrc/targets.cu hold the same weights in constant memory)."""
+    _caches = {}
+    ksize = 11
+
+    @staticmethod
+    def _generate_sobel_kernel(shape, axis):
+        """axis 0: column offset / r^2, axis 1: row offset / r^2 (float64 quotient stored to float32); centre 0"""
+        cj, ci = int((shape[0] - 1) / 2.0), int((shape[1] - 1) / 2.0)
+        jj, ii = np.mgrid[-cj:shape[0] - cj, -ci:shape[1] - ci]
+        r2 = (ii * ii + jj * jj).astype(np.float64)
+        odd = shape[0] % 2 == 1 and shape[1] % 2 == 1
+        if odd:
+            r2[cj, ci] = 1.0
+        k = ((ii if axis == 0 else jj) / r2).astype(np.float32)
+        if odd:
+            k[cj, ci] = 0.0
+        return torch.from_numpy(k).unsqueeze(0)
+
+    @classmethod
+    def kernel(cls, ksize=None):
+        if ksize is None:
+            ksize = cls.ksize
+        if ksize not in cls._caches:
+            sobel_x, sobel_y = (cls._generate_sobel_kernel((ksize, ksize), i) for i in (0, 1))
+            cls._caches[ksize] = torch.cat([sobel_y, sobel_x], dim=0).view(2, 1, ksize, ksize)
+        return cls._caches[ksize]
 
 
 class DTOffsetHelper(object):

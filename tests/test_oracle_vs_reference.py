@@ -152,3 +152,11 @@ def test_tta_merge(ref):
             for y, x in ((0, 0), (H - 1, 0), (0, W - 1), (H - 1, W - 1), (3, 7), (11, 2)):
                 r, c = O.tta_source_index(v, y, x, H, W)
                 assert b[y, x] == a[0, r, c]
+
+
+def test_sobel_drop_in(ref):
+    from cdnet_b200.training import Sobel
+    for k in (3, 5, 11, 15):
+        a, b = ref.Sobel.kernel(ksize=k), Sobel.kernel(ksize=k)
+        assert a.dtype == b.dtype and a.shape == b.shape and bool((a == b).all()), k
+    assert Sobel.kernel() is Sobel.kernel(11)
