@@ -158,3 +158,29 @@ def test_tta_merge_feeds_postprocess(kernel_api):
     ref = O.dam_postprocess(prob[0].cpu().numpy().copy(), point[0].cpu().numpy(), dcm[0].cpu().numpy(), 9, 20, 2, 0,
                             literal=False)["pred_labeled"]
     assert np.array_equal(lab[0].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("seed,H,W,n", [(71, 128, 160, 14), (72, 250, 200, 60)])
+def test_config3_chain_16_directions(kernel_api, seed, H, W, n):
+    """BASELINE configs[3]: 16-direction target generation, the direction-difference map of the produced class map
+    (17 classes: the '8 of 16 channels' quirk of getDirectionDiffMap.py:69-90) and the 4-connected labelling of the
+    interior mask -- device-resident from the label image to the three results"""
+    import torch
+    from scipy import ndimage as ndi
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    lab = synth.as_uint8_label(synth.instance_map(seed, H, W, n))
+    tern, point, direction = O.label_encoding(lab, num_classes=16, literal=False)
+    ids = to_dev(kernel_api, torch.from_numpy(lab[:, :, 0].copy())[None])
+    g_tern, g_point, g_dir = kernel_api.encode_targets_cuda(ids, True, 16)
+    assert np.array_equal(g_tern[0].cpu().numpy(), tern)
+    assert np.array_equal(g_point[0].cpu().numpy().view(np.uint16), point.view(np.uint16))
+    _check_direction(g_dir[0].cpu().numpy(), direction, lab, 16, "config3 seed %d" % seed)
+    # DDM of the class map the device produced (uint8 on the device, like test_dam.py:459 hands it over)
+    ddm = kernel_api.ddm_cuda(g_dir.to(torch.uint8), 17)
+    ref_ddm = O.generate_dd_map(g_dir[0].cpu().numpy().astype(np.uint8), 17)
+    assert np.array_equal(ddm[0].cpu().numpy(), ref_ddm, equal_nan=True)
+    interior = (g_tern == 127)
+    got, cnt = kernel_api.label_cuda(interior, connectivity=4, return_num=True)
+    ref_lab, ref_n = ndi.label(tern == 127)
+    assert int(cnt[0]) == ref_n and np.array_equal(got[0].cpu().numpy(), ref_lab)
