@@ -184,3 +184,64 @@ def test_config3_chain_16_directions(kernel_api, seed, H, W, n):
     got, cnt = kernel_api.label_cuda(interior, connectivity=4, return_num=True)
     ref_lab, ref_n = ndi.label(tern == 127)
     assert int(cnt[0]) == ref_n and np.array_equal(got[0].cpu().numpy(), ref_lab)
+
+
+def test_primitives_fuzz(kernel_api):
+    """random small shapes and densities (1 x 1 up to 70 x 90, every W % 4 residue): labelling, hole filling,
+    small-object removal, EDT and label dilation against scipy / the oracle"""
+    from scipy import ndimage as ndi
+    from oracle import restate as O
+    rng = np.random.default_rng(2024)
+    for it in range(48):
+        H, W = int(rng.integers(1, 71)), int(rng.integers(1, 91))
+        p = float(rng.choice([0.05, 0.3, 0.5, 0.6, 0.75, 0.95]))
+        m = rng.random((H, W)) < p
+        if it % 6 == 0:  # blobs instead of salt and pepper
+            m = ndi.binary_dilation(rng.random((H, W)) < 0.03, iterations=int(rng.integers(1, 4)))
+        tag = (it, H, W, p)
+        assert np.array_equal(kernel_api.label(m, connectivity=1), ndi.label(m)[0]), tag
+        assert np.array_equal(kernel_api.label(m), O.label8(m)), tag
+        assert np.array_equal(kernel_api.binary_fill_holes(m), ndi.binary_fill_holes(m)), tag
+        k = int(rng.integers(1, 12))
+        assert np.array_equal(kernel_api.remove_small_objects(m, k), O.remove_small_objects(m, k)), tag
+        if not m.all():
+            assert np.array_equal(kernel_api.distance_transform_edt(m), ndi.distance_transform_edt(m)), tag
+        lab = ndi.label(m)[0]
+        r = int(rng.integers(1, 3))
+        assert np.array_equal(kernel_api.dilation(lab, radius=r), O.dilate(lab, O.disk(r))), tag
+        assert np.array_equal(kernel_api.remove_small_objects(lab, k), O.remove_small_objects(lab, k)), tag
+
+
+def test_ddm_fuzz(kernel_api):
+    """random class maps (5 / 9 / 17 classes, ids beyond the table, constant maps) against the restatement"""
+    from oracle import restate as O
+    rng = np.random.default_rng(77)
+    for it in range(36):
+        cls = (5, 9, 17)[it % 3]
+        H, W = int(rng.integers(1, 60)), int(rng.integers(1, 75))
+        x = rng.integers(0, cls + (2 if it % 5 == 0 else 0), size=(H, W)).astype(np.uint8)
+        x[rng.random((H, W)) < float(rng.choice([0.0, 0.3, 0.8]))] = 0
+        if it % 11 == 0:
+            x[:] = x.flat[0]
+        got = kernel_api.generate_dd_map(x, cls)
+        assert np.array_equal(got, O.generate_dd_map(x, cls), equal_nan=True), (it, cls, H, W)
+
+
+def test_process_fuzz(kernel_api):
+    """postproc_other.process on random masks: watershed branch and the no-watershed head, several min_size"""
+    from scipy import ndimage as ndi
+    from oracle import restate as O
+    rng = np.random.default_rng(99)
+    for it in range(24):
+        H, W = int(rng.integers(6, 64)), int(rng.integers(6, 80))
+        seeds = rng.random((H, W)) < 0.02
+        m = ndi.binary_dilation(seeds, iterations=int(rng.integers(2, 6)))
+        m &= rng.random((H, W)) < 0.97  # pinholes
+        if m.all() or not m.any():
+            continue
+        ms = int(rng.choice([1, 5, 10]))
+        src = m.astype(np.uint8) * 255
+        for mode in ("modelName", "unet"):
+            ref = O.process(src.copy(), mode, min_size=ms, literal=False)
+            got = kernel_api.process(src.copy(), mode, min_size=ms)
+            assert got.dtype == ref.dtype and np.array_equal(got, ref), (it, H, W, ms, mode)
