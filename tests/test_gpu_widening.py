@@ -245,3 +245,20 @@ def test_process_fuzz(kernel_api):
             ref = O.process(src.copy(), mode, min_size=ms, literal=False)
             got = kernel_api.process(src.copy(), mode, min_size=ms)
             assert got.dtype == ref.dtype and np.array_equal(got, ref), (it, H, W, ms, mode)
+
+
+def test_label_encoding_fuzz(kernel_api):
+    """target transform on random instance maps of ragged sizes (8 and 16 direction classes)"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    rng = np.random.default_rng(4242)
+    for it in range(10):
+        H, W = int(rng.integers(24, 100)), int(rng.integers(24, 120))
+        n = int(rng.integers(1, max(2, H * W // 350)))
+        classes = 8 if it % 2 == 0 else 16
+        lab = synth.as_uint8_label(synth.instance_map(9000 + it, H, W, n, axes=(3, 9)))
+        ref = O.label_encoding(lab, num_classes=classes, literal=False)
+        res = kernel_api.LabelEncoding(3, 1, 1, num_classes=classes)((None, None, lab.copy()))
+        assert np.array_equal(np.asarray(res[2]), ref[0]), (it, H, W)
+        assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), (it, H, W)
+        _check_direction(res[4], ref[2], lab, classes, "fuzz %d" % it)
