@@ -56,3 +56,26 @@ def test_no_cpu_fallback_without_cuda():
     from cdnet_b200 import api, CdnetError
     with pytest.raises(CdnetError):
         api.generate_dd_map(np.zeros((4, 4), np.uint8), 9)
+
+
+def test_compat_modules_mirror_the_reference_names():
+    """cdnet_b200.compat.* carry the reference's module and callable names (import-line drop-in)"""
+    import importlib
+    want = {"postproc_other": ["process"],
+            "data_prepare.getDirectionDiffMap": ["generate_dd_map", "circshift"],
+            "data_prepare.SegFix_offset_helper": ["DTOffsetHelper", "DTOffsetConfig", "Sobel"],
+            "my_transforms_direction": ["LabelEncoding", "get_centerpoint2"],
+            "my_transforms": ["LabelEncoding"],
+            "stats_utils": ["get_fast_aji", "get_fast_aji_plus", "get_fast_pq", "get_dice_1", "get_dice_2",
+                            "get_fast_dice_2", "remap_label"],
+            "utils": ["DcmVoting2"]}
+    for mod, names in want.items():
+        m = importlib.import_module("cdnet_b200.compat." + mod)
+        for n in names:
+            assert callable(getattr(m, n)), (mod, n)
+    from cdnet_b200 import api, training
+    from cdnet_b200.compat import my_transforms, my_transforms_direction
+    assert my_transforms_direction.LabelEncoding is api.LabelEncoding
+    assert my_transforms.LabelEncoding is training.LabelEncoding
+    for n in ("label_to_vector", "align_angle", "angle_to_vector", "vector_to_label", "angle_to_direction_label"):
+        assert callable(getattr(training.DTOffsetHelper, n))
