@@ -131,6 +131,38 @@ def emulated_api():
                 m.torch = proxy
         api._plans.clear()
         api._ws_cache.clear()
+        fill = os.environ.get("CDNET_SIMT_WS_FILL")
+        if fill:
+            # initcheck: hand every call a workspace (and every torch.empty result) full of a junk byte, so a kernel
+            # that reads scratch it has not written (fresh host pages are zero, recycled device memory is not)
+            # changes its answer
+            junk = int(fill, 0) & 0xff
+            plain_ws = api._workspace
+            saved.append((api, "_workspace", plain_ws))
+
+            def dirty_ws(nbytes, dev):
+                buf = plain_ws(nbytes, dev)
+                buf.fill_(junk)
+                return buf
+            api._workspace = dirty_ws
+            for m in (metrics, training):
+                saved.append((m, "_workspace", m._workspace))
+                m._workspace = dirty_ws
+            real_empty_fn = proxy.empty
+
+            def dirty_empty(*a, **k):
+                t = real_empty_fn(*a, **k)
+                t.view(torch.uint8).fill_(junk) if t.numel() else None
+                return t
+            proxy.empty = dirty_empty
+            be_empty = sharded.CudaBackend.empty
+            saved.append((sharded.CudaBackend, "empty", be_empty))
+
+            def dirty_be_empty(self, shape, dtype):
+                t = be_empty(self, shape, dtype)
+                t.view(torch.uint8).fill_(junk) if t.numel() else None
+                return t
+            sharded.CudaBackend.empty = dirty_be_empty
         if os.environ.get("CDNET_SIMT_LIB"):
             # sanitizer builds may put guard gaps between the workspace slices: leave room for them
             real_ws = api._workspace
