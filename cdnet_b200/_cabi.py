@@ -20,6 +20,7 @@ SIGNATURES = {
     "cdnet_circshift": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cdnet_ccl_workspace_bytes": (c_size_t, [c_int] * 3),
     "cdnet_ccl": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "cdnet_label_values": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cdnet_fill_holes_workspace_bytes": (c_size_t, [c_int] * 3),
     "cdnet_fill_holes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cdnet_remove_small_mask_workspace_bytes": (c_size_t, [c_int] * 3),

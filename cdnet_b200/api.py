@@ -97,6 +97,23 @@ def label_cuda(mask, connectivity=4, return_num=False):
     return (out, n) if return_num else out
 
 
+def label_values_cuda(ids, return_num=False):
+    """ids uint8 [B,H,W] -> int32 labels of the 8-connected components of equal non-zero value, raster-first ids
+    (skimage.measure.label of a multi-valued image)."""
+    L = _cabi.lib()
+    dev = _device(ids.device)
+    assert ids.dtype == torch.uint8
+    m = ids.contiguous()
+    B, H, W = m.shape
+    out = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    n = torch.zeros((B,), dtype=torch.int32, device=dev)
+    nb = L.cdnet_ccl_workspace_bytes(B, H, W)
+    ws = _workspace(nb, dev)
+    check(L.cdnet_label_values(_ptr(m), _ptr(out), _ptr(n), B, H, W, _ptr(ws), ws.numel(), _stream()),
+          "cdnet_label_values")
+    return (out, n) if return_num else out
+
+
 def fill_holes_cuda(mask):
     L = _cabi.lib()
     dev = _device(mask.device)
@@ -256,10 +273,17 @@ def circshift(matrix_ori, direction, shiftnum1, shiftnum2):
 
 
 def label(input, connectivity=None, return_num=False):
-    """skimage.measure.label (default: 8-connected, int64) for a binary image; pass connectivity=1
-    for scipy.ndimage.label semantics (4-connected, int32)."""
+    """skimage.measure.label (default: 8-connected, int64; components of equal value for a multi-valued uint8-range
+    image); pass connectivity=1 for scipy.ndimage.label semantics on a binary image (4-connected, int32)."""
     x = np.asarray(input)
     conn = 8 if (connectivity is None or connectivity == 2) else 4
+    if x.dtype != bool and x.size and x.max() > 1 and np.unique(x[x != 0]).size > 1:
+        # measure.label joins pixels of EQUAL value: a multi-valued image takes the value-aware kernel
+        if conn != 8 or x.ndim != 2 or x.min() < 0 or x.max() > 255:
+            raise CdnetError("multi-valued label images are supported as 2-D, 8-connected, values 0..255")
+        lab, n = label_values_cuda(_h2d(x.astype(np.uint8))[None], return_num=True)
+        res = lab[0].cpu().numpy().astype(np.int64)
+        return (res, int(n[0])) if return_num else res
     lab, n = label_cuda(_h2d((x != 0).astype(np.uint8))[None], conn, return_num=True)
     res = lab[0].cpu().numpy()
     res = res.astype(np.int64) if conn == 8 else res
@@ -553,7 +577,9 @@ def label_stats_cuda(ids):
 
 def encode_targets_cuda(ids, instance_level=True, num_classes=8, want_inst=False, want_dir=False):
     """ids uint8 [B,H,W] (channel 0 of the label image) ->
-    (ternary uint8 [B,H,W], point float16 [B,H,W], direction int64 [B,H,W][, inst int32][, dir f32 [B,H,W,2]])."""
+    (ternary uint8 [B,H,W], point float16 [B,H,W], direction int64 [B,H,W][, inst int32][, dir f32 [B,H,W,2]]).
+    instance_level: True / 1 = instance ids, False / 0 = {0,255} label (both out_c == 3); 2 / 3 = the same two input
+    kinds for out_c != 3 (my_transforms_direction.py:721-739; for 3 pass max(channel 0, channel 1))."""
     L = _cabi.lib()
     dev = _device(ids.device)
     ids = _cu8(ids)
@@ -567,7 +593,7 @@ def encode_targets_cuda(ids, instance_level=True, num_classes=8, want_inst=False
     nb = L.cdnet_encode_targets_workspace_bytes(B, H, W)
     ws = _workspace(nb, dev)
     gw = _gauss_weights()
-    check(L.cdnet_encode_targets(_ptr(ids), 1 if instance_level else 0, _ptr(ternary), _ptr(point), _ptr(direction),
+    check(L.cdnet_encode_targets(_ptr(ids), int(instance_level), _ptr(ternary), _ptr(point), _ptr(direction),
                                  _ptr(inst), _ptr(dirm), _ptr(status), B, H, W, int(num_classes), gw.ctypes.data,
                                  _ptr(ws), ws.numel(), _stream()), "cdnet_encode_targets")
     res = [ternary, point, direction]
@@ -606,7 +632,8 @@ def get_centerpoint2(mask, n=None, m=None):
 class LabelEncoding(object):
     """Drop-in for my_transforms_direction.LabelEncoding (:687-885): `LabelEncoding(out_c, radius,
     do_direction)(imgs)` with imgs = (img, weight_map, label) returns
-    (img, weight_map, PIL 'L' ternary label {0,127,255}[, float16 point map, int64 direction classes]).
+    (img, weight_map, PIL 'L' ternary label {0,127,255}[, float16 point map, int64 direction classes]);
+    out_c != 3 (options.py:42: multi_class off) gives a {0,255} label image without a boundary class.
 
     The number of direction classes is the reference's env `dt_num_classes` (default 8;
     data_prepare/SegFix_offset_helper.py:37-39) unless `num_classes` is given.  CUDA cannot be
@@ -619,8 +646,6 @@ class LabelEncoding(object):
         self.radius = 1  # the reference ignores its argument (:694)
         self.do_direction = do_direction
         self.num_classes = int(os.environ.get("dt_num_classes", 8)) if num_classes is None else int(num_classes)
-        if self.out_c != 3:
-            raise NotImplementedError("out_c != 3 (my_transforms_direction.py:721-739) is out of scope")
 
     @staticmethod
     def _channel0(label):
@@ -644,18 +669,31 @@ class LabelEncoding(object):
         d_ids = torch.from_numpy(ids).to(dev)
         ndist, _ = label_stats_cuda(d_ids)
         level = (ndist > 2).cpu().numpy()
+        d_bin = d_ids
+        if self.out_c != 3:
+            # :721-739 index label[:, :, 0] (and [:, :, 1] for a {0,255} label): 2-D label images cannot be indexed
+            for l in labels:
+                if np.ndim(l) == 2:
+                    raise IndexError("too many indices for array: array is 2-dimensional, but 3 were indexed")
+            if not level.all():
+                # new_label = 2 where channel 0 OR channel 1 exceeds 127.5 (:730-731)  <=>  max(ch0, ch1) > 127.5
+                ch1 = np.stack([np.ascontiguousarray(np.asarray(l)[:, :, 1]).astype(np.uint8) for l in labels])
+                d_bin = torch.maximum(d_ids, torch.from_numpy(ch1).to(dev))
         out = [None] * len(labels)
         for lv in (True, False):
             sel = np.nonzero(level == lv)[0]
             if sel.size == 0:
                 continue
-            sub = d_ids[torch.from_numpy(sel).to(dev)] if sel.size != len(labels) else d_ids
-            tern, point, direction, inst = encode_targets_cuda(sub, instance_level=lv, num_classes=self.num_classes,
+            src = d_ids if (lv or self.out_c == 3) else d_bin
+            sub = src[torch.from_numpy(sel).to(dev)] if sel.size != len(labels) else src
+            mode = (1 if lv else 0) if self.out_c == 3 else (2 if lv else 3)
+            tern, point, direction, inst = encode_targets_cuda(sub, instance_level=mode, num_classes=self.num_classes,
                                                                want_inst=True)
             # the reference skips the first entry of np.unique(label_instance) as "background" (:797-800); on a
             # tile whose dilated instances leave no background pixel that drops a nucleus and its
             # `assert int(label_point.sum() / 255) == markers_len` (:836) fires
-            if int(inst.reshape(inst.shape[0], -1).min(dim=1).values.max()) > 0:
+            # (for out_c != 3 the same slip only drops the smallest instance: the kernels reproduce that)
+            if self.out_c == 3 and int(inst.reshape(inst.shape[0], -1).min(dim=1).values.max()) > 0:
                 raise AssertionError("label_instance has no background pixel (my_transforms_direction.py:836)")
             tern, point, direction = tern.cpu().numpy(), point.cpu().numpy(), direction.cpu().numpy()
             for j, i in enumerate(sel):

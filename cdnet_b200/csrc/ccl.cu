@@ -727,6 +727,42 @@ int ccl_label_launch(const uint8_t* mask, int32_t* labels, int32_t* n_out, int32
     return number_and_relabel(L, mask, idmap, rowcnt, labels, n_out, B, H, W, st);
 }
 
+// ---- skimage.measure.label of a multi-valued image ------------------------------------------------------
+// 8-connected components of EQUAL non-zero value (my_transforms_direction.py:723-725: the instance map of the
+// out_c != 3 form of LabelEncoding).  Rare path, kept simple: identity forest, every pixel is united with its
+// equal-valued left / upper-left / upper / upper-right neighbour, then the usual raster-order numbering.
+__global__ void k_values_init(int* __restrict__ L, size_t n, int plane) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        L[i] = (int)(i % (size_t)plane);
+}
+
+__global__ void __launch_bounds__(kBX* kBY) k_values_link(const uint8_t* __restrict__ ids, int* __restrict__ L, int H, int W) {
+    CCL_COORDS
+    if (!inb) return;
+    const uint8_t* I = ids + tile;
+    const int v = I[p];
+    if (v == 0) return;
+    int* Lt = L + tile;
+    const bool left = x > 0 && I[p - 1] == v;
+    if (left) uf_union(Lt, p, p - 1);
+    if (y > 0) {
+        const bool up = I[p - W] == v;
+        if (up) uf_union(Lt, p, p - W);
+        // a diagonal link is implied when the pixel between the two is already joined to both
+        if (x > 0 && I[p - W - 1] == v && !(up || left)) uf_union(Lt, p, p - W - 1);
+        if (x + 1 < W && I[p - W + 1] == v && !up) uf_union(Lt, p, p - W + 1);
+    }
+}
+
+int ccl_label_values_launch(const uint8_t* ids, int32_t* labels, int32_t* n_out, int32_t* L, int32_t* idmap,
+                            int32_t* rowcnt, int B, int H, int W, cudaStream_t st) {
+    const size_t n = (size_t)B * H * W;
+    const size_t blocks = (n + 1023) / 1024;
+    CDNET_LAUNCH(k_values_init, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, L, n, H * W);
+    CDNET_LAUNCH(k_values_link, ccl_grid(B, H, W), ccl_block(), 0, st, ids, L, H, W);
+    return number_and_relabel(L, ids, idmap, rowcnt, labels, n_out, B, H, W, st);
+}
+
 // ---- fill holes ----------------------------------------------------------------------------------
 // frame pixels that are background mark the root of their background component
 __global__ void k_border_touch(const uint8_t* __restrict__ mask, const int* __restrict__ L, int* __restrict__ touch,
@@ -906,6 +942,18 @@ extern "C" int cdnet_ccl(const uint8_t* mask, int32_t* labels, int32_t* n_out, i
     int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
     if (!ar.ok) return CDNET_E_WORKSPACE;
     return ccl_label_launch(mask, labels, n_out, L, idmap, rowcnt, B, H, W, connectivity, (cudaStream_t)stream);
+}
+
+extern "C" int cdnet_label_values(const uint8_t* ids, int32_t* labels, int32_t* n_out, int B, int H, int W, void* ws,
+                                  size_t ws_bytes, void* stream) {
+    if (!ids || !labels || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    Arena ar(ws, ws_bytes);
+    const size_t n = (size_t)B * H * W;
+    int32_t* L = ar.take<int32_t>(n);
+    int32_t* idmap = ar.take<int32_t>(n);
+    int32_t* rowcnt = ar.take<int32_t>((size_t)B * H);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    return ccl_label_values_launch(ids, labels, n_out, L, idmap, rowcnt, B, H, W, (cudaStream_t)stream);
 }
 
 extern "C" size_t cdnet_fill_holes_workspace_bytes(int B, int H, int W) {

@@ -13,6 +13,9 @@ int ddm_codes_launch(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, 
 // L, idmap: int32 [B,H,W] scratch; rowcnt: int32 [B,H] scratch.  conn 4 or 8.
 int ccl_label_launch(const uint8_t* mask, int32_t* labels, int32_t* n_out, int32_t* L, int32_t* idmap,
                      int32_t* rowcnt, int B, int H, int W, int conn, cudaStream_t st);
+// skimage.measure.label of a multi-valued uint8 image: 8-connected components of equal non-zero value
+int ccl_label_values_launch(const uint8_t* ids, int32_t* labels, int32_t* n_out, int32_t* L, int32_t* idmap,
+                            int32_t* rowcnt, int B, int H, int W, cudaStream_t st);
 // forest of the 4-connected components of `mask` only (L[p] = root = first raster pixel; background L[p] = p)
 int ccl_forest_launch(const uint8_t* mask, int32_t* L, int B, int H, int W, int conn, cudaStream_t st);
 // state[p] in {0 bg, 1 fg, 2 filled hole} from a 0/1 mask (scipy binary_fill_holes); leaves in L the

@@ -84,6 +84,25 @@ __global__ void __launch_bounds__(kBX* kBY) k_t_ternary(const uint8_t* __restric
     PX_COORDS
     if (!inb) return;
     const uint8_t* I = ids + tile;
+    if (instance_level >= 2) {
+        // out_c != 3 (:721-739): no boundary class.  Mode 2: 2 where an instance id is set; mode 3: erosion (cross
+        // minimum) of 2 * (label > 127.5), the caller hands in max(channel 0, channel 1).  new_label_inside is a
+        // copy of new_label, and the instances are labelled from it (mode 3) or from the ids themselves (mode 2).
+        bool on;
+        if (instance_level == 2) {
+            on = I[p] > 0;
+        } else {
+            on = I[p] > 127;
+            if (y > 0) on = on && I[p - W] > 127;
+            if (y + 1 < H) on = on && I[p + W] > 127;
+            if (x > 0) on = on && I[p - 1] > 127;
+            if (x + 1 < W) on = on && I[p + 1] > 127;
+        }
+        ternary[tile + p] = on ? 255 : 0;
+        inside[tile + p] = on;
+        interior[tile + p] = on;
+        return;
+    }
     auto val = [&](int q) -> int { const int v = I[q]; return instance_level ? v : (v > 127 ? 1 : 0); };
     const int v = val(p);
     int mx = v, mn = v;
@@ -99,6 +118,29 @@ __global__ void __launch_bounds__(kBX* kBY) k_t_ternary(const uint8_t* __restric
     ternary[tile + p] = nl == 0 ? 0 : (nl == 1 ? 127 : 255);
     inside[tile + p] = ins;
     interior[tile + p] = nl == 1;
+}
+
+// ---- a tile without background (out_c != 3 only) ---------------------------------------------------------
+// The reference iterates `np.unique(label_instance)[1:]` (:797-800): it takes the first value for background.
+// Where the instance map has no zero pixel that silently drops the smallest instance id (no centre, no support;
+// its pixels stay foreground).  tile_min[b] = smallest id of tile b, then that id is cleared when it is not 0.
+__global__ void k_t_inst_min(const int* __restrict__ inst, int* __restrict__ tile_min, size_t plane) {
+    const int b = blockIdx.y;
+    const int* I = inst + (size_t)b * plane;
+    int m = 0x7fffffff;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x)
+        m = min(m, I[i]);
+    m = __reduce_min_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMin(tile_min + b, m);
+}
+
+__global__ void k_t_drop_first(int* __restrict__ inst, const int* __restrict__ tile_min, size_t plane) {
+    const int b = blockIdx.y;
+    const int m = tile_min[b];
+    if (m <= 0) return;
+    int* I = inst + (size_t)b * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x)
+        if (I[i] == m) I[i] = 0;
 }
 
 // ---- centre search (my_transforms_direction.py:651-685) ---------------------------------------------
@@ -595,6 +637,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
                                     void* stream) {
     if (!ids || !ternary || !point || !direction || bad_dims(B, H, W)) return CDNET_E_BADARG;
     if (num_classes != 8 && num_classes != 16) return CDNET_E_BADARG;
+    if (instance_level < 0 || instance_level > 3) return CDNET_E_BADARG;
     if (ws_bytes < cdnet_encode_targets_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)B * H * W;
@@ -646,18 +689,30 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     CDNET_LAUNCH(k_t_ternary, px_grid(B, H, W), px_block(), 0, st, ids, fg, instance_level, ternary, inside, interior, H, W);
     // 2. instances: process(interior*255, min_size=5) (:759) or measure.label (:773), then dilation disk(1)
     int rc;
-    if (instance_level) {
+    if (instance_level == 1) {
         rc = ws_process_launch(interior, inst_raw, status, B, H, W, 5, 1, sub_ws, sub_bytes, st);
     } else {
         Arena sub(sub_ws, sub_bytes);
         int32_t* Lp = sub.take<int32_t>(n);
         int32_t* idmap = sub.take<int32_t>(n);
         if (!sub.ok) return CDNET_E_WORKSPACE;
-        rc = ccl_label_launch(interior, inst_raw, nullptr, Lp, idmap, rowcnt, B, H, W, 8, st);
+        // out_c != 3 (:723-725, :734): the labelling itself is the instance map, nothing is dilated
+        int32_t* dst = instance_level >= 2 ? inst : inst_raw;
+        if (instance_level == 2) rc = ccl_label_values_launch(ids, dst, nullptr, Lp, idmap, rowcnt, B, H, W, st);
+        else rc = ccl_label_launch(interior, dst, nullptr, Lp, idmap, rowcnt, B, H, W, 8, st);
     }
     if (rc) return rc;
-    rc = label_dilate_launch(inst_raw, inst, 4, B, H, W, 1, st);
-    if (rc) return rc;
+    if (instance_level < 2) {
+        rc = label_dilate_launch(inst_raw, inst, 4, B, H, W, 1, st);
+        if (rc) return rc;
+    } else {
+        const size_t plane = (size_t)H * W;
+        const size_t gx = (plane + 256 * 8 - 1) / (256 * 8);
+        const dim3 grid((unsigned)(gx > 1024 ? 1024 : gx), B);
+        CDNET_CUDA_OK(cudaMemsetAsync(fg, 0x7f, sizeof(int32_t) * (size_t)B, st));  // fg is free again: tile minima
+        CDNET_LAUNCH(k_t_inst_min, grid, 256, 0, st, inst, fg, plane);
+        CDNET_LAUNCH(k_t_drop_first, grid, 256, 0, st, inst, fg, plane);
+    }
     // 3. centres, support maxima, direction classes, point map
     rc = centres_launch(inst, cness, best, centre, maxd2, tab, B, H, W, st);
     if (rc) return rc;

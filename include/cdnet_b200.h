@@ -70,6 +70,12 @@ size_t cdnet_ccl_workspace_bytes(int B, int H, int W);
 int cdnet_ccl(const uint8_t* mask, int32_t* labels, int32_t* n_out, int B, int H, int W,
               int connectivity, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- skimage.measure.label of a multi-valued image (my_transforms_direction.py:723-725) ----------
+ * ids: uint8 [B,H,W]; labels: int32 [B,H,W], 8-connected components of EQUAL non-zero value, numbered 1..n in
+ * raster order of their first pixel; n_out (may be NULL): int32 [B].  Workspace: cdnet_ccl_workspace_bytes. */
+int cdnet_label_values(const uint8_t* ids, int32_t* labels, int32_t* n_out, int B, int H, int W, void* ws,
+                       size_t ws_bytes, void* stream);
+
 /* ---- scipy.ndimage.binary_fill_holes (test_dam.py:546, test.py:277, postproc_other.py:42,51) --
  * out may alias mask. */
 size_t cdnet_fill_holes_workspace_bytes(int B, int H, int W);
@@ -158,8 +164,10 @@ int cdnet_label_stats(const uint8_t* ids, int32_t* presence, int32_t* fg_count, 
 
 /* ---- LabelEncoding.__call__ (out_c = 3, do_direction = 1), my_transforms_direction.py:697-885 --
  * ids:       uint8 [B,H,W]  channel 0 of the label image (data_folder.py:29,37)
- * instance_level != 0: ids are instance ids (reference: > 2 unique values, :743-760), else a
- *            {0,255} three-class label (:763-774); applies to all B tiles of the call
+ * instance_level: 1 = ids are instance ids (reference: > 2 unique values, :743-760), 0 = a {0,255} three-class
+ *            label (:763-774); the out_c != 3 forms of the transform (:721-739, no boundary class, instances
+ *            not dilated, ternary in {0,255}): 2 = instance ids, 3 = {0,255} label with ids = max(channel 0,
+ *            channel 1).  Applies to all B tiles of the call
  * ternary:   uint8 [B,H,W]  {0,127,255}
  * point:     float16 bits [B,H,W] Gaussian point map (sigma 2)
  * direction: int64 [B,H,W]  classes 0..num_classes; num_classes in {8, 16} (the reference's env

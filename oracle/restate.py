@@ -425,13 +425,27 @@ def get_centerpoint2(mask, n=None, m=None, window=None, windowed=False):
     return [int(by), int(bx)]
 
 
-def ternary_and_instances(label, literal=True, order="stable"):
+def ternary_and_instances(label, literal=True, order="stable", out_c=3):
     """my_transforms_direction.py:714-782 for out_c == 3.
     Returns (new_label u8 {0,1,2}, inside u8 {0,1}, label_instance int, instance_level bool)."""
     label = np.asarray(label)
     inside_src = label if label.ndim == 2 else label[:, :, 0]
     instance_level = len(np.unique(inside_src)) > 2
     new_label = np.zeros(inside_src.shape, dtype=np.uint8)
+    if out_c != 3:
+        # my_transforms_direction.py:721-739: no boundary class, instances are NOT dilated, inside holds 2s
+        if instance_level:
+            # measure.label(measure.label(label)[:, :, 0]) == the 2-D equal-value 8-connected components of
+            # channel 0, whatever the other channels hold (3-D links can only join what the 2-D relabelling
+            # separates again)
+            inst = label8_values(label[:, :, 0])
+            new_label[inst > 0] = 2
+        else:
+            new_label[label[:, :, 0] > 255 * 0.5] = 2
+            new_label[label[:, :, 1] > 255 * 0.5] = 2
+            new_label = erode(new_label, disk(1))  # :733
+            inst = label8(new_label)
+        return new_label, new_label.copy(), inst, instance_level
     if instance_level:
         new_label[inside_src > 0] = 1
         new_label = remove_small_objects(new_label, 5)  # :746 (value 1 treated as ONE label)
@@ -453,14 +467,12 @@ def ternary_and_instances(label, literal=True, order="stable"):
 
 def label_encoding(label, out_c=3, radius=1, do_direction=1, num_classes=8, literal=True,
                    order="stable", conv="fma", return_parts=False):
-    """LabelEncoding.__call__, my_transforms_direction.py:697-885 (out_c == 3).
+    """LabelEncoding.__call__, my_transforms_direction.py:697-885.
 
     Returns (ternary u8 {0,127,255}, point f16 [H,W], direction int64 [H,W]); the last two are None
     when do_direction != 1.  `num_classes` plays the role of env `dt_num_classes`
     (SegFix_offset_helper.py:37-39)."""
-    if out_c != 3:
-        raise NotImplementedError("out_c != 3 (my_transforms_direction.py:721-739) is out of scope")
-    new_label, inside, inst, _ = ternary_and_instances(label, literal=literal, order=order)
+    new_label, inside, inst, _ = ternary_and_instances(label, literal=literal, order=order, out_c=out_c)
     ternary = (new_label / 2 * 255).astype(np.uint8)  # :781
     if do_direction != 1:
         return ternary, None, None

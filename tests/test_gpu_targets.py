@@ -22,12 +22,12 @@ def _labels(meta, three_class=False):
     return lab
 
 
-def _check_direction(got, ref, lab, n, name):
+def _check_direction(got, ref, lab, n, name, out_c=3):
     if np.array_equal(got, ref):
         return
     from oracle import restate as O
     bad = np.argwhere(got != ref)
-    parts = O.label_encoding(lab, num_classes=n, literal=False, return_parts=True)[3]
+    parts = O.label_encoding(lab, out_c=out_c, num_classes=n, literal=False, return_parts=True)[3]
     step = 360.0 / n
     for y, x in bad:
         a = float(parts["angle"][y, x])

@@ -262,3 +262,45 @@ def test_label_encoding_fuzz(kernel_api):
         assert np.array_equal(np.asarray(res[2]), ref[0]), (it, H, W)
         assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), (it, H, W)
         _check_direction(res[4], ref[2], lab, classes, "fuzz %d" % it)
+
+
+def test_label_multi_valued_image(kernel_api):
+    """skimage.measure.label on an id image: 8-connected components of equal value, raster-first numbering"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    rng = np.random.default_rng(31)
+    imgs = [ids for _, ids in synth.label_edge_cases()]
+    imgs += [synth.as_uint8_label(synth.instance_map(800 + i, 90 + 7 * i, 101 + 3 * i, 20))[:, :, 0] for i in range(3)]
+    imgs += [rng.integers(0, 4, size=(33, 47)).astype(np.uint8), rng.integers(0, 3, size=(1, 29)).astype(np.uint8),
+             rng.integers(0, 3, size=(31, 1)).astype(np.uint8), np.full((5, 6), 7, np.uint8)]
+    for i, ids in enumerate(imgs):
+        got, n = kernel_api.label(ids, return_num=True)
+        ref = O.label8_values(ids) if np.unique(ids[ids != 0]).size > 1 else O.label8(ids)
+        assert got.dtype == np.int64 and np.array_equal(got, ref), i
+        assert n == int(ref.max())
+
+
+def test_label_encoding_out_c_1(kernel_api):
+    """my_transforms_direction.LabelEncoding with out_c != 3 (options.py:42, multi_class off; :721-739): no boundary
+    class, undilated instances; the restatement is pinned to the verbatim reference for the same inputs in
+    tests/test_oracle_vs_reference.py"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    lab = synth.as_uint8_label(synth.instance_map(779, 70, 90, 6))
+    binary = np.repeat(((lab[:, :, 0] > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    shifted = binary.copy()
+    shifted[:, :, 1] = np.roll(binary[:, :, 0], 5, axis=1)   # channel 1 matters for a {0,255} label (:730-731)
+    cases = [("instance", lab, 8), ("instance16", lab, 16), ("binary", binary, 8), ("binary_ch1", shifted, 8),
+             ("dense", synth.as_uint8_label(synth.instance_map(23, 250, 300, 330)), 8)]
+    cases += [(name, np.repeat(ids[:, :, None], 3, axis=2), 8) for name, ids in synth.label_edge_cases()]
+    for name, img, n in cases:
+        for dd in (1, 0):
+            ref = O.label_encoding(img.copy(), out_c=1, do_direction=dd, num_classes=n, literal=False)
+            res = kernel_api.LabelEncoding(1, 1, dd, num_classes=n)((None, None, img.copy()))
+            assert len(res) == (5 if dd else 3), name
+            assert np.array_equal(np.asarray(res[2]), ref[0]), name
+            if dd:
+                assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16)), name
+                _check_direction(res[4], ref[2], img, n, name, out_c=1)
+    with pytest.raises(IndexError):
+        kernel_api.LabelEncoding(1, 1, 1)((None, None, lab[:, :, 0].copy()))

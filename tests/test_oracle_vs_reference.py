@@ -160,3 +160,36 @@ def test_sobel_drop_in(ref):
         a, b = ref.Sobel.kernel(ksize=k), Sobel.kernel(ksize=k)
         assert a.dtype == b.dtype and a.shape == b.shape and bool((a == b).all()), k
     assert Sobel.kernel() is Sobel.kernel(11)
+
+
+def test_label_encoding_out_c_1(ref):
+    """out_c != 3 (my_transforms_direction.py:721-739) with and without direction targets: verbatim reference ==
+    restatement (both forms), same exception types on the inputs the reference cannot index"""
+    n = ref.DTOffsetConfig.num_classes
+    lab = synth.as_uint8_label(synth.instance_map(779, 70, 90, 6))
+    binary = np.repeat(((lab[:, :, 0] > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    shifted = binary.copy()
+    shifted[:, :, 1] = np.roll(binary[:, :, 0], 5, axis=1)
+    const1 = lab.copy()
+    const1[:, :, 1] = 7
+    cases = [lab, binary, shifted, const1, lab[:, :, 0].copy()]
+    cases += [np.repeat(ids[:, :, None], 3, axis=2) for _, ids in synth.label_edge_cases()]
+    for i, img in enumerate(cases):
+        for dd in (1, 0):
+            try:
+                r = ("ok", ref.LabelEncoding(1, 1, dd)((None, None, img.copy())))
+            except Exception as e:  # noqa: BLE001 -- the point is the exception TYPE
+                r = (type(e).__name__, None)
+            for literal in (True, False):
+                try:
+                    o = ("ok", O.label_encoding(img.copy(), out_c=1, do_direction=dd, num_classes=n, literal=literal))
+                except Exception as e:  # noqa: BLE001
+                    o = (type(e).__name__, None)
+                assert o[0] == r[0], (i, dd, literal, o[0], r[0])
+                if r[1] is None:
+                    continue
+                assert len(r[1]) == (5 if dd else 3)
+                assert np.array_equal(np.asarray(r[1][2]), o[1][0]), (i, dd, literal)
+                if dd:
+                    assert np.array_equal(r[1][3].view(np.uint16), o[1][1].view(np.uint16)), (i, dd, literal)
+                    assert np.array_equal(r[1][4], o[1][2]), (i, dd, literal)
