@@ -439,13 +439,14 @@ _plans = {}
 
 
 def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_area=20, radius=2, postproc=0,
-                    model_name="modelName", mutate_prob=True):
+                    model_name="modelName", mutate_prob=True, voting_first=False):
     """test_dam.py:455-563 as a function.
 
     prob_maps  float32 [3,H,W]  (channel 2 is overwritten in place with the boosted boundary
                                 probability, like the reference does at :536, unless mutate_prob=False)
     point_maps float32 [1,H,W]
     dcm_tta    uint8 [8,H,W] or [H,W,8]: prob_dcm, _hf, _vf, _hvf, _r90, _r90_hf, _r90_vf, _r90_hvf
+    voting_first: the block's `voting_firt` switch (:471), off in the reference as shipped
     Returns pred_labeled [H,W]: int64 (postproc 0, measure.label) or int32 (postproc 1, process)."""
     if model_name in ("unet", "micronet", "dcan") and int(postproc) == 1:
         raise NotImplementedError("postproc=1 with model_mode %r is out of scope" % model_name)
@@ -454,6 +455,23 @@ def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_are
     dcm = np.asarray(dcm_tta)
     if dcm.shape == (H, W, 8) and dcm.shape != (8, H, W):
         dcm = np.moveaxis(dcm, 2, 0)
+    if voting_first:
+        # the reference's `voting_firt = 1` switch (test_dam.py:471-477): DcmVoting2 over the 8 maps, then ONE
+        # direction-difference map instead of the mean of eight -- all on the device
+        dev = _device()
+        d8 = torch.from_numpy(np.ascontiguousarray(dcm, dtype=np.uint8)).to(dev)[None]
+        p = torch.from_numpy(np.ascontiguousarray(prob, dtype=np.float32)).to(dev)[None]
+        q = torch.from_numpy(np.ascontiguousarray(np.asarray(point_maps, dtype=np.float32).reshape(1, 1, H, W))).to(dev)
+        labels, status = dam_postprocess_cuda(dcm_voting2_cuda(d8)[:, None].contiguous(), p, q, direction_classes,
+                                              min_area, radius, postproc, write_prob=mutate_prob)
+        st = int(status[0])
+        if st & _cabi.S_DDM_CONSTANT:
+            raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
+        if st & _cabi.S_NO_BACKGROUND:
+            raise ValueError(_NO_BACKGROUND_MSG)
+        if mutate_prob and isinstance(prob_maps, np.ndarray):
+            prob_maps[2, :, :] = p[0, 2].cpu().numpy()
+        return labels[0].cpu().numpy()
     key = (H, W, int(direction_classes), int(min_area), int(radius), int(postproc), bool(mutate_prob),
            torch.cuda.current_device())
     plan = _plans.get(key)

@@ -118,7 +118,7 @@ class _Sink(object):
 
 
 def _dam_postprocess(ns, prob_maps, point_maps, dcm_tta, direction_classes=9, min_area=20,
-                     radius=2, postproc=0, model_name="modelName"):
+                     radius=2, postproc=0, model_name="modelName", voting_first=False):
     """Runs test_dam.py:455-563 verbatim.  dcm_tta: 8 maps [8,H,W] (uint8); prob_maps f32 [3,H,W]
     (modified in place like the reference does, :536); point_maps f32 [1,H,W].
     Returns dict(pred_labeled, pred_inside, pred2, prob_direction_maps)."""
@@ -143,6 +143,10 @@ def _dam_postprocess(ns, prob_maps, point_maps, dcm_tta, direction_classes=9, mi
     for i, n in enumerate(names):
         g[n] = np.asarray(dcm_tta[i])[None]
     code = _read_block(ns.root, "test_dam.py", 455, 563)
+    if voting_first:
+        # the block's own hard-wired switch (test_dam.py:471): DcmVoting2 first, then ONE direction-difference map
+        assert code.count("voting_firt = 0") == 1
+        code = code.replace("voting_firt = 0", "voting_firt = 1")
     exec(compile(code, "test_dam.py:455-563", "exec"), g)
     return {"pred_labeled": g["pred_labeled"], "pred_inside": g["pred_inside"],
             "pred2": g["pred2"], "prob_direction_maps": g["prob_direction_maps"]}

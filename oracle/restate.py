@@ -285,14 +285,18 @@ def process(pred, model_mode="modelName", min_size=10, ws=True, literal=True, or
 # inference post-processing blocks
 # --------------------------------------------------------------------------------------------
 def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_area=20, radius=2,
-                    postproc=0, model_name="modelName", literal=True, order="stable"):
+                    postproc=0, model_name="modelName", literal=True, order="stable", voting_first=False):
     """test_dam.py:455-563 with its hard-wired switches (dcm_combined=1, voting_firt=0,
     DDM_switch=100, mseloss=1, direction=1).  prob_maps f32 [3,H,W] (channel 2 is overwritten in
     place, :536), point_maps f32 [1,H,W], dcm_tta 8 maps [8,H,W].
     Returns dict(pred_labeled, pred_inside, pred2, ddm_mean)."""
     prob_maps = np.asarray(prob_maps)
     H, W = prob_maps.shape[1:]
-    if len(dcm_tta) == 1:
+    if voting_first:
+        # test_dam.py:471-477 with `voting_firt = 1`: vote the 8 TTA maps, then ONE float32 DDM, no mean
+        voted = dcm_voting2(np.stack([np.asarray(m) for m in dcm_tta], axis=2).astype(np.uint8))
+        ddm = generate_dd_map(voted, direction_classes)
+    elif len(dcm_tta) == 1:
         # single-map variant, test_dam.py:499-502 (the `dcm_combined != 1` branch): float32 DDM, no mean
         ddm = generate_dd_map(np.asarray(dcm_tta[0]).astype(np.uint8), direction_classes)
     else:

@@ -304,3 +304,17 @@ def test_label_encoding_out_c_1(kernel_api):
                 _check_direction(res[4], ref[2], img, n, name, out_c=1)
     with pytest.raises(IndexError):
         kernel_api.LabelEncoding(1, 1, 1)((None, None, lab[:, :, 0].copy()))
+
+
+@pytest.mark.parametrize("seed,H,W,n", [(781, 130, 150, 16), (782, 64, 200, 10)])
+def test_dam_postprocess_voting_first(kernel_api, seed, H, W, n):
+    """`voting_firt = 1` (test_dam.py:471-477): TTA direction voting on the device, then the single-map pipeline"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    d = synth.postproc_inputs(seed, H, W, n)
+    for pp in (0, 1):
+        p_ref, p_got = d["prob"].copy(), d["prob"].copy()
+        ref = O.dam_postprocess(p_ref, d["point"], d["dcm"], 9, 20, 2, pp, literal=False, voting_first=True)["pred_labeled"]
+        got = kernel_api.dam_postprocess(p_got, d["point"], d["dcm"], 9, 20, 2, pp, voting_first=True)
+        assert got.dtype == ref.dtype and np.array_equal(got, ref), (seed, pp)
+        assert np.array_equal(p_ref.view(np.uint32), p_got.view(np.uint32))  # prob_maps[2] updated in place (:536)

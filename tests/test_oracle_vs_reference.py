@@ -193,3 +193,15 @@ def test_label_encoding_out_c_1(ref):
                 if dd:
                     assert np.array_equal(r[1][3].view(np.uint16), o[1][1].view(np.uint16)), (i, dd, literal)
                     assert np.array_equal(r[1][4], o[1][2]), (i, dd, literal)
+
+
+def test_postprocess_voting_first(ref):
+    """the block's `voting_firt` switch flipped in the text that is exec-ed (test_dam.py:471): DcmVoting2, one DDM"""
+    d = synth.postproc_inputs(780, 130, 150, 16)
+    for pp in (0, 1):
+        r = ref.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp, voting_first=True)
+        o = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp, voting_first=True)
+        assert r["pred_labeled"].dtype == o["pred_labeled"].dtype
+        assert np.array_equal(r["pred_labeled"], o["pred_labeled"])
+        plain = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
+        assert not np.array_equal(plain["ddm_mean"], o["ddm_mean"])  # the switch does change the map
