@@ -438,6 +438,18 @@ class DamPostprocessPlan(object):
 _plans = {}
 
 
+def _process_mode(postproc, model_name):
+    """postproc 1 hands the mask to postproc_other.process(model_mode=model_name): 'unet' runs it without the
+    watershed (postproc_other.py:35) = mode 2 of the C ABI; the micronet / dcan tails are out of scope"""
+    postproc = int(postproc)
+    if postproc == 1:
+        if model_name in ("micronet", "dcan"):
+            raise NotImplementedError("postproc=1 with model_mode %r is out of scope" % model_name)
+        if model_name == "unet":
+            return 2
+    return postproc
+
+
 def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_area=20, radius=2, postproc=0,
                     model_name="modelName", mutate_prob=True, voting_first=False):
     """test_dam.py:455-563 as a function.
@@ -448,8 +460,7 @@ def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_are
     dcm_tta    uint8 [8,H,W] or [H,W,8]: prob_dcm, _hf, _vf, _hvf, _r90, _r90_hf, _r90_vf, _r90_hvf
     voting_first: the block's `voting_firt` switch (:471), off in the reference as shipped
     Returns pred_labeled [H,W]: int64 (postproc 0, measure.label) or int32 (postproc 1, process)."""
-    if model_name in ("unet", "micronet", "dcan") and int(postproc) == 1:
-        raise NotImplementedError("postproc=1 with model_mode %r is out of scope" % model_name)
+    postproc = _process_mode(postproc, model_name)
     prob = np.asarray(prob_maps)
     H, W = prob.shape[1:]
     dcm = np.asarray(dcm_tta)
@@ -490,8 +501,7 @@ def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_are
 
 def plain_postprocess(prob_maps, min_area=20, radius=2, postproc=0, model_name="modelName", multi_class=True):
     """test.py:270-295 as a function -> pred_labeled [H,W] (int64 for postproc 0, int32 for 1)."""
-    if model_name in ("unet", "micronet", "dcan") and int(postproc) == 1:
-        raise NotImplementedError("postproc=1 with model_mode %r is out of scope" % model_name)
+    postproc = _process_mode(postproc, model_name)
     prob = _h2d(np.asarray(prob_maps), np.float32)[None]
     out, status = plain_postprocess_cuda(prob, min_area, radius, postproc, multi_class)
     if int(status[0]) & _cabi.S_NO_BACKGROUND:

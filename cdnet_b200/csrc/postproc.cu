@@ -282,12 +282,14 @@ static size_t tail_workspace(int B, int H, int W) {
     return a > c ? a : c;
 }
 
-// inside -> labels (postproc 0: fill/remove/label8; 1: process()) -> dilation
+// inside -> labels (postproc 0: fill/remove/label8; 1: process(); 2: process() as it runs for model_mode 'unet',
+// i.e. without the watershed, postproc_other.py:35,50-54) -> dilation
 static int tail_launch(const uint8_t* inside, int32_t* labels, void* out, int out_elem_bytes, int32_t* status, int B,
                        int H, int W, int min_area, int ws_min_size, int radius, int postproc, void* ws, size_t ws_bytes,
                        cudaStream_t st) {
     int rc;
-    if (postproc == 1) rc = ws_process_launch(inside, labels, status, B, H, W, ws_min_size, 1, ws, ws_bytes, st);
+    if (postproc == 1 || postproc == 2)
+        rc = ws_process_launch(inside, labels, status, B, H, W, ws_min_size, postproc == 1 ? 1 : 0, ws, ws_bytes, st);
     else rc = fill_remove_label_launch(inside, labels, nullptr, B, H, W, min_area, ws, ws_bytes, st);
     if (rc) return rc;
     return label_dilate_launch(labels, out, out_elem_bytes, B, H, W, radius, st);
@@ -310,7 +312,7 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
                                   int min_area, int radius, int postproc, int write_prob, void* ws, size_t ws_bytes,
                                   void* stream) {
     if (!dcm || !prob || !point || !out || bad_dims(B, H, W) || (out_elem_bytes != 4 && out_elem_bytes != 8) ||
-        (postproc != 0 && postproc != 1) || radius < 0 || radius > 4 || (n_maps != 1 && n_maps != 8))
+        postproc < 0 || postproc > 2 || radius < 0 || radius > 4 || (n_maps != 1 && n_maps != 8))
         return CDNET_E_BADARG;
     if (direction_classes != 5 && direction_classes != 9 && direction_classes != 17) return CDNET_E_BADARG;
     if (ws_bytes < cdnet_dam_postproc_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
@@ -353,7 +355,7 @@ extern "C" int cdnet_plain_postproc(const float* prob, int C, void* out, int out
                                     int W, int multi_class, int min_area, int radius, int postproc, void* ws,
                                     size_t ws_bytes, void* stream) {
     if (!prob || !out || C <= 0 || bad_dims(B, H, W) || (out_elem_bytes != 4 && out_elem_bytes != 8) ||
-        (postproc != 0 && postproc != 1) || radius < 0 || radius > 4)
+        postproc < 0 || postproc > 2 || radius < 0 || radius > 4)
         return CDNET_E_BADARG;
     if (ws_bytes < cdnet_plain_postproc_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;

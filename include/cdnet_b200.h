@@ -127,6 +127,8 @@ int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t* status, i
  * point: float32 [B,1,H,W]  point map
  * out:   labels [B,H,W], int32 or int64 (out_elem_bytes 4 / 8; the reference returns int64
  *        from measure.label when postproc == 0 and int32 from process() when postproc == 1)
+ * postproc: 0 = fill holes / remove small / measure.label (:546-561), 1 = postproc_other.process with the
+ *        watershed (:559), 2 = process as it runs for model_mode 'unet' (no watershed, postproc_other.py:35,50-54)
  * status: int32 [B] (CDNET_S_*), may be NULL. */
 size_t cdnet_dam_postproc_workspace_bytes(int B, int H, int W);
 int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, const float* point, void* out,

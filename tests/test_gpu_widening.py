@@ -318,3 +318,18 @@ def test_dam_postprocess_voting_first(kernel_api, seed, H, W, n):
         got = kernel_api.dam_postprocess(p_got, d["point"], d["dcm"], 9, 20, 2, pp, voting_first=True)
         assert got.dtype == ref.dtype and np.array_equal(got, ref), (seed, pp)
         assert np.array_equal(p_ref.view(np.uint32), p_got.view(np.uint32))  # prob_maps[2] updated in place (:536)
+
+
+def test_postprocess_with_unet_model_mode(kernel_api):
+    """postproc = 1 with model_mode 'unet': process() skips the watershed (postproc_other.py:35,50-54)"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    d = synth.postproc_inputs(783, 110, 140, 14)
+    ref = O.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="unet", literal=False)["pred_labeled"]
+    got = kernel_api.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="unet")
+    assert got.dtype == ref.dtype and np.array_equal(got, ref)
+    ref = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, model_name="unet", literal=False)["pred_labeled"]
+    got = kernel_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, model_name="unet")
+    assert got.dtype == ref.dtype and np.array_equal(got, ref)
+    with pytest.raises(NotImplementedError):
+        kernel_api.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="dcan")

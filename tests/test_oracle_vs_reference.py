@@ -205,3 +205,13 @@ def test_postprocess_voting_first(ref):
         assert np.array_equal(r["pred_labeled"], o["pred_labeled"])
         plain = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp)
         assert not np.array_equal(plain["ddm_mean"], o["ddm_mean"])  # the switch does change the map
+
+
+def test_postprocess_unet_model_mode(ref):
+    d = synth.postproc_inputs(783, 110, 140, 14)
+    r = ref.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="unet")["pred_labeled"]
+    o = O.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="unet", literal=False)["pred_labeled"]
+    assert r.dtype == o.dtype and np.array_equal(r, o)
+    r = ref.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, model_name="unet")["pred_labeled"]
+    o = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, model_name="unet")["pred_labeled"]
+    assert r.dtype == o.dtype and np.array_equal(r, o)
