@@ -9,7 +9,7 @@ cd "$REPO"
 LIB="$(python tests/simt/build.py --asan | tail -1)"
 ASAN_RT="$(/usr/bin/gcc -print-file-name=libasan.so)"
 [ -f "$LIB" ] && [ -f "$ASAN_RT" ] || { echo "no AddressSanitizer build / runtime"; exit 1; }
-[ $# -eq 0 ] && set -- tests/test_gpu_postproc.py tests/test_gpu_targets.py tests/test_gpu_training.py tests/test_gpu_metrics.py tests/test_gpu_sharded.py
+[ $# -eq 0 ] && set -- tests/test_gpu_postproc.py tests/test_gpu_targets.py tests/test_gpu_training.py tests/test_gpu_metrics.py tests/test_gpu_sharded.py tests/test_gpu_widening.py
 rm -f tests/simt/_build/asan/report.*
 CDNET_SIMT_LIB="$LIB" LD_PRELOAD="$ASAN_RT" \
 ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1:log_path=tests/simt/_build/asan/report \
