@@ -263,6 +263,39 @@ def gold_training(ns):
     _save("training", meta, **out)
 
 
+def gold_widening(ns):
+    """Round-1 widening features executed verbatim: the TTA block + get_probmaps (test_dam.py:314-450, :930-1034),
+    LabelEncoding with out_c != 3 (my_transforms_direction.py:721-739), the `voting_firt` switch (:471) and
+    model_mode 'unet' (postproc_other.py:35).  Inputs come from seeds (synth / torch.Generator)."""
+    import torch
+    out, meta = {}, {}
+    g = torch.Generator().manual_seed(2025)
+    H, W, C = 36, 52, 9
+    shapes = [(H, W)] * 4 + [(W, H)] * 4
+    ml = [torch.randn((3,) + s, generator=g) * 3 for s in shapes]
+    pt = [torch.randn((1,) + s, generator=g) for s in shapes]
+    dl = [torch.randn((C,) + s, generator=g) * 3 for s in shapes]
+    prob, point, dcm = ns.tta_merge(ml, pt, dl)
+    out["tta_prob"], out["tta_point"], out["tta_dcm"] = prob, point, dcm.astype(np.uint8)
+    meta["tta"] = {"seed": 2025, "H": H, "W": W, "C": C,
+                   "digest": synth.digest(*[t.numpy() for t in ml + pt + dl])}
+    lab = synth.as_uint8_label(synth.instance_map(779, 70, 90, 6))
+    binary = np.repeat(((lab[:, :, 0] > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    binary[:, :, 1] = np.roll(binary[:, :, 0], 5, axis=1)
+    for name, img in (("inst", lab), ("bin", binary)):
+        r = ns.LabelEncoding(1, 1, 1)((None, None, img.copy()))
+        out["c1_%s_tern" % name], out["c1_%s_point" % name], out["c1_%s_dir" % name] = np.asarray(r[2]), r[3], r[4]
+    meta["c1"] = {"seed": 779, "H": 70, "W": 90, "n_target": 6, "digest": synth.digest(lab, binary)}
+    d = synth.postproc_inputs(780, 130, 150, 16)
+    meta["pp"] = {"seed": 780, "H": 130, "W": 150, "n_target": 16, "digest": synth.digest(d["dcm"], d["prob"], d["point"])}
+    for pp in (0, 1):
+        out["vote_pp%d" % pp] = ns.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp,
+                                                   voting_first=True)["pred_labeled"]
+    out["unet_plain"] = ns.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="unet")["pred_labeled"]
+    out["unet_dam"] = ns.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, model_name="unet")["pred_labeled"]
+    _save("widening", meta, **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -280,7 +313,7 @@ def main():
         return
     ns = ref_loader.load()
     assert ns.DTOffsetConfig.num_classes == 8
-    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16", "metrics", "training"]
+    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16", "metrics", "training", "widening"]
     if "ddm" in todo:
         gold_ddm(ns)
     if "process" in todo:
@@ -295,6 +328,8 @@ def main():
         gold_metrics()
     if "training" in todo:
         gold_training(ns)
+    if "widening" in todo:
+        gold_widening(ns)
     if "t16" in todo:
         env = dict(os.environ, dt_num_classes="16")
         subprocess.check_call([sys.executable, "-m", "oracle.make_goldens", "--child16"], env=env,

@@ -333,3 +333,49 @@ def test_postprocess_with_unet_model_mode(kernel_api):
     assert got.dtype == ref.dtype and np.array_equal(got, ref)
     with pytest.raises(NotImplementedError):
         kernel_api.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="dcan")
+
+
+def _widening_golden():
+    import torch
+    from cdnet_b200 import synth
+    z, meta = load_golden("widening")
+    t = meta["tta"]
+    g = torch.Generator().manual_seed(t["seed"])
+    shapes = [(t["H"], t["W"])] * 4 + [(t["W"], t["H"])] * 4
+    ml = [torch.randn((3,) + s, generator=g) * 3 for s in shapes]
+    pt = [torch.randn((1,) + s, generator=g) for s in shapes]
+    dl = [torch.randn((t["C"],) + s, generator=g) * 3 for s in shapes]
+    assert synth.digest(*[x.numpy() for x in ml + pt + dl]) == t["digest"], "torch.Generator stream differs from the goldens'"
+    return z, meta, ml, pt, dl
+
+
+def test_widening_golden(kernel_api):
+    """the widening features straight against vectors generated from the verbatim reference
+    (oracle/make_goldens.py gold_widening): TTA hand-off, LabelEncoding out_c != 3, voting first, 'unet' mode"""
+    from cdnet_b200 import synth
+    z, meta, ml, pt, dl = _widening_golden()
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t[None]) for t in ml],
+                                                 [to_dev(kernel_api, t[None]) for t in pt],
+                                                 [to_dev(kernel_api, t[None]) for t in dl])
+    assert np.allclose(prob[0].cpu().numpy(), z["tta_prob"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(point[0].cpu().numpy().view(np.uint32), z["tta_point"].view(np.uint32))
+    assert (dcm[0].cpu().numpy() != z["tta_dcm"]).mean() < 2e-3  # float near-ties only
+    c = meta["c1"]
+    lab = synth.as_uint8_label(synth.instance_map(c["seed"], c["H"], c["W"], c["n_target"]))
+    binary = np.repeat(((lab[:, :, 0] > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    binary[:, :, 1] = np.roll(binary[:, :, 0], 5, axis=1)
+    assert synth.digest(lab, binary) == c["digest"]
+    for name, img in (("inst", lab), ("bin", binary)):
+        r = kernel_api.LabelEncoding(1, 1, 1, num_classes=8)((None, None, img.copy()))
+        assert np.array_equal(np.asarray(r[2]), z["c1_%s_tern" % name]), name
+        assert np.array_equal(r[3].view(np.uint16), z["c1_%s_point" % name].view(np.uint16)), name
+        _check_direction(r[4], z["c1_%s_dir" % name].astype(np.int64), img, 8, "golden c1 " + name, out_c=1)
+    p = meta["pp"]
+    d = synth.postproc_inputs(p["seed"], p["H"], p["W"], p["n_target"])
+    assert synth.digest(d["dcm"], d["prob"], d["point"]) == p["digest"]
+    for pp in (0, 1):
+        got = kernel_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, pp, voting_first=True)
+        assert got.dtype == z["vote_pp%d" % pp].dtype and np.array_equal(got, z["vote_pp%d" % pp]), pp
+    assert np.array_equal(kernel_api.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="unet"), z["unet_plain"])
+    assert np.array_equal(kernel_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, model_name="unet"),
+                          z["unet_dam"])
