@@ -131,6 +131,14 @@ def emulated_api():
                 m.torch = proxy
         api._plans.clear()
         api._ws_cache.clear()
+        if os.environ.get("CDNET_SIMT_WS_EXACT"):
+            # hand every call EXACTLY *_workspace_bytes(): a size formula that undercounts fails with E_WORKSPACE
+            # instead of hiding in the 5 % slack the host layer normally adds
+            saved.append((api, "_workspace", api._workspace))
+            api._workspace = lambda nbytes, dev: torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+            for m in (metrics, training):
+                saved.append((m, "_workspace", m._workspace))
+                m._workspace = api._workspace
         fill = os.environ.get("CDNET_SIMT_WS_FILL")
         if fill:
             # initcheck: hand every call a workspace (and every torch.empty result) full of a junk byte, so a kernel
