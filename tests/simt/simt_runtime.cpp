@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <sys/mman.h>
 #include <ucontext.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -26,6 +27,12 @@ thread_local dim3 blockDim, gridDim;
 
 namespace simt {
 namespace {
+
+// fatal emulator diagnostics end the process without a core dump
+[[noreturn]] void die() {
+    fflush(stderr);
+    _exit(70);
+}
 
 constexpr size_t kStackBytes = 256 * 1024;
 constexpr int kMaxThreads = 1024;
@@ -120,7 +127,7 @@ void fiber_main() {
     }
     if (e->alive > 0 && e->b_arrived >= e->alive) release_block_barrier(e);
     to_scheduler(e);
-    abort();  // a finished fiber is never resumed
+    die();  // a finished fiber is never resumed
 }
 
 void run_block(BlockExec* e, unsigned bx, unsigned by, unsigned bz) {
@@ -178,7 +185,7 @@ void run_block(BlockExec* e, unsigned bx, unsigned by, unsigned bz) {
             }
             fprintf(stderr, "simt: deadlock in %s, block (%u,%u,%u): %d threads wait at __syncthreads, %d in a warp "
                             "collective, %d alive\n", e->name, bx, by, bz, wb, ww, e->alive);
-            abort();
+            die();
         }
     }
     e->cur = -1;
@@ -190,7 +197,7 @@ void worker_main(int wid) {
     e->warps = new WarpState[kMaxThreads / 32];
     e->stacks = (char*)mmap(nullptr, kStackBytes * kMaxThreads, PROT_READ | PROT_WRITE,
                             MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-    if (e->stacks == (char*)MAP_FAILED) { perror("simt: mmap"); abort(); }
+    if (e->stacks == (char*)MAP_FAILED) { perror("simt: mmap"); die(); }
     t_exec = e;
     unsigned long long seen = 0;
     if (const char* sch = getenv("SIMT_SCHEDULE"))
@@ -207,7 +214,7 @@ void worker_main(int wid) {
         e->name = g.name;
         if (g.dyn_bytes > e->dyn_cap) {
             free(e->dyn);
-            if (posix_memalign(&e->dyn, 256, g.dyn_bytes)) abort();
+            if (posix_memalign(&e->dyn, 256, g.dyn_bytes)) die();
             e->dyn_cap = g.dyn_bytes;
         }
         for (;;) {
@@ -227,6 +234,8 @@ void worker_main(int wid) {
 }
 
 }  // namespace
+
+static void die_public() { die(); }
 
 int lane_id() { return t_exec->cur & 31; }
 void* dyn_smem() { return t_exec->dyn; }
@@ -252,7 +261,7 @@ void warp_exchange(unsigned mask, unsigned long long v, unsigned long long* out)
     if (!((mask >> lane) & 1u)) {
         fprintf(stderr, "simt: %s: lane %d calls a warp collective whose mask %08x does not name it\n", e->name, lane,
                 mask);
-        abort();
+        die_public();
     }
     Rendezvous* r = nullptr;
     for (int i = 0; i < w.n_rv; ++i)
@@ -260,7 +269,7 @@ void warp_exchange(unsigned mask, unsigned long long v, unsigned long long* out)
     if (!r) {
         if (w.n_rv == (int)(sizeof w.rv / sizeof w.rv[0])) {
             fprintf(stderr, "simt: %s: too many distinct collective masks in one warp\n", e->name);
-            abort();
+            die_public();
         }
         r = &w.rv[w.n_rv++];
         r->mask = mask;
@@ -269,7 +278,7 @@ void warp_exchange(unsigned mask, unsigned long long v, unsigned long long* out)
     if ((r->arrived >> lane) & 1u) {
         fprintf(stderr, "simt: %s: lane %d re-enters a collective (mask %08x) that is still pending\n", e->name, lane,
                 mask);
-        abort();
+        die_public();
     }
     r->vals[lane] = v;
     r->arrived |= 1u << lane;
@@ -289,7 +298,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
         dyn_bytes > 232448) {
         fprintf(stderr, "simt: invalid launch configuration for %s: grid %ux%ux%u block %ux%ux%u smem %zu\n", name,
                 grid.x, grid.y, grid.z, block.x, block.y, block.z, dyn_bytes);
-        abort();
+        die_public();
     }
     static std::mutex launch_mu;  // launches are serialised, like work on one stream
     std::lock_guard<std::mutex> guard(launch_mu);
