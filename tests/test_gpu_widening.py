@@ -101,7 +101,7 @@ def test_tta_merge_vs_oracle(kernel_api, B, H, W, C):
             q = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
             q[0] *= p[0]
             top = np.sort(q, axis=0)
-            clear = O.tta_variant_to_original(((top[-1] - top[-2]) > 1e-6)[None], v)[0]
+            clear = O.tta_variant_to_original(((top[-1] - top[-2]) > 3e-6)[None], v)[0]
             assert np.array_equal(got[v][clear], rd[v][clear]), (b, v)
             assert clear.mean() > 0.99
 
@@ -121,7 +121,7 @@ def test_hand_off_without_tta(kernel_api):
         qq = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
         qq[0] *= p[0]
         top = np.sort(qq, axis=0)
-        clear = (top[-1] - top[-2]) > 1e-6
+        clear = (top[-1] - top[-2]) > 3e-6
         assert np.array_equal(dcm[b, 0].cpu().numpy().astype(np.int64)[clear], c[0][clear]) and clear.mean() > 0.99
 
 
