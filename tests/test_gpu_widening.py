@@ -66,100 +66,6 @@ def test_label_encoding_degenerate_sweep(kernel_api):
                 _check_direction(res[4], ref[2], lab if lab.ndim == 3 else np.repeat(lab[:, :, None], 3, axis=2), n, name)
 
 
-def _tta_inputs(seed, B, H, W, C):
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    shapes = [(H, W)] * 4 + [(W, H)] * 4
-    ml = [torch.randn((B, 3) + s, generator=g) * 3 for s in shapes]
-    pt = [torch.randn((B, 1) + s, generator=g) for s in shapes]
-    dl = [torch.randn((B, C) + s, generator=g) * 3 for s in shapes]
-    return ml, pt, dl
-
-
-# H % 4 == W % 4 == 0 takes the 4-pixel (128-bit) kernel, everything else the scalar one
-@pytest.mark.parametrize("B,H,W,C", [(1, 21, 34, 9), (2, 64, 96, 9), (1, 33, 31, 17), (1, 1, 1, 5), (1, 70, 5, 9),
-                                     (1, 36, 100, 17), (2, 100, 36, 5), (1, 4, 4, 9), (1, 8, 132, 9)])
-def test_tta_merge_vs_oracle(kernel_api, B, H, W, C):
-    """fused TTA hand-off (test_dam.py:299-450, :983-1013) vs the restatement (pinned to the verbatim reference in
-    tests/test_oracle_vs_reference.py).  Probabilities: 1e-5 relative (the softmax's expf is the device's, the
-    reference's is torch's); point map: bit-exact; direction classes: exact wherever the top-2 margin exceeds
-    the float noise."""
-    from oracle import restate as O
-    ml, pt, dl = _tta_inputs(B * 100 + H, B, H, W, C)
-    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t) for t in ml], [to_dev(kernel_api, t) for t in pt],
-                                                 [to_dev(kernel_api, t) for t in dl])
-    assert prob.dtype == kernel_api.torch.float32 and dcm.dtype == kernel_api.torch.uint8
-    assert tuple(prob.shape) == (B, 3, H, W) and tuple(point.shape) == (B, 1, H, W) and tuple(dcm.shape) == (B, 8, H, W)
-    for b in range(B):
-        rp, rq, rd = O.tta_merge([t[b].numpy() for t in ml], [t[b].numpy() for t in pt], [t[b].numpy() for t in dl])
-        assert np.allclose(prob[b].cpu().numpy(), rp, rtol=1e-5, atol=1e-7)
-        assert np.array_equal(point[b].cpu().numpy().view(np.uint32), rq.view(np.uint32))
-        got = dcm[b].cpu().numpy().astype(np.int64)
-        for v in range(8):
-            p, _, _ = O.variant_probmaps(ml[v][b].numpy(), pt[v][b].numpy(), dl[v][b].numpy())
-            z = dl[v][b].numpy().astype(np.float64)
-            q = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
-            q[0] *= p[0]
-            top = np.sort(q, axis=0)
-            clear = O.tta_variant_to_original(((top[-1] - top[-2]) > 3e-6)[None], v)[0]
-            assert np.array_equal(got[v][clear], rd[v][clear]), (b, v)
-            assert clear.mean() > 0.99
-
-
-def test_hand_off_without_tta(kernel_api):
-    """one variant (tta off): soft-max / argmax only, nothing averaged; dcm has one map (test_dam.py:499-502)"""
-    from oracle import restate as O
-    ml, pt, dl = _tta_inputs(7, 2, 40, 56, 9)
-    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, ml[0])], [to_dev(kernel_api, pt[0])],
-                                                 [to_dev(kernel_api, dl[0])])
-    assert tuple(dcm.shape) == (2, 1, 40, 56)
-    for b in range(2):
-        p, q, c = O.variant_probmaps(ml[0][b].numpy(), pt[0][b].numpy(), dl[0][b].numpy())
-        assert np.allclose(prob[b].cpu().numpy(), p, rtol=1e-5, atol=1e-7)
-        assert np.array_equal(point[b].cpu().numpy(), q)
-        z = dl[0][b].numpy().astype(np.float64)
-        qq = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
-        qq[0] *= p[0]
-        top = np.sort(qq, axis=0)
-        clear = (top[-1] - top[-2]) > 3e-6
-        assert np.array_equal(dcm[b, 0].cpu().numpy().astype(np.int64)[clear], c[0][clear]) and clear.mean() > 0.99
-
-
-def test_tta_merge_feeds_postprocess(kernel_api):
-    """hand-off -> dam_postprocess_cuda without leaving the device == the same two steps through the oracle"""
-    from oracle import restate as O
-    from cdnet_b200 import synth
-    torch = kernel_api.torch
-    d = synth.postproc_inputs(88, 96, 80, 9)
-    H, W = 96, 80
-    # logits whose softmax / argmax reproduce the synthetic tile in every variant's frame
-    def to_variant(a, v):
-        a = np.asarray(a)
-        if v & 4:
-            a = np.rot90(a, k=1, axes=(1, 2))
-        if v & 2:
-            a = np.flip(a, 1)
-        if v & 1:
-            a = np.flip(a, 2)
-        return np.ascontiguousarray(a)
-    ml, pt, dl = [], [], []
-    for v in range(8):
-        ml.append(torch.from_numpy(to_variant(np.log(d["prob"] + 1e-6), v))[None])
-        pt.append(torch.from_numpy(to_variant(d["point"], v))[None])
-        onehot = (np.arange(9)[:, None, None] == d["dcm"][v][None]).astype(np.float32) * 12.0
-        dl.append(torch.from_numpy(to_variant(onehot, v))[None])
-    for v in range(8):  # to_variant inverts tta_variant_to_original
-        assert np.array_equal(O.tta_variant_to_original(to_variant(d["point"], v), v), d["point"])
-    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t) for t in ml], [to_dev(kernel_api, t) for t in pt],
-                                                 [to_dev(kernel_api, t) for t in dl])
-    assert np.array_equal(dcm[0].cpu().numpy(), d["dcm"])
-    lab, status = kernel_api.dam_postprocess_cuda(dcm, prob, point, 9, 20, 2, 0)
-    assert int(status[0]) == 0
-    ref = O.dam_postprocess(prob[0].cpu().numpy().copy(), point[0].cpu().numpy(), dcm[0].cpu().numpy(), 9, 20, 2, 0,
-                            literal=False)["pred_labeled"]
-    assert np.array_equal(lab[0].cpu().numpy(), ref)
-
-
 @pytest.mark.parametrize("seed,H,W,n", [(71, 128, 160, 14), (72, 250, 200, 60)])
 def test_config3_chain_16_directions(kernel_api, seed, H, W, n):
     """BASELINE configs[3]: 16-direction target generation, the direction-difference map of the produced class map
@@ -351,15 +257,9 @@ def _widening_golden():
 
 def test_widening_golden(kernel_api):
     """the widening features straight against vectors generated from the verbatim reference
-    (oracle/make_goldens.py gold_widening): TTA hand-off, LabelEncoding out_c != 3, voting first, 'unet' mode"""
+    (oracle/make_goldens.py gold_widening): LabelEncoding out_c != 3, voting first, 'unet' mode"""
     from cdnet_b200 import synth
     z, meta, ml, pt, dl = _widening_golden()
-    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t[None]) for t in ml],
-                                                 [to_dev(kernel_api, t[None]) for t in pt],
-                                                 [to_dev(kernel_api, t[None]) for t in dl])
-    assert np.allclose(prob[0].cpu().numpy(), z["tta_prob"], rtol=1e-5, atol=1e-7)
-    assert np.array_equal(point[0].cpu().numpy().view(np.uint32), z["tta_point"].view(np.uint32))
-    assert (dcm[0].cpu().numpy() != z["tta_dcm"]).mean() < 2e-3  # float near-ties only
     c = meta["c1"]
     lab = synth.as_uint8_label(synth.instance_map(c["seed"], c["H"], c["W"], c["n_target"]))
     binary = np.repeat(((lab[:, :, 0] > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
@@ -379,3 +279,110 @@ def test_widening_golden(kernel_api):
     assert np.array_equal(kernel_api.plain_postprocess(d["prob"].copy(), 20, 2, 1, model_name="unet"), z["unet_plain"])
     assert np.array_equal(kernel_api.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, model_name="unet"),
                           z["unet_dam"])
+
+
+
+# ---- the fused TTA hand-off (csrc/handoff.cu) last: its 4-pixel form has not run on a GPU yet ----
+def _tta_inputs(seed, B, H, W, C):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(H, W)] * 4 + [(W, H)] * 4
+    ml = [torch.randn((B, 3) + s, generator=g) * 3 for s in shapes]
+    pt = [torch.randn((B, 1) + s, generator=g) for s in shapes]
+    dl = [torch.randn((B, C) + s, generator=g) * 3 for s in shapes]
+    return ml, pt, dl
+
+
+# H % 4 == W % 4 == 0 takes the 4-pixel (128-bit) kernel, everything else the scalar one
+@pytest.mark.parametrize("B,H,W,C", [(1, 21, 34, 9), (2, 64, 96, 9), (1, 33, 31, 17), (1, 1, 1, 5), (1, 70, 5, 9),
+                                     (1, 36, 100, 17), (2, 100, 36, 5), (1, 4, 4, 9), (1, 8, 132, 9)])
+def test_tta_merge_vs_oracle(kernel_api, B, H, W, C):
+    """fused TTA hand-off (test_dam.py:299-450, :983-1013) vs the restatement (pinned to the verbatim reference in
+    tests/test_oracle_vs_reference.py).  Probabilities: 1e-5 relative (the softmax's expf is the device's, the
+    reference's is torch's); point map: bit-exact; direction classes: exact wherever the top-2 margin exceeds
+    the float noise."""
+    from oracle import restate as O
+    ml, pt, dl = _tta_inputs(B * 100 + H, B, H, W, C)
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t) for t in ml], [to_dev(kernel_api, t) for t in pt],
+                                                 [to_dev(kernel_api, t) for t in dl])
+    assert prob.dtype == kernel_api.torch.float32 and dcm.dtype == kernel_api.torch.uint8
+    assert tuple(prob.shape) == (B, 3, H, W) and tuple(point.shape) == (B, 1, H, W) and tuple(dcm.shape) == (B, 8, H, W)
+    for b in range(B):
+        rp, rq, rd = O.tta_merge([t[b].numpy() for t in ml], [t[b].numpy() for t in pt], [t[b].numpy() for t in dl])
+        assert np.allclose(prob[b].cpu().numpy(), rp, rtol=1e-5, atol=1e-7)
+        assert np.array_equal(point[b].cpu().numpy().view(np.uint32), rq.view(np.uint32))
+        got = dcm[b].cpu().numpy().astype(np.int64)
+        for v in range(8):
+            p, _, _ = O.variant_probmaps(ml[v][b].numpy(), pt[v][b].numpy(), dl[v][b].numpy())
+            z = dl[v][b].numpy().astype(np.float64)
+            q = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
+            q[0] *= p[0]
+            top = np.sort(q, axis=0)
+            clear = O.tta_variant_to_original(((top[-1] - top[-2]) > 3e-6)[None], v)[0]
+            assert np.array_equal(got[v][clear], rd[v][clear]), (b, v)
+            assert clear.mean() > 0.99
+
+
+def test_hand_off_without_tta(kernel_api):
+    """one variant (tta off): soft-max / argmax only, nothing averaged; dcm has one map (test_dam.py:499-502)"""
+    from oracle import restate as O
+    ml, pt, dl = _tta_inputs(7, 2, 40, 56, 9)
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, ml[0])], [to_dev(kernel_api, pt[0])],
+                                                 [to_dev(kernel_api, dl[0])])
+    assert tuple(dcm.shape) == (2, 1, 40, 56)
+    for b in range(2):
+        p, q, c = O.variant_probmaps(ml[0][b].numpy(), pt[0][b].numpy(), dl[0][b].numpy())
+        assert np.allclose(prob[b].cpu().numpy(), p, rtol=1e-5, atol=1e-7)
+        assert np.array_equal(point[b].cpu().numpy(), q)
+        z = dl[0][b].numpy().astype(np.float64)
+        qq = np.exp(z - z.max(axis=0)) / np.exp(z - z.max(axis=0)).sum(axis=0)
+        qq[0] *= p[0]
+        top = np.sort(qq, axis=0)
+        clear = (top[-1] - top[-2]) > 3e-6
+        assert np.array_equal(dcm[b, 0].cpu().numpy().astype(np.int64)[clear], c[0][clear]) and clear.mean() > 0.99
+
+
+def test_tta_merge_feeds_postprocess(kernel_api):
+    """hand-off -> dam_postprocess_cuda without leaving the device == the same two steps through the oracle"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    torch = kernel_api.torch
+    d = synth.postproc_inputs(88, 96, 80, 9)
+    H, W = 96, 80
+    # logits whose softmax / argmax reproduce the synthetic tile in every variant's frame
+    def to_variant(a, v):
+        a = np.asarray(a)
+        if v & 4:
+            a = np.rot90(a, k=1, axes=(1, 2))
+        if v & 2:
+            a = np.flip(a, 1)
+        if v & 1:
+            a = np.flip(a, 2)
+        return np.ascontiguousarray(a)
+    ml, pt, dl = [], [], []
+    for v in range(8):
+        ml.append(torch.from_numpy(to_variant(np.log(d["prob"] + 1e-6), v))[None])
+        pt.append(torch.from_numpy(to_variant(d["point"], v))[None])
+        onehot = (np.arange(9)[:, None, None] == d["dcm"][v][None]).astype(np.float32) * 12.0
+        dl.append(torch.from_numpy(to_variant(onehot, v))[None])
+    for v in range(8):  # to_variant inverts tta_variant_to_original
+        assert np.array_equal(O.tta_variant_to_original(to_variant(d["point"], v), v), d["point"])
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t) for t in ml], [to_dev(kernel_api, t) for t in pt],
+                                                 [to_dev(kernel_api, t) for t in dl])
+    assert np.array_equal(dcm[0].cpu().numpy(), d["dcm"])
+    lab, status = kernel_api.dam_postprocess_cuda(dcm, prob, point, 9, 20, 2, 0)
+    assert int(status[0]) == 0
+    ref = O.dam_postprocess(prob[0].cpu().numpy().copy(), point[0].cpu().numpy(), dcm[0].cpu().numpy(), 9, 20, 2, 0,
+                            literal=False)["pred_labeled"]
+    assert np.array_equal(lab[0].cpu().numpy(), ref)
+
+
+def test_tta_merge_golden(kernel_api):
+    """the fused TTA hand-off against the vectors of the reference's TTA block executed verbatim"""
+    z, meta, ml, pt, dl = _widening_golden()
+    prob, point, dcm = kernel_api.tta_merge_cuda([to_dev(kernel_api, t[None]) for t in ml],
+                                                 [to_dev(kernel_api, t[None]) for t in pt],
+                                                 [to_dev(kernel_api, t[None]) for t in dl])
+    assert np.allclose(prob[0].cpu().numpy(), z["tta_prob"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(point[0].cpu().numpy().view(np.uint32), z["tta_point"].view(np.uint32))
+    assert (dcm[0].cpu().numpy() != z["tta_dcm"]).mean() < 2e-3  # float near-ties only
