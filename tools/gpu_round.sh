@@ -21,3 +21,7 @@ timeout 200 ncu --set full --clock-control none --import-source on -k "regex:$KE
 timeout 120 ncu --set full --clock-control none --import-source on -k "regex:k_tta_merge" -s 1 -c 1 -f -o $OUT/${TAG}_tta \
     python tools/ncu_tta.py > $OUT/${TAG}_tta.log 2>&1; echo "ncu tta rc=$?"
 tail -3 $OUT/${TAG}_tests.log; head -c 600 $OUT/${TAG}_bench.json
+# target-transform kernels: full captures with stall reasons (one launch each)
+timeout 200 ncu --set full --clock-control none --import-source on \
+    -k "regex:k_t_direction_lab|k_t_centerness|k_flood|k_t_gauss|k_edt_cols|k_edt_rows" -s 12 -c 8 -f -o $OUT/${TAG}_tpath \
+    python tools/bench_extra.py --what targets --steps 1 > $OUT/${TAG}_tpath.log 2>&1; echo "ncu tpath rc=$?"
