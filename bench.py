@@ -42,6 +42,7 @@ ALG_BYTES_PER_PX = 28.0  # 8 u8 maps + 3 f32 + 1 f32 i
 KERNEL_BYTES_PER_PX = {
     "k_ddm_codes": 10.0,        # 8 class maps (u8) in, 2-byte code word out
     "k_ddm_codes_simd": 10.0,
+    "k_ddm_bits": 10.0,         # bit-sliced form of the same pass
     "k_point_max": 4.0,         # f32 point map in
     "k_point_max4": 4.0,
     "k_boost_inside": 19.0,     # codes 2 + point 4 + prob 12 in, inside mask 1 out

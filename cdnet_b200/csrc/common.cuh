@@ -102,6 +102,17 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     if (b0 != r) atomicMin(L + b0, r);
 }
 
+// bitwise select (m ? x : y) in ONE LOP3 -- ptxas does not always fuse the two masked halves itself
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(m), "r"(x), "r"(y));
+    return r;
+}
+#else
+static inline uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
+#endif
+
 // float <-> order-preserving uint32 (for atomicMax on floats of any sign)
 __device__ __forceinline__ unsigned int f32_to_ordered(float f) {
     unsigned int u = __float_as_uint(f);

@@ -360,6 +360,335 @@ __global__ void __launch_bounds__(128, CDNET_DDM_MINB) k_ddm_codes_simd(const ui
     if (threadIdx.x == 0 && seen) atomicOr(flags + b, seen);
 }
 
+// ---- bit-sliced variant (5 / 9 classes, W % 8 == 0) ---------------------------------------------------
+// One 32-bit register holds ONE BIT of 32 consecutive pixels, so the whole stencil is LOP3 work on 32 pixels at
+// a time: ~6 thread-instructions per (pixel, map) instead of ~31 for the byte-SIMD kernel above.
+//   * a lane owns 32 pixels of a row (a warp spans 1024 columns); per row and map it loads the 32 class bytes
+//     (4 x 64-bit loads), packs two pixels into one byte (ids < 16: one multiply-add per word pair, which is also
+//     the first transpose stage) and transposes 16 bytes x 8 bits -> the 4 id-bit planes (a 4x4 byte transpose
+//     with PRMT + two mask/shift stages);
+//   * class planes P_k = "pixel has direction class k" are decoded from the four id bits, ids >= n decode to the
+//     "unknown" plane (zero vector as a neighbour, centre code 1), ids >= 16 are mapped to 15 first (rare branch);
+//   * 3-wide horizontal OR: neighbour bits come from the adjacent lanes (rotating shuffle + funnel shift); the
+//     3-row OR is a rolling window down the strip;
+//   * d = 2 iff the centre's class has an opposing class (ring distance 3..5 of 8, or 2 of 4) in its neighbourhood
+//     set, d = 0 iff the set lies within ring distance 1 (resp. 0) and holds no zero vector -- the same table
+//     ddm_build_lut derives from the reference's arithmetic (the launcher checks that it has this ring form);
+//   * warp w of a block handles map w (T = 8) or the w-th sub-strip of rows (T = 1); the two code bit-planes of
+//     every (row, map) go to shared memory, then the block transposes 16 planes x 32 pixels -> 32 uint16 code words
+//     and stores them with 128-bit stores in the layout k_boost_inside reads.
+// Columns: a tile up to 1023 px wide is one chunk (the rotating shuffle hands lane 0 the pixel right of the
+// chunk, which lies outside the image = zero vector, exactly what the left border needs); wider tiles are cut
+// into chunks of 960 owned pixels with one halo lane on either side.
+constexpr int kBitsWarps = 8;
+
+// ids >= 16 -> 15 (still "unknown", but it survives the nibble packing)
+__device__ __forceinline__ void bits_clamp_ids(uint32_t w[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t m = w[i] & 0xf0f0f0f0u;
+        m |= m >> 1;
+        m |= m >> 2;
+        m = ((m >> 4) & 0x01010101u) * 0xffu;  // 0xff in every byte whose high nibble is non-zero
+        w[i] = (w[i] & ~m) | (m & 0x0f0f0f0fu);
+    }
+}
+
+// 32 class bytes of one row (8 words, pixel 4i + b in byte b of word i) -> the 4 id-bit planes (bit p = pixel p)
+__device__ __forceinline__ void bits_transpose_row(uint32_t w[8], uint32_t G[4]) {
+    if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) & 0xf0f0f0f0u)
+        bits_clamp_ids(w);  // ids >= 16 somewhere in these 32 pixels (never, for an argmax over <= 9 channels)
+    // nibble packing does the first transpose stage for free: byte b of E[m] = pixel 8m+b (low) | pixel 8m+4+b (high)
+    uint32_t E[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) E[m] = w[2 * m + 1] * 16u + w[2 * m];
+    // 4x4 byte transpose: G[b] = bytes b of E[0..3]
+    const uint32_t t0 = __byte_perm(E[0], E[1], 0x5140), t1 = __byte_perm(E[2], E[3], 0x5140);
+    const uint32_t t2 = __byte_perm(E[0], E[1], 0x7362), t3 = __byte_perm(E[2], E[3], 0x7362);
+    uint32_t g0 = __byte_perm(t0, t1, 0x5410), g1 = __byte_perm(t0, t1, 0x7632);
+    uint32_t g2 = __byte_perm(t2, t3, 0x5410), g3 = __byte_perm(t2, t3, 0x7632);
+    // two bit stages inside every nibble: register index (b1 b0) <-> id bit index (j1 j0)
+    {
+        const uint32_t a0 = g0, c0 = g2, a1 = g1, c1 = g3;
+        g0 = bitsel(0x33333333u, a0, c0 << 2);
+        g2 = bitsel(0x33333333u, a0 >> 2, c0);
+        g1 = bitsel(0x33333333u, a1, c1 << 2);
+        g3 = bitsel(0x33333333u, a1 >> 2, c1);
+    }
+    G[0] = bitsel(0x55555555u, g0, g1 << 1);
+    G[1] = bitsel(0x55555555u, g0 >> 1, g1);
+    G[2] = bitsel(0x55555555u, g2, g3 << 1);
+    G[3] = bitsel(0x55555555u, g2 >> 1, g3);
+}
+
+// NC direction classes (8: ring of 45-degree steps, 4: ring of 90-degree steps) + plane NC = "acts as the zero vector"
+template <int NC>
+struct BitRow {
+    uint32_t H[NC + 1];  // NC == 8: 3-wide horizontal OR of the class planes; NC == 4: left | right only
+    uint32_t P[NC + 1];  // the pixel's own class planes (NC == 4 also uses them as the vertical neighbours)
+    uint32_t act, odd;   // valid direction class / non-zero unknown id
+};
+
+template <int NC>
+__device__ __forceinline__ void bits_decode_row(const uint32_t B[4], int lane, BitRow<NC>& r) {
+    const uint32_t B0 = B[0], B1 = B[1], B2 = B[2], B3 = B[3];
+    const uint32_t m0 = ~B3 & ~B2, m1 = ~B3 & B2;
+    r.P[0] = m0 & ~B1 & B0;
+    r.P[1] = m0 & B1 & ~B0;
+    r.P[2] = m0 & B1 & B0;
+    r.P[3] = m1 & ~B1 & ~B0;
+    if (NC == 8) {
+        const uint32_t nz = B2 | B1 | B0;
+        r.P[4] = m1 & ~B1 & B0;
+        r.P[5] = m1 & B1 & ~B0;
+        r.P[6] = m1 & B1 & B0;
+        r.P[7] = B3 & ~nz;
+        r.act = B3 ^ nz;
+        r.odd = B3 & nz;
+    } else {
+        r.act = r.P[0] | r.P[1] | r.P[2] | r.P[3];
+        r.odd = (B3 | B2 | B1 | B0) & ~r.act;
+    }
+    r.P[NC] = ~r.act;  // class 0, unknown ids and everything outside the image: the zero vector
+    const int src_l = (lane + 31) & 31, src_r = (lane + 1) & 31;
+#pragma unroll
+    for (int k = 0; k <= NC; ++k) {
+        const uint32_t x = r.P[k];
+        const uint32_t l = __shfl_sync(0xffffffffu, x, src_l), rr = __shfl_sync(0xffffffffu, x, src_r);
+        const uint32_t lr = __funnelshift_l(l, x, 1) | __funnelshift_r(x, rr, 1);
+        r.H[k] = NC == 8 ? (lr | x) : lr;
+    }
+}
+
+// code bit-planes of the centre row c; upV / dnV = the planes the rows above / below contribute (their 3-wide OR
+// for the 8-neighbourhood, their own planes for the axial one)
+template <int NC>
+__device__ __forceinline__ void bits_codes(const uint32_t upV[NC + 1], const BitRow<NC>& c, const uint32_t dnV[NC + 1],
+                                           uint32_t& b0, uint32_t& b1) {
+    uint32_t S[NC + 1];
+#pragma unroll
+    for (int k = 0; k <= NC; ++k) S[k] = upV[k] | c.H[k] | dnV[k];
+    uint32_t neg = 0, np = 0;
+#pragma unroll
+    for (int a = 0; a < NC; ++a) {
+        uint32_t N, NZ;
+        if (NC == 8) {
+            N = S[(a + 3) & 7] | S[(a + 4) & 7] | S[(a + 5) & 7];  // cos rounds to -1: ring distance 3..5
+            NZ = N | S[(a + 2) & 7] | S[(a + 6) & 7];              // ... or to 0: ring distance 2
+        } else {
+            N = S[(a + 2) & 3];                                    // opposite diagonal
+            NZ = N | S[(a + 1) & 3] | S[(a + 3) & 3];              // perpendicular diagonals
+        }
+        neg |= c.P[a] & N;
+        np |= c.P[a] & NZ;
+    }
+    np |= c.act & S[NC];
+    b1 = neg;
+    b0 = (np & ~neg) | c.odd;
+}
+
+template <int T, int NC, int MB>
+__global__ void __launch_bounds__(32 * kBitsWarps, MB) k_ddm_bits(const uint8_t* __restrict__ cls_maps,
+                                                                 uint16_t* __restrict__ codes, uint32_t* __restrict__ flags,
+                                                                 int H, int W, int R, int chunk_px, int halo, int row_lo,
+                                                                 int row_hi) {
+    CDNET_DYN_SHARED(uint32_t, s_planes);  // [block rows][2 T planes][32 lanes]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    constexpr int SUB = kBitsWarps / T;  // row sub-strips per block (1 for T = 8, 8 for T = 1)
+    const int t = T == 8 ? wid : 0;
+    const int sub = T == 8 ? 0 : wid;
+    const int yb = blockIdx.y * (R * SUB);  // first row of the block
+    const int y0 = yb + sub * R;            // first row of this warp
+    const int xl = blockIdx.x * chunk_px + (lane - halo) * 32;  // first pixel of this lane's word
+    const size_t plane_sz = (size_t)H * W;
+    const uint8_t* plane = cls_maps + ((size_t)b * T + t) * plane_sz;
+    // pixels of this word inside the image and owned by this lane (halo lanes own nothing)
+    uint32_t own = 0;
+    if (!(halo && (lane == 0 || lane == 31))) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (xl + 8 * k >= 0 && xl + 8 * k < W) own |= 0xffu << (8 * k);
+    }
+    auto load_row = [&](int y, uint32_t w[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = 0;
+        if ((unsigned)y < (unsigned)H) {
+            const uint8_t* row = plane + (size_t)y * W + xl;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x = xl + 8 * k;
+                if (x >= 0 && x < W) {  // W % 8 == 0: an 8-pixel group is inside or outside as a whole
+                    const uint2 v = __ldg((const uint2*)(row + 8 * k));
+                    w[2 * k] = v.x;
+                    w[2 * k + 1] = v.y;
+                }
+            }
+        }
+    };
+    uint32_t seen0 = 0, seen1 = 0, seen2 = 0;
+    if (y0 < H) {
+        uint32_t w[8], nw[8];
+        load_row(y0 - 1, w);
+        const int rows_here = min(R, H - y0);
+        auto emit = [&](const uint32_t upV[NC + 1], const BitRow<NC>& c, const uint32_t dnV[NC + 1], int y) {
+            // y = row of c, y0 <= y < y0 + rows_here
+            uint32_t b0, b1;
+            bits_codes<NC>(upV, c, dnV, b0, b1);
+            uint32_t* dst = s_planes + ((size_t)(y - yb) * (2 * T) + 2 * t) * 32 + lane;
+            dst[0] = b0;
+            dst[32] = b1;
+            if (y >= row_lo && y < row_hi) {
+                seen2 |= b1 & own;
+                seen1 |= b0 & own;
+                seen0 |= ~(b1 | b0) & own;
+            }
+        };
+        // rolling window: the vertical-neighbour planes of the row two back, the whole previous row, the new row
+        uint32_t upV[NC + 1];
+        BitRow<NC> prev;
+#pragma unroll
+        for (int k = 0; k <= NC; ++k) { upV[k] = 0; prev.P[k] = 0; prev.H[k] = 0; }
+        prev.act = prev.odd = 0;
+        // step i brings in row y0 - 1 + i and emits the centre row y0 + i - 2 (three steps rotate the window once)
+#pragma unroll 3
+        for (int i = 0; i < rows_here + 2; ++i) {
+            load_row(y0 + i, nw);  // request the next row before the arithmetic
+            uint32_t G[4];
+            bits_transpose_row(w, G);
+            BitRow<NC> rc;
+            bits_decode_row<NC>(G, lane, rc);
+            if (i >= 2) emit(upV, prev, NC == 8 ? rc.H : rc.P, y0 + i - 2);
+#pragma unroll
+            for (int k = 0; k <= NC; ++k) upV[k] = NC == 8 ? prev.H[k] : prev.P[k];
+            prev = rc;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = nw[k];
+        }
+    }
+    {
+        const uint32_t s = ((seen0 ? 1u : 0u) | (seen1 ? 2u : 0u) | (seen2 ? 4u : 0u)) << (3 * t);
+        const uint32_t all = __reduce_or_sync(0xffffffffu, s);
+        if (lane == 0 && all) atomicOr(flags + b, all);
+    }
+    __syncthreads();
+    // ---- 2 T bit-planes x 32 pixels -> 32 code words per (row, lane) cell --------------------------------
+    const int block_rows = min(R * SUB, H - yb);
+    uint16_t* cout = codes + (size_t)b * plane_sz;
+    for (int cell = threadIdx.x; cell < block_rows * 32; cell += 32 * kBitsWarps) {
+        const int r = cell >> 5, l = cell & 31;
+        if (halo && (l == 0 || l == 31)) continue;
+        const int x = blockIdx.x * chunk_px + (l - halo) * 32;
+        if (x >= W) continue;
+        const uint32_t* src = s_planes + (size_t)r * (2 * T) * 32 + l;
+        uint32_t p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[j] = j < 2 * T ? src[j * 32] : 0u;
+        // 16x16 bit transpose of both halves: afterwards p[i] = code(pixel i) | code(pixel i + 16) << 16
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t a = p[j], c = p[j + 8];
+            p[j] = __byte_perm(a, c, 0x6240);
+            p[j + 8] = __byte_perm(a, c, 0x7351);
+        }
+#pragma unroll
+        for (int h = 0; h < 16; h += 8)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t a = p[h + j], c = p[h + j + 4];
+                p[h + j] = bitsel(0x0f0f0f0fu, a, c << 4);
+                p[h + j + 4] = bitsel(0x0f0f0f0fu, a >> 4, c);
+            }
+#pragma unroll
+        for (int h = 0; h < 16; h += 4)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t a = p[h + j], c = p[h + j + 2];
+                p[h + j] = bitsel(0x33333333u, a, c << 2);
+                p[h + j + 2] = bitsel(0x33333333u, a >> 2, c);
+            }
+#pragma unroll
+        for (int h = 0; h < 16; h += 2) {
+            const uint32_t a = p[h], c = p[h + 1];
+            p[h] = bitsel(0x55555555u, a, c << 1);
+            p[h + 1] = bitsel(0x55555555u, a >> 1, c);
+        }
+        uint16_t* dst = cout + (size_t)(yb + r) * W + x;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+            if (x + 8 * g8 >= W) break;
+            // pixels 8 g8 .. 8 g8 + 7: low halves of p[8 g8 ..] for g8 < 2, high halves of p[8 (g8 - 2) ..] otherwise
+            const int base = 8 * (g8 & 1);
+            const uint32_t sel = g8 < 2 ? 0x5410u : 0x7632u;
+            uint4 v;
+            v.x = __byte_perm(p[base + 0], p[base + 1], sel);
+            v.y = __byte_perm(p[base + 2], p[base + 3], sel);
+            v.z = __byte_perm(p[base + 4], p[base + 5], sel);
+            v.w = __byte_perm(p[base + 6], p[base + 7], sel);
+            *(uint4*)(dst + 8 * g8) = v;
+        }
+    }
+}
+
+// the bit-sliced kernel hard-wires the ring structure of the table: check it against the table derived from the
+// reference's arithmetic before trusting it
+static bool lut_is_ring(const DdmLut& lut) {
+    const int nc = lut.n - 1;
+    if (nc != 8 && nc != 4) return false;
+    for (int a = 1; a <= nc; ++a)
+        for (int bq = 0; bq <= nc; ++bq) {
+            int want;  // rounded cosine
+            if (bq == 0) want = 0;
+            else {
+                const int d = ((a - bq) % nc + nc) % nc;
+                const int dist = d < nc - d ? d : nc - d;
+                if (nc == 8) want = dist <= 1 ? 1 : (dist == 2 ? 0 : -1);
+                else want = dist == 0 ? 1 : (dist == 1 ? 0 : -1);
+            }
+            const int have = ((lut.pos[a] >> bq) & 1u) ? 1 : (((lut.neg[a] >> bq) & 1u) ? -1 : 0);
+            if (have != want) return false;
+        }
+    return true;
+}
+
+static int bits_rows_per_warp() {
+    static int rows = 0;
+    if (!rows) {
+        const char* e = getenv("CDNET_DDM_BITS_ROWS");
+        rows = e ? atoi(e) : 16;
+        if (rows < 2 || rows > 64 || (rows & 1)) rows = 16;
+    }
+    return rows;
+}
+
+template <int T, int NC, int MB>
+static int launch_bits_mb(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int B, int H, int W, cudaStream_t st,
+                          int row_lo, int row_hi) {
+    const int R = bits_rows_per_warp();
+    constexpr int SUB = kBitsWarps / T;
+    const int halo = W > 1023 ? 1 : 0;
+    const int chunk_px = halo ? 960 : 1024;
+    const size_t smem = (size_t)R * SUB * 2 * T * 32 * sizeof(uint32_t);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CDNET_CUDA_OK(cudaFuncSetAttribute(k_ddm_bits<T, NC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(W, chunk_px), ceil_div(H, R * SUB), B);
+    CDNET_LAUNCH((k_ddm_bits<T, NC, MB>), grid, 32 * kBitsWarps, smem, st, cls_maps, codes, flags, H, W, R, chunk_px, halo,
+                 row_lo, row_hi);
+    return last_error();
+}
+
+template <int T, int NC>
+static int launch_bits(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, int B, int H, int W, cudaStream_t st,
+                       int row_lo, int row_hi) {
+    static int mb = 0;  // resident blocks per SM the kernel is compiled for: 3 (80 registers) or 2 (96)
+    if (!mb) { const char* e = getenv("CDNET_DDM_BITS_MB"); mb = (e && atoi(e) == 2) ? 2 : 3; }
+    if (mb == 2) return launch_bits_mb<T, NC, 2>(cls_maps, codes, flags, B, H, W, st, row_lo, row_hi);
+    return launch_bits_mb<T, NC, 3>(cls_maps, codes, flags, B, H, W, st, row_lo, row_hi);
+}
+
 // normalised value of code d for a map whose present-value bits are f (3 bits): (d-min)/(max-min)
 // in f32 (getDirectionDiffMap.py:104-106); constant map -> 0/0 = NaN.
 __device__ __forceinline__ float ddm_value(uint32_t d, uint32_t f) {
@@ -442,8 +771,18 @@ int ddm_codes_launch(const uint8_t* cls_maps, uint16_t* codes, uint32_t* flags, 
     dim3 block(32, 4);
     dim3 grid(ceil_div(W, 128), ceil_div(H, 4 * kRows), B);
     const bool fast = (W % 4 == 0) && (((uintptr_t)cls_maps & 3) == 0) && (((uintptr_t)codes & 7) == 0);
+    static int impl = -1;  // CDNET_DDM_IMPL=simd keeps the byte-SIMD kernel (A/B timing)
+    if (impl < 0) { const char* e = getenv("CDNET_DDM_IMPL"); impl = (e && e[0] == 's') ? 1 : 0; }
+    if (n_classes <= 9 && impl == 0 && W % 8 == 0 && (((uintptr_t)cls_maps & 7) == 0) && (((uintptr_t)codes & 15) == 0) &&
+        lut_is_ring(lut)) {
+        // bit-sliced kernel: 32 pixels per register
+        if (n_classes == 9) return T == 8 ? launch_bits<8, 8>(cls_maps, codes, flags, B, H, W, st, row_lo, row_hi)
+                                          : launch_bits<1, 8>(cls_maps, codes, flags, B, H, W, st, row_lo, row_hi);
+        return T == 8 ? launch_bits<8, 4>(cls_maps, codes, flags, B, H, W, st, row_lo, row_hi)
+                      : launch_bits<1, 4>(cls_maps, codes, flags, B, H, W, st, row_lo, row_hi);
+    }
     if (n_classes <= 9) {
-        // <= 8 direction classes: byte-SIMD kernel
+        // ragged widths / unaligned planes: byte-SIMD kernel
         if (T == 8) launch_simd<8>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st, row_lo, row_hi);
         else launch_simd<1>(cls_maps, codes, flags, H, W, lut, fast, grid, block, st, row_lo, row_hi);
     } else if (T == 8) {

@@ -230,6 +230,7 @@ __device__ __forceinline__ void flood_box(WarpBox& S, const uint8_t* __restrict_
             if (S.lab[qq] == 0) { q = qq; v = S.val[qq]; }
         }
         unsigned m = __ballot_sync(0xffffffffu, q >= 0);
+        __syncwarp();  // every lane has read head[cur] / lab / nxt before lane 0 rewrites the queue
         if (lane == 0) {
             S.head[cur] = nx;
             if (nx == 0xffff) S.tail[cur] = 0xffff;

@@ -302,6 +302,9 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
     }
     static std::mutex launch_mu;  // launches are serialised, like work on one stream
     std::lock_guard<std::mutex> guard(launch_mu);
+    static const bool trace = getenv("SIMT_TRACE") != nullptr;  // kernel names to stderr (which variant ran?)
+    if (trace) fprintf(stderr, "simt: launch %s grid %ux%ux%u block %ux%ux%u smem %zu\n", name, grid.x, grid.y, grid.z,
+                       block.x, block.y, block.z, dyn_bytes);
     if (g.workers.empty()) {
         if (const char* sch = getenv("SIMT_SCHEDULE")) {
             if (!strncmp(sch, "reverse", 7)) g_schedule = 1;

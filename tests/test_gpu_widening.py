@@ -133,6 +133,39 @@ def test_ddm_fuzz(kernel_api):
         assert np.array_equal(got, O.generate_dd_map(x, cls), equal_nan=True), (it, cls, H, W)
 
 
+def test_ddm_bitsliced_shapes(kernel_api):
+    """the bit-sliced kernel's shapes (W % 8 == 0): single chunk, exactly / just over 1024 columns (halo lanes),
+    several chunks, odd row counts, ids beyond the table (>= n and >= 16), both ring tables"""
+    from oracle import restate as O
+    rng = np.random.default_rng(5)
+    for (H, W, n) in [(37, 64, 9), (16, 1024, 9), (33, 1032, 9), (5, 2000, 9), (40, 96, 5), (18, 1992, 5), (1, 8, 9),
+                      (2, 8, 5), (19, 1000, 9), (35, 1016, 5)]:
+        lab = rng.integers(0, n, size=(H, W)).astype(np.uint8)
+        lab[:, :W // 3] = rng.integers(0, n)
+        lab[rng.random((H, W)) < 0.01] = rng.integers(n, 256)
+        lab[rng.random((H, W)) < 0.005] = 15
+        got = kernel_api.generate_dd_map(lab, n)
+        assert np.array_equal(got, O.generate_dd_map(lab, n), equal_nan=True), (H, W, n)
+
+
+def test_dam_bitsliced_eight_maps(kernel_api):
+    """the 8-map form of the bit-sliced kernel on noisy direction maps (every code value in every map), widths
+    around the one-chunk limit"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    rng = np.random.default_rng(6)
+    for (H, W) in [(21, 1000), (34, 1024), (9, 1048)]:
+        d = synth.postproc_inputs(300 + H, H, W, 12)
+        dcm = d["dcm"].copy()
+        noise = rng.random(dcm.shape) < 0.2
+        dcm[noise] = rng.integers(0, 12, size=int(noise.sum())).astype(np.uint8)
+        pr, pg = d["prob"].copy(), d["prob"].copy()
+        ref = O.dam_postprocess(pr, d["point"], dcm, 9, 20, 2, 0, literal=False)
+        got = kernel_api.dam_postprocess(pg, d["point"], dcm, 9, 20, 2, 0)
+        assert np.array_equal(got, ref["pred_labeled"]), (H, W)
+        assert np.array_equal(pg[2], pr[2]), (H, W)  # the boosted boundary channel, written in place by both
+
+
 def test_process_fuzz(kernel_api):
     """postproc_other.process on random masks: watershed branch and the no-watershed head, several min_size"""
     from scipy import ndimage as ndi
