@@ -132,53 +132,110 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def reference_kind():
+    """'reference' = the reference's own Python executed verbatim (oracle/ref_loader.py: /root/reference here,
+    the unmodified copy under baseline/_ref on the GPU box), 'port' = oracle/restate.py when no tree is found"""
+    try:
+        from oracle import ref_loader
+        return "reference" if ref_loader.available() else "port"
+    except Exception:
+        return "port"
+
+
 def cpu_one_tile(args):
-    seed, literal = args
+    seed, kind, rows = args
     from cdnet_b200 import synth
-    from oracle import restate as O
     d = synth.postproc_inputs(seed, H, W)
+    if rows < H:  # bounded sample: the top `rows` rows of the tile (the post-processing cost is linear in pixels)
+        d = {k: np.ascontiguousarray(v[..., :rows, :]) for k, v in d.items() if k in ("prob", "point", "dcm")}
+    if kind == "reference":
+        from oracle import ref_loader
+        fn = ref_loader.load().dam_postprocess
+        t0 = time.perf_counter()
+        fn(d["prob"], d["point"], d["dcm"], DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC)
+        return time.perf_counter() - t0
+    from oracle import restate as O
     t0 = time.perf_counter()
-    O.dam_postprocess(d["prob"], d["point"], d["dcm"], DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC,
-                      literal=literal)
+    O.dam_postprocess(d["prob"], d["point"], d["dcm"], DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC, literal=True)
     return time.perf_counter() - t0
 
 
+def host_info():
+    model = None
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                model = l.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        import torch
+        tt = torch.get_num_threads()
+    except Exception:
+        tt = None
+    return {"os_cpu_count": os.cpu_count(), "sched_affinity": len(os.sched_getaffinity(0)), "torch_num_threads": tt,
+            "cpu_model": model}
+
+
+def _sample_text(kind, n, how, rows=H):
+    what = ("the reference's test_dam.py:455-563 executed verbatim (oracle/ref_loader.py; scikit-image subset from "
+            "oracle/refshim)" if kind == "reference" else
+            "oracle/restate.py dam_postprocess (literal numpy/scipy restatement of test_dam.py:455-563)")
+    crop = "" if rows >= H else " (top %d rows of each)" % rows
+    return "%d of the %d 1000x1000 tiles%s, %s, postproc=0, %s" % (n, TILES, crop, what, how)
+
+
 def cpu_baseline(n_tiles=2):
-    ts = [cpu_one_tile((100 + i, True)) for i in range(n_tiles)]
+    kind = reference_kind()
+    cpu_one_tile((100, kind, 200))  # warm-up: imports, numba JIT, thread pools
+    ts = [cpu_one_tile((100 + i, kind, H)) for i in range(n_tiles)]
     mpx = n_tiles * H * W / 1e6
-    return {"value": mpx / sum(ts), "unit": "Mpixel/s", "cores": 1, "kind": "port",
-            "sample": "%d of the %d 1000x1000 tiles, oracle/restate.py dam_postprocess (literal numpy/scipy "
-                      "restatement of test_dam.py:455-563, postproc=0), 1 process" % (n_tiles, TILES)}
+    out = {"value": mpx / sum(ts), "unit": "Mpixel/s", "cores": 1, "kind": kind,
+           "sample": _sample_text(kind, n_tiles, "1 process, after one warm-up call"), "host": host_info()}
+    return out
 
 
 def run_reference(a):
-    """the reference's CPU path (oracle port; the reference is Python and its scikit-image dependency is
-    absent, so there is no oracle/_ref build) on all host cores."""
+    """the reference's own CPU implementation of the path on all host cores: one tile per worker process per step
+    (mirrors DataLoader(num_workers) / one image per process); verbatim reference when its tree is present."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    kind = reference_kind()
+    cores = len(os.sched_getaffinity(0)) or 1
     workers = max(1, min(cores, TILES))
     ctx = mp.get_context("spawn")
+    budget_s = float(os.environ.get("CDNET_REF_BUDGET_S", "150"))
+    rows = H
     with ctx.Pool(workers) as pool:
-        jobs = [(100 + i, True) for i in range(workers)]
-        for _ in range(a.warmup):
-            pool.map(cpu_one_tile, jobs[:workers])
+        jobs = [(100 + i, kind, H) for i in range(workers)]
+        single = None
+        for w in range(a.warmup):
+            single = pool.map(cpu_one_tile, jobs[:1])[0]  # one process alone (also the import / JIT warm-up) ...
+            t0 = time.perf_counter()
+            pool.map(cpu_one_tile, jobs)                  # ... and every worker once
+            t_full = time.perf_counter() - t0
+            if w == 0 and t_full * (a.steps + a.warmup - 1) > budget_s:
+                # bounded sample: whole tiles would take longer than the budget -> the top `rows` rows of every tile
+                rows = max(100, int(H * budget_s / (t_full * (a.steps + a.warmup - 1))) // 50 * 50)
+                jobs = [(100 + i, kind, rows) for i in range(workers)]
         t0 = time.perf_counter()
         for _ in range(a.steps):
             pool.map(cpu_one_tile, jobs)
         dt = time.perf_counter() - t0
-    mpx = a.steps * workers * H * W / 1e6
+    mpx = a.steps * workers * rows * W / 1e6
     val = mpx / dt
-    sample = ("%d 1000x1000 tiles per step (one per worker process, %d workers), oracle/restate.py "
-              "dam_postprocess literal port, postproc=0" % (workers, workers))
+    sample = _sample_text(kind, workers, "one tile per worker process per step, %d worker processes" % workers, rows)
     line = {"impl": "reference", "metric": "Mpixel/s CDNet DAM post-processing (test_dam.py:455-563)",
             "value": val, "unit": "Mpixel/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/f32/f64->int64", "data": "synthetic",
             "config": workload_config(),
-            "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": workers, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": workers, "kind": kind, "sample": sample,
+                             "single_process_mpx_per_s": (H * W / 1e6 / single) if single else None,
+                             "host": host_info()},
             "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -189,54 +246,136 @@ def workload_config():
                         "radius=%d, direction_classes=%d" % (TILES, H, W, POSTPROC, MIN_AREA, RADIUS,
                                                               DIRECTION_CLASSES),
             "tiles_per_gpu": TILES, "tile": [H, W], "l2_policy": "inputs larger than L2 (336 MB per step)",
+            "write_prob": "value: off (device-resident prob is not overwritten between steps); e2e: on (the updated "
+                          "prob_maps[2], test_dam.py:536, is copied back to the host every step)",
             "parallelism": "independent tiles per rank, no collective"}
 
 
-def extra_paths(torch, api, peak):
-    """device-resident timings of the paths around the headline (CUDA events, 3 warm-ups + 10 calls each)"""
+def _fenced(out, key, fn):
+    try:
+        out[key] = fn()
+    except Exception as e:  # noqa: BLE001  -- an extra never takes the contract line down
+        import traceback
+        out[key] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300]), "where": traceback.format_exc()[-400:]}
+
+
+def extra_paths(torch, dist, api, peak, rank, world, plan, timed, skip):
+    """the other BASELINE configs and the paths around the headline, AFTER every number of the contract has been
+    taken (tools/bench_configs.py); every rank takes part (the multi-GPU ones are collective), rank 0 reports."""
+    from tools import bench_configs as BC
     out = {}
+    if "slide" not in skip:
+        _fenced(out, "whole_slide", lambda: BC.whole_slide(torch, dist, rank, world, peak=peak))
+    if "targets" not in skip:
+        _fenced(out, "targets", lambda: BC.targets_config2(torch, dist, rank, world, peak=peak))
+    if "config3" not in skip:
+        _fenced(out, "config3", lambda: BC.config3(torch, dist, rank, world, peak=peak))
+    if world > 1 or rank != 0:
+        return out
+    # ---- N = 1 only -----------------------------------------------------------------------------------
+    _fenced(out, "config0", lambda: BC.config0(torch))
 
-    def timed_ms(fn, iters=10, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
-
-    try:  # BASELINE configs[2] shape: CPM17-like 500x500 label tiles -> ternary / point / direction targets
-        from cdnet_b200 import synth
-        n_tiles = 64
-        ids = np.stack([synth.as_uint8_label(synth.instance_map(1000 + i, 500, 500, 120))[:, :, 0] for i in range(n_tiles)])
-        d_ids = torch.from_numpy(ids).cuda()
-        ms = timed_ms(lambda: api.encode_targets_cuda(d_ids, True, 8))
-        px = n_tiles * 500 * 500
-        out["targets"] = {"workload": "configs[2]-shaped: %d synthetic 500x500 label tiles (~120 nuclei), LabelEncoding "
-                                      "path, 8 direction classes, device-resident" % n_tiles,
-                          "ms_per_batch": ms, "value": px / 1e6 / (ms * 1e-3), "unit": "Mpixel/s",
-                          "alg_bytes_per_px": 12.0, "alg_frac_of_peak": 12.0 * px / (ms * 1e-3) / 1e9 / peak}
-        del d_ids
-    except Exception as e:  # noqa: BLE001
-        out["targets"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
-    try:  # the fused TTA hand-off (csrc/handoff.cu): 8 variants of raw logits -> prob / point / dcm
+    def tta():
+        # the fused TTA hand-off (csrc/handoff.cu): 8 variants of raw logits -> prob / point / dcm, then the
+        # device-resident chain the reference's real flow has (test_dam.py:299-450, :984-1013 -> :455-563):
+        # logits already on the GPU -> tta_merge_cuda -> dam_postprocess_cuda -> D2H of the labels only
         B, C = TILES, DIRECTION_CLASSES
+        # raw outputs a trained network would give for the benchmark's synthetic tiles: log of the synthetic class
+        # probabilities, the synthetic point map, direction logits = 6 * one-hot(direction map of variant v) + noise,
+        # each moved into the variant's own frame (inverse of the un-flip / un-rotate the hand-off undoes)
         g = torch.Generator(device="cuda").manual_seed(0)
-        ml = [torch.randn((B, 3, H, W), device="cuda", generator=g) for _ in range(8)]
-        pt = [torch.randn((B, 1, H, W), device="cuda", generator=g) for _ in range(8)]
-        dl = [torch.randn((B, C, H, W), device="cuda", generator=g) for _ in range(8)]
-        ms = timed_ms(lambda: api.tta_merge_cuda(ml, pt, dl), iters=5, warm=2)
+        prob0 = plan.d_prob.clamp_min(1e-12).log()
+        ml, pt, dl = [], [], []
+        for v in range(8):
+            dirv = torch.zeros((B, C, H, W), device="cuda")
+            dirv.scatter_(1, plan.d_dcm[:, v:v + 1].long().clamp_(0, C - 1), 6.0)
+            dirv += 0.3 * torch.randn((B, C, H, W), device="cuda", generator=g)
+            outs = []
+            for t in (prob0, plan.d_point, dirv):
+                if v & 4:
+                    t = torch.rot90(t, 1, dims=(2, 3))
+                if v & 2:
+                    t = torch.flip(t, dims=(2,))
+                if v & 1:
+                    t = torch.flip(t, dims=(3,))
+                outs.append(t.contiguous())
+            ml.append(outs[0]); pt.append(outs[1]); dl.append(outs[2])
+            del dirv
+        host = torch.empty((B, H, W), dtype=torch.int64, pin_memory=True)
+
+        def merge_only():
+            api.tta_merge_cuda(ml, pt, dl)
+
+        def chain():
+            prob, point, dcm = api.tta_merge_cuda(ml, pt, dl)
+            lab, _ = api.dam_postprocess_cuda(dcm, prob, point, DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC)
+            host.copy_(lab, non_blocking=True)
+
+        def ms_of(fn, iters, warm):
+            for _ in range(warm):
+                fn()
+            return timed(fn, iters) / iters
         px = B * H * W
         bpp = 8 * (3 + 1 + C) * 4 + 16 + 8
-        out["tta_merge"] = {"workload": "%d tiles of %dx%d, 8 TTA variants, %d direction classes" % (B, H, W, C),
-                            "ms_per_batch": ms, "value": px / 1e6 / (ms * 1e-3), "unit": "Mpixel/s",
-                            "alg_bytes_per_px": float(bpp), "alg_frac_of_peak": bpp * px / (ms * 1e-3) / 1e9 / peak}
-        del ml, pt, dl
-    except Exception as e:  # noqa: BLE001
-        out["tta_merge"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        ms = ms_of(merge_only, 5, 2)
+        r = {"tta_merge": {"workload": "%d tiles of %dx%d, 8 TTA variants, %d direction classes" % (B, H, W, C),
+                           "ms_per_batch": ms, "value": px / 1e6 / (ms * 1e-3), "unit": "Mpixel/s",
+                           "alg_bytes_per_px": float(bpp), "alg_frac_of_peak": bpp * px / (ms * 1e-3) / 1e9 / peak}}
+        ms = ms_of(chain, 5, 2)
+        r["e2e_handoff"] = {"workload": "device-resident hand-off: raw CNN outputs of the 8 TTA variants already in HBM "
+                                        "(random logits) -> tta_merge_cuda -> dam_postprocess_cuda -> D2H of the int64 "
+                                        "labels into pinned host memory; %d tiles of %dx%d" % (B, H, W),
+                            "ms_per_step": ms, "value": px / 1e6 / (ms * 1e-3), "unit": "Mpixel/s",
+                            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(host.numel() * 8)}
+        return r
+    if "tta" not in skip:
+        try:
+            out.update(tta())
+        except Exception as e:  # noqa: BLE001
+            out["tta_merge"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        torch.cuda.empty_cache()
+
+    def single_tile():
+        # the reference's actual call pattern: ONE tile through the numpy signature (api.dam_postprocess)
+        from cdnet_b200 import synth
+        t = synth.postproc_inputs(100, H, W)
+        prob0 = t["prob"].copy()
+        for _ in range(3):
+            api.dam_postprocess(prob0.copy(), t["point"], t["dcm"], DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC)
+        n, t0 = 10, time.perf_counter()
+        for _ in range(n):
+            p = prob0.copy()
+            api.dam_postprocess(p, t["point"], t["dcm"], DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC)
+        ms = 1e3 * (time.perf_counter() - t0) / n
+        r = {"workload": "ONE %dx%d tile through api.dam_postprocess(numpy prob, point, dcm) -- the reference signature: "
+                         "staging memcpy + H2D + 16 kernels + D2H + copy-out, prob_maps[2] updated in place" % (H, W),
+             "ms_per_tile": ms, "value": H * W / 1e6 / (ms * 1e-3), "unit": "Mpixel/s"}
+        try:
+            p1 = api.DamPostprocessPlan(1, H, W, DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC, write_prob=True)
+            p1.h_dcm[0], p1.h_prob[0], p1.h_point[0] = t["dcm"], prob0, t["point"]
+            want = p1.run().copy()
+            p1.capture_graph()
+            for _ in range(3):
+                p1.h_prob[0] = prob0
+                p1.replay()
+            torch.cuda.synchronize()
+            assert np.array_equal(p1.h_labels, want), "CUDA-graph replay differs"
+            t0 = time.perf_counter()
+            for _ in range(n):
+                p1.replay()
+                torch.cuda.current_stream().synchronize()
+            r["plan_graph_ms_per_tile"] = 1e3 * (time.perf_counter() - t0) / n
+            t0 = time.perf_counter()
+            for _ in range(n):
+                p1.launch(chunk=1)
+                torch.cuda.current_stream().synchronize()
+            r["plan_stream_ms_per_tile"] = 1e3 * (time.perf_counter() - t0) / n
+            r["graph_note"] = ("the per-tile chain (H2D, kernels, D2H) captured once in a CUDA graph "
+                               "(DamPostprocessPlan.capture_graph / replay) vs launched kernel by kernel")
+        except Exception as e:  # noqa: BLE001
+            r["graph_error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+        return r
+    _fenced(out, "single_tile", single_tile)
     return out
 
 
@@ -247,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extra", default="", help="comma list of extras to skip: slide,targets,config3,tta,all")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     if a.impl == "reference":
@@ -259,17 +399,26 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
+    from cdnet_b200 import numa
+    # pinned staging of this rank on the NUMA node of its GPU (before anything is pinned)
+    numa_info = numa.bind_to_gpu(local_rank) if os.environ.get("CDNET_NO_NUMA_BIND") is None else {"disabled": True}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from cdnet_b200 import api, _cabi
     L = _cabi.lib()
 
     tiles = make_inputs(rank)
+    # device-resident plan: prob stays untouched on the device (with the in-place update of prob[2] step k+1 would
+    # post-process step k's output); host-buffer plan: the drop-in's default, prob_maps[2] comes back to the host
     plan = api.DamPostprocessPlan(TILES, H, W, DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC, write_prob=False)
-    for i, t in enumerate(tiles):
-        plan.h_dcm[i], plan.h_prob[i], plan.h_point[i] = t["dcm"], t["prob"], t["point"]
+    plan_e2e = api.DamPostprocessPlan(TILES, H, W, DIRECTION_CLASSES, MIN_AREA, RADIUS, POSTPROC, write_prob=True)
+    for pl in (plan, plan_e2e):
+        for i, t in enumerate(tiles):
+            pl.h_dcm[i], pl.h_prob[i], pl.h_point[i] = t["dcm"], t["prob"], t["point"]
     plan.run()  # populates the device buffers; first-call checks
     first = plan.h_labels.copy()
+    plan_e2e.run()
+    assert np.array_equal(first, plan_e2e.h_labels)
 
     def barrier():
         if world > 1:
@@ -300,12 +449,12 @@ def main():
     n0 = api.launch_count()
     ms_dev = timed(plan.launch_device, a.steps)
     launches = api.launch_count() - n0
-    # end to end through the host-buffer API
+    # end to end through the host-buffer API (H2D of every input, kernels, D2H of labels + updated prob_maps[2])
     for _ in range(2):
-        plan.run()
-    ms_e2e = timed(plan.launch, a.steps)
+        plan_e2e.run()
+    ms_e2e = timed(plan_e2e.launch, a.steps)
     clocks = sampler.finish()
-    assert np.array_equal(first, plan.h_labels), "results changed between runs"
+    assert np.array_equal(first, plan.h_labels) and np.array_equal(first, plan_e2e.h_labels), "results changed between runs"
 
     # per-kernel CUDA-event times (library profiler), separate pass so the headline is untouched
     L.cdnet_profile_enable(1)
@@ -357,14 +506,20 @@ def main():
             "dtype": "u8/f32/f64->int64", "data": "synthetic", "config": workload_config(),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "ms_per_step": ms_e2e / a.steps,
-                    "h2d_bytes_per_step": int(plan.h2d_bytes), "d2h_bytes_per_step": int(plan.d2h_bytes)},
+                    "h2d_bytes_per_step": int(plan_e2e.h2d_bytes), "d2h_bytes_per_step": int(plan_e2e.d2h_bytes),
+                    "api": "DamPostprocessPlan(write_prob=True).launch: pinned host buffers, chunks of 2 tiles, copies "
+                           "overlapped with kernels on three streams", "numa": numa_info},
             "gpu_launches": int(launches), "roofline": roofline}
+    # the other BASELINE configs (whole slide over NCCL, target generation, 16-direction chain) at EVERY N, after every
+    # number of the contract has been taken; each is fenced: a failure is recorded, not raised
+    skip = set(x for x in a.skip_extra.split(",") if x)
+    del plan_e2e
+    torch.cuda.empty_cache()
+    extra = {} if "all" in skip else extra_paths(torch, dist, api, peak, rank, world, plan, timed, skip)
     if rank == 0:
+        line["extra"] = extra
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-            # informative extras, AFTER every number of the contract has been taken: the other half of BASELINE's
-            # metric (label -> direction maps) and the hand-off kernel.  Each is fenced: a failure is recorded, not raised.
-            line["extra"] = extra_paths(torch, api, peak)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

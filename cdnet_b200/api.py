@@ -15,21 +15,31 @@ Device-resident batched variants (`*_cuda`, torch CUDA tensors [B,...]) keep the
 between the CNN and the post-processing, and `DamPostprocessPlan` pre-allocates pinned staging +
 device buffers for repeated host-buffer calls (what bench.py's e2e measures).
 """
+import collections
+import functools
+import types
+
 import numpy as np
 import torch
 
 from . import _cabi
 from ._cabi import CdnetError, check
 
-_ws_cache = {}
+_ws_cache = collections.OrderedDict()  # (device index, stream handle) -> scratch buffer
+_WS_CACHE_MAX = 8
 _dev_checked = set()
 
 
 def _device(device=None):
     if not torch.cuda.is_available():
         raise CdnetError("cdnet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
-        if not isinstance(device, torch.device) else device
+    if isinstance(device, torch.device):
+        if device.type != "cuda":
+            raise CdnetError("expected a CUDA device, got %s" % device)
+        idx = device.index
+    else:
+        idx = device
+    dev = torch.device("cuda", torch.cuda.current_device() if idx is None else int(idx))
     if dev.index not in _dev_checked:
         if not _cabi.lib().cdnet_device_ok(dev.index):
             raise CdnetError("device %s is not a compute-capability 10.x GPU; libcdnet_b200 is sm_100a-only" % dev)
@@ -38,18 +48,61 @@ def _device(device=None):
 
 
 def _workspace(nbytes, dev):
-    key = dev.index
+    """scratch for one library call: one growing buffer per (device, stream), so that calls issued on different
+    streams (or from different threads with their own streams) never share scratch memory"""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        _ws_cache.pop(key, None)
         buf = None
-        _ws_cache[key] = None
         buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=dev)
-        _ws_cache[key] = buf
+        while len(_ws_cache) >= _WS_CACHE_MAX:
+            _ws_cache.popitem(last=False)
+    else:
+        _ws_cache.pop(key)
+    _ws_cache[key] = buf  # most recently used last
     return buf
 
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _first_cuda_tensor(args, kwargs):
+    for x in list(args) + list(kwargs.values()):
+        if isinstance(x, torch.Tensor):
+            if x.is_cuda:
+                return x
+        elif isinstance(x, (list, tuple)) and x and isinstance(x[0], torch.Tensor) and x[0].is_cuda:
+            return x[0]
+    return None
+
+
+def _on_tensor_device(fn):
+    """Device guard: the library launches on the CURRENT device and on its current stream, so a call whose tensors
+    live on another GPU runs inside `torch.cuda.device(tensor.device)` (stream, scratch memory and kernels then all
+    belong to the tensors' device)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(args, kwargs)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+def guard_public_functions(ns):
+    """wrap every public function (and static method of every public class) of a module namespace"""
+    for name, obj in list(ns.items()):
+        if name.startswith("_") or getattr(obj, "__module__", None) != ns.get("__name__"):
+            continue
+        if isinstance(obj, types.FunctionType):
+            ns[name] = _on_tensor_device(obj)
+        elif isinstance(obj, type):
+            for k, v in list(vars(obj).items()):
+                if isinstance(v, staticmethod) and not k.startswith("__"):
+                    setattr(obj, k, staticmethod(_on_tensor_device(v.__func__)))
 
 
 def _ptr(t):
@@ -277,13 +330,26 @@ def label(input, connectivity=None, return_num=False):
     image); pass connectivity=1 for scipy.ndimage.label semantics on a binary image (4-connected, int32)."""
     x = np.asarray(input)
     conn = 8 if (connectivity is None or connectivity == 2) else 4
-    if x.dtype != bool and x.size and x.max() > 1 and np.unique(x[x != 0]).size > 1:
-        # measure.label joins pixels of EQUAL value: a multi-valued image takes the value-aware kernel
-        if conn != 8 or x.ndim != 2 or x.min() < 0 or x.max() > 255:
+    if x.dtype != bool and x.size and x.max() > 1:
+        # measure.label joins pixels of EQUAL value: an image with more than one distinct non-zero value takes the
+        # value-aware kernel.  The decision is made on the device (256-bin presence table of cdnet_label_stats);
+        # only images outside the uint8 range -- unsupported in multi-valued form -- are inspected on the host.
+        if x.ndim == 2 and x.min() >= 0 and x.max() <= 255:
+            d = _h2d(x.astype(np.uint8))[None]
+            L = _cabi.lib()
+            pres = torch.empty((1, 256), dtype=torch.int32, device=d.device)
+            fg = torch.empty((1,), dtype=torch.int32, device=d.device)
+            check(L.cdnet_label_stats(_ptr(d), _ptr(pres), _ptr(fg), 1, x.shape[0], x.shape[1], _stream()),
+                  "cdnet_label_stats")
+            multi = int((pres[0, 1:] != 0).sum()) > 1
+            if multi and conn != 8:
+                raise CdnetError("multi-valued label images are supported as 2-D, 8-connected, values 0..255")
+            if multi:
+                lab, n = label_values_cuda(d, return_num=True)
+                res = lab[0].cpu().numpy().astype(np.int64)
+                return (res, int(n[0])) if return_num else res
+        elif np.unique(x[x != 0]).size > 1:
             raise CdnetError("multi-valued label images are supported as 2-D, 8-connected, values 0..255")
-        lab, n = label_values_cuda(_h2d(x.astype(np.uint8))[None], return_num=True)
-        res = lab[0].cpu().numpy().astype(np.int64)
-        return (res, int(n[0])) if return_num else res
     lab, n = label_cuda(_h2d((x != 0).astype(np.uint8))[None], conn, return_num=True)
     res = lab[0].cpu().numpy()
     res = res.astype(np.int64) if conn == 8 else res
@@ -382,13 +448,24 @@ class DamPostprocessPlan(object):
         self.d_status = torch.zeros((B,), dtype=torch.int32, device=self.dev)
         self.h2d_bytes = self.t_dcm.numel() + 4 * self.t_prob.numel() + 4 * self.t_point.numel()
         self.d2h_bytes = self.t_labels.numel() * self.t_labels.element_size() + 4 * B
+        # the boosted boundary channel (test_dam.py:536 updates prob_maps[2] in place) comes back in its OWN pinned
+        # buffer: the staged inputs stay what the caller wrote, so a plan can be re-launched on the same inputs
+        self.t_prob2 = torch.empty((B, H, W), dtype=torch.float32, **pin) if write_prob else None
+        self.h_prob2 = self.t_prob2.numpy() if write_prob else None
+        if write_prob:
+            self.d2h_bytes += 4 * self.t_prob2.numel()
         self._s_in = self._s_out = None
+        self._graph = None
 
     def launch(self, chunk=2):
         """H2D, kernels, D2H.  The batch is cut into chunks of `chunk` tiles: the pinned-host -> device copy
         of chunk i+1 (copy-in stream) and the device -> host copy of chunk i-1 (copy-out stream) overlap the
         kernels of chunk i (current stream).  On return the current stream has been made to wait for the last
         copy-out, so synchronising it (or recording an event on it) covers the whole step."""
+        with torch.cuda.device(self.dev):
+            self._launch(chunk)
+
+    def _launch(self, chunk):
         B = self.t_dcm.shape[0]
         cur = torch.cuda.current_stream()
         if self._s_in is None:
@@ -415,18 +492,36 @@ class DamPostprocessPlan(object):
                 self.t_labels[a:b].copy_(self.d_labels[a:b], non_blocking=True)
                 self.t_status[a:b].copy_(self.d_status[a:b], non_blocking=True)
                 if wp:
-                    self.t_prob[a:b, 2].copy_(self.d_prob[a:b, 2], non_blocking=True)
+                    self.t_prob2[a:b].copy_(self.d_prob[a:b, 2], non_blocking=True)
         cur.wait_stream(s_out)
 
     def launch_device(self):
-        """kernels only, inputs already resident in d_dcm / d_prob / d_point."""
+        """kernels only, inputs already resident in d_dcm / d_prob / d_point (write_prob then updates d_prob[:, 2]
+        in place, as dam_postprocess_cuda does)."""
         dc, ma, ra, pp, wp = self.args
-        dam_postprocess_cuda(self.d_dcm, self.d_prob, self.d_point, dc, ma, ra, pp, wp, out=self.d_labels,
-                             status=self.d_status)
+        with torch.cuda.device(self.dev):
+            dam_postprocess_cuda(self.d_dcm, self.d_prob, self.d_point, dc, ma, ra, pp, wp, out=self.d_labels,
+                                 status=self.d_status)
+
+    def capture_graph(self, chunk=None):
+        """Captures one launch() (H2D copies, every kernel, D2H copies) in a CUDA graph: replay() then costs one
+        graph launch instead of ~20 stream operations -- what matters for the reference's call pattern of ONE tile
+        per call.  Call run() once before (scratch memory and kernel attributes are set up outside the capture)."""
+        B = self.t_dcm.shape[0]
+        with torch.cuda.device(self.dev):
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(B if chunk is None else chunk)
+            self._graph = g
+        return g
+
+    def replay(self):
+        self._graph.replay()
 
     def run(self):
         self.launch()
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()
         if (self.h_status & _cabi.S_DDM_CONSTANT).any():
             # the reference: NaN direction-difference map -> `assert(np.min(enhanced_boundary) >= 0)` fails
             raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
@@ -435,7 +530,8 @@ class DamPostprocessPlan(object):
         return self.h_labels
 
 
-_plans = {}
+_plans = collections.OrderedDict()  # a few recently used single-tile plans (pinned staging is expensive to allocate)
+_PLANS_MAX = 4
 
 
 def _process_mode(postproc, model_name):
@@ -485,17 +581,18 @@ def dam_postprocess(prob_maps, point_maps, dcm_tta, direction_classes=9, min_are
         return labels[0].cpu().numpy()
     key = (H, W, int(direction_classes), int(min_area), int(radius), int(postproc), bool(mutate_prob),
            torch.cuda.current_device())
-    plan = _plans.get(key)
+    plan = _plans.pop(key, None)
     if plan is None:
-        _plans.clear()
-        plan = _plans[key] = DamPostprocessPlan(1, H, W, direction_classes, min_area, radius, postproc,
-                                                write_prob=mutate_prob)
+        while len(_plans) >= _PLANS_MAX:
+            _plans.popitem(last=False)  # least recently used tile shape goes
+        plan = DamPostprocessPlan(1, H, W, direction_classes, min_area, radius, postproc, write_prob=mutate_prob)
+    _plans[key] = plan
     plan.h_dcm[0] = dcm
     plan.h_prob[0] = prob
     plan.h_point[0] = np.asarray(point_maps).reshape(1, H, W)
     labels = plan.run()[0].copy()
     if mutate_prob and isinstance(prob_maps, np.ndarray):
-        prob_maps[2, :, :] = plan.h_prob[0, 2]
+        prob_maps[2, :, :] = plan.h_prob2[0]
     return labels
 
 
@@ -762,6 +859,10 @@ class EncodeTargetsPlan(object):
         self._s_in = self._s_out = None
 
     def launch(self, chunk=32):
+        with torch.cuda.device(self.dev):
+            self._launch(chunk)
+
+    def _launch(self, chunk):
         B = self.t_ids.shape[0]
         cur = torch.cuda.current_stream()
         if self._s_in is None:
@@ -791,5 +892,8 @@ class EncodeTargetsPlan(object):
 
     def run(self):
         self.launch()
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()
         return self.h_ternary, self.h_point, self.h_direction
+
+
+guard_public_functions(globals())

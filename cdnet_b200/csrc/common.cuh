@@ -37,7 +37,7 @@ void prof_end(cudaStream_t st);
     } while (0)
 
 static inline int last_error() {
-    cudaError_t e = cudaPeekAtLastError();
+    cudaError_t e = cudaGetLastError();  // returns AND clears: an error is attributed to the call that caused it
     return e == cudaSuccess ? 0 : -(int)e;
 }
 

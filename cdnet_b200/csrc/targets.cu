@@ -21,12 +21,23 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <string.h>
+
+#include <mutex>
+
 #include "internal.h"
 
 namespace cdnet {
 
 __constant__ float c_sobel[2][121];
 __constant__ double c_gauss[17];
+// host-side record of what has been uploaded to the constants of each device
+constexpr int kMaxDevices = 64;
+struct TargetConsts {
+    bool sobel_done = false, gauss_done = false;
+    double gauss[17];
+    int n_sm = 0;
+};
 // (sin, cos)(2*pi/8*k) exactly as CPython/numba's libm produces them (my_transforms_direction.py:657-658)
 __constant__ double c_rays[8][2] = {
     {0x0.0p+0, 0x1.0000000000000p+0},
@@ -664,10 +675,11 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     int32_t* inst = inst_out ? inst_out : inst_ws;
     if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
 
-    // constants
-    float sob[2][121];
-    sobel_weights(sob);
-    CDNET_CUDA_OK(cudaMemcpyToSymbolAsync(c_sobel, sob, sizeof sob, 0, cudaMemcpyHostToDevice, st));
+    // constants: uploaded once per device (and again only when the caller's Gaussian weights change) -- a
+    // pageable-source cudaMemcpyToSymbolAsync on every call would serialise the stream with the host and rewrite
+    // tables that kernels of another stream may be reading
+    int dev_id = 0;
+    CDNET_CUDA_OK(cudaGetDevice(&dev_id));
     double gw[17];
     if (gauss_w) {
         for (int i = 0; i < 17; ++i) gw[i] = gauss_w[i];
@@ -677,7 +689,28 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
         for (int i = 0; i < 17; ++i) { const double t = (double)(i - 8); gw[i] = exp(-0.5 / 4.0 * t * t); s += gw[i]; }
         for (int i = 0; i < 17; ++i) gw[i] /= s;
     }
-    CDNET_CUDA_OK(cudaMemcpyToSymbolAsync(c_gauss, gw, sizeof gw, 0, cudaMemcpyHostToDevice, st));
+    int n_sm = 148;
+    {
+        static std::mutex mu;
+        static TargetConsts consts[kMaxDevices];
+        std::lock_guard<std::mutex> lock(mu);
+        TargetConsts& c = consts[dev_id % kMaxDevices];
+        if (!c.sobel_done) {
+            float sob[2][121];
+            sobel_weights(sob);
+            CDNET_CUDA_OK(cudaMemcpyToSymbol(c_sobel, sob, sizeof sob));
+            cudaDeviceGetAttribute(&c.n_sm, cudaDevAttrMultiProcessorCount, dev_id);
+            if (c.n_sm <= 0) c.n_sm = 148;
+            c.sobel_done = true;
+        }
+        if (!c.gauss_done || memcmp(c.gauss, gw, sizeof gw) != 0) {
+            CDNET_CUDA_OK(cudaStreamSynchronize(st));  // nothing of this stream still reads the old weights
+            CDNET_CUDA_OK(cudaMemcpyToSymbol(c_gauss, gw, sizeof gw));
+            memcpy(c.gauss, gw, sizeof gw);
+            c.gauss_done = true;
+        }
+        n_sm = c.n_sm;
+    }
 
     // 1. ternary label, fg mask, interior
     CDNET_CUDA_OK(cudaMemsetAsync(fg, 0, sizeof(int32_t) * (size_t)B, st));
@@ -725,13 +758,6 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
         CDNET_LAUNCH(k_t_label_list, (unsigned)(nblk > 65535 ? 65535 : nblk), 256, 0, st, centre, lablist, rowcnt, tab, nt);
         CDNET_LAUNCH(k_t_dir_default, px_grid(B, H, W), px_block(), 0, st, inside, (long long*)direction, dir_out,
                      num_classes, H, W);
-        static int n_sm = 0;
-        if (!n_sm) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            if (n_sm <= 0) n_sm = 148;
-        }
         CDNET_LAUNCH(k_t_direction_lab, n_sm * 8, 128, 0, st, inst, centre, maxd2, inside, (long long*)direction, dir_out,
                      lablist, rowcnt, rowcnt + 1, tab, num_classes, H, W);
     }

@@ -271,3 +271,7 @@ def instance_metrics_cuda(true, pred, match_iou=0.5):
         out.append({"aji": aji[0], "ana_FP": aji[1], "ana_FN": aji[2], "ana_less": aji[3], "ana_more": aji[4],
                     "dice": dice1_from_table(T), "dq": dq, "sq": sq, "pq": pq})
     return out
+
+
+from .api import guard_public_functions as _guard  # noqa: E402  (device guard, see api._on_tensor_device)
+_guard(globals())

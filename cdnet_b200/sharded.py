@@ -335,7 +335,8 @@ def _seam_tables(be, comm, S, valid_of, attr_of, round_id):
     return comm.allgather_tensor(be, tables)
 
 
-def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64"):
+def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64",
+                      timings=None):
     """Direction-aware post-processing (test_dam.py:455-563, postproc = 0) of an H x W slide whose rows
     are partitioned over comm.world ranks.
 
@@ -343,12 +344,19 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
     backend arrays -- dcm uint8 [T,Hl,W] (T = 1 or 8), prob float32 [3,Hl,W], point float32 [1,Hl,W] -- or
     with the extended buffers of `alloc_shard_buffers` (no plane-sized copies).
     Returns the list of label arrays [Hl,W] (backend arrays) of the local ranks.  Raises the
-    reference's AssertionError for a constant direction map (checked once, at the end)."""
+    reference's AssertionError for a constant direction map (checked once, at the end).
+    timings: optional dict; when given, the device is synchronised after every phase and the dict receives
+    {phase name: milliseconds} (a diagnostic mode: the synchronisations cost time themselves)."""
     G = comm.world
     parts = row_partition(H, G)
+    if G > 1 and min(b - a for a, b in parts) < max(2, int(radius)):
+        # phase 6 fetches radius-1 label rows from each row neighbour only: a shard thinner than the radius would need
+        # rows from two shards away
+        raise ValueError("whole-slide shards need at least max(2, radius) = %d rows each (H = %d over %d ranks)"
+                         % (max(2, int(radius)), H, G))
     import os
     import time
-    _timing = os.environ.get("CDNET_SHARD_TIMING") is not None
+    _timing = timings is not None or os.environ.get("CDNET_SHARD_TIMING") is not None
     _marks = []
 
     def _mark(name):
@@ -357,7 +365,7 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
             torch.cuda.synchronize()
             _marks.append((name, time.perf_counter()))
 
-    _mark("start")
+    _mark("phase 0: set-up")
     S = []
     for rank, d in zip(comm.local_ranks, shards):
         sh = _Shard()
@@ -489,7 +497,10 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         out = be.dilate(sh.lab_big, r, out_dtype)[top:top + sh.Hl]
         outs.append(out)
     _mark("end")
-    if _timing and S and S[0].rank == 0:
+    if timings is not None:
+        for i in range(len(_marks) - 1):
+            timings[_marks[i][0]] = 1e3 * (_marks[i + 1][1] - _marks[i][1])
+    if _timing and timings is None and S and S[0].rank == 0:
         print("shard timing (ms):", ", ".join("%s %.2f" % (_marks[i][0], 1e3 * (_marks[i + 1][1] - _marks[i][1]))
                                               for i in range(len(_marks) - 1)), flush=True)
     # ---- the only host round trip: status of the whole slide

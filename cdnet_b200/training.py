@@ -349,3 +349,7 @@ class LabelEncoding(object):
         out_imgs = list(imgs)
         out_imgs[2] = Image.fromarray(self.encode(imgs[2]))
         return tuple(out_imgs)
+
+
+from .api import guard_public_functions as _guard  # noqa: E402  (device guard, see api._on_tensor_device)
+_guard(globals())

@@ -26,7 +26,9 @@ SHIM_DIR = os.path.join(HERE, "refshim")
 
 
 def find_reference():
-    for p in (os.environ.get("CDNET_REF"), "/root/reference"):
+    """the mounted tree (build container) or the unmodified copy oracle/install_ref.py put under baseline/_ref
+    (what travels to the GPU box)"""
+    for p in (os.environ.get("CDNET_REF"), "/root/reference", os.path.join(os.path.dirname(HERE), "baseline", "_ref")):
         if p and os.path.isfile(os.path.join(p, "postproc_other.py")):
             return p
     return None

@@ -84,6 +84,9 @@ class _CudaProxy(object):
     def set_device(self, d):
         pass
 
+    def device(self, d):
+        return contextlib.nullcontext()
+
 
 class _TorchProxy(object):
     """`torch` as seen by cdnet_b200's host layer under emulation: no pinning, no CUDA streams"""

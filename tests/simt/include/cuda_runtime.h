@@ -85,6 +85,11 @@ static inline cudaError_t cudaMemcpyToSymbolAsync(T& sym, const void* s, size_t 
     memcpy((char*)&sym + off, s, n);
     return 0;
 }
+template <typename T>
+static inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* s, size_t n, size_t off = 0) {
+    memcpy((char*)&sym + off, s, n);
+    return 0;
+}
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }

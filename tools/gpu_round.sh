@@ -13,11 +13,11 @@ timeout 240 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; e
 timeout 60 python tools/time_widening.py > $OUT/${TAG}_widening_times.json 2> $OUT/${TAG}_widening.err; echo "widening rc=$?"
 # launch list of the bench command: shares per kernel (cold-cache, serialised: compare shares, not absolutes)
 timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -s 120 -c 80 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline \
+    -s 120 -c 80 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --skip-extra all \
     > $OUT/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
 # one full capture per dominant kernel (post-processing step, then the hand-off kernel)
 timeout 200 ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s 8 -c 4 -f -o $OUT/${TAG}_top \
-    python bench.py --steps 2 --warmup 2 --no-cpu-baseline > $OUT/${TAG}_top.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --steps 2 --warmup 2 --no-cpu-baseline --skip-extra all > $OUT/${TAG}_top.log 2>&1; echo "ncu full rc=$?"
 timeout 120 ncu --set full --clock-control none --import-source on -k "regex:k_tta_merge" -s 1 -c 1 -f -o $OUT/${TAG}_tta \
     python tools/ncu_tta.py > $OUT/${TAG}_tta.log 2>&1; echo "ncu tta rc=$?"
 tail -3 $OUT/${TAG}_tests.log; head -c 600 $OUT/${TAG}_bench.json
