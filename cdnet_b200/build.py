@@ -49,7 +49,7 @@ def build(force=False, verbose=False, extra=()):
         if verbose or "warning" in out:
             sys.stderr.write(out)
     tmp = LIB + ".tmp%d" % os.getpid()
-    subprocess.check_call([NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     os.replace(tmp, LIB)
     return LIB
 

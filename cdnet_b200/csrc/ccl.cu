@@ -695,6 +695,11 @@ __global__ void __launch_bounds__(kBX* kBY) k_relabel(const int* __restrict__ L,
     out[tile + p] = keep[tile + p] ? idmap[tile + L[tile + p]] : 0;
 }
 
+int scan_rows_launch(int32_t* rowcnt, int32_t* n_out, int B, int H, cudaStream_t st) {
+    CDNET_LAUNCH(k_scan_rows, B, 1024, 0, st, rowcnt, n_out, H);
+    return last_error();
+}
+
 static int number_roots(int32_t* L, const uint8_t* keep, const uint8_t* excluded, int32_t* idmap, int32_t* rowcnt,
                         int32_t* n_out, int B, int H, int W, cudaStream_t st) {
     CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, sizeof(int32_t) * (size_t)B * H, st));

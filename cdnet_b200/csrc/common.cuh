@@ -5,6 +5,9 @@
 #include <stddef.h>
 
 #include "../../include/cdnet_b200.h"
+#if defined(__CUDACC__) && !defined(CDNET_NO_NVTX)
+#include <nvtx3/nvToolsExt.h>
+#endif
 
 namespace cdnet {
 
@@ -28,6 +31,22 @@ void prof_end(cudaStream_t st);
 #define CDNET_DYN_SHARED(type, name) extern __shared__ type name[]
 // pins a 64-bit value in one register pair (stops ptxas from rematerialising it per use)
 #define CDNET_KEEP_IN_REG64(x) asm volatile("" : "+l"(x))
+#endif
+
+// NVTX ranges around the pipeline phases (visible in nsys / ncu timelines; header-only NVTX v3, a no-op unless a
+// profiler injects its library).  CDNET_RANGE("name") covers the rest of the enclosing scope.
+#if defined(__CUDACC__) && !defined(CDNET_NO_NVTX)
+struct NvtxScope {
+    explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+};
+#define CDNET_RANGE_CAT2(a, b) a##b
+#define CDNET_RANGE_CAT(a, b) CDNET_RANGE_CAT2(a, b)
+#define CDNET_RANGE(name) ::cdnet::NvtxScope CDNET_RANGE_CAT(nvtx_scope_, __LINE__)(name)
+static inline void nvtx_mark(const char* name) { nvtxMarkA(name); }
+#else
+#define CDNET_RANGE(name) ((void)0)
+static inline void nvtx_mark(const char*) {}
 #endif
 
 #define CDNET_CUDA_OK(expr)                                 \
@@ -112,6 +131,31 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) {
 #else
 static inline uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
 #endif
+
+// find with path halving: every visited node is re-pointed at its grandparent (a fire-and-forget atomicMin keeps the
+// parent pointers monotone under concurrent unions).  For forests with one very large tree (the background of a tile).
+__device__ __forceinline__ int uf_find_c(int* L, int p) {
+    int q = L[p];
+    while (q != p) {
+        const int g = L[q];
+        if (g != q) atomicMin(L + p, g);
+        p = q;
+        q = g;
+    }
+    return p;
+}
+
+__device__ __forceinline__ void uf_union_c(int* L, int a, int b) {
+    for (;;) {
+        a = uf_find_c(L, a);
+        b = uf_find_c(L, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicMin(L + a, b);  // a > b: hang a under b
+        if (old == a) return;
+        a = old;
+    }
+}
 
 // float <-> order-preserving uint32 (for atomicMax on floats of any sign)
 __device__ __forceinline__ unsigned int f32_to_ordered(float f) {

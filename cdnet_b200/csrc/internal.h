@@ -29,6 +29,15 @@ int fill_remove_label_launch(const uint8_t* inside, int32_t* labels, uint8_t* pr
 // per-value pixel counts -> zero labels with count < min_size (integer remove_small_objects)
 int remove_small_labels_launch(int32_t* labels, int32_t* counts, int B, int H, int W, int min_size, cudaStream_t st);
 
+// exclusive scan of rowcnt [B,H] over the rows of each tile, in place; n_out[b] = total (may be null)
+int scan_rows_launch(int32_t* rowcnt, int32_t* n_out, int B, int H, cudaStream_t st);
+
+// rle.cu: the run-based form of fill holes -> remove small -> 8-connected labels -> dilation by disk(radius <= 2)
+size_t rle_tail_workspace(int B, int H, int W);
+bool rle_tail_supported(int radius);
+int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
+
 // morph.cu ----------------------------------------------------------------------------------------
 int label_dilate_launch(const int32_t* labels, void* out, int out_elem_bytes, int B, int H, int W, int radius,
                         cudaStream_t st);

@@ -277,8 +277,9 @@ __global__ void __launch_bounds__(256) k_plain_inside(const float* __restrict__ 
 }
 
 static size_t tail_workspace(int B, int H, int W) {
-    const size_t a = fill_remove_label_workspace(B, H, W);
-    const size_t c = ws_process_workspace(B, H, W);
+    size_t a = fill_remove_label_workspace(B, H, W);
+    const size_t c = ws_process_workspace(B, H, W), r = rle_tail_workspace(B, H, W);
+    if (r > a) a = r;
     return a > c ? a : c;
 }
 
@@ -287,7 +288,10 @@ static size_t tail_workspace(int B, int H, int W) {
 static int tail_launch(const uint8_t* inside, int32_t* labels, void* out, int out_elem_bytes, int32_t* status, int B,
                        int H, int W, int min_area, int ws_min_size, int radius, int postproc, void* ws, size_t ws_bytes,
                        cudaStream_t st) {
+    CDNET_RANGE("fill holes / remove small / label / dilate");
     int rc;
+    if (postproc == 0 && rle_tail_supported(radius))  // run-based chain, labels and dilation in one pass (rle.cu)
+        return rle_tail_launch(inside, out, out_elem_bytes, B, H, W, min_area, radius, ws, ws_bytes, st);
     if (postproc == 1 || postproc == 2)
         rc = ws_process_launch(inside, labels, status, B, H, W, ws_min_size, postproc == 1 ? 1 : 0, ws, ws_bytes, st);
     else rc = fill_remove_label_launch(inside, labels, nullptr, B, H, W, min_area, ws, ws_bytes, st);
@@ -328,8 +332,14 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
     void* tail_ws = (char*)ws + ar.off;
     const size_t tail_bytes = ws_bytes - ar.off;
     if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
-    int rc = ddm_codes_launch(dcm, codes, flags, B, n_maps, H, W, direction_classes, st);
+    CDNET_RANGE("cdnet_dam_postproc");
+    int rc;
+    {
+        CDNET_RANGE("ddm codes");
+        rc = ddm_codes_launch(dcm, codes, flags, B, n_maps, H, W, direction_classes, st);
+    }
     if (rc) return rc;
+    CDNET_RANGE("point gate + boost + argmax, then labels");
     CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, st));
     point_max_launch(point, pmax, B, plane, st);
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)

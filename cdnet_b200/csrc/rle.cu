@@ -1,0 +1,550 @@
+// rle.cu -- run-based tail of the inference post-processing (K6, K7, K8, K13 of SURVEY.md section 2.1 in one chain):
+//   binary_fill_holes -> remove_small_objects(min_area, 4-connected) -> measure.label (8-connected, raster-first
+//   numbering) -> dilation by disk(radius)                                   test_dam.py:546-563, test.py:277-295
+//
+// The per-pixel union-find chain of ccl.cu streams a 4-byte parent plane eight times.  Here the mask lives as ONE
+// BIT per pixel (a 1000 x 1000 tile is 125 KB) and the graph nodes are the horizontal RUNS of equal mask value
+// (a MoNuSeg-shaped row has ~30 of them, not 1000 pixels): every stage but the last is a pass over the bit-planes
+// with one warp per row -- run starts, run membership and row-to-row adjacency are a handful of bit operations per
+// 32-pixel word -- plus SPARSE accesses to two pixel-indexed int32 planes (parent / area-or-id), touched only at run
+// starts.  The only pixel-granular pass is the last one, which writes the dilated labels.
+//
+//   k_rle_pack     mask bytes -> bit-plane M; parent[start] = start, aux[start] = 0 at every run start
+//   k_rle_link     runs of equal value that overlap in adjacent rows are united (4-connectivity; foreground AND
+//                  background components in one forest; the root is the component's first raster pixel)
+//   k_rle_touch    background components that reach the image frame are flagged at their root
+//   k_rle_holes    bit-plane F = M | (background runs whose component is not flagged) = binary_fill_holes(M)
+//   k_rle_fill     hole runs are united with the foreground runs they touch (left / right / above / below)
+//   k_rle_area     per-component pixel counts (one atomicAdd per filled segment of a word); flattens the run starts
+//   k_rle_diag     components with area >= min_area that touch only diagonally are united (8-connectivity of the
+//                  kept mask; removed components never join anything)
+//   k_rle_count / scan / k_rle_assign   raster-order rank of the surviving roots = the label ids
+//   k_rle_labels   every pixel looks up the id of its run's root (0 outside F / for removed components), a block
+//                  stages TR + 2R label rows in shared memory and writes max over disk(R) as int32 or int64
+//
+// A pixel's run is found without any per-pixel table: the run start is the highest set bit of the row's transition
+// mask at or below the pixel, or -- when the word holds none -- the carry-in start that a warp-wide max-scan over the
+// row's words provides.  Two runs of adjacent rows overlap iff they share a column, and the first shared column is a
+// run start of one of them, so the adjacency events of a word are  same_value & (starts_cur | starts_prev).
+#include <stdlib.h>
+
+#include "internal.h"
+
+namespace cdnet {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kRleWarps = 8;  // rows per block, one warp per row
+
+struct RowScan {
+    uint32_t m;      // mask bits of this lane's word (bit k = pixel wx + k), 0 beyond the row
+    uint32_t t;      // run starts: pixels whose value differs from their left neighbour (and pixel 0)
+    uint32_t valid;  // pixels of the word that exist
+    int cin;         // latest run start left of this word (-1 for the first word) = start of the run of pixel wx - 1
+    int wx;          // x of bit 0
+};
+
+// run starts of one word from the word, the last pixel of its left neighbour and the stored carry-in start
+__device__ __forceinline__ RowScan row_word(uint32_t word, uint32_t left_word, int cin, int W, int wj) {
+    RowScan r;
+    r.wx = wj * 32;
+    const int rem = W - r.wx;
+    r.valid = rem >= 32 ? kFull : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+    r.m = word & r.valid;
+    r.t = (r.m ^ ((r.m << 1) | (left_word >> 31))) & r.valid;
+    if (wj == 0) r.t |= 1u;
+    r.cin = cin;
+    return r;
+}
+
+// row_bits / row_cin: the row's words of the mask bit-plane and of the carry-in plane; words beyond the row read as 0
+__device__ __forceinline__ RowScan row_load(const uint32_t* __restrict__ row_bits, const int* __restrict__ row_cin, int NW,
+                                            int W, int wj) {
+    const bool in = wj < NW;
+    return row_word(in ? row_bits[wj] : 0u, (in && wj > 0) ? row_bits[wj - 1] : 0u, in ? row_cin[wj] : -1, W, wj);
+}
+
+// start (x) of the run that contains bit k of the word
+__device__ __forceinline__ int run_start(const RowScan& r, int k) {
+    const uint32_t tt = r.t & (kFull >> (31 - k));
+    return tt ? (r.wx + 31 - __clz(tt)) : r.cin;
+}
+
+// bit k = value of the LEFT neighbour of pixel k (the last pixel of the previous word for k = 0)
+__device__ __forceinline__ uint32_t left_bits(const uint32_t* __restrict__ row, int NW, int wj, uint32_t own) {
+    return (own << 1) | ((wj > 0 && wj <= NW) ? (row[wj - 1] >> 31) : 0u);
+}
+
+#define RLE_ROW_COORDS                                          \
+    const int lane = threadIdx.x & 31;                          \
+    const int y = blockIdx.x * kRleWarps + (threadIdx.x >> 5);  \
+    const int b = blockIdx.y;                                   \
+    if (y >= H) return;                                         \
+    const size_t tile = (size_t)b * H * W;                      \
+    const int NW = (W + 31) >> 5;                               \
+    const int nchunks = (NW + 31) >> 5;                         \
+    const size_t rowbits = ((size_t)b * H + y) * NW;            \
+    (void)tile; (void)nchunks; (void)rowbits; (void)lane;
+
+static inline dim3 rle_grid(int B, int H) { return dim3(ceil_div(H, kRleWarps), B); }
+
+// 32 mask bytes -> 32 bits
+__device__ __forceinline__ uint32_t nz_nibble(uint32_t w) {  // 4 bytes -> 4 bits (bit i = byte i != 0)
+    const uint32_t nz = ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) >> 7) & 0x01010101u;
+    return (nz * 0x10204080u) >> 28;
+}
+
+// the only warp-synchronous kernel of the chain: the carry-in starts are a max-scan over the words of a row
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M,
+                                                             int* __restrict__ C, int* __restrict__ P, int* __restrict__ A,
+                                                             int H, int W) {
+    RLE_ROW_COORDS
+    const uint8_t* row = mask + tile + (size_t)y * W;
+    const bool vec = (W % 8 == 0) && (((uintptr_t)mask & 7) == 0);
+    uint32_t carry_word = 0;  // last word of the previous chunk
+    int carry_start = -1;     // latest run start of the previous chunks
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int wj = ch * 32 + lane;
+        const int x0 = wj * 32;
+        uint32_t word = 0;
+        if (x0 < W) {
+            if (vec) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (x0 + 8 * k < W) {
+                        const uint2 v = __ldg((const uint2*)(row + x0 + 8 * k));
+                        word |= (nz_nibble(v.x) | (nz_nibble(v.y) << 4)) << (8 * k);
+                    }
+                }
+            } else {
+                const int n = min(32, W - x0);
+                for (int k = 0; k < n; ++k) word |= (uint32_t)(__ldg(row + x0 + k) != 0) << k;
+            }
+        }
+        const uint32_t up = __shfl_up_sync(kFull, word, 1);
+        RowScan r = row_word(word, lane ? up : carry_word, -1, W, wj);
+        const int last = r.t ? (r.wx + 31 - __clz(r.t)) : -1;
+        int incl = last;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl = max(incl, v);
+        }
+        int excl = __shfl_up_sync(kFull, incl, 1);
+        if (lane == 0) excl = -1;
+        r.cin = max(carry_start, excl);
+        carry_start = max(carry_start, __shfl_sync(kFull, incl, 31));
+        carry_word = __shfl_sync(kFull, word, 31);
+        if (wj < NW) {
+            M[rowbits + wj] = r.m;
+            C[rowbits + wj] = r.cin;
+        }
+        uint32_t t = r.t;
+        while (t) {
+            const int k = __ffs(t) - 1;
+            t &= t - 1;
+            const int gid = y * W + r.wx + k;
+            P[tile + gid] = gid;
+            A[tile + gid] = 0;
+        }
+    }
+}
+
+// rows y with y % mod_lo == 0 and (mod_hi == 0 or y % mod_hi != 0) are linked to the row above them.  Three launches
+// (rows inside groups of 8, the seams of those inside groups of 64, the remaining seams) keep the trees shallow and the
+// atomics spread out: the one huge component of a tile -- its background -- is then assembled from a few dozen
+// sub-trees instead of being fought over by every row at once.
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_link(const uint32_t* __restrict__ M, const int* __restrict__ C,
+                                                             int* __restrict__ P, int H, int W, int mod_lo, int mod_hi) {
+    RLE_ROW_COORDS
+    if (y == 0 || (y % mod_lo) != 0 || (mod_hi && (y % mod_hi) == 0)) return;
+    int* Pt = P + tile;
+    for (int wj = lane; wj < NW; wj += 32) {
+        const RowScan cur = row_load(M + rowbits, C + rowbits, NW, W, wj);
+        const RowScan prv = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
+        uint32_t e = ~(cur.m ^ prv.m) & cur.valid & (cur.t | prv.t);
+        while (e) {
+            const int k = __ffs(e) - 1;
+            e &= e - 1;
+            uf_union_c(Pt, y * W + run_start(cur, k), (y - 1) * W + run_start(prv, k));
+        }
+    }
+}
+
+// every run start is pointed at its root; background components that reach the image frame are flagged at the root
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_flatten_touch(const uint32_t* __restrict__ M,
+                                                                      const int* __restrict__ C, int* __restrict__ P,
+                                                                      int* __restrict__ A, int H, int W) {
+    RLE_ROW_COORDS
+    int* Pt = P + tile;
+    const bool frame_row = (y == 0 || y == H - 1);
+    for (int wj = lane; wj < NW; wj += 32) {
+        const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
+        uint32_t s = r.t;
+        while (s) {
+            const int k = __ffs(s) - 1;
+            s &= s - 1;
+            const int gid = y * W + r.wx + k;
+            const int root = uf_find_c(Pt, gid);
+            if (root != gid) Pt[gid] = root;
+            if (frame_row && !((r.m >> k) & 1u)) A[tile + root] = 1;  // every background run of the first / last row
+        }
+        if (!frame_row) {
+            if (wj == 0 && !(r.m & 1u)) A[tile + uf_find_c(Pt, y * W)] = 1;
+            if (wj == NW - 1) {
+                const int k = (W - 1) & 31;
+                if (!((r.m >> k) & 1u)) A[tile + uf_find_c(Pt, y * W + run_start(r, k))] = 1;
+            }
+        }
+    }
+}
+
+// segments of set bits inside one word: calls fn(first bit, bit mask of the segment)
+template <typename Fn>
+__device__ __forceinline__ void for_each_segment(uint32_t bits, Fn fn) {
+    uint32_t s = bits & ~(bits << 1);
+    while (s) {
+        const int k0 = __ffs(s) - 1;
+        s &= s - 1;
+        const uint32_t inv = ~(bits >> k0);
+        const int len = inv ? (__ffs(inv) - 1) : (32 - k0);
+        const uint32_t seg = (len >= 32 ? kFull : ((1u << len) - 1u)) << k0;
+        fn(k0, seg);
+    }
+}
+
+// F = M | holes, and every hole run is united with the foreground runs it touches (left, right, above, below), so that
+// afterwards the forest holds the 4-connected components of the FILLED mask.  A background run is a hole iff the root
+// of its component carries no frame flag; once a hole has been united with foreground the root it reaches is a
+// foreground root, whose aux entry is still 0 (areas come later) -- the test stays right under concurrent unions.
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __restrict__ M, const int* __restrict__ C,
+                                                              int* __restrict__ P, const int* __restrict__ A,
+                                                              uint32_t* __restrict__ F, int H, int W) {
+    RLE_ROW_COORDS
+    int* Pt = P + tile;
+    for (int wj = lane; wj < NW; wj += 32) {
+        const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
+        uint32_t hole = 0;
+        for_each_segment(~r.m & r.valid, [&](int k0, uint32_t seg) {
+            const int sx = run_start(r, k0);
+            const int me = y * W + sx;
+            if (A[tile + uf_find(Pt, me)] != 0) return;  // its component reaches the frame
+            hole |= seg;
+            // a hole never touches the frame: it has a left and a right neighbour, a row above and a row below
+            const int k1 = 31 - __clz(seg);              // last bit of the segment
+            if (sx >= r.wx) uf_union_c(Pt, me, y * W + (k0 ? run_start(r, k0 - 1) : r.cin));  // run starts here: left
+            if (k1 < 31) {
+                if ((r.valid >> (k1 + 1)) & 1u) uf_union_c(Pt, me, y * W + r.wx + k1 + 1);     // ends here: right
+            } else if (wj + 1 < NW && (M[rowbits + wj + 1] & 1u)) {
+                uf_union_c(Pt, me, y * W + r.wx + 32);
+            }
+            if (y > 0) {
+                const RowScan up = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
+                for_each_segment(up.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y - 1) * W + run_start(up, j0)); });
+            }
+            if (y + 1 < H) {
+                const RowScan dn = row_load(M + rowbits + NW, C + rowbits + NW, NW, W, wj);
+                for_each_segment(dn.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y + 1) * W + run_start(dn, j0)); });
+            }
+        });
+        F[rowbits + wj] = r.m | hole;
+    }
+}
+
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_area(const uint32_t* __restrict__ M, const int* __restrict__ C,
+                                                             const uint32_t* __restrict__ F, int* __restrict__ P,
+                                                             int* __restrict__ A, int H, int W) {
+    RLE_ROW_COORDS
+    int* Pt = P + tile;
+    for (int wj = lane; wj < NW; wj += 32) {
+        const uint32_t f = F[rowbits + wj];
+        if (!f) continue;
+        const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
+        // one atomicAdd per filled segment of the word: a foreground run next to a hole run is one component already
+        for_each_segment(f, [&](int k0, uint32_t seg) {
+            const int sx = run_start(r, k0);
+            const int s = y * W + sx;
+            const int root = uf_find_c(Pt, s);
+            if (sx >= r.wx && root != s) Pt[s] = root;  // flatten the starts that live in this word
+            atomicAdd(A + tile + root, __popc(seg));
+        });
+    }
+}
+
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_diag(const uint32_t* __restrict__ M, const int* __restrict__ C,
+                                                             const uint32_t* __restrict__ F, int* __restrict__ P,
+                                                             const int* __restrict__ A, int min_area, int H, int W) {
+    RLE_ROW_COORDS
+    if (y == 0) return;
+    int* Pt = P + tile;
+    const int* At = A + tile;
+    for (int wj = lane; wj < NW; wj += 32) {
+        const uint32_t fc = F[rowbits + wj], fp = F[rowbits - NW + wj];
+        const uint32_t fcl = left_bits(F + rowbits, NW, wj, fc), fpl = left_bits(F + rowbits - NW, NW, wj, fp);
+        // (y, x) and (y-1, x-1) filled, (y, x-1) and (y-1, x) not: only the diagonal joins them
+        uint32_t dl = fc & fpl & ~fcl & ~fp;
+        // (y-1, x) and (y, x-1) filled, (y-1, x-1) and (y, x) not: the other diagonal, seen from the upper pixel
+        uint32_t dr = fp & fcl & ~fpl & ~fc;
+        if (wj == 0) { dl &= ~1u; dr &= ~1u; }
+        if (!(dl | dr)) continue;
+        const RowScan cur = row_load(M + rowbits, C + rowbits, NW, W, wj);
+        const RowScan prv = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
+        while (dl) {
+            const int k = __ffs(dl) - 1;
+            dl &= dl - 1;
+            const int ra = uf_find(Pt, y * W + run_start(cur, k));
+            const int rb = uf_find(Pt, (y - 1) * W + (k ? run_start(prv, k - 1) : prv.cin));
+            if (ra != rb && At[ra] >= min_area && At[rb] >= min_area) uf_union(Pt, ra, rb);
+        }
+        while (dr) {
+            const int k = __ffs(dr) - 1;
+            dr &= dr - 1;
+            const int ra = uf_find(Pt, (y - 1) * W + run_start(prv, k));
+            const int rb = uf_find(Pt, y * W + (k ? run_start(cur, k - 1) : cur.cin));
+            if (ra != rb && At[ra] >= min_area && At[rb] >= min_area) uf_union(Pt, ra, rb);
+        }
+    }
+}
+
+// surviving roots of a row: foreground run starts that are their own parent and whose component is large enough
+template <bool ASSIGN>
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* __restrict__ M, const int* __restrict__ P,
+                                                               int* __restrict__ A, int* __restrict__ rowcnt, int min_area,
+                                                               int H, int W) {
+    RLE_ROW_COORDS
+    const int* Pt = P + tile;
+    int* At = A + tile;
+    int running = ASSIGN ? rowcnt[(size_t)b * H + y] + 1 : 0;  // ASSIGN: rowcnt holds the exclusive scan
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int wj = ch * 32 + lane;
+        const bool in = wj < NW;
+        const RowScan r = row_word(in ? M[rowbits + wj] : 0u, (in && wj > 0) ? M[rowbits + wj - 1] : 0u, -1, W, wj);
+        uint32_t s = r.t & r.m, roots = 0, dead = 0;
+        while (s) {
+            const int k = __ffs(s) - 1;
+            s &= s - 1;
+            const int gid = y * W + r.wx + k;
+            if (Pt[gid] == gid) {
+                if (At[gid] >= min_area) roots |= 1u << k;
+                else dead |= 1u << k;
+            }
+        }
+        const int n = __popc(roots);
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (ASSIGN) {
+            int id = running + incl - n;
+            while (roots) {
+                const int k = __ffs(roots) - 1;
+                roots &= roots - 1;
+                At[y * W + r.wx + k] = id++;
+            }
+            while (dead) {  // removed components label their pixels 0
+                const int k = __ffs(dead) - 1;
+                dead &= dead - 1;
+                At[y * W + r.wx + k] = 0;
+            }
+        }
+        running += __shfl_sync(kFull, incl, 31);
+    }
+    if (!ASSIGN && lane == 0) rowcnt[(size_t)b * H + y] = running;
+}
+
+// ---- labels + dilation ------------------------------------------------------------------------------------------
+// A block owns TR output rows of one column chunk.  Phase 1: warp per staged row, lane per pixel of a 32-pixel
+// word: label = id of the root of the pixel's run (F bit set) or 0; the row goes to shared memory (4 zero columns
+// of padding left and right).  Phase 2: max over disk(R) from shared memory, 4 pixels per thread, written as OUT.
+constexpr int kLabRows = 16;
+constexpr int kLabPad = 4;
+constexpr int kLabTW = 1024 + 2 * kLabPad;
+
+template <int R, typename OUT>
+__global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__ M, const int* __restrict__ C,
+                                                    const uint32_t* __restrict__ F, const int* __restrict__ P,
+                                                    const int* __restrict__ A, OUT* __restrict__ out, int H, int W,
+                                                    int chunk_px, int halo) {
+    CDNET_DYN_SHARED(int, s_lab);  // [(kLabRows + 2 R)][kLabTW]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * kLabRows;
+    const int NW = (W + 31) >> 5;
+    const int w0 = blockIdx.x * (chunk_px >> 5) - halo;  // first word of the staged window (may be -1)
+    const size_t tile = (size_t)b * H * W;
+    const int* Pt = P + tile;
+    const int* At = A + tile;
+    constexpr int SR = kLabRows + 2 * R;
+    // zero padding columns
+    for (int i = threadIdx.x; i < SR * 2 * kLabPad; i += 256) {
+        const int rr = i / (2 * kLabPad), c = i % (2 * kLabPad);
+        s_lab[rr * kLabTW + (c < kLabPad ? c : 1024 + c)] = 0;
+    }
+    for (int rr = wid; rr < SR; rr += 8) {
+        const int y = y0 - R + rr;
+        int* dst = s_lab + rr * kLabTW + kLabPad;
+        if (y < 0 || y >= H) {
+            for (int w = 0; w < 32; ++w) dst[32 * w + lane] = 0;
+            continue;
+        }
+        const size_t rowbits = ((size_t)b * H + y) * NW;
+        const int wj = w0 + lane;
+        const bool in = wj >= 0 && wj < NW;
+        const RowScan r = in ? row_load(M + rowbits, C + rowbits, NW, W, wj) : row_word(0u, 0u, -1, W, NW);
+        const uint32_t f = in ? F[rowbits + wj] : 0u;
+        // lane = word: the labels of (up to four) filled segments of the word are looked up with every lane's loads in
+        // flight together; a filled segment is one component (a foreground run and a hole run side by side have
+        // been united).  Then the 32 pixels of the word go to shared memory, skewed by the lane so that the 32 lanes
+        // hit 32 different banks.
+        uint32_t smask[4];
+        int slab[4];
+        uint32_t rest = f;
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi) {
+            smask[sgi] = 0;
+            slab[sgi] = 0;
+            if (rest) {
+                const int k0 = __ffs(rest) - 1;
+                const uint32_t inv = ~(rest >> k0);
+                const int len = inv ? (__ffs(inv) - 1) : (32 - k0);
+                const uint32_t seg = (len >= 32 ? kFull : ((1u << len) - 1u)) << k0;
+                smask[sgi] = seg;
+                rest &= ~seg;
+                slab[sgi] = At[uf_find(Pt, y * W + run_start(r, k0))];
+            }
+        }
+        for (int k = 0; k < 32; ++k) {
+            const int p = (k + lane) & 31;
+            int lab = 0;
+#pragma unroll
+            for (int sgi = 0; sgi < 4; ++sgi)
+                if ((smask[sgi] >> p) & 1u) lab = slab[sgi];
+            if ((rest >> p) & 1u) lab = At[uf_find(Pt, y * W + run_start(r, p))];  // more than four segments: rare
+            dst[32 * lane + p] = lab;
+        }
+    }
+    __syncthreads();
+    // ---- phase 2
+    const int xbase = w0 * 32;                       // x of staged column 0
+    const int own_lo = (w0 + halo) * 32;             // first owned x
+    const int own_hi = min(W, own_lo + chunk_px);    // one past the last owned x
+    const int rows = min(kLabRows, H - y0);
+    OUT* ot = out + tile;
+    if ((W & 3) == 0 && (((uintptr_t)out) & 15) == 0) {
+        const int nq = (own_hi - own_lo) >> 2;
+        for (int i = threadIdx.x; i < rows * nq; i += 256) {
+            const int ry = i / nq, q = i - ry * nq;
+            const int x4 = own_lo + 4 * q;
+            const int col = x4 - xbase + kLabPad;  // staged column of pixel x4 (multiple of 4)
+            int m[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int dy = -R; dy <= R; ++dy) {
+                const int* rowp = s_lab + (ry + R + dy) * kLabTW + col;
+                const int reach = (R == 0) ? 0 : (R == 1 ? (dy == 0 ? 1 : 0) : (dy == 0 ? 2 : ((dy == 1 || dy == -1) ? 1 : 0)));
+                const int4 cv = *(const int4*)rowp;
+                int v[8] = {0, 0, cv.x, cv.y, cv.z, cv.w, 0, 0};
+                if (reach >= 1) {
+                    const int2 l = *(const int2*)(rowp - 2), rg = *(const int2*)(rowp + 4);
+                    v[0] = l.x; v[1] = l.y; v[6] = rg.x; v[7] = rg.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int mx = v[j + 2];
+                    if (reach >= 1) mx = max(mx, max(v[j + 1], v[j + 3]));
+                    if (reach >= 2) mx = max(mx, max(v[j], v[j + 4]));
+                    m[j] = max(m[j], mx);
+                }
+            }
+            OUT* o = ot + (size_t)(y0 + ry) * W + x4;
+            if (sizeof(OUT) == 4) {
+                *(int4*)o = make_int4(m[0], m[1], m[2], m[3]);
+            } else {
+                *(longlong2*)o = make_longlong2((long long)m[0], (long long)m[1]);
+                *(longlong2*)(o + 2) = make_longlong2((long long)m[2], (long long)m[3]);
+            }
+        }
+    } else {
+        const int nx = own_hi - own_lo;
+        for (int i = threadIdx.x; i < rows * nx; i += 256) {
+            const int ry = i / nx, x = own_lo + (i - ry * nx);
+            const int col = x - xbase + kLabPad;
+            int m = 0;
+#pragma unroll
+            for (int dy = -R; dy <= R; ++dy)
+#pragma unroll
+                for (int dx = -R; dx <= R; ++dx)
+                    if (dx * dx + dy * dy <= R * R) m = max(m, s_lab[(ry + R + dy) * kLabTW + col + dx]);
+            ot[(size_t)(y0 + ry) * W + x] = (OUT)m;
+        }
+    }
+}
+
+template <int R, typename OUT>
+static int rle_labels_launch(const uint32_t* M, const int* C, const uint32_t* F, const int* P, const int* A, OUT* out,
+                             int B, int H, int W, cudaStream_t st) {
+    // one chunk of 1024 columns when the tile fits; otherwise chunks of 32 words whose first and last word are halo
+    // (30 owned words): the window then starts at word 30 * blockIdx.x - 1
+    const int halo = W > 1024 ? 1 : 0;
+    const int chunk_px = halo ? 960 : 1024;
+    const size_t smem = (size_t)(kLabRows + 2 * R) * kLabTW * sizeof(int);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_labels<R, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(W, chunk_px), ceil_div(H, kLabRows), B);
+    CDNET_LAUNCH((k_rle_labels<R, OUT>), grid, 256, smem, st, M, C, F, P, A, out, H, W, chunk_px, halo);
+    return last_error();
+}
+
+size_t rle_tail_workspace(int B, int H, int W) {
+    const size_t n = (size_t)B * H * W;
+    const size_t nbits = (size_t)B * H * ((W + 31) / 32) * sizeof(uint32_t);
+    return 2 * pad256(n * 4) + 3 * pad256(nbits) + pad256((size_t)B * H * 4);
+}
+
+bool rle_tail_supported(int radius) {
+    static int off = -1;
+    if (off < 0) off = getenv("CDNET_NO_RLE") ? 1 : 0;
+    return !off && radius >= 0 && radius <= 2;
+}
+
+// inside (0 / non-zero bytes) -> out = dilation(label8(remove_small(fill_holes(inside), min_area)), disk(radius))
+int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t n = (size_t)B * H * W;
+    const size_t nbits = (size_t)B * H * ((W + 31) / 32);
+    Arena ar(ws, ws_bytes);
+    int* P = ar.take<int>(n);
+    int* A = ar.take<int>(n);
+    uint32_t* M = ar.take<uint32_t>(nbits);
+    uint32_t* F = ar.take<uint32_t>(nbits);
+    int* C = ar.take<int>(nbits);
+    int* rowcnt = ar.take<int>((size_t)B * H);
+    if (!ar.ok) return CDNET_E_WORKSPACE;
+    const dim3 grid = rle_grid(B, H);
+    const int threads = 32 * kRleWarps;
+    CDNET_RANGE("run-based tail (rle.cu)");
+    CDNET_LAUNCH(k_rle_pack, grid, threads, 0, st, inside, M, C, P, A, H, W);
+    CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 1, 8);
+    if (H > 8) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 8, 64);
+    if (H > 64) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 64, 0);
+    CDNET_LAUNCH(k_rle_flatten_touch, grid, threads, 0, st, M, C, P, A, H, W);
+    CDNET_LAUNCH(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
+    CDNET_LAUNCH(k_rle_area, grid, threads, 0, st, M, C, F, P, A, H, W);
+    CDNET_LAUNCH(k_rle_diag, grid, threads, 0, st, M, C, F, P, A, min_area, H, W);
+    CDNET_LAUNCH(k_rle_number<false>, grid, threads, 0, st, M, P, A, rowcnt, min_area, H, W);
+    { int rc = scan_rows_launch(rowcnt, nullptr, B, H, st); if (rc) return rc; }
+    CDNET_LAUNCH(k_rle_number<true>, grid, threads, 0, st, M, P, A, rowcnt, min_area, H, W);
+    if (out_elem_bytes == 4) {
+        if (radius == 0) return rle_labels_launch<0, int32_t>(M, C, F, P, A, (int32_t*)out, B, H, W, st);
+        if (radius == 1) return rle_labels_launch<1, int32_t>(M, C, F, P, A, (int32_t*)out, B, H, W, st);
+        return rle_labels_launch<2, int32_t>(M, C, F, P, A, (int32_t*)out, B, H, W, st);
+    }
+    if (radius == 0) return rle_labels_launch<0, long long>(M, C, F, P, A, (long long*)out, B, H, W, st);
+    if (radius == 1) return rle_labels_launch<1, long long>(M, C, F, P, A, (long long*)out, B, H, W, st);
+    return rle_labels_launch<2, long long>(M, C, F, P, A, (long long*)out, B, H, W, st);
+}
+
+}  // namespace cdnet

@@ -712,6 +712,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
         n_sm = c.n_sm;
     }
 
+    CDNET_RANGE("cdnet_encode_targets");
     // 1. ternary label, fg mask, interior
     CDNET_CUDA_OK(cudaMemsetAsync(fg, 0, sizeof(int32_t) * (size_t)B, st));
     {
@@ -721,6 +722,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     }
     CDNET_LAUNCH(k_t_ternary, px_grid(B, H, W), px_block(), 0, st, ids, fg, instance_level, ternary, inside, interior, H, W);
     // 2. instances: process(interior*255, min_size=5) (:759) or measure.label (:773), then dilation disk(1)
+    nvtx_mark("targets: instances (process / label + dilation)");
     int rc;
     if (instance_level == 1) {
         rc = ws_process_launch(interior, inst_raw, status, B, H, W, 5, 1, sub_ws, sub_bytes, st);
@@ -747,6 +749,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
         CDNET_LAUNCH(k_t_drop_first, grid, 256, 0, st, inst, fg, plane);
     }
     // 3. centres, support maxima, direction classes, point map
+    nvtx_mark("targets: centres, direction classes, point map");
     rc = centres_launch(inst, cness, best, centre, maxd2, tab, B, H, W, st);
     if (rc) return rc;
     CDNET_LAUNCH(k_t_support_max, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, cflag, tab, H, W);

@@ -386,6 +386,7 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
                       int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st) {
     const size_t n = (size_t)B * H * W;
     if (n >= 4294967296ull) return CDNET_E_BADARG;  // root list holds 32-bit batch-global pixel indices
+    CDNET_RANGE("process(): EDT, markers, watershed, remove small");
     Arena ar(ws, ws_bytes);
     int32_t* A = ar.take<int32_t>(n);    // forest of pred
     int32_t* Bp = ar.take<int32_t>(n);   // g2 -> touch / idmap -> ymax

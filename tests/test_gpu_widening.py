@@ -166,6 +166,40 @@ def test_dam_bitsliced_eight_maps(kernel_api):
         assert np.array_equal(pg[2], pr[2]), (H, W)  # the boosted boundary channel, written in place by both
 
 
+def test_run_based_tail_fuzz(kernel_api):
+    """fill holes -> remove small -> 8-connected labels -> dilation on adversarial masks (noise of several densities:
+    one-pixel runs, nested holes, diagonal-only contacts; blobs with pinholes), ragged shapes (W below / not a multiple
+    of 32, one row, one column, wider than one 1024-column chunk), every radius and min_area incl. 1"""
+    from scipy import ndimage as ndi
+    from oracle import restate as O
+    rng = np.random.default_rng(2024)
+    shapes = [(1, 1), (1, 37), (40, 1), (7, 31), (9, 32), (23, 33), (50, 64), (31, 100), (64, 257), (12, 1024), (6, 1100),
+              (5, 2100), (3, 3000)]
+    for it, (H, W) in enumerate(shapes * 2):
+        kind = it % 4
+        if kind == 0:
+            m = rng.random((H, W)) < float(rng.choice([0.3, 0.5, 0.7]))
+        elif kind == 1:
+            m = ndi.binary_dilation(rng.random((H, W)) < 0.03, iterations=int(rng.integers(1, 5)))
+            m &= rng.random((H, W)) < 0.95
+        elif kind == 2:
+            m = (np.add.outer(np.arange(H), np.arange(W)) % 2 == 0)  # checkerboard: diagonal contacts only
+            m &= rng.random((H, W)) < 0.9
+        else:
+            m = np.ones((H, W), bool)
+            m[rng.random((H, W)) < 0.1] = False
+        prob = np.zeros((3, H, W), np.float32)
+        prob[0] = 0.5
+        prob[1] = m
+        for radius in (0, 1, 2):
+            min_area = int(rng.choice([1, 2, 5, 20]))
+            ref = O.plain_postprocess(prob.copy(), min_area, radius, 0)
+            got = kernel_api.plain_postprocess(prob.copy(), min_area, radius, 0)
+            ref = ref["pred_labeled"] if isinstance(ref, dict) else ref
+            assert got.dtype == ref.dtype and np.array_equal(got, ref), (it, H, W, kind, radius, min_area,
+                                                                        int((got != ref).sum()))
+
+
 def test_process_fuzz(kernel_api):
     """postproc_other.process on random masks: watershed branch and the no-watershed head, several min_size"""
     from scipy import ndimage as ndi
