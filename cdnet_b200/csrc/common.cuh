@@ -132,13 +132,15 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) {
 static inline uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
 #endif
 
-// find with path halving: every visited node is re-pointed at its grandparent (a fire-and-forget atomicMin keeps the
-// parent pointers monotone under concurrent unions).  For forests with one very large tree (the background of a tile).
+// find with path halving: every visited node is re-pointed at its grandparent with a PLAIN store.  Parent pointers
+// only ever point at smaller indices of the same tree, so a stale store can at worst undo a little compression --
+// it cannot break the forest -- and there is no atomic traffic on the hot upper levels of a very large tree (the
+// background of a tile).
 __device__ __forceinline__ int uf_find_c(int* L, int p) {
     int q = L[p];
     while (q != p) {
         const int g = L[q];
-        if (g != q) atomicMin(L + p, g);
+        if (g != q) L[p] = g;
         p = q;
         q = g;
     }

@@ -149,6 +149,114 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __re
     }
 }
 
+// ---- tiles up to 1024 columns: pack + the links INSIDE groups of kRleWarps rows in one kernel ---------------------
+// A block owns kRleWarps consecutive rows.  Their runs are united in shared memory first (parent slots indexed by the
+// pixel position inside the group, ~30-cycle hops, no global atomics), then every run start is written out already
+// pointing at the root of its group-local tree.  What is left for global memory are the links across the group seams
+// (k_rle_link on rows y % kRleWarps == 0): an eighth of the unions, on trees of depth one.
+__device__ __forceinline__ int sm_find(const int* P, int p) {
+    int q = P[p];
+    while (q != p) { p = q; q = P[p]; }
+    return p;
+}
+__device__ __forceinline__ void sm_union(int* P, int a, int b) {
+    for (;;) {
+        a = sm_find(P, a);
+        b = sm_find(P, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicMin(P + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack_link(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M,
+                                                                  int* __restrict__ C, int* __restrict__ P,
+                                                                  int* __restrict__ A, int H, int W) {
+    __shared__ int s_par[kRleWarps * 1024];
+    __shared__ uint32_t s_m[kRleWarps][32], s_t[kRleWarps][32];
+    __shared__ int s_c[kRleWarps][32];
+    const int lane = threadIdx.x & 31, rw = threadIdx.x >> 5;
+    const int y0 = blockIdx.x * kRleWarps, y = y0 + rw;
+    const int b = blockIdx.y;
+    const size_t tile = (size_t)b * H * W;
+    const int NW = (W + 31) >> 5;  // <= 32
+    const bool row_ok = y < H;
+    RowScan r = row_word(0u, 0u, -1, W, lane);
+    if (row_ok) {
+        const uint8_t* row = mask + tile + (size_t)y * W;
+        const bool vec = (W % 8 == 0) && (((uintptr_t)mask & 7) == 0);
+        const int x0 = lane * 32;
+        uint32_t word = 0;
+        if (x0 < W) {
+            if (vec) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (x0 + 8 * k < W) {
+                        const uint2 v = __ldg((const uint2*)(row + x0 + 8 * k));
+                        word |= (nz_nibble(v.x) | (nz_nibble(v.y) << 4)) << (8 * k);
+                    }
+                }
+            } else {
+                const int n = min(32, W - x0);
+                for (int k = 0; k < n; ++k) word |= (uint32_t)(__ldg(row + x0 + k) != 0) << k;
+            }
+        }
+        const uint32_t up = __shfl_up_sync(kFull, word, 1);
+        r = row_word(word, lane ? up : 0u, -1, W, lane);
+        int incl = r.t ? (r.wx + 31 - __clz(r.t)) : -1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl = max(incl, v);
+        }
+        int excl = __shfl_up_sync(kFull, incl, 1);
+        if (lane == 0) excl = -1;
+        r.cin = excl;
+        if (lane < NW) {
+            const size_t rowbits = ((size_t)b * H + y) * NW;
+            M[rowbits + lane] = r.m;
+            C[rowbits + lane] = r.cin;
+        }
+        uint32_t t = r.t;
+        while (t) {
+            const int k = __ffs(t) - 1;
+            t &= t - 1;
+            const int li = rw * 1024 + r.wx + k;
+            s_par[li] = li;
+        }
+    }
+    s_m[rw][lane] = r.m;
+    s_t[rw][lane] = r.t;
+    s_c[rw][lane] = r.cin;
+    __syncthreads();
+    if (row_ok && rw > 0) {
+        RowScan prv = r;  // same wx / valid
+        prv.m = s_m[rw - 1][lane];
+        prv.t = s_t[rw - 1][lane];
+        prv.cin = s_c[rw - 1][lane];
+        uint32_t e = ~(r.m ^ prv.m) & r.valid & (r.t | prv.t);
+        while (e) {
+            const int k = __ffs(e) - 1;
+            e &= e - 1;
+            sm_union(s_par, rw * 1024 + run_start(r, k), (rw - 1) * 1024 + run_start(prv, k));
+        }
+    }
+    __syncthreads();
+    if (row_ok) {
+        uint32_t t = r.t;
+        while (t) {
+            const int k = __ffs(t) - 1;
+            t &= t - 1;
+            const int root = sm_find(s_par, rw * 1024 + r.wx + k);
+            const int gid = y * W + r.wx + k;
+            P[tile + gid] = (y0 + (root >> 10)) * W + (root & 1023);
+            A[tile + gid] = 0;
+        }
+    }
+}
+
 // rows y with y % mod_lo == 0 and (mod_hi == 0 or y % mod_hi != 0) are linked to the row above them.  Three launches
 // (rows inside groups of 8, the seams of those inside groups of 64, the remaining seams) keep the trees shallow and the
 // atomics spread out: the one huge component of a tile -- its background -- is then assembled from a few dozen
@@ -170,30 +278,36 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_link(const uint32_t* __r
     }
 }
 
-// every run start is pointed at its root; background components that reach the image frame are flagged at the root
-__global__ void __launch_bounds__(32 * kRleWarps) k_rle_flatten_touch(const uint32_t* __restrict__ M,
-                                                                      const int* __restrict__ C, int* __restrict__ P,
-                                                                      int* __restrict__ A, int H, int W) {
-    RLE_ROW_COORDS
+// background components that reach the image frame are flagged at their root: one thread per frame position
+// (the words of the first and last row, the first and last pixel of every other row)
+__global__ void __launch_bounds__(256) k_rle_touch(const uint32_t* __restrict__ M, const int* __restrict__ C,
+                                                   int* __restrict__ P, int* __restrict__ A, int H, int W) {
+    const int b = blockIdx.y;
+    const int NW = (W + 31) >> 5;
+    const size_t tile = (size_t)b * H * W;
     int* Pt = P + tile;
-    const bool frame_row = (y == 0 || y == H - 1);
-    for (int wj = lane; wj < NW; wj += 32) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < 2 * NW) {
+        const int y = i < NW ? 0 : H - 1, wj = i < NW ? i : i - NW;
+        if (i >= NW && H == 1) return;
+        const size_t rowbits = ((size_t)b * H + y) * NW;
         const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
-        uint32_t s = r.t;
+        uint32_t s = r.t & ~r.m;  // every background run of the first / last row
         while (s) {
             const int k = __ffs(s) - 1;
             s &= s - 1;
-            const int gid = y * W + r.wx + k;
-            const int root = uf_find_c(Pt, gid);
-            if (root != gid) Pt[gid] = root;
-            if (frame_row && !((r.m >> k) & 1u)) A[tile + root] = 1;  // every background run of the first / last row
+            A[tile + uf_find_c(Pt, y * W + r.wx + k)] = 1;
         }
-        if (!frame_row) {
-            if (wj == 0 && !(r.m & 1u)) A[tile + uf_find_c(Pt, y * W)] = 1;
-            if (wj == NW - 1) {
-                const int k = (W - 1) & 31;
-                if (!((r.m >> k) & 1u)) A[tile + uf_find_c(Pt, y * W + run_start(r, k))] = 1;
-            }
+    } else if (i < 2 * NW + 2 * (H - 2)) {
+        const int j = i - 2 * NW;
+        const int y = 1 + (j >> 1);
+        const size_t rowbits = ((size_t)b * H + y) * NW;
+        if (j & 1) {
+            const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, NW - 1);
+            const int k = (W - 1) & 31;
+            if (!((r.m >> k) & 1u)) A[tile + uf_find_c(Pt, y * W + run_start(r, k))] = 1;
+        } else if (!(M[rowbits] & 1u)) {
+            A[tile + uf_find_c(Pt, y * W)] = 1;
         }
     }
 }
@@ -227,7 +341,7 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __
         for_each_segment(~r.m & r.valid, [&](int k0, uint32_t seg) {
             const int sx = run_start(r, k0);
             const int me = y * W + sx;
-            if (A[tile + uf_find(Pt, me)] != 0) return;  // its component reaches the frame
+            if (A[tile + uf_find_c(Pt, me)] != 0) return;  // its component reaches the frame
             hole |= seg;
             // a hole never touches the frame: it has a left and a right neighbour, a row above and a row below
             const int k1 = 31 - __clz(seg);              // last bit of the segment
@@ -313,7 +427,15 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
     RLE_ROW_COORDS
     const int* Pt = P + tile;
     int* At = A + tile;
-    int running = ASSIGN ? rowcnt[(size_t)b * H + y] + 1 : 0;  // ASSIGN: rowcnt holds the exclusive scan
+    int running = 0;
+    if (ASSIGN) {
+        // id base of this row = surviving roots of the rows above (the per-row counts of a tile are a few KB in L2:
+        // summing them here is cheaper than a separate scan launch)
+        const int* rc = rowcnt + (size_t)b * H;
+        int sum = 0;
+        for (int i = lane; i < y; i += 32) sum += rc[i];
+        running = __reduce_add_sync(kFull, sum) + 1;
+    }
     for (int ch = 0; ch < nchunks; ++ch) {
         const int wj = ch * 32 + lane;
         const bool in = wj < NW;
@@ -357,7 +479,10 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
 // A block owns TR output rows of one column chunk.  Phase 1: warp per staged row, lane per pixel of a 32-pixel
 // word: label = id of the root of the pixel's run (F bit set) or 0; the row goes to shared memory (4 zero columns
 // of padding left and right).  Phase 2: max over disk(R) from shared memory, 4 pixels per thread, written as OUT.
-constexpr int kLabRows = 16;
+#ifndef CDNET_LAB_ROWS
+#define CDNET_LAB_ROWS 8
+#endif
+constexpr int kLabRows = CDNET_LAB_ROWS;
 constexpr int kLabPad = 4;
 constexpr int kLabTW = 1024 + 2 * kLabPad;
 
@@ -526,16 +651,28 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
     const dim3 grid = rle_grid(B, H);
     const int threads = 32 * kRleWarps;
     CDNET_RANGE("run-based tail (rle.cu)");
-    CDNET_LAUNCH(k_rle_pack, grid, threads, 0, st, inside, M, C, P, A, H, W);
-    CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 1, 8);
-    if (H > 8) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 8, 64);
-    if (H > 64) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 64, 0);
-    CDNET_LAUNCH(k_rle_flatten_touch, grid, threads, 0, st, M, C, P, A, H, W);
+    static int fused = -1;  // CDNET_RLE_NO_LOCAL=1: every link through global memory
+    if (fused < 0) fused = getenv("CDNET_RLE_NO_LOCAL") ? 0 : 1;
+    if (fused && W <= 1024) {
+        CDNET_LAUNCH(k_rle_pack_link, grid, threads, 0, st, inside, M, C, P, A, H, W);
+        if (H > kRleWarps) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, kRleWarps, 0);
+    } else {
+        CDNET_LAUNCH(k_rle_pack, grid, threads, 0, st, inside, M, C, P, A, H, W);
+        static int phases = 0;  // CDNET_RLE_LINK_PHASES=3: rows inside groups of 8, then of 64, then the rest (slower on B200)
+        if (!phases) { const char* e = getenv("CDNET_RLE_LINK_PHASES"); phases = (e && atoi(e) == 3) ? 3 : 1; }
+        if (phases == 1 || H <= 8) {
+            CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 1, 0);
+        } else {
+            CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 1, 8);
+            CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 8, 64);
+            if (H > 64) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 64, 0);
+        }
+    }
+    CDNET_LAUNCH(k_rle_touch, dim3(ceil_div(2 * ((W + 31) / 32) + 2 * (H > 2 ? H - 2 : 0) + 1, 256), B), 256, 0, st, M, C, P, A, H, W);
     CDNET_LAUNCH(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
     CDNET_LAUNCH(k_rle_area, grid, threads, 0, st, M, C, F, P, A, H, W);
     CDNET_LAUNCH(k_rle_diag, grid, threads, 0, st, M, C, F, P, A, min_area, H, W);
     CDNET_LAUNCH(k_rle_number<false>, grid, threads, 0, st, M, P, A, rowcnt, min_area, H, W);
-    { int rc = scan_rows_launch(rowcnt, nullptr, B, H, st); if (rc) return rc; }
     CDNET_LAUNCH(k_rle_number<true>, grid, threads, 0, st, M, P, A, rowcnt, min_area, H, W);
     if (out_elem_bytes == 4) {
         if (radius == 0) return rle_labels_launch<0, int32_t>(M, C, F, P, A, (int32_t*)out, B, H, W, st);
