@@ -330,6 +330,30 @@ __device__ __forceinline__ void for_each_segment(uint32_t bits, Fn fn) {
 // afterwards the forest holds the 4-connected components of the FILLED mask.  A background run is a hole iff the root
 // of its component carries no frame flag; once a hole has been united with foreground the root it reaches is a
 // foreground root, whose aux entry is still 0 (areas come later) -- the test stays right under concurrent unions.
+// the rare part of k_rle_holes, kept out of line so that the common loop (no hole anywhere near) stays small
+__device__ __noinline__ void rle_join_hole(const uint32_t* __restrict__ M, const int* __restrict__ C, int* Pt,
+                                           const RowScan r, uint32_t seg, int k0, int y, int H, int W, int NW,
+                                           size_t rowbits, int wj) {
+    const int sx = run_start(r, k0);
+    const int me = y * W + sx;
+    // a hole never touches the frame: it has a left and a right neighbour, a row above and a row below
+    const int k1 = 31 - __clz(seg);  // last bit of the segment
+    if (sx >= r.wx) uf_union_c(Pt, me, y * W + (k0 ? run_start(r, k0 - 1) : r.cin));  // the run starts here: left
+    if (k1 < 31) {
+        if ((r.valid >> (k1 + 1)) & 1u) uf_union_c(Pt, me, y * W + r.wx + k1 + 1);     // the run ends here: right
+    } else if (wj + 1 < NW && (M[rowbits + wj + 1] & 1u)) {
+        uf_union_c(Pt, me, y * W + r.wx + 32);
+    }
+    if (y > 0) {
+        const RowScan up = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
+        for_each_segment(up.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y - 1) * W + run_start(up, j0)); });
+    }
+    if (y + 1 < H) {
+        const RowScan dn = row_load(M + rowbits + NW, C + rowbits + NW, NW, W, wj);
+        for_each_segment(dn.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y + 1) * W + run_start(dn, j0)); });
+    }
+}
+
 __global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __restrict__ M, const int* __restrict__ C,
                                                               int* __restrict__ P, const int* __restrict__ A,
                                                               uint32_t* __restrict__ F, int H, int W) {
@@ -338,29 +362,12 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __
     for (int wj = lane; wj < NW; wj += 32) {
         const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
         uint32_t hole = 0;
+        // common case first: which background segments of the word belong to a component without a frame flag?
         for_each_segment(~r.m & r.valid, [&](int k0, uint32_t seg) {
-            const int sx = run_start(r, k0);
-            const int me = y * W + sx;
-            if (A[tile + uf_find_c(Pt, me)] != 0) return;  // its component reaches the frame
-            hole |= seg;
-            // a hole never touches the frame: it has a left and a right neighbour, a row above and a row below
-            const int k1 = 31 - __clz(seg);              // last bit of the segment
-            if (sx >= r.wx) uf_union_c(Pt, me, y * W + (k0 ? run_start(r, k0 - 1) : r.cin));  // run starts here: left
-            if (k1 < 31) {
-                if ((r.valid >> (k1 + 1)) & 1u) uf_union_c(Pt, me, y * W + r.wx + k1 + 1);     // ends here: right
-            } else if (wj + 1 < NW && (M[rowbits + wj + 1] & 1u)) {
-                uf_union_c(Pt, me, y * W + r.wx + 32);
-            }
-            if (y > 0) {
-                const RowScan up = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
-                for_each_segment(up.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y - 1) * W + run_start(up, j0)); });
-            }
-            if (y + 1 < H) {
-                const RowScan dn = row_load(M + rowbits + NW, C + rowbits + NW, NW, W, wj);
-                for_each_segment(dn.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y + 1) * W + run_start(dn, j0)); });
-            }
+            if (A[tile + uf_find_c(Pt, y * W + run_start(r, k0))] == 0) hole |= seg;
         });
         F[rowbits + wj] = r.m | hole;
+        if (hole) for_each_segment(hole, [&](int k0, uint32_t seg) { rle_join_hole(M, C, Pt, r, seg, k0, y, H, W, NW, rowbits, wj); });
     }
 }
 
@@ -655,7 +662,18 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
     if (fused < 0) fused = getenv("CDNET_RLE_NO_LOCAL") ? 0 : 1;
     if (fused && W <= 1024) {
         CDNET_LAUNCH(k_rle_pack_link, grid, threads, 0, st, inside, M, C, P, A, H, W);
-        if (H > kRleWarps) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, kRleWarps, 0);
+        // the seams between the groups in one launch (CDNET_RLE_SEAM_PHASES=2 links the seams inside super-groups of 64
+        // rows first: measured slower on B200, 0.057 vs 0.042 ms for 14 x 1000^2)
+        static int seam2 = -1;
+        if (seam2 < 0) { const char* e = getenv("CDNET_RLE_SEAM_PHASES"); seam2 = (e && atoi(e) == 2) ? 1 : 0; }
+        if (H > kRleWarps) {
+            if (seam2 && H > 64) {
+                CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, kRleWarps, 64);
+                CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 64, 0);
+            } else {
+                CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, kRleWarps, 0);
+            }
+        }
     } else {
         CDNET_LAUNCH(k_rle_pack, grid, threads, 0, st, inside, M, C, P, A, H, W);
         static int phases = 0;  // CDNET_RLE_LINK_PHASES=3: rows inside groups of 8, then of 64, then the rest (slower on B200)

@@ -72,8 +72,10 @@ def label_pairs_cuda(true, pred, cap=None):
     full = H * W + 1                                     # distinct pairs can never exceed the pixel count
     cap = int(cap) if cap else min(full, max(4096, (H * W) // 32))
     while True:
-        keys = torch.empty((B, cap), dtype=torch.int64, device=dev)
-        counts = torch.empty((B, cap), dtype=torch.int32, device=dev)
+        # zero-filled: tiles with fewer pairs than the fullest one leave their tail entries unwritten, and the
+        # rectangular device -> host copy below would otherwise read uninitialised memory (compute-sanitizer initcheck)
+        keys = torch.zeros((B, cap), dtype=torch.int64, device=dev)
+        counts = torch.zeros((B, cap), dtype=torch.int32, device=dev)
         n_out = torch.empty((B,), dtype=torch.int32, device=dev)
         status = torch.empty((B,), dtype=torch.int32, device=dev)
         ws = _workspace(L.cdnet_label_pairs_workspace_bytes(B, cap), dev)

@@ -81,47 +81,50 @@ class DistComm(object):
         self.rank = dist.get_rank(group)
         self.local_ranks = [self.rank]
 
+    def _gather(self, t):
+        """[...] per rank -> [G, ...]: ONE collective on a contiguous buffer (NCCL all-gather into a tensor; gloo and
+        older back ends take the list form)"""
+        out = t.new_empty((self.world,) + tuple(t.shape))
+        try:
+            self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        except (RuntimeError, AttributeError, NotImplementedError):
+            self.dist.all_gather([out[r] for r in range(self.world)], t.contiguous(), group=self.group)
+        return out
+
     def exchange(self, be, up, down):
-        """point-to-point halo exchange with the two row neighbours (NCCL send/recv on device tensors, gloo on
-        CPU tensors); what arrives from a neighbour has the shape of what is sent to it"""
-        dist = self.dist
+        """halo exchange with the two row neighbours as ONE all-gather: every rank contributes the rows for its upper
+        and for its lower neighbour ([2, ...]; zeros where it has no neighbour) and picks its neighbours' slots.  The
+        messages are a few rows (<= a few MB over all ranks), so the redundant data costs nothing on NVLink while one
+        collective replaces a group of point-to-point sends and receives."""
         r, n = self.rank, self.world
-        ops, recv_up, recv_down = [], None, None
         t_up = be.to_torch(up[0]) if up[0] is not None else None
         t_down = be.to_torch(down[0]) if down[0] is not None else None
-        if r > 0 and t_up is not None:
-            recv_up = t_up.new_empty(t_up.shape)
-            ops += [dist.P2POp(dist.isend, t_up, r - 1, self.group), dist.P2POp(dist.irecv, recv_up, r - 1, self.group)]
-        if r < n - 1 and t_down is not None:
-            recv_down = t_down.new_empty(t_down.shape)
-            ops += [dist.P2POp(dist.isend, t_down, r + 1, self.group), dist.P2POp(dist.irecv, recv_down, r + 1, self.group)]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        like = t_up if t_up is not None else t_down
+        if like is None:
+            return [None], [None]
+        buf = like.new_zeros((2,) + tuple(like.shape))
+        if t_up is not None:
+            buf[0] = t_up
+        if t_down is not None:
+            buf[1] = t_down
+        g = self._gather(buf)
+        recv_up = g[r - 1, 1] if r > 0 else None      # the upper neighbour's bottom rows
+        recv_down = g[r + 1, 0] if r < n - 1 else None  # the lower neighbour's top rows
         return ([be.from_torch(recv_up) if recv_up is not None else None],
                 [be.from_torch(recv_down) if recv_down is not None else None])
 
     def send_up(self, be, tensors, like):
-        """rank r > 0 sends tensors[0] to rank r-1; rank r < n-1 receives a tensor shaped `like` from r+1"""
-        dist = self.dist
+        """rank r > 0 hands tensors[0] to rank r-1; rank r < n-1 receives a tensor shaped `like` from r+1 (one all-gather)"""
         r, n = self.rank, self.world
-        ops, recv = [], None
-        if r > 0:
-            ops.append(dist.P2POp(dist.isend, be.to_torch(tensors[0]), r - 1, self.group))
-        if r < n - 1:
-            recv = be.to_torch(like).new_empty(like.shape)
-            ops.append(dist.P2POp(dist.irecv, recv, r + 1, self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        return [be.from_torch(recv) if recv is not None else None]
+        src = tensors[0] if tensors[0] is not None else like
+        t = be.to_torch(src)
+        if tensors[0] is None:
+            t = t.new_zeros(t.shape)
+        g = self._gather(t)
+        return [be.from_torch(g[r + 1]) if r < n - 1 else None]
 
     def allgather_tensor(self, be, tensors):
-        t = be.to_torch(tensors[0])
-        out = t.new_empty((self.world,) + tuple(t.shape))
-        # views of one contiguous buffer: NCCL gathers straight into it (no copies), gloo accepts the list form
-        self.dist.all_gather([out[r] for r in range(self.world)], t, group=self.group)
-        return [be.from_torch(out)]
+        return [be.from_torch(self._gather(be.to_torch(tensors[0])))]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -323,6 +326,28 @@ class _Shard(object):
     pass
 
 
+def _cat_bytes(arrays):
+    """[array, ...] (torch tensors or numpy arrays of any dtype) -> one flat uint8 array with the bytes of all"""
+    if isinstance(arrays[0], np.ndarray):
+        return np.concatenate([np.ascontiguousarray(a).view(np.uint8).reshape(-1) for a in arrays])
+    import torch
+    return torch.cat([a.contiguous().view(torch.uint8).reshape(-1) for a in arrays])
+
+
+def _split_bytes(buf, like):
+    """inverse of _cat_bytes: views of `buf` shaped and typed like the arrays of `like`"""
+    out, off = [], 0
+    for a in like:
+        if isinstance(a, np.ndarray):
+            n = a.size * a.dtype.itemsize
+            out.append(buf[off:off + n].view(a.dtype).reshape(a.shape))
+        else:
+            n = a.numel() * a.element_size()
+            out.append(buf[off:off + n].view(a.dtype).reshape(a.shape))
+        off += n
+    return out
+
+
 def _seam_tables(be, comm, S, valid_of, attr_of, round_id):
     """export + all-gather of one seam round; returns the gathered table of every local shard"""
     tops = [be.seam_gid(sh.L, valid_of(sh), 0, sh.off) if sh.has_top else None for sh in S]
@@ -412,8 +437,17 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
             ext[..., ext.shape[-2] - below.shape[-2]:, :] = below
 
     # ---- phase 1: DDM codes (1-row class-map halo), slide-global value flags and point maximum
-    h_dcm = halo(lambda sh, a, b: sh.dcm[:, a:b], 1)
-    h_pt = halo(lambda sh, a, b: sh.point[:, a:b], 1)
+    # the class-map row and the point-map row travel in ONE message (bytes of both, concatenated)
+    def both_rows(sh, a, b):
+        return _cat_bytes([sh.point[:, a:b], sh.dcm[:, a:b]])  # the float rows first: their view stays 4-byte aligned
+    h_both = halo(both_rows, 1)
+    h_dcm, h_pt = [], []
+    for sh, (above, below) in zip(S, h_both):
+        like = [sh.point[:, 0:1], sh.dcm[:, 0:1]]
+        ua = _split_bytes(above, like) if above is not None else (None, None)
+        ub = _split_bytes(below, like) if below is not None else (None, None)
+        h_pt.append((ua[0], ub[0]))
+        h_dcm.append((ua[1], ub[1]))
     loc = []
     for sh, (da, db), (pa, pb) in zip(S, h_dcm, h_pt):
         fill_ghosts(sh, sh.dcm_ext, da, db)

@@ -22,6 +22,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __constant__
 #define __shared__ static thread_local

@@ -103,7 +103,16 @@ def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(
             tm = {}
             _barrier(torch, dist, world)
             step(tm)
-            phases = {k: round(_sync_max(torch, dist, world, v), 3) for k, v in tm.items()}
+            phases = {}
+            for k, v in tm.items():
+                if world > 1:
+                    t = torch.tensor([v], device="cuda", dtype=torch.float64)
+                    g = torch.empty((world,), device="cuda", dtype=torch.float64)
+                    dist.all_gather_into_tensor(g, t)
+                    vals = g.cpu().tolist()
+                else:
+                    vals = [v]
+                phases[k] = {"max": round(max(vals), 3), "min": round(min(vals), 3), "mean": round(sum(vals) / len(vals), 3)}
         return lab, times, phases, (r0, r1)
 
     # ---- verification on a slide one GPU can also process alone: sharded == single-GPU, bit for bit
@@ -134,7 +143,7 @@ def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(
     ms = float(np.median(times))
     out.update({"slide": [H, W], "ms_per_slide": ms, "times_ms": [round(t, 3) for t in times],
                 "value": H * W / 1e6 / (ms * 1e-3), "unit": "Mpixel/s", "phases_ms": phases,
-                "phases_note": "one extra step with a device synchronisation after every phase (max over ranks); "
+                "phases_note": "one extra step with a device synchronisation after every phase (max / min / mean over ranks); "
                                "the phases contain their halo exchanges / seam all-gathers"})
     if peak:
         out["alg_frac_of_peak"] = 21.0 * H * W / (ms * 1e-3) / 1e9 / (peak * world)

@@ -10,7 +10,7 @@ SEL="($SEL) and not p_1000 and not 333x517"
 for TOOL in ${TOOLS:-memcheck racecheck initcheck}; do
     EXTRA=""
     [ "$TOOL" = "racecheck" ] && EXTRA="--racecheck-report all"
-    [ "$TOOL" = "initcheck" ] && EXTRA="--track-unused-memory no"
+    [ "$TOOL" = "initcheck" ] && EXTRA=""
     timeout ${TMO:-420} compute-sanitizer --tool $TOOL $EXTRA --print-limit 40 --error-exitcode 0 \
         --log-file $OUT/${TAG}_sanitizer_${TOOL}.log \
         python -m pytest tests -m gpu -q -x -k "$SEL" -p no:cacheprovider > $OUT/${TAG}_sanitizer_${TOOL}_pytest.log 2>&1
