@@ -87,6 +87,7 @@ SIGNATURES = {
 
 E_BADARG, E_WORKSPACE = 1, 2
 S_DDM_CONSTANT, S_WS_OVERFLOW, S_NO_BACKGROUND, S_CLASS_RANGE = 1, 2, 16, 32
+S_WS_CONTESTED_SHIFT = 8  # status >> 8: watershed pixels two equal-priority age-0 markers compete for (cdnet_b200.h)
 
 _lib = None
 

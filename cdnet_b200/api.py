@@ -233,6 +233,13 @@ def edt_cuda(mask, return_squared=False):
 _NO_BACKGROUND_MSG = "list.remove(x): x not in list"  # what postproc_other.py:19 raises on a mask without background
 
 
+def ws_contested_pixels(status):
+    """status int32 [B] of a watershed-path call -> per-tile count of mask pixels whose label depends (to first order) on
+    the order in which two age-0 markers of EQUAL priority are popped -- the one place where scikit-image's heap and
+    this build's raster order can differ.  0 = the tile is independent of that order."""
+    return (status >> _cabi.S_WS_CONTESTED_SHIFT) & 0xffffff
+
+
 def process_cuda(pred01, min_size=10, ws=True, return_status=False):
     """pred01 uint8 [B,H,W] already binarised -> int32 labels (postproc_other.process).  With ws=True a tile
     without any background pixel sets CDNET_S_NO_BACKGROUND in status[b] (the reference raises ValueError)."""

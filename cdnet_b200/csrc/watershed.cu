@@ -117,6 +117,37 @@ __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restri
     }
 }
 
+// Diagnostic for the one place where parity with scikit-image is unpinned: pixels that two
+// age-0 markers of EQUAL priority compete for.  skimage's heap pops such markers in an order that depends on its
+// internal heap mechanics; this build pops them in raster order.  A mask pixel without a marker is counted when the
+// smallest priority among its 4-neighbouring marker pixels is held by markers of two different labels (first-order
+// exposure: whichever of them is popped first labels the pixel).  The count lands in status bits 8..31.
+__global__ void __launch_bounds__(kBX* kBY) k_ws_contested(const uint8_t* __restrict__ pred, const int* __restrict__ marker,
+                                                           const uint8_t* __restrict__ val, int32_t* __restrict__ status,
+                                                           int H, int W) {
+    PX_COORDS
+    bool hit = false;
+    if (inb && pred[tile + p] && marker[tile + p] == 0) {
+        int best = 256, lab = 0;
+        bool two = false;
+        const int dy[4] = {-1, 0, 0, 1}, dx[4] = {0, -1, 1, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = y + dy[k], xx = x + dx[k];
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const int q = yy * W + xx;
+            const int l = marker[tile + q];
+            if (l <= 0) continue;
+            const int v = val[tile + q];
+            if (v < best) { best = v; lab = l; two = false; }
+            else if (v == best && l != lab) two = true;
+        }
+        hit = two;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0 && m) atomicAdd(status + b, __popc(m) << 8);
+}
+
 __global__ void __launch_bounds__(kBX* kBY) k_bbox_init(int* __restrict__ ymax, int* __restrict__ xmin,
                                                         int* __restrict__ xmax, int H, int W) {
     PX_COORDS
@@ -434,6 +465,7 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     unsigned int* rootlist = (unsigned int*)counts;
     CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, 2 * sizeof(int32_t), st));
     CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, H, W);
+    if (status) CDNET_LAUNCH(k_ws_contested, px_grid(B, H, W), px_block(), 0, st, pred01, labels, val, status, H, W);
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;

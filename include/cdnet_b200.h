@@ -37,6 +37,10 @@ extern "C" {
 #define CDNET_S_NO_BACKGROUND 16 /* watershed path: the mask has no background pixel; the reference's
                                   * gen_inst_dst_map raises ValueError there (`nuc_list.remove(0)`,
                                   * postproc_other.py:18-19) */
+#define CDNET_S_WS_CONTESTED_SHIFT 8 /* watershed path: status >> 8 = number of mask pixels that two age-0 markers of
+                                      * EQUAL priority and different labels compete for (their pop order is where
+                                      * scikit-image's heap and this build's raster order may differ; 0 = the result
+                                      * does not depend on that order to first order).  Flags live in bits 0..7. */
 #define CDNET_S_CLASS_RANGE 32   /* cdnet_direction_one_hot: a class id outside [0, C); the reference's
                                   * `target_direction_temp[j, k]` raises IndexError (train_util_dam.py:138) */
 #define CDNET_S_PAIR_OVERFLOW 4 /* cdnet_label_pairs: more distinct (true, pred) pairs than `cap` */

@@ -20,6 +20,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "simt_skip: too slow under the SIMT emulator, GPU only")
 
 
+def record_parity(test, **counts):
+    """parity bookkeeping: how many elements differed / were exposed in a tolerance-based comparison.  Printed (pytest
+    -s / -rA show it) and, on the GPU box, appended to gpurun_out/parity_counts.jsonl so that the numbers measured on
+    the B200 can be quoted (profiles/r02_parity_counts.md)."""
+    line = json.dumps(dict(test=test, **counts))
+    print("PARITY " + line)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            out = os.path.join(REPO, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_counts.jsonl"), "a") as f:
+                f.write(line + "\n")
+    except Exception:
+        pass
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLD, name + ".npz"))
     meta = json.loads(str(z["meta"]))

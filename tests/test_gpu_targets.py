@@ -23,18 +23,25 @@ def _labels(meta, three_class=False):
 
 
 def _check_direction(got, ref, lab, n, name, out_c=3):
+    """direction classes are compared EXACTLY.  (Round 1 allowed a few differences within 1e-4 degrees of a bin edge,
+    because numpy's float32 arctan2 is not correctly rounded; on the B200 not one pixel of any golden, seeded or
+    degenerate tile differed -- profiles/r02_parity_counts.md -- so the allowance is gone.  A failure reports how far
+    from a bin edge the offending angles lie.)"""
+    from conftest import record_parity
+    record_parity("direction_class:" + name, differing_px=int((got != ref).sum()), px=int(got.size))
     if np.array_equal(got, ref):
         return
     from oracle import restate as O
     bad = np.argwhere(got != ref)
     parts = O.label_encoding(lab, out_c=out_c, num_classes=n, literal=False, return_parts=True)[3]
     step = 360.0 / n
-    for y, x in bad:
+    dists = []
+    for y, x in bad[:20]:
         a = float(parts["angle"][y, x])
-        dist_to_edge = abs(((a + 180.0 - step / 2.0) % step))
-        dist_to_edge = min(dist_to_edge, step - dist_to_edge)
-        assert dist_to_edge < EDGE_TOL, "%s: class differs at (%d,%d) away from a bin edge (angle %r)" % (name, y, x, a)
-    assert len(bad) <= max(2, got.size // 200000), "%s: %d near-edge class differences" % (name, len(bad))
+        d = abs(((a + 180.0 - step / 2.0) % step))
+        dists.append(min(d, step - d))
+    raise AssertionError("%s: %d direction classes differ; distance of the first angles to a bin edge (degrees): %r"
+                         % (name, len(bad), dists))
 
 
 @pytest.mark.parametrize("name", ["t_64_single", "t_128", "t_256", "t_250x300_dense", "t_500", "t_1000",
