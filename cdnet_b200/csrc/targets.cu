@@ -75,10 +75,35 @@ __global__ void __launch_bounds__(256) k_label_stats(const uint8_t* __restrict__
     __syncthreads();
     const uint8_t* I = ids + (size_t)b * plane;
     int cnt = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = I[i];
-        s_pres[v] = 1;
-        cnt += v != 0;
+    if (plane % 16 == 0 && (((uintptr_t)I) & 15) == 0) {
+        // 16 pixels per load; words that are all background (most of a tile) touch shared memory once at most
+        const uint4* I4 = (const uint4*)I;
+        const size_t n4 = plane / 16;
+        bool zero_seen = false;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 q = __ldg(I4 + i);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t nz = (((w[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w[j]) & 0x80808080u;
+                cnt += __popc(nz);
+                zero_seen |= nz != 0x80808080u;
+                if (nz) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t v = (w[j] >> (8 * k)) & 0xffu;
+                        if (v) s_pres[v] = 1;
+                    }
+                }
+            }
+        }
+        if (zero_seen) s_pres[0] = 1;
+    } else {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+            const int v = I[i];
+            s_pres[v] = 1;
+            cnt += v != 0;
+        }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);

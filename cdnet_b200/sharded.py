@@ -318,6 +318,17 @@ class CudaBackend(object):
         """error bits of the exported tables (one device->host read, at the very end)"""
         return int(self.torch.stack([t[0, 1] for t in tables]).max().item()) if tables else 0
 
+    def pack_status(self, flags, tables):
+        """[flags word, max error word of the seam tables] as ONE device tensor (enqueue only)"""
+        t = self.torch
+        err = t.stack([x[0, 1] for x in tables]).max().reshape(1).to(t.int32) if tables else self.zeros((1,), "int32")
+        return t.cat([flags.reshape(-1)[:1].to(t.int32), err])
+
+    def status_to_host(self, packed):
+        """the step's single device -> host read: (flags as uint32, seam error bits)"""
+        h = packed.cpu().numpy()
+        return int(h[:1].view(np.uint32)[0]), int(h[1])
+
 
 # --------------------------------------------------------------------------------------------------
 # whole-slide post-processing
@@ -361,7 +372,7 @@ def _seam_tables(be, comm, S, valid_of, attr_of, round_id):
 
 
 def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64",
-                      timings=None):
+                      timings=None, defer_checks=False):
     """Direction-aware post-processing (test_dam.py:455-563, postproc = 0) of an H x W slide whose rows
     are partitioned over comm.world ranks.
 
@@ -371,7 +382,10 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
     Returns the list of label arrays [Hl,W] (backend arrays) of the local ranks.  Raises the
     reference's AssertionError for a constant direction map (checked once, at the end).
     timings: optional dict; when given, the device is synchronised after every phase and the dict receives
-    {phase name: milliseconds} (a diagnostic mode: the synchronisations cost time themselves)."""
+    {phase name: milliseconds} (a diagnostic mode: the synchronisations cost time themselves).
+    defer_checks: return (labels, check) instead, where check() performs the one host round trip (status of the whole
+    slide) and raises like the plain call -- everything before it is enqueue-only, so it can be captured in a CUDA
+    graph (SlidePlan)."""
     G = comm.world
     parts = row_partition(H, G)
     if G > 1 and min(b - a for a, b in parts) < max(2, int(radius)):
@@ -537,18 +551,58 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
     if _timing and timings is None and S and S[0].rank == 0:
         print("shard timing (ms):", ", ".join("%s %.2f" % (_marks[i][0], 1e3 * (_marks[i + 1][1] - _marks[i][1]))
                                               for i in range(len(_marks) - 1)), flush=True)
-    # ---- the only host round trip: status of the whole slide
-    flags = be.flags_to_host(S[0].flags)
-    for t in range(n_maps):
-        f = (flags >> (3 * t)) & 7
-        if f in (0, 1, 2, 4):
-            raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
-    err = max(be.seam_errors(sh.tables) for sh in S)
-    if err & 1:
-        raise RuntimeError("seam pixels were classified differently by two neighbouring ranks")
-    if err & 2:
-        raise RuntimeError("seam table overflow")
+    # ---- the only host round trip: status of the whole slide (one small tensor, packed while enqueueing)
+    packed = [be.pack_status(sh.flags, sh.tables) for sh in S] if hasattr(be, "pack_status") else None
+
+    def check():
+        if packed is not None:
+            st = [be.status_to_host(p) for p in packed]
+            flags, err = st[0][0], max(e for _, e in st)
+        else:
+            flags = be.flags_to_host(S[0].flags)
+            err = max(be.seam_errors(sh.tables) for sh in S)
+        for t in range(n_maps):
+            f = (flags >> (3 * t)) & 7
+            if f in (0, 1, 2, 4):
+                raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
+        if err & 1:
+            raise RuntimeError("seam pixels were classified differently by two neighbouring ranks")
+        if err & 2:
+            raise RuntimeError("seam table overflow")
+    if defer_checks:
+        return outs, check
+    check()
     return outs
+
+
+class SlidePlan(object):
+    """One rank's whole-slide post-processing step captured in a CUDA graph.
+
+    A step is ~100 kernel launches, a dozen small torch ops and ~10 NCCL all-gathers; issued from Python it costs
+    about a millisecond of host time per step and leaves gaps on the device between the short kernels of a shard.
+    The shapes are fixed for a given slide, so the whole enqueue sequence (collectives included: NCCL calls are
+    capturable) is recorded once and replayed.  `bufs` are the rank's extended buffers (alloc_shard_buffers); fill the
+    dcm / prob / point views, call run(), read `labels` ([Hl, W], the rank's own rows).  CUDA backend only."""
+
+    def __init__(self, bufs, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64"):
+        import torch
+        self.torch, self.be = torch, be
+        args = ([bufs], comm, H, W, be, direction_classes, min_area, radius, out_dtype)
+        postprocess_slide(*args)  # eager warm-up: scratch memory, kernel attributes, NCCL channels
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        # thread_local: the NCCL watchdog thread may query events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            outs, self._check = postprocess_slide(*args, defer_checks=True)
+        self.labels = outs[0]
+
+    def launch(self):
+        self.graph.replay()
+
+    def run(self):
+        self.graph.replay()
+        self._check()
+        return self.labels
 
 
 def alloc_shard_buffers(be, rank, world, H, W, n_maps):

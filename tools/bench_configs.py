@@ -80,12 +80,23 @@ def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(
            "n_gpus": world, "scaling": "strong", "alg_bytes_per_px": 21.0}
     bands = slide_bands(torch, max(W, verify_hw[1]), 1)
 
-    def run(h, w, n_steps, want_phases):
+    graph_state = {"used": False}
+
+    def run(h, w, n_steps, want_phases, use_graph=False):
         r0, r1 = sharded.row_partition(h, world)[rank]
         bw = [{k: b[k][..., :w] for k in b} for b in bands] if w != bands[0]["dcm"].shape[-1] else bands
         bufs = sharded.alloc_shard_buffers(be, rank, world, h, w, 1)
         fill_slide_rows(bw, bufs, r0, r1)
-        step = lambda tm=None: sharded.postprocess_slide([bufs], comm, h, w, be, 9, 20, 2, timings=tm)[0]
+        eager = lambda tm=None: sharded.postprocess_slide([bufs], comm, h, w, be, 9, 20, 2, timings=tm)[0]
+        step = eager
+        if use_graph:
+            # the whole step (kernels, torch ops, NCCL all-gathers) recorded once in a CUDA graph and replayed
+            try:
+                plan = sharded.SlidePlan(bufs, comm, h, w, be, 9, 20, 2)
+                step = lambda tm=None: plan.run() if tm is None else eager(tm)
+                graph_state["used"] = True
+            except Exception as e:  # noqa: BLE001
+                graph_state["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
         lab = step()
         times = []
         for _ in range(n_steps):
@@ -98,6 +109,10 @@ def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(
             torch.cuda.synchronize()
             ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
             times.append(_sync_max(torch, dist, world, ms))
+        if graph_state.get("used") and use_graph:
+            ref = eager()
+            graph_state["equals_eager"] = bool(torch.equal(ref, lab))
+            del ref
         phases = None
         if want_phases:
             tm = {}
@@ -139,7 +154,8 @@ def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(
     out["verified"] = ok
     torch.cuda.empty_cache()
     # ---- the timed slide
-    lab, times, phases, _ = run(H, W, steps, True)
+    lab, times, phases, _ = run(H, W, steps, True, use_graph=os.environ.get("CDNET_SLIDE_NO_GRAPH") is None)
+    out["cuda_graph"] = graph_state
     ms = float(np.median(times))
     out.update({"slide": [H, W], "ms_per_slide": ms, "times_ms": [round(t, 3) for t in times],
                 "value": H * W / 1e6 / (ms * 1e-3), "unit": "Mpixel/s", "phases_ms": phases,
