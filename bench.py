@@ -251,6 +251,29 @@ def workload_config():
             "parallelism": "independent tiles per rank, no collective"}
 
 
+def cpu_targets_baseline():
+    """the reference's LabelEncoding(3, 1, 1) (my_transforms_direction.py:687-885) on ONE CPM17-shaped 500x500 tile of
+    configs[2] (its cost grows with nuclei x pixels: ~10 s per tile), after a small warm-up tile (numba JIT)"""
+    from cdnet_b200 import synth
+    kind = reference_kind()
+    if kind == "reference":
+        from oracle import ref_loader
+        enc = ref_loader.load().LabelEncoding(3, 1, 1)
+        run = lambda lab: enc((None, None, lab))
+    else:
+        from oracle import restate as O
+        run = lambda lab: O.label_encoding(lab, out_c=3, num_classes=8, literal=True)
+    run(synth.as_uint8_label(synth.instance_map(7, 96, 96, 6)))
+    lab = synth.as_uint8_label(synth.instance_map(1000, 500, 500, 120))
+    t0 = time.perf_counter()
+    run(lab)
+    dt = time.perf_counter() - t0
+    return {"value": 0.25 / dt, "unit": "Mpixel/s", "cores": 1, "kind": kind, "seconds": dt,
+            "sample": "1 of the 256 500x500 tiles (seed 1000, ~120 nuclei), %s, 1 process (torch intra-op threads: %s)"
+                      % ("the reference's LabelEncoding executed verbatim" if kind == "reference" else
+                         "oracle/restate.py label_encoding (literal)", host_info()["torch_num_threads"])}
+
+
 def _fenced(out, key, fn):
     try:
         out[key] = fn()
@@ -554,6 +577,8 @@ def main():
         line["extra"] = extra
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            if isinstance(extra.get("targets"), dict) and "error" not in extra["targets"]:
+                _fenced(extra["targets"], "cpu_baseline", cpu_targets_baseline)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

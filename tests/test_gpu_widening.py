@@ -386,7 +386,7 @@ def test_widening_golden(kernel_api):
 
 
 
-# ---- the fused TTA hand-off (csrc/handoff.cu) last: its 4-pixel form has not run on a GPU yet ----
+# ---- the fused TTA hand-off (csrc/handoff.cu): scalar and 4-pixel forms ----
 def _tta_inputs(seed, B, H, W, C):
     import torch
     g = torch.Generator().manual_seed(seed)
