@@ -68,6 +68,17 @@ KERNEL_BYTES_PER_PX = {
     "k_relabel4": 13.0,
     "k_label_dilate": 12.0,     # labels 4 in, int64 8 out
     "k_label_dilate4": 12.0,
+    # run-based tail (csrc/rle.cu): the mask is 1 bit per pixel, the union-find planes are touched at run starts only
+    "k_rle_pack_link": 1.25,    # mask bytes in, bit-plane + carry-in starts out (the sparse parent writes come on top)
+    "k_rle_pack": 1.25,
+    "k_rle_link": 0.25,
+    "k_rle_touch": 0.0,
+    "k_rle_holes": 0.375,
+    "k_rle_area": 0.375,
+    "k_rle_diag": 0.375,
+    "k_rle_number": 0.25,
+    "k_rle_labels": 8.375,      # two bit-planes + carry-in starts in, int64 labels out
+    "k_boost_prep": 0.0,
 }
 
 

@@ -427,11 +427,13 @@ struct BitRow {
     uint32_t H[NC + 1];  // NC == 8: 3-wide horizontal OR of the class planes; NC == 4: left | right only
     uint32_t P[NC + 1];  // the pixel's own class planes (NC == 4 also uses them as the vertical neighbours)
     uint32_t act, odd;   // valid direction class / non-zero unknown id
+    uint32_t idb[3];     // the three low id bits of the pixel's class (NC == 8: selectors of the per-centre muxes)
 };
 
 template <int NC>
 __device__ __forceinline__ void bits_decode_row(const uint32_t B[4], int lane, BitRow<NC>& r) {
     const uint32_t B0 = B[0], B1 = B[1], B2 = B[2], B3 = B[3];
+    r.idb[0] = B0; r.idb[1] = B1; r.idb[2] = B2;
     const uint32_t m0 = ~B3 & ~B2, m1 = ~B3 & B2;
     r.P[0] = m0 & ~B1 & B0;
     r.P[1] = m0 & B1 & ~B0;
@@ -468,17 +470,35 @@ __device__ __forceinline__ void bits_codes(const uint32_t upV[NC + 1], const Bit
     uint32_t S[NC + 1];
 #pragma unroll
     for (int k = 0; k <= NC; ++k) S[k] = upV[k] | c.H[k] | dnV[k];
+    if (NC == 8) {
+        // Per-centre selection with muxes on the centre's id bits instead of eight AND-OR terms per test.  For class k
+        // (a = k - 1 on the ring) the opposing set is the 3-window centred at a + 4 and the perpendicular pair is
+        // {a + 2, a + 6}.  With the mux index i = k mod 8 (class 8 -> 0; the pixel's low id bits as they are):
+        //   neg  <- T[(i + 3) & 7],  T[c] = S[c-1] | S[c] | S[c+1]
+        //   zero <- X[(i + 1) & 3],  X[j] = S[j] | S[j+4]
+        uint32_t Tw[8], X[4];
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) Tw[cidx] = S[(cidx + 7) & 7] | S[cidx] | S[(cidx + 1) & 7];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) X[j] = S[j] | S[j + 4];
+        const uint32_t i0 = c.idb[0], i1 = c.idb[1], i2 = c.idb[2];
+        uint32_t m4[4], m2[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m4[j] = bitsel(i0, Tw[(2 * j + 1 + 3) & 7], Tw[(2 * j + 3) & 7]);  // index 2j+1 : 2j
+        m2[0] = bitsel(i1, m4[1], m4[0]);
+        m2[1] = bitsel(i1, m4[3], m4[2]);
+        const uint32_t tsel = bitsel(i2, m2[1], m2[0]);
+        const uint32_t x0 = bitsel(i0, X[(1 + 1) & 3], X[(0 + 1) & 3]), x1 = bitsel(i0, X[(3 + 1) & 3], X[(2 + 1) & 3]);
+        const uint32_t xsel = bitsel(i1, x1, x0);
+        b1 = c.act & tsel;
+        b0 = (c.act & (xsel | S[NC]) & ~tsel) | c.odd;
+        return;
+    }
     uint32_t neg = 0, np = 0;
 #pragma unroll
     for (int a = 0; a < NC; ++a) {
-        uint32_t N, NZ;
-        if (NC == 8) {
-            N = S[(a + 3) & 7] | S[(a + 4) & 7] | S[(a + 5) & 7];  // cos rounds to -1: ring distance 3..5
-            NZ = N | S[(a + 2) & 7] | S[(a + 6) & 7];              // ... or to 0: ring distance 2
-        } else {
-            N = S[(a + 2) & 3];                                    // opposite diagonal
-            NZ = N | S[(a + 1) & 3] | S[(a + 3) & 3];              // perpendicular diagonals
-        }
+        const uint32_t N = S[(a + 2) & 3];                           // opposite diagonal: cos rounds to -1
+        const uint32_t NZ = N | S[(a + 1) & 3] | S[(a + 3) & 3];     // ... or perpendicular: cos rounds to 0
         neg |= c.P[a] & N;
         np |= c.P[a] & NZ;
     }
@@ -550,6 +570,7 @@ __global__ void __launch_bounds__(32 * kBitsWarps, MB) k_ddm_bits(const uint8_t*
 #pragma unroll
         for (int k = 0; k <= NC; ++k) { upV[k] = 0; prev.P[k] = 0; prev.H[k] = 0; }
         prev.act = prev.odd = 0;
+        prev.idb[0] = prev.idb[1] = prev.idb[2] = 0;
         // step i brings in row y0 - 1 + i and emits the centre row y0 + i - 2 (three steps rotate the window once)
 #pragma unroll 3
         for (int i = 0; i < rows_here + 2; ++i) {

@@ -143,7 +143,10 @@ __global__ void __launch_bounds__(256) k_boost_inside(const uint16_t* __restrict
 //   low / high byte of the code word give 16*mean;
 // * where the boost is zero (gate open or DDM 0) prob[2] is unchanged bit for bit, so the f64 path only
 //   runs on boundary pixels.
-constexpr int kBoostRows = 4;
+#ifndef CDNET_BOOST_ROWS
+#define CDNET_BOOST_ROWS 4
+#endif
+constexpr int kBoostRows = CDNET_BOOST_ROWS;
 
 __device__ __forceinline__ float gate_threshold(float mx) {
     float t = __fmul_rn(0.2f, mx);
@@ -152,17 +155,30 @@ __device__ __forceinline__ float gate_threshold(float mx) {
     return t;
 }
 
+// per-tile constants of k_boost_inside4, computed once per tile by k_boost_prep instead of once per block
+struct BoostPrep {
+    uint8_t lo[256], hi[256];
+    float thr;
+    int is_const, use_div;
+};
+
+template <bool PREP>
 __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restrict__ codes, const uint32_t* __restrict__ flags,
                                                        const float* __restrict__ point, const unsigned int* __restrict__ pmax,
                                                        float* __restrict__ prob, uint8_t* __restrict__ inside,
                                                        int32_t* __restrict__ status, int H, int W, int write_prob,
-                                                       int n_maps) {
+                                                       int n_maps, const BoostPrep* __restrict__ prep) {
     __shared__ uint8_t s_lo[256], s_hi[256];
     __shared__ float s_thr;
     __shared__ int s_const, s_div;
     const int b = blockIdx.z;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    {
+    if (PREP) {
+        const BoostPrep& P0 = prep[b];
+        s_lo[tid] = P0.lo[tid];
+        s_hi[tid] = P0.hi[tid];
+        if (tid == 0) { s_thr = P0.thr; s_const = P0.is_const; s_div = P0.use_div; }
+    } else {
         // 2 * normalised value of code d for each map (0, 1, 2); constant maps flagged
         const uint32_t fl = flags[b];
         int bad = 0, lo = 0, hi = 0;
@@ -254,6 +270,36 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
     }
 }
 
+// one block per tile: the two 256-entry LUTs (16 * mean of the normalised maps over the low / high byte of the code
+// word), the gate threshold and the constant-map flag -- what every block of k_boost_inside4<false> recomputes for itself
+__global__ void __launch_bounds__(256) k_boost_prep(const uint32_t* __restrict__ flags, const unsigned int* __restrict__ pmax,
+                                                    int32_t* __restrict__ status, BoostPrep* __restrict__ prep, int n_maps) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const uint32_t fl = flags[b];
+    int bad = 0, lo = 0, hi = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        if (t >= n_maps) continue;
+        const uint32_t f = (fl >> (3 * t)) & 7u;
+        const int mn = (f & 1) ? 0 : ((f & 2) ? 1 : 2);
+        const int mx = (f & 4) ? 2 : ((f & 2) ? 1 : 0);
+        if (mx == mn) bad = 1;
+        const int d = (tid >> (2 * (t & 3))) & 3;
+        const int v2 = (mx > mn && d < 3) ? ((16 / n_maps) * (d - mn)) / (mx - mn) : 0;
+        if (t < 4) lo += v2; else hi += v2;
+    }
+    prep[b].lo[tid] = (uint8_t)lo;
+    prep[b].hi[tid] = (uint8_t)hi;
+    if (tid == 0) {
+        const float mxv = ordered_to_f32(pmax[b]);
+        const bool ok = mxv > 0.0f && mxv < INFINITY;
+        prep[b].is_const = bad;
+        prep[b].use_div = ok ? 0 : 1;
+        prep[b].thr = ok ? gate_threshold(mxv) : 0.0f;
+        if (bad && status) atomicOr(status + b, CDNET_S_DDM_CONSTANT);
+    }
+}
+
 // test.py:270-275: inside = argmax over C channels == 1, or prob[0] >= 0.5
 __global__ void __launch_bounds__(256) k_plain_inside(const float* __restrict__ prob, int C, uint8_t* __restrict__ inside,
                                                       size_t plane, int multi_class) {
@@ -308,7 +354,8 @@ static bool bad_dims(int B, int H, int W) { return B <= 0 || H <= 0 || W <= 0 ||
 extern "C" size_t cdnet_dam_postproc_workspace_bytes(int B, int H, int W) {
     if (bad_dims(B, H, W)) return 0;
     const size_t n = (size_t)B * H * W;
-    return pad256(n * 2) + 2 * pad256((size_t)B * 4) + pad256(n) + pad256(n * 4) + tail_workspace(B, H, W);
+    return pad256(n * 2) + 2 * pad256((size_t)B * 4) + pad256((size_t)B * sizeof(BoostPrep)) + pad256(n) + pad256(n * 4) +
+           tail_workspace(B, H, W);
 }
 
 extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, const float* point, void* out,
@@ -326,6 +373,7 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
     uint16_t* codes = ar.take<uint16_t>(n);
     uint32_t* flags = ar.take<uint32_t>(B);
     unsigned int* pmax = ar.take<unsigned int>(B);
+    BoostPrep* prep = ar.take<BoostPrep>(B);
     uint8_t* inside = ar.take<uint8_t>(n);
     int32_t* labels = ar.take<int32_t>(n);
     if (!ar.ok) return CDNET_E_WORKSPACE;
@@ -342,12 +390,14 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
     CDNET_RANGE("point gate + boost + argmax, then labels");
     CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, st));
     point_max_launch(point, pmax, B, plane, st);
-    if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
-        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes, flags, point,
-                     pmax, prob, inside, status, H, W, write_prob, n_maps);
-    else
+    if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0) {
+        CDNET_LAUNCH(k_boost_prep, B, 256, 0, st, flags, pmax, status, prep, n_maps);
+        CDNET_LAUNCH(k_boost_inside4<true>, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes,
+                     flags, point, pmax, prob, inside, status, H, W, write_prob, n_maps, prep);
+    } else {
         CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
                      pmax, prob, inside, status, H, W, write_prob, n_maps);
+    }
     rc = last_error();
     if (rc) return rc;
     // test_dam.py:559 calls process() with its default min_size = 10
@@ -417,8 +467,8 @@ extern "C" int cdnet_shard_boost(const uint16_t* codes, const uint32_t* flags, c
     cudaStream_t st = (cudaStream_t)stream;
     const int H = He, B = 1;
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0)
-        CDNET_LAUNCH(k_boost_inside4, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes, flags, point,
-                     pmax, prob, inside, status, H, W, write_prob, n_maps);
+        CDNET_LAUNCH(k_boost_inside4<false>, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes,
+                     flags, point, pmax, prob, inside, status, H, W, write_prob, n_maps, (const BoostPrep*)nullptr);
     else
         CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,
                      pmax, prob, inside, status, H, W, write_prob, n_maps);

@@ -362,8 +362,33 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __
     for (int wj = lane; wj < NW; wj += 32) {
         const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
         uint32_t hole = 0;
-        // common case first: which background segments of the word belong to a component without a frame flag?
-        for_each_segment(~r.m & r.valid, [&](int k0, uint32_t seg) {
+        // common case first: which background segments of the word belong to a component without a frame flag?  The
+        // first four segments are looked up together (parent, its parent, flag: three rounds of independent loads)
+        uint32_t rest = ~r.m & r.valid;
+        uint32_t seg4[4];
+        int par[4], root[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            seg4[i] = 0;
+            par[i] = -1;
+            if (rest) {
+                const int k0 = __ffs(rest) - 1;
+                const uint32_t inv = ~(rest >> k0);
+                const int len = inv ? (__ffs(inv) - 1) : (32 - k0);
+                seg4[i] = (len >= 32 ? kFull : ((1u << len) - 1u)) << k0;
+                rest &= ~seg4[i];
+                par[i] = Pt[y * W + run_start(r, k0)];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) root[i] = par[i] >= 0 ? Pt[par[i]] : -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (root[i] >= 0 && root[i] != par[i]) root[i] = uf_find_c(Pt, root[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (root[i] >= 0 && A[tile + root[i]] == 0) hole |= seg4[i];
+        for_each_segment(rest, [&](int k0, uint32_t seg) {  // more than four background segments in one word
             if (A[tile + uf_find_c(Pt, y * W + run_start(r, k0))] == 0) hole |= seg;
         });
         F[rowbits + wj] = r.m | hole;
@@ -449,12 +474,25 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
         const RowScan r = row_word(in ? M[rowbits + wj] : 0u, (in && wj > 0) ? M[rowbits + wj - 1] : 0u, -1, W, wj);
         uint32_t s = r.t & r.m, roots = 0, dead = 0;
         while (s) {
-            const int k = __ffs(s) - 1;
-            s &= s - 1;
-            const int gid = y * W + r.wx + k;
-            if (Pt[gid] == gid) {
-                if (At[gid] >= min_area) roots |= 1u << k;
-                else dead |= 1u << k;
+            // four run starts per round: their parent and area loads are independent of each other
+            int kk[4], pv[4], av[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                kk[i] = -1;
+                if (s) { kk[i] = __ffs(s) - 1; s &= s - 1; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int gid = y * W + r.wx + max(kk[i], 0);
+                pv[i] = kk[i] >= 0 ? Pt[gid] : -1;
+                av[i] = kk[i] >= 0 ? At[gid] : 0;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (kk[i] >= 0 && pv[i] == y * W + r.wx + kk[i]) {
+                    if (av[i] >= min_area) roots |= 1u << kk[i];
+                    else dead |= 1u << kk[i];
+                }
             }
         }
         const int n = __popc(roots);
@@ -517,7 +555,8 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
         const int y = y0 - R + rr;
         int* dst = s_lab + rr * kLabTW + kLabPad;
         if (y < 0 || y >= H) {
-            for (int w = 0; w < 32; ++w) dst[32 * w + lane] = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *(int4*)(dst + 32 * lane + 4 * ((q + lane) & 7)) = make_int4(0, 0, 0, 0);
             continue;
         }
         const size_t rowbits = ((size_t)b * H + y) * NW;
@@ -530,12 +569,12 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
         // been united).  Then the 32 pixels of the word go to shared memory, skewed by the lane so that the 32 lanes
         // hit 32 different banks.
         uint32_t smask[4];
-        int slab[4];
+        int slab[4], sidx[4];
         uint32_t rest = f;
 #pragma unroll
         for (int sgi = 0; sgi < 4; ++sgi) {
             smask[sgi] = 0;
-            slab[sgi] = 0;
+            sidx[sgi] = -1;
             if (rest) {
                 const int k0 = __ffs(rest) - 1;
                 const uint32_t inv = ~(rest >> k0);
@@ -543,17 +582,41 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
                 const uint32_t seg = (len >= 32 ? kFull : ((1u << len) - 1u)) << k0;
                 smask[sgi] = seg;
                 rest &= ~seg;
-                slab[sgi] = At[uf_find(Pt, y * W + run_start(r, k0))];
+                sidx[sgi] = y * W + run_start(r, k0);
             }
         }
-        for (int k = 0; k < 32; ++k) {
-            const int p = (k + lane) & 31;
-            int lab = 0;
+        // the look-ups of the four segments are issued together: parent of the run start (the area pass left it pointing
+        // at its root, the diagonal pass may have re-rooted that) -> root -> id.  Three rounds of independent loads
+        // instead of up to twelve dependent ones.
+        int par[4], root[4];
 #pragma unroll
-            for (int sgi = 0; sgi < 4; ++sgi)
-                if ((smask[sgi] >> p) & 1u) lab = slab[sgi];
-            if ((rest >> p) & 1u) lab = At[uf_find(Pt, y * W + run_start(r, p))];  // more than four segments: rare
-            dst[32 * lane + p] = lab;
+        for (int sgi = 0; sgi < 4; ++sgi) par[sgi] = sidx[sgi] >= 0 ? Pt[sidx[sgi]] : -1;
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi) root[sgi] = par[sgi] >= 0 ? Pt[par[sgi]] : -1;
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi) {
+            if (root[sgi] >= 0 && root[sgi] != par[sgi]) root[sgi] = uf_find(Pt, root[sgi]);  // rare: a longer chain
+            slab[sgi] = 0;
+        }
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi)
+            if (root[sgi] >= 0) slab[sgi] = At[root[sgi]];
+        // the row is zero-filled with 128-bit stores (skewed by the lane: each quarter-warp covers all 32 banks), then
+        // only the pixels of labelled segments are written -- a quarter of a tile is nucleus, not all of it
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *(int4*)(dst + 32 * lane + 4 * ((q + lane) & 7)) = make_int4(0, 0, 0, 0);
+        __syncwarp();
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi) {
+            if (slab[sgi]) {
+                const int k0 = __ffs(smask[sgi]) - 1, len = __popc(smask[sgi]);
+                for (int k = 0; k < len; ++k) dst[32 * lane + k0 + k] = slab[sgi];
+            }
+        }
+        while (rest) {  // more than four segments in one word: rare
+            const int pbit = __ffs(rest) - 1;
+            rest &= rest - 1;
+            dst[32 * lane + pbit] = At[uf_find(Pt, y * W + run_start(r, pbit))];
         }
     }
     __syncthreads();
@@ -564,36 +627,51 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
     const int rows = min(kLabRows, H - y0);
     OUT* ot = out + tile;
     if ((W & 3) == 0 && (((uintptr_t)out) & 15) == 0) {
+        // a thread owns a 4-pixel column of the block and walks down the staged rows ONCE: per staged row the centre
+        // values, their 3-wide and their 5-wide horizontal maxima are formed once and serve every output row whose
+        // disk touches that row (disk(2): rows y-2 / y+2 contribute their centre, y-1 / y+1 three pixels, y five)
         const int nq = (own_hi - own_lo) >> 2;
-        for (int i = threadIdx.x; i < rows * nq; i += 256) {
-            const int ry = i / nq, q = i - ry * nq;
+        for (int q = threadIdx.x; q < nq; q += 256) {
             const int x4 = own_lo + 4 * q;
             const int col = x4 - xbase + kLabPad;  // staged column of pixel x4 (multiple of 4)
-            int m[4] = {0, 0, 0, 0};
+            int a1[SR][4], a3[SR][4], a5[SR][4];
 #pragma unroll
-            for (int dy = -R; dy <= R; ++dy) {
-                const int* rowp = s_lab + (ry + R + dy) * kLabTW + col;
-                const int reach = (R == 0) ? 0 : (R == 1 ? (dy == 0 ? 1 : 0) : (dy == 0 ? 2 : ((dy == 1 || dy == -1) ? 1 : 0)));
+            for (int sr = 0; sr < SR; ++sr) {
+                const int* rowp = s_lab + sr * kLabTW + col;
                 const int4 cv = *(const int4*)rowp;
-                int v[8] = {0, 0, cv.x, cv.y, cv.z, cv.w, 0, 0};
-                if (reach >= 1) {
+                a1[sr][0] = cv.x; a1[sr][1] = cv.y; a1[sr][2] = cv.z; a1[sr][3] = cv.w;
+                if (R >= 1) {
                     const int2 l = *(const int2*)(rowp - 2), rg = *(const int2*)(rowp + 4);
-                    v[0] = l.x; v[1] = l.y; v[6] = rg.x; v[7] = rg.y;
+                    a3[sr][0] = max(max(l.y, cv.x), cv.y);
+                    a3[sr][1] = max(max(cv.x, cv.y), cv.z);
+                    a3[sr][2] = max(max(cv.y, cv.z), cv.w);
+                    a3[sr][3] = max(max(cv.z, cv.w), rg.x);
+                    if (R >= 2) {
+                        a5[sr][0] = max(a3[sr][0], max(l.x, cv.z));
+                        a5[sr][1] = max(a3[sr][1], max(l.y, cv.w));
+                        a5[sr][2] = max(a3[sr][2], max(cv.x, rg.x));
+                        a5[sr][3] = max(a3[sr][3], max(cv.y, rg.y));
+                    }
                 }
+                if (sr >= 2 * R) {
+                    const int ry = sr - 2 * R;  // output row whose disk ends at staged row sr
+                    if (ry < rows) {
+                        int m[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int mx = v[j + 2];
-                    if (reach >= 1) mx = max(mx, max(v[j + 1], v[j + 3]));
-                    if (reach >= 2) mx = max(mx, max(v[j], v[j + 4]));
-                    m[j] = max(m[j], mx);
+                        for (int j = 0; j < 4; ++j) {
+                            if (R == 0) m[j] = a1[ry][j];
+                            else if (R == 1) m[j] = max(a3[ry + 1][j], max(a1[ry][j], a1[ry + 2][j]));
+                            else m[j] = max(max(a5[ry + 2][j], max(a3[ry + 1][j], a3[ry + 3][j])), max(a1[ry][j], a1[ry + 4][j]));
+                        }
+                        OUT* o = ot + (size_t)(y0 + ry) * W + x4;
+                        if (sizeof(OUT) == 4) {
+                            *(int4*)o = make_int4(m[0], m[1], m[2], m[3]);
+                        } else {
+                            *(longlong2*)o = make_longlong2((long long)m[0], (long long)m[1]);
+                            *(longlong2*)(o + 2) = make_longlong2((long long)m[2], (long long)m[3]);
+                        }
+                    }
                 }
-            }
-            OUT* o = ot + (size_t)(y0 + ry) * W + x4;
-            if (sizeof(OUT) == 4) {
-                *(int4*)o = make_int4(m[0], m[1], m[2], m[3]);
-            } else {
-                *(longlong2*)o = make_longlong2((long long)m[0], (long long)m[1]);
-                *(longlong2*)(o + 2) = make_longlong2((long long)m[2], (long long)m[3]);
             }
         }
     } else {
