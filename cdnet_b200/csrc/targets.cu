@@ -608,6 +608,69 @@ static void sobel_weights(float out[2][121]) {
         }
 }
 
+// ---- centres of my_transforms.LabelEncoding with do_direction = 1 (my_transforms.py:771-778) -------------------------
+// `peak_local_max(distance_transform_edt(nucleus), exclude_border=0, num_peaks=1)`: the maximum of the nucleus's OWN
+// distance transform (distance to the nearest pixel that is not part of this instance -- background or another
+// nucleus -- with no implicit background outside the frame), first in raster order among equals.  One separable,
+// exact pass for all instances at once: a pixel of another instance is a zero for this one.
+__global__ void __launch_bounds__(kBX* kBY) k_ledt_cols(const int* __restrict__ inst, int* __restrict__ g2, int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const int* L = inst + tile;
+    const int own = L[p];
+    int r = 0;
+    if (own > 0) {
+        r = 1 << 30;
+        const int kmax = max(y, H - 1 - y);
+        for (int k = 1; k <= kmax; ++k) {
+            const bool up = (y - k >= 0) && L[p - k * W] != own;
+            const bool dn = (y + k < H) && L[p + k * W] != own;
+            if (up || dn) { r = k * k; break; }
+        }
+    }
+    g2[tile + p] = r;
+}
+
+__global__ void __launch_bounds__(kBX* kBY) k_ledt_rows(const int* __restrict__ inst, const int* __restrict__ g2,
+                                                        double* __restrict__ cness, unsigned long long* __restrict__ best,
+                                                        int tab, int H, int W) {
+    PX_COORDS
+    if (!inb) return;
+    const int* L = inst + tile + (size_t)y * W;
+    const int* G = g2 + tile + (size_t)y * W;
+    const int own = L[x];
+    if (own <= 0 || own >= tab) return;
+    const int kInf = 1 << 30;
+    int d2 = G[x];
+    const int kmax = max(x, W - 1 - x);
+    for (int k = 1; k <= kmax; ++k) {
+        const int kk = k * k;
+        if (kk >= d2) break;
+        if (x - k >= 0) d2 = min(d2, kk + (L[x - k] == own ? min(G[x - k], kInf - kk) : 0));
+        if (x + k < W) d2 = min(d2, kk + (L[x + k] == own ? min(G[x + k], kInf - kk) : 0));
+    }
+    const double c = (double)d2;  // sqrt is monotone: the maximum of d is the maximum of d^2
+    cness[tile + p] = c;
+    atomicMax(best + (size_t)b * tab + own, (unsigned long long)__double_as_longlong(c));
+}
+
+static int centres_edt_launch(const int32_t* inst, int32_t* g2, double* cness, unsigned long long* best, int32_t* centre,
+                              int32_t* maxd2, int tab, int B, int H, int W, cudaStream_t st) {
+    const size_t nt = (size_t)B * tab;
+    const size_t blocks = (nt + 255) / 256;
+    CDNET_LAUNCH(k_t_table_init, (unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, st, best, centre, maxd2, nt);
+    CDNET_LAUNCH(k_ledt_cols, px_grid(B, H, W), px_block(), 0, st, inst, g2, H, W);
+    CDNET_LAUNCH(k_ledt_rows, px_grid(B, H, W), px_block(), 0, st, inst, g2, cness, best, tab, H, W);
+    CDNET_LAUNCH(k_t_center_pick, px_grid(B, H, W), px_block(), 0, st, inst, cness, best, centre, tab, H, W);
+    return last_error();
+}
+
+// new_label_inside of my_transforms.LabelEncoding: ids > 0 (instance ids, :717) or label > 127.5 ({0,255} label, :733)
+__global__ void k_t_inside_plain(const uint8_t* __restrict__ ids, uint8_t* __restrict__ inside, size_t n, int thr) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        inside[i] = ids[i] > thr;
+}
+
 static int centres_launch(const int32_t* inst, double* cness, unsigned long long* best, int32_t* centre, int32_t* maxd2,
                           int tab, int B, int H, int W, cudaStream_t st) {
     const size_t nt = (size_t)B * tab;
@@ -673,7 +736,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
                                     void* stream) {
     if (!ids || !ternary || !point || !direction || bad_dims(B, H, W)) return CDNET_E_BADARG;
     if (num_classes != 8 && num_classes != 16) return CDNET_E_BADARG;
-    if (instance_level < 0 || instance_level > 3) return CDNET_E_BADARG;
+    if (instance_level < 0 || instance_level > 5) return CDNET_E_BADARG;
     if (ws_bytes < cdnet_encode_targets_workspace_bytes(B, H, W)) return CDNET_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)B * H * W;
@@ -745,7 +808,17 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
         int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
         CDNET_LAUNCH(k_label_stats, dim3(gx, B), 256, 0, st, ids, pres, fg, plane);
     }
-    CDNET_LAUNCH(k_t_ternary, px_grid(B, H, W), px_block(), 0, st, ids, fg, instance_level, ternary, inside, interior, H, W);
+    if (instance_level >= 4) {
+        // my_transforms.LabelEncoding (do_direction = 1, out_c = 3): its own ternary rule (csrc/training.cu) and
+        // new_label_inside; modes 4 / 5 = instance ids / {0,255} label
+        int rc0 = cdnet_ternary_label(ids, nullptr, instance_level == 4 ? 0 : 1, ternary, B, H, W, stream);
+        if (rc0) return rc0;
+        const size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+        CDNET_LAUNCH(k_t_inside_plain, (unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, st, ids, inside, n,
+                     instance_level == 4 ? 0 : 127);
+    } else {
+        CDNET_LAUNCH(k_t_ternary, px_grid(B, H, W), px_block(), 0, st, ids, fg, instance_level, ternary, inside, interior, H, W);
+    }
     // 2. instances: process(interior*255, min_size=5) (:759) or measure.label (:773), then dilation disk(1)
     nvtx_mark("targets: instances (process / label + dilation)");
     int rc;
@@ -758,7 +831,7 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
         if (!sub.ok) return CDNET_E_WORKSPACE;
         // out_c != 3 (:723-725, :734): the labelling itself is the instance map, nothing is dilated
         int32_t* dst = instance_level >= 2 ? inst : inst_raw;
-        if (instance_level == 2) rc = ccl_label_values_launch(ids, dst, nullptr, Lp, idmap, rowcnt, B, H, W, st);
+        if (instance_level == 2 || instance_level >= 4) rc = ccl_label_values_launch(ids, dst, nullptr, Lp, idmap, rowcnt, B, H, W, st);
         else rc = ccl_label_launch(interior, dst, nullptr, Lp, idmap, rowcnt, B, H, W, 8, st);
     }
     if (rc) return rc;
@@ -775,7 +848,8 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     }
     // 3. centres, support maxima, direction classes, point map
     nvtx_mark("targets: centres, direction classes, point map");
-    rc = centres_launch(inst, cness, best, centre, maxd2, tab, B, H, W, st);
+    if (instance_level >= 4) rc = centres_edt_launch(inst, inst_raw, cness, best, centre, maxd2, tab, B, H, W, st);
+    else rc = centres_launch(inst, cness, best, centre, maxd2, tab, B, H, W, st);
     if (rc) return rc;
     CDNET_LAUNCH(k_t_support_max, px_grid(B, H, W), px_block(), 0, st, inst, centre, maxd2, cflag, tab, H, W);
     {

@@ -297,17 +297,22 @@ class LabelEncoding(object):
     options.py builds for the models without a direction branch: `LabelEncoding(out_c, radius, do_direction)(imgs)`
     replaces imgs[2] by the PIL 'L' label image {0,127,255}.
 
-    do_direction = 1 in THIS module centres nuclei with skimage.feature.peak_local_max, whose tie-breaking is
-    not pinned by anything in the reference: NotImplementedError (the direction-aware training path is
-    cdnet_b200.api.LabelEncoding = my_transforms_direction.LabelEncoding)."""
+    do_direction = 1 (my_transforms.py:763-836; dead in the reference's own flows, which pair this module with
+    direction = 0 models, train.py:77-81) is built for out_c = 3: instances = `measure.label` of the label (not
+    dilated, no watershed), nucleus centre = `peak_local_max(distance_transform_edt(nucleus), exclude_border=0,
+    num_peaks=1)` = the first raster maximum of the nucleus's own distance transform -- scikit-image's order among
+    EQUAL maxima is unpinned (numpy's unstable argsort) -- then the same distance-to-centre / Sobel / quantiser chain
+    as the direction-aware transform.  Returns (img, weight, PIL ternary, float16 point map, int64 direction classes).
+    The number of direction classes is env `dt_num_classes` (default 8) unless `num_classes` is given."""
 
-    def __init__(self, out_c=3, radius=1, do_direction=0):
+    def __init__(self, out_c=3, radius=1, do_direction=0, num_classes=None):
+        import os
         self.out_c = out_c
         self.radius = 1  # the reference ignores its argument (:668)
         self.do_direction = do_direction
-        if do_direction == 1:
-            raise NotImplementedError("my_transforms.LabelEncoding with do_direction=1 (peak_local_max centres, "
-                                      "my_transforms.py:763-836) is out of scope; use cdnet_b200.api.LabelEncoding")
+        self.num_classes = int(os.environ.get("dt_num_classes", 8)) if num_classes is None else int(num_classes)
+        if do_direction == 1 and out_c != 3:
+            raise NotImplementedError("my_transforms.LabelEncoding with do_direction=1 is built for out_c=3 only")
 
     @staticmethod
     def _u8(a):
@@ -344,9 +349,28 @@ class LabelEncoding(object):
             mode = 0 if instance_level else 1
         return ternary_label_cuda(d0, mode, ch1)[0].cpu().numpy()
 
+    def encode_direction(self, label):
+        """label image -> (ternary uint8, point float16, direction int64) of do_direction = 1 (out_c = 3)"""
+        if not isinstance(label, np.ndarray):
+            label = np.array(label)
+        ch0 = self._u8(label if label.ndim == 2 else label[:, :, 0])
+        from .api import encode_targets_cuda, label_stats_cuda
+        dev = _device()
+        d0 = torch.from_numpy(ch0).to(dev)[None]
+        instance_level = int(label_stats_cuda(d0)[0][0]) > 2
+        tern, point, direction = encode_targets_cuda(d0, instance_level=4 if instance_level else 5,
+                                                     num_classes=self.num_classes)
+        return tern[0].cpu().numpy(), point[0].cpu().numpy(), direction[0].cpu().numpy()
+
     def __call__(self, imgs):
         from PIL import Image
         out_imgs = list(imgs)
+        if self.do_direction == 1:
+            tern, point, direction = self.encode_direction(imgs[2])
+            out_imgs[2] = Image.fromarray(tern)
+            out_imgs.append(point)
+            out_imgs.append(direction)
+            return tuple(out_imgs)
         out_imgs[2] = Image.fromarray(self.encode(imgs[2]))
         return tuple(out_imgs)
 

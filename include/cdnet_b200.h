@@ -173,7 +173,11 @@ int cdnet_label_stats(const uint8_t* ids, int32_t* presence, int32_t* fg_count, 
  * instance_level: 1 = ids are instance ids (reference: > 2 unique values, :743-760), 0 = a {0,255} three-class
  *            label (:763-774); the out_c != 3 forms of the transform (:721-739, no boundary class, instances
  *            not dilated, ternary in {0,255}): 2 = instance ids, 3 = {0,255} label with ids = max(channel 0,
- *            channel 1).  Applies to all B tiles of the call
+ *            channel 1).  4 / 5 = my_transforms.LabelEncoding with do_direction = 1 (my_transforms.py:661-836, out_c = 3)
+ *            on instance ids / on a {0,255} label: that module's ternary rule, instances = measure.label of the label
+ *            (8-connected, equal value, not dilated, no watershed), nucleus centre = first raster maximum of the
+ *            nucleus's own exact distance transform (peak_local_max(..., exclude_border=0, num_peaks=1), :775).
+ *            Applies to all B tiles of the call
  * ternary:   uint8 [B,H,W]  {0,127,255}
  * point:     float16 bits [B,H,W] Gaussian point map (sigma 2)
  * direction: int64 [B,H,W]  classes 0..num_classes; num_classes in {8, 16} (the reference's env

@@ -263,6 +263,26 @@ def gold_training(ns):
     _save("training", meta, **out)
 
 
+PLAINDIR_CASES = [("pd_64", 3, 64, 64, 5), ("pd_96x120", 4, 96, 120, 14), ("pd_150x130", 5, 150, 130, 30),
+                  ("pd_256_dense", 8, 256, 256, 110)]
+
+
+def gold_plain_direction(ns):
+    """my_transforms.LabelEncoding(3, 1, do_direction=1) executed verbatim (my_transforms.py:661-836; peak_local_max
+    from oracle/refshim/skimage/feature.py, 8 direction classes) on instance-id and {0,255} labels."""
+    out, meta = {}, {"cases": []}
+    for name, seed, H, W, n in PLAINDIR_CASES:
+        ids = synth.instance_map(seed, H, W, n)
+        labs = {"inst": synth.as_uint8_label(ids), "bin": np.repeat(((ids > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)}
+        for kind, lab in labs.items():
+            r = ns.LabelEncodingPlain(3, 1, 1)((None, None, lab.copy()))
+            out["%s_%s_ternary" % (name, kind)] = np.asarray(r[2])
+            out["%s_%s_point" % (name, kind)] = r[3]
+            out["%s_%s_direction" % (name, kind)] = r[4].astype(np.int8)
+        meta["cases"].append({"name": name, "seed": seed, "H": H, "W": W, "n": n, "digest": synth.digest(labs["inst"])})
+    _save("plaindir", meta, **out)
+
+
 def gold_widening(ns):
     """Round-1 widening features executed verbatim: the TTA block + get_probmaps (test_dam.py:314-450, :930-1034),
     LabelEncoding with out_c != 3 (my_transforms_direction.py:721-739), the `voting_firt` switch (:471) and
@@ -313,7 +333,7 @@ def main():
         return
     ns = ref_loader.load()
     assert ns.DTOffsetConfig.num_classes == 8
-    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16", "metrics", "training", "widening"]
+    todo = a.only.split(",") if a.only else ["ddm", "process", "centre", "postproc", "targets", "t16", "metrics", "training", "widening", "plaindir"]
     if "ddm" in todo:
         gold_ddm(ns)
     if "process" in todo:
@@ -330,6 +350,8 @@ def main():
         gold_training(ns)
     if "widening" in todo:
         gold_widening(ns)
+    if "plaindir" in todo:
+        gold_plain_direction(ns)
     if "t16" in todo:
         env = dict(os.environ, dt_num_classes="16")
         subprocess.check_call([sys.executable, "-m", "oracle.make_goldens", "--child16"], env=env,

@@ -584,6 +584,69 @@ def label_encoding_plain(label, out_c=3):
     return (new_label / 2 * 255).astype(np.uint8)
 
 
+def label_encoding_plain_direction(label, out_c=3, num_classes=8, literal=True, conv="fma", return_parts=False):
+    """my_transforms.LabelEncoding with do_direction=1 (my_transforms.py:661-836): like the direction-aware transform
+    but on `measure.label(label_inside)` (8-connected components of equal value, NOT dilated, no watershed), and with
+    the nucleus centre taken as `peak_local_max(distance_transform_edt(nucleus), exclude_border=0, num_peaks=1)`
+    (:775) = the first raster maximum of the nucleus's own distance transform (tie order UNPINNED, see
+    oracle/refshim/skimage/feature.py).  Returns (ternary u8, point f16, direction int64)."""
+    assert out_c == 3, "restated for the three-class output only"
+    label = np.asarray(label)
+    label_inside = label if label.ndim == 2 else label[:, :, 0]
+    instance_level = len(np.unique(label_inside)) > 2
+    ternary = label_encoding_plain(label, out_c)
+    inst = label8_values(label_inside)  # :713 / :741 (measure.label of the ids resp. of the {0,255} label)
+    inside = (inst > 0) if instance_level else (label_inside > 127.5)  # new_label_inside (:717 / :733)
+    H, W = inst.shape
+    dir_map = np.zeros((H, W, 2), dtype=np.float32)
+    label_point = np.zeros((H, W), dtype=np.float64)
+    ker = sobel_kernels(11)
+    ids = np.unique(inst)[1:]  # :765-768 (takes the first value for background)
+    centres = []
+    boxes = ndi.find_objects(inst.astype(np.int64)) if not literal else None
+    for k in ids:
+        if literal:
+            y0, y1, x0, x1 = 0, H, 0, W
+        else:
+            sl = boxes[int(k) - 1]
+            y0, y1 = max(0, sl[0].start - 7), min(H, sl[0].stop + 7)
+            x0, x1 = max(0, sl[1].start - 7), min(W, sl[1].stop + 7)
+        nucleus = (inst[y0:y1, x0:x1] == k).astype(np.int64)
+        dist_i = ndi.distance_transform_edt(nucleus)  # :771
+        flat = int(np.argmax(dist_i))  # first raster maximum = peak_local_max(..., num_peaks=1) under a stable order
+        cy, cx = y0 + flat // (x1 - x0), x0 + flat % (x1 - x0)
+        centres.append((cy, cx))
+        label_point[cy, cx] = 255.0  # :778
+        nucleus = dilate(nucleus, disk(1))  # :781
+        yy, xx = np.mgrid[y0:y1, x0:x1]
+        dist = np.sqrt(((yy - cy) ** 2 + (xx - cx) ** 2).astype(np.float64))  # :782-784 EDT(1 - point)
+        int_pos = dist * nucleus
+        dc = (1 - int_pos / (int_pos.max() + 0.0000001)) * nucleus  # :786
+        dc32 = dc.astype(np.float32)
+        if conv == "fma":
+            g = clib.conv11_fma(dc32, ker)  # restates F.conv2d (:792-795)
+        else:
+            import torch
+            g = torch.nn.functional.conv2d(torch.from_numpy(dc32).view(1, 1, *dc32.shape),
+                                           torch.from_numpy(ker).view(2, 1, 11, 11), padding=5)[0].numpy()
+        g = np.moveaxis(g, 0, -1).copy()
+        g[nucleus == 0, :] = 0  # :796
+        sub = dir_map[y0:y1, x0:x1]
+        sub[nucleus != 0, :] = 0  # :797
+        sub += g  # :798
+    point = ndi.gaussian_filter(label_point, sigma=2, order=0).astype(np.float16)  # :802
+    angle = np.degrees(np.arctan2(dir_map[:, :, 0], dir_map[:, :, 1]))  # :810
+    angle[inside == 0] = 0  # :811
+    vec = angle_to_vector(angle, num_classes)  # :812
+    direction = vector_to_label(vec, num_classes)  # :814
+    direction[inside == 0] = -1  # :817-822
+    direction = direction + 1
+    if return_parts:
+        return ternary, point, direction, {"inst": inst, "inside": inside, "dir_map": dir_map,
+                                           "centres": np.asarray(centres, dtype=np.int64), "angle": angle}
+    return ternary, point, direction
+
+
 def label8_values(x):
     """skimage.measure.label(x) for a multi-valued image: 8-connected components of EQUAL value,
     background 0, ids in raster order of each component's first pixel."""

@@ -163,7 +163,7 @@ def test_label_encoding_plain_golden(T):
         with pytest.raises(IndexError):
             T.LabelEncoding(1, 1, 0)((None, None, ids.copy()))
     with pytest.raises(NotImplementedError):
-        T.LabelEncoding(3, 1, 1)
+        T.LabelEncoding(2, 1, 1)  # do_direction = 1 is built for out_c = 3 only
 
 
 @pytest.mark.parametrize("seed,H,W,n", [(61, 97, 143, 14), (62, 256, 200, 60), (63, 1, 9, 1), (64, 33, 1, 1)])
@@ -178,3 +178,40 @@ def test_label_encoding_plain_vs_oracle(T, seed, H, W, n):
     for out_c in (3, 1):
         assert np.array_equal(np.asarray(T.LabelEncoding(out_c, 1, 0)((None, None, binary.copy()))[2]),
                               O.label_encoding_plain(binary.copy(), out_c)), out_c
+
+
+@pytest.mark.parametrize("seed,H,W,n,classes", [(3, 64, 64, 5, 8), (4, 96, 120, 14, 8), (5, 150, 130, 30, 16), (6, 200, 256, 60, 8)])
+def test_label_encoding_plain_direction_vs_oracle(T, seed, H, W, n, classes):
+    """my_transforms.LabelEncoding(3, 1, do_direction=1) (my_transforms.py:763-836): centres from the nucleus's own
+    distance transform; instance ids and {0,255} labels.  The restatement is pinned to the verbatim reference in
+    tests/test_oracle_vs_reference.py (tie order among equal EDT maxima: unpinned, raster-first on both sides)."""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    ids = synth.instance_map(seed, H, W, n)
+    binary = np.repeat(((ids > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    for lab in (synth.as_uint8_label(ids), binary):
+        ref = O.label_encoding_plain_direction(lab.copy(), 3, classes, literal=False)
+        res = T.LabelEncoding(3, 1, 1, num_classes=classes)((None, None, lab.copy()))
+        assert len(res) == 5
+        assert np.array_equal(np.asarray(res[2]), ref[0])
+        assert res[3].dtype == np.float16 and np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16))
+        assert res[4].dtype == np.int64 and np.array_equal(res[4], ref[2]), int((res[4] != ref[2]).sum())
+
+
+def test_label_encoding_plain_direction_scope(T):
+    with pytest.raises(NotImplementedError):
+        T.LabelEncoding(2, 1, 1)
+
+
+def test_label_encoding_plain_direction_golden(T):
+    """goldens from the verbatim my_transforms.LabelEncoding(3, 1, 1)"""
+    z, meta = load_golden("plaindir")
+    for c in meta["cases"]:
+        ids = synth.instance_map(c["seed"], c["H"], c["W"], c["n"])
+        labs = {"inst": synth.as_uint8_label(ids), "bin": np.repeat(((ids > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)}
+        for kind, lab in labs.items():
+            res = T.LabelEncoding(3, 1, 1, num_classes=8)((None, None, lab.copy()))
+            key = "%s_%s_" % (c["name"], kind)
+            assert np.array_equal(np.asarray(res[2]), z[key + "ternary"]), key
+            assert np.array_equal(res[3].view(np.uint16), z[key + "point"].view(np.uint16)), key
+            assert np.array_equal(res[4], z[key + "direction"].astype(np.int64)), key

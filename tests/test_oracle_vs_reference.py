@@ -128,6 +128,20 @@ def test_training_consumers(ref):
             assert np.array_equal(r, O.label_encoding_plain(img.copy(), out_c)), (img.shape, out_c)
 
 
+def test_label_encoding_plain_with_direction(ref):
+    """my_transforms.LabelEncoding(3, 1, do_direction=1) verbatim (peak_local_max from the shim) vs the restatement,
+    literal (full-canvas per-instance loops) and windowed"""
+    for seed, H, W, n in ((31, 72, 90, 9), (32, 130, 110, 25)):
+        ids = synth.instance_map(seed, H, W, n)
+        for lab in (synth.as_uint8_label(ids), np.repeat(((ids > 0) * 255).astype(np.uint8)[:, :, None], 3, axis=2)):
+            r = ref.LabelEncodingPlain(3, 1, 1)((None, None, lab.copy()))
+            for literal in (True, False):
+                o = O.label_encoding_plain_direction(lab.copy(), 3, 8, literal=literal)
+                assert np.array_equal(np.asarray(r[2]), o[0])
+                assert np.array_equal(r[3].view(np.uint16), o[1].view(np.uint16))
+                assert np.array_equal(r[4], o[2])
+
+
 def test_tta_merge(ref):
     """the TTA block (test_dam.py:314-450) and get_probmaps (:930-1034) executed verbatim with stand-in model /
     image objects vs the restatement: point maps and direction classes exact, probabilities to float32 rounding
