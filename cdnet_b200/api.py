@@ -696,9 +696,18 @@ def _gauss_weights():
 
 
 def label_stats_cuda(ids):
-    """ids uint8 [B,H,W] -> (n_distinct int32 [B], fg_count int32 [B]) on the device."""
+    """ids uint8 (or int32) [B,H,W] -> (n_distinct int32 [B], fg_count int32 [B]) on the device; for int32 ids n_distinct
+    is capped at 3 (the reference only asks `> 2`)."""
     L = _cabi.lib()
     dev = _device(ids.device)
+    if ids.dtype == torch.int32:
+        ids = ids.contiguous()
+        B, H, W = ids.shape
+        nd = torch.empty((B,), dtype=torch.int32, device=dev)
+        fg = torch.empty((B,), dtype=torch.int32, device=dev)
+        scratch = torch.empty((B, 5), dtype=torch.int32, device=dev)
+        check(L.cdnet_label_stats_i32(_ptr(ids), _ptr(nd), _ptr(fg), _ptr(scratch), B, H, W, _stream()), "cdnet_label_stats_i32")
+        return nd, fg
     ids = _cu8(ids)
     B, H, W = ids.shape
     pres = torch.empty((B, 256), dtype=torch.int32, device=dev)
@@ -711,10 +720,15 @@ def encode_targets_cuda(ids, instance_level=True, num_classes=8, want_inst=False
     """ids uint8 [B,H,W] (channel 0 of the label image) ->
     (ternary uint8 [B,H,W], point float16 [B,H,W], direction int64 [B,H,W][, inst int32][, dir f32 [B,H,W,2]]).
     instance_level: True / 1 = instance ids, False / 0 = {0,255} label (both out_c == 3); 2 / 3 = the same two input
-    kinds for out_c != 3 (my_transforms_direction.py:721-739; for 3 pass max(channel 0, channel 1))."""
+    kinds for out_c != 3 (my_transforms_direction.py:721-739; for 3 pass max(channel 0, channel 1)); 4 / 5 =
+    my_transforms.LabelEncoding with do_direction = 1.  int32 ids (labels loaded without the uint8 truncation) take the
+    out_c == 3 forms (0 / 1) through cdnet_encode_targets_i32."""
     L = _cabi.lib()
     dev = _device(ids.device)
-    ids = _cu8(ids)
+    wide = ids.dtype == torch.int32
+    ids = ids.contiguous() if wide else _cu8(ids)
+    if wide and int(instance_level) > 1:
+        raise CdnetError("int32 label ids are supported for the out_c == 3 transform only")
     B, H, W = ids.shape
     ternary = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
     point = torch.empty((B, H, W), dtype=torch.float16, device=dev)
@@ -725,9 +739,10 @@ def encode_targets_cuda(ids, instance_level=True, num_classes=8, want_inst=False
     nb = L.cdnet_encode_targets_workspace_bytes(B, H, W)
     ws = _workspace(nb, dev)
     gw = _gauss_weights()
-    check(L.cdnet_encode_targets(_ptr(ids), int(instance_level), _ptr(ternary), _ptr(point), _ptr(direction),
-                                 _ptr(inst), _ptr(dirm), _ptr(status), B, H, W, int(num_classes), gw.ctypes.data,
-                                 _ptr(ws), ws.numel(), _stream()), "cdnet_encode_targets")
+    fn = L.cdnet_encode_targets_i32 if wide else L.cdnet_encode_targets
+    check(fn(_ptr(ids), int(instance_level), _ptr(ternary), _ptr(point), _ptr(direction), _ptr(inst), _ptr(dirm),
+             _ptr(status), B, H, W, int(num_classes), gw.ctypes.data, _ptr(ws), ws.numel(), _stream()),
+          "cdnet_encode_targets")
     res = [ternary, point, direction]
     if want_inst:
         res.append(inst)
@@ -781,12 +796,18 @@ class LabelEncoding(object):
 
     @staticmethod
     def _channel0(label):
+        """channel 0 of the label image as the kernels take it: uint8 (what data_folder.py:26-37 delivers), or int32
+        when the ids do not fit a byte (label images loaded with compat.data_folder.img_loader(keep_ids=True))"""
         if not isinstance(label, np.ndarray):
             label = np.array(label)
         inside = label if label.ndim == 2 else label[:, :, 0]
         if inside.dtype != np.uint8:
-            if inside.size and (inside.min() < 0 or inside.max() > 255):
-                raise CdnetError("label ids must fit uint8, as data_folder.py:29,37 delivers them")
+            if inside.size and inside.min() < 0:
+                raise CdnetError("label ids must be non-negative")
+            if inside.size and inside.max() > 255:
+                if inside.max() > 2 ** 31 - 1:
+                    raise CdnetError("label ids must fit int32")
+                return np.ascontiguousarray(inside, dtype=np.int32)
             inside = inside.astype(np.uint8)
         return np.ascontiguousarray(inside)
 

@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
 // word: label = id of the root of the pixel's run (F bit set) or 0; the row goes to shared memory (4 zero columns
 // of padding left and right).  Phase 2: max over disk(R) from shared memory, 4 pixels per thread, written as OUT.
 #ifndef CDNET_LAB_ROWS
-#define CDNET_LAB_ROWS 8
+#define CDNET_LAB_ROWS 4
 #endif
 constexpr int kLabRows = CDNET_LAB_ROWS;
 constexpr int kLabPad = 4;

@@ -112,14 +112,67 @@ __global__ void __launch_bounds__(256) k_label_stats(const uint8_t* __restrict__
     if (threadIdx.x == 0 && s_cnt) atomicAdd(fg + b, s_cnt);
 }
 
+// int32 ids (label images loaded without the uint8 truncation of data_folder.py:26-37): stats[b] = {non-zero pixels,
+// zero present, smallest non-zero id, largest id}; a second pass looks for a third distinct non-zero value
+__global__ void __launch_bounds__(256) k_label_stats_wide(const int* __restrict__ ids, int* __restrict__ stats, size_t plane) {
+    const int b = blockIdx.y;
+    const int* I = ids + (size_t)b * plane;
+    int cnt = 0, zero = 0, mn = 0x7fffffff, mx = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = I[i];
+        if (v != 0) { ++cnt; mn = min(mn, v); mx = max(mx, v); } else zero = 1;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    zero = __reduce_max_sync(0xffffffffu, zero);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(stats + 4 * b, cnt);
+        if (zero) atomicMax(stats + 4 * b + 1, 1);
+        atomicMin(stats + 4 * b + 2, mn);
+        atomicMax(stats + 4 * b + 3, mx);
+    }
+}
+__global__ void __launch_bounds__(256) k_label_third_wide(const int* __restrict__ ids, const int* __restrict__ stats,
+                                                          int* __restrict__ third, size_t plane) {
+    const int b = blockIdx.y;
+    const int* I = ids + (size_t)b * plane;
+    const int mn = stats[4 * b + 2], mx = stats[4 * b + 3];
+    int hit = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = I[i];
+        hit |= (v != 0 && v != mn && v != mx);
+    }
+    if (__any_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicMax(third + b, 1);
+}
+__global__ void k_stats_init(int* __restrict__ stats, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { stats[4 * b] = 0; stats[4 * b + 1] = 0; stats[4 * b + 2] = 0x7fffffff; stats[4 * b + 3] = 0; }
+}
+__global__ void k_stats_distinct(const int* __restrict__ stats, const int* __restrict__ third, int* __restrict__ n_distinct,
+                                 int* __restrict__ fg, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int cnt = stats[4 * b], zero = stats[4 * b + 1], mn = stats[4 * b + 2], mx = stats[4 * b + 3];
+    int d = zero + (cnt > 0 ? 1 : 0) + ((cnt > 0 && mn != mx) ? 1 : 0) + third[b];
+    n_distinct[b] = d > 3 ? 3 : d;
+    fg[b] = cnt;
+}
+// fg[b] <- stats[b][0]
+__global__ void k_stats_to_fg(const int* __restrict__ stats, int* __restrict__ fg, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) fg[b] = stats[4 * b];
+}
+
 // ---- ternary label / interior (my_transforms_direction.py:743-751, 763-770, 781) --------------------
-__global__ void __launch_bounds__(kBX* kBY) k_t_ternary(const uint8_t* __restrict__ ids, const int* __restrict__ fg,
+template <typename IdT>
+__global__ void __launch_bounds__(kBX* kBY) k_t_ternary(const IdT* __restrict__ ids, const int* __restrict__ fg,
                                                         int instance_level, uint8_t* __restrict__ ternary,
                                                         uint8_t* __restrict__ inside, uint8_t* __restrict__ interior,
                                                         int H, int W) {
     PX_COORDS
     if (!inb) return;
-    const uint8_t* I = ids + tile;
+    const IdT* I = ids + tile;
     if (instance_level >= 2) {
         // out_c != 3 (:721-739): no boundary class.  Mode 2: 2 where an instance id is set; mode 3: erosion (cross
         // minimum) of 2 * (label > 127.5), the caller hands in max(channel 0, channel 1).  new_label_inside is a
@@ -139,7 +192,7 @@ __global__ void __launch_bounds__(kBX* kBY) k_t_ternary(const uint8_t* __restric
         interior[tile + p] = on;
         return;
     }
-    auto val = [&](int q) -> int { const int v = I[q]; return instance_level ? v : (v > 127 ? 1 : 0); };
+    auto val = [&](int q) -> int { const int v = (int)I[q]; return instance_level ? v : (v > 127 ? 1 : 0); };
     const int v = val(p);
     int mx = v, mn = v;
     if (y > 0) { const int u = val(p - W); mx = max(mx, u); mn = min(mn, u); }
@@ -730,10 +783,12 @@ extern "C" size_t cdnet_encode_targets_workspace_bytes(int B, int H, int W) {
            pad256((size_t)B * 4) + pad256((size_t)B * 1024) + pad256((size_t)B * H * 4) + ws_process_workspace(B, H, W);
 }
 
-extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternary, uint16_t* point,
-                                    int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status, int B, int H,
-                                    int W, int num_classes, const double* gauss_w, void* ws, size_t ws_bytes,
-                                    void* stream) {
+template <typename IdT>
+static int encode_targets_impl(const IdT* ids, int instance_level, uint8_t* ternary, uint16_t* point, int64_t* direction,
+                               int32_t* inst_out, float* dir_out, int32_t* status, int B, int H, int W, int num_classes,
+                               const double* gauss_w, void* ws, size_t ws_bytes, void* stream) {
+    constexpr bool kWide = sizeof(IdT) == 4;
+    if (kWide && instance_level > 1) return CDNET_E_BADARG;  // int32 ids: the out_c = 3 transform only
     if (!ids || !ternary || !point || !direction || bad_dims(B, H, W)) return CDNET_E_BADARG;
     if (num_classes != 8 && num_classes != 16) return CDNET_E_BADARG;
     if (instance_level < 0 || instance_level > 5) return CDNET_E_BADARG;
@@ -806,18 +861,27 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
     {
         const size_t plane = (size_t)H * W;
         int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
-        CDNET_LAUNCH(k_label_stats, dim3(gx, B), 256, 0, st, ids, pres, fg, plane);
+        if (kWide) {
+            int* stats = pres;  // [B][4] in the (otherwise unused) presence table
+            CDNET_LAUNCH(k_stats_init, ceil_div(B, 256), 256, 0, st, stats, B);
+            CDNET_LAUNCH(k_label_stats_wide, dim3(gx, B), 256, 0, st, (const int*)ids, stats, plane);
+            CDNET_LAUNCH(k_stats_to_fg, ceil_div(B, 256), 256, 0, st, stats, fg, B);
+        } else {
+            CDNET_LAUNCH(k_label_stats, dim3(gx, B), 256, 0, st, (const uint8_t*)ids, pres, fg, plane);
+        }
     }
     if (instance_level >= 4) {
         // my_transforms.LabelEncoding (do_direction = 1, out_c = 3): its own ternary rule (csrc/training.cu) and
         // new_label_inside; modes 4 / 5 = instance ids / {0,255} label
-        int rc0 = cdnet_ternary_label(ids, nullptr, instance_level == 4 ? 0 : 1, ternary, B, H, W, stream);
-        if (rc0) return rc0;
-        const size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
-        CDNET_LAUNCH(k_t_inside_plain, (unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, st, ids, inside, n,
-                     instance_level == 4 ? 0 : 127);
+        if constexpr (!kWide) {
+            int rc0 = cdnet_ternary_label(ids, nullptr, instance_level == 4 ? 0 : 1, ternary, B, H, W, stream);
+            if (rc0) return rc0;
+            const size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+            CDNET_LAUNCH(k_t_inside_plain, (unsigned)(blocks > 65535 ? 65535 : blocks), 256, 0, st, ids, inside, n,
+                         instance_level == 4 ? 0 : 127);
+        }
     } else {
-        CDNET_LAUNCH(k_t_ternary, px_grid(B, H, W), px_block(), 0, st, ids, fg, instance_level, ternary, inside, interior, H, W);
+        CDNET_LAUNCH(k_t_ternary<IdT>, px_grid(B, H, W), px_block(), 0, st, ids, fg, instance_level, ternary, inside, interior, H, W);
     }
     // 2. instances: process(interior*255, min_size=5) (:759) or measure.label (:773), then dilation disk(1)
     nvtx_mark("targets: instances (process / label + dilation)");
@@ -831,8 +895,12 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
         if (!sub.ok) return CDNET_E_WORKSPACE;
         // out_c != 3 (:723-725, :734): the labelling itself is the instance map, nothing is dilated
         int32_t* dst = instance_level >= 2 ? inst : inst_raw;
-        if (instance_level == 2 || instance_level >= 4) rc = ccl_label_values_launch(ids, dst, nullptr, Lp, idmap, rowcnt, B, H, W, st);
-        else rc = ccl_label_launch(interior, dst, nullptr, Lp, idmap, rowcnt, B, H, W, 8, st);
+        rc = CDNET_E_BADARG;
+        if (instance_level == 2 || instance_level >= 4) {
+            if constexpr (!kWide) rc = ccl_label_values_launch(ids, dst, nullptr, Lp, idmap, rowcnt, B, H, W, st);
+        } else {
+            rc = ccl_label_launch(interior, dst, nullptr, Lp, idmap, rowcnt, B, H, W, 8, st);
+        }
     }
     if (rc) return rc;
     if (instance_level < 2) {
@@ -864,5 +932,40 @@ extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint
                      lablist, rowcnt, rowcnt + 1, tab, num_classes, H, W);
     }
     CDNET_LAUNCH(k_t_gauss, dim3(ceil_div(W, kGX), ceil_div(H, kGY), B), dim3(kGX, kGY), 0, st, cflag, (__half*)point, H, W);
+    return last_error();
+}
+
+extern "C" int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternary, uint16_t* point,
+                                    int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status, int B, int H,
+                                    int W, int num_classes, const double* gauss_w, void* ws, size_t ws_bytes,
+                                    void* stream) {
+    return encode_targets_impl<uint8_t>(ids, instance_level, ternary, point, direction, inst_out, dir_out, status, B, H, W,
+                                        num_classes, gauss_w, ws, ws_bytes, stream);
+}
+
+// int32 instance ids (no uint8 wrap at 256): the out_c = 3 transform, instance_level 0 / 1
+extern "C" int cdnet_encode_targets_i32(const int32_t* ids, int instance_level, uint8_t* ternary, uint16_t* point,
+                                        int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status, int B,
+                                        int H, int W, int num_classes, const double* gauss_w, void* ws, size_t ws_bytes,
+                                        void* stream) {
+    return encode_targets_impl<int32_t>(ids, instance_level, ternary, point, direction, inst_out, dir_out, status, B, H, W,
+                                        num_classes, gauss_w, ws, ws_bytes, stream);
+}
+
+// int32 ids: n_distinct[b] = min(number of distinct values, 3) (the reference only asks `> 2`), fg_count[b] = non-zero
+// pixels.  scratch: int32 [B,5]
+extern "C" int cdnet_label_stats_i32(const int32_t* ids, int32_t* n_distinct, int32_t* fg_count, int32_t* scratch, int B,
+                                     int H, int W, void* stream) {
+    if (!ids || !n_distinct || !fg_count || !scratch || bad_dims(B, H, W)) return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane = (size_t)H * W;
+    int gx = (int)((plane + 256 * 16 - 1) / (256 * 16));
+    int* stats = scratch;
+    int* third = scratch + 4 * (size_t)B;
+    CDNET_LAUNCH(k_stats_init, ceil_div(B, 256), 256, 0, st, stats, B);
+    CDNET_CUDA_OK(cudaMemsetAsync(third, 0, sizeof(int) * (size_t)B, st));
+    CDNET_LAUNCH(k_label_stats_wide, dim3(gx, B), 256, 0, st, ids, stats, plane);
+    CDNET_LAUNCH(k_label_third_wide, dim3(gx, B), 256, 0, st, ids, stats, third, plane);
+    CDNET_LAUNCH(k_stats_distinct, ceil_div(B, 256), 256, 0, st, stats, third, n_distinct, fg_count, B);
     return last_error();
 }

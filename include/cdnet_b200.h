@@ -192,6 +192,19 @@ int cdnet_encode_targets(const uint8_t* ids, int instance_level, uint8_t* ternar
                          int B, int H, int W, int num_classes, const double* gauss_w, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* The same transform on int32 instance ids, i.e. on label images loaded WITHOUT the uint8 truncation of
+ * data_folder.py:26,29,37 (`img.astype(np.uint8)` wraps ids at 256, so two touching nuclei whose ids are congruent
+ * mod 256 lose the boundary between them).  out_c = 3 forms only: instance_level 1 (instance ids) or 0 ({0,255} label).
+ * cdnet_label_stats_i32: n_distinct[b] = min(number of distinct values of tile b, 3) -- the reference only asks
+ * `len(np.unique(label_inside)) > 2` (my_transforms_direction.py:714-719) --, fg_count[b] = non-zero pixels;
+ * scratch: int32 [B,5]. */
+int cdnet_encode_targets_i32(const int32_t* ids, int instance_level, uint8_t* ternary, uint16_t* point,
+                             int64_t* direction, int32_t* inst_out, float* dir_out, int32_t* status,
+                             int B, int H, int W, int num_classes, const double* gauss_w, void* ws,
+                             size_t ws_bytes, void* stream);
+int cdnet_label_stats_i32(const int32_t* ids, int32_t* n_distinct, int32_t* fg_count, int32_t* scratch, int B, int H,
+                          int W, void* stream);
+
 /* ---- device-resident hand-off from the CNN ---------------------------
  * test_dam.py:299-450 + get_probmaps :983-1013 in one kernel: for each of the 8 test-time-augmentation
  * variants (order: identity, hf, vf, hvf, r90, r90_hf, r90_vf, r90_hvf; the rotated ones live in a [W,H] frame)

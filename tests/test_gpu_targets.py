@@ -137,3 +137,29 @@ def test_encode_targets_plan_host_buffers(kernel_api):
     assert np.array_equal(tern[0], z["ternary"])
     assert np.array_equal(point[0].view(np.uint16), z["point"].view(np.uint16))
     _check_direction(direction[0], z["direction"].astype(np.int64), lab, meta["num_classes"], "plan t_128")
+
+
+def test_label_encoding_int32_ids(kernel_api, tmp_path):
+    """more than 255 nuclei with their ORIGINAL ids (no uint8 wrap, data_folder.py:26-37): int32 label image from
+    compat.data_folder.img_loader(keep_ids=True) through the int32 entry point of the target transform, against the
+    restatement run on the same int32 image; the default loader reproduces the reference's wrap"""
+    from oracle import restate as O
+    from cdnet_b200 import synth
+    from cdnet_b200.compat import data_folder
+    ids = synth.instance_map(77, 300, 320, 400).astype(np.int64)
+    assert ids.max() > 255
+    path = str(tmp_path / "tile.npy")
+    np.save(path, ids)
+    wide = data_folder.img_loader(path, 3, keep_ids=True)
+    assert wide.dtype == np.int32 and np.array_equal(wide, ids)
+    wrapped = np.asarray(data_folder.img_loader(path, 3))
+    assert wrapped.dtype == np.uint8 and np.array_equal(wrapped, ids.astype(np.uint8))
+    ref = O.label_encoding(wide.copy(), 3, num_classes=8, literal=False)
+    res = kernel_api.LabelEncoding(3, 1, 1, num_classes=8)((None, None, wide.copy()))
+    assert np.array_equal(np.asarray(res[2]), ref[0])
+    assert np.array_equal(res[3].view(np.uint16), ref[1].view(np.uint16))
+    _check_direction(res[4], ref[2], wide, 8, "int32 ids")
+    # a {0, 70000} two-valued int32 image is NOT instance level (two distinct values)
+    two = (ids > 0).astype(np.int32) * 70000
+    nd, fg = kernel_api.label_stats_cuda(to_dev(kernel_api, kernel_api.torch.from_numpy(two)[None]))
+    assert int(nd[0]) == 2 and int(fg[0]) == int((ids > 0).sum())
