@@ -533,3 +533,26 @@ def test_tta_merge_golden(kernel_api):
     assert np.allclose(prob[0].cpu().numpy(), z["tta_prob"], rtol=1e-5, atol=1e-7)
     assert np.array_equal(point[0].cpu().numpy().view(np.uint32), z["tta_point"].view(np.uint32))
     assert (dcm[0].cpu().numpy() != z["tta_dcm"]).mean() < 2e-3  # float near-ties only
+
+
+@pytest.mark.gpu
+def test_device_guard_other_gpu(cuda_api):
+    """tensors on cuda:1 while cuda:0 is the current device: the call runs on the tensors' device (api._on_tensor_device)
+    and gives the same labels as on cuda:0.  Needs two GPUs (skipped on the single-GPU test box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from cdnet_b200 import synth
+    api = cuda_api
+    d = synth.postproc_inputs(5, 160, 200, 20)
+    torch.cuda.set_device(0)
+    on0 = [torch.from_numpy(np.ascontiguousarray(d[k])).to("cuda:0")[None] for k in ("dcm", "prob", "point")]
+    on1 = [t.to("cuda:1") for t in on0]
+    lab0, _ = api.dam_postprocess_cuda(*on0, 9, 20, 2, 0)
+    assert torch.cuda.current_device() == 0
+    lab1, _ = api.dam_postprocess_cuda(*on1, 9, 20, 2, 0)
+    assert lab1.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(lab0.cpu(), lab1.cpu())
+    plan = api.DamPostprocessPlan(1, 160, 200, 9, 20, 2, 0, device=1)
+    plan.h_dcm[0], plan.h_prob[0], plan.h_point[0] = d["dcm"], d["prob"], d["point"]
+    assert np.array_equal(plan.run()[0], lab0[0].cpu().numpy())
