@@ -207,6 +207,18 @@ def cpu_baseline(n_tiles=2):
     return out
 
 
+def _worker_single_thread():
+    """pool workers are single-threaded, like torch DataLoader workers (which call torch.set_num_threads(1)): with the
+    default of one intra-op thread per core in EVERY process, 14 workers on 16 cores fight over 224 threads"""
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+
+
 def run_reference(a):
     """the reference's own CPU implementation of the path on all host cores: one tile per worker process per step
     (mirrors DataLoader(num_workers) / one image per process); verbatim reference when its tree is present."""
@@ -220,7 +232,7 @@ def run_reference(a):
     ctx = mp.get_context("spawn")
     budget_s = float(os.environ.get("CDNET_REF_BUDGET_S", "150"))
     rows = H
-    with ctx.Pool(workers) as pool:
+    with ctx.Pool(workers, initializer=_worker_single_thread) as pool:
         jobs = [(100 + i, kind, H) for i in range(workers)]
         single = None
         for w in range(a.warmup):
@@ -238,7 +250,8 @@ def run_reference(a):
         dt = time.perf_counter() - t0
     mpx = a.steps * workers * rows * W / 1e6
     val = mpx / dt
-    sample = _sample_text(kind, workers, "one tile per worker process per step, %d worker processes" % workers, rows)
+    sample = _sample_text(kind, workers, "one tile per worker process per step, %d single-threaded worker processes "
+                          "(like DataLoader workers)" % workers, rows)
     line = {"impl": "reference", "metric": "Mpixel/s CDNet DAM post-processing (test_dam.py:455-563)",
             "value": val, "unit": "Mpixel/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
