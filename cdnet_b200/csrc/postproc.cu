@@ -14,6 +14,7 @@
 //     or process() = watershed chain (watershed.cu) when postproc == 1             test_dam.py:559
 //   k_label_dilate    disk(radius)                                                 test_dam.py:563
 #include <math.h>
+#include <stdlib.h>
 
 #include "internal.h"
 
@@ -322,6 +323,33 @@ __global__ void __launch_bounds__(256) k_plain_inside(const float* __restrict__ 
     }
 }
 
+// one side stream + two events per (host thread, device), created on first use; CDNET_NO_SIDE_STREAM=1 turns the
+// overlap off (everything on the caller's stream)
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static SideStream* side_stream() {
+#ifdef CDNET_SIMT  // the host emulator of the test tier has no streams
+    return nullptr;
+#else
+    static int off = -1;
+    if (off < 0) off = getenv("CDNET_NO_SIDE_STREAM") ? 1 : 0;
+    if (off) return nullptr;
+    static thread_local SideStream cache[16];
+    static thread_local bool ready[16] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (!ready[dev]) {
+        if (cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ready[dev] = true;
+    }
+    return &cache[dev];
+#endif
+}
+
 static size_t tail_workspace(int B, int H, int W) {
     size_t a = fill_remove_label_workspace(B, H, W);
     const size_t c = ws_process_workspace(B, H, W), r = rle_tail_workspace(B, H, W);
@@ -382,14 +410,27 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
     if (status) CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, st));
     CDNET_RANGE("cdnet_dam_postproc");
     int rc;
+    // the point-map maximum (DRAM-bound) does not depend on the direction-difference codes (ALU-bound): it runs on a
+    // side stream next to them and joins before the boost (fork / join with events, capturable in a CUDA graph)
+    SideStream* side = g_prof_on ? nullptr : side_stream();  // the per-kernel profiler times kernels one at a time
+    if (side) {
+        CDNET_CUDA_OK(cudaEventRecord(side->fork, st));
+        CDNET_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, side->stream));
+        point_max_launch(point, pmax, B, plane, side->stream);
+        CDNET_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    }
     {
         CDNET_RANGE("ddm codes");
         rc = ddm_codes_launch(dcm, codes, flags, B, n_maps, H, W, direction_classes, st);
     }
+    if (side) CDNET_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
     if (rc) return rc;
     CDNET_RANGE("point gate + boost + argmax, then labels");
-    CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, st));
-    point_max_launch(point, pmax, B, plane, st);
+    if (!side) {
+        CDNET_CUDA_OK(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * (size_t)B, st));
+        point_max_launch(point, pmax, B, plane, st);
+    }
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0) {
         CDNET_LAUNCH(k_boost_prep, B, 256, 0, st, flags, pmax, status, prep, n_maps);
         CDNET_LAUNCH(k_boost_inside4<true>, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes,

@@ -108,6 +108,7 @@ template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 
 // ---- kernel launch --------------------------------------------------------------------------------
