@@ -425,7 +425,7 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
             dcm, prob, point = asdev(d["dcm"]), asdev(d["prob"]), asdev(d["point"])
             assert dcm.shape[-2] == sh.Hl and dcm.shape[-1] == W
             sh.dcm_ext = be.empty((dcm.shape[0], sh.He, W), "uint8")
-            sh.prob_ext = be.empty((3, sh.He, W), "float32")
+            sh.prob_ext = be.zeros((3, sh.He, W), "float32")
             sh.point_ext = be.empty((1, sh.He, W), "float32")
             sh.dcm_ext[:, sh.lo:sh.lo + sh.Hl] = dcm
             sh.prob_ext[:, sh.lo:sh.lo + sh.Hl] = prob
@@ -616,4 +616,8 @@ def alloc_shard_buffers(be, rank, world, H, W, n_maps):
          "point_ext": be.empty((1, He, W), "float32")}
     for k in ("dcm", "prob", "point"):
         d[k] = d[k + "_ext"][:, lo:lo + (r1 - r0)]
+    # the ghost rows of prob are never exchanged (the boost is pointwise in prob and its result on ghost rows is replaced by
+    # the neighbour's): give them a defined value once, so that no kernel ever reads uninitialised memory
+    d["prob_ext"][:, :lo] = 0
+    d["prob_ext"][:, lo + (r1 - r0):] = 0
     return d

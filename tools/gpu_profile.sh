@@ -5,8 +5,8 @@ TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-extra all --device-only"
-# one step = 12 launches; skip the population launch + 3 warm-ups, list two steps
+# one step = 13 launches; skip the population launch + 3 warm-ups, list two steps
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -s 48 -c 24 --csv --log-file $OUT/${TAG}_launches.csv $B > $OUT/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
-timeout 500 ncu --set full --clock-control none --import-source on -s 48 -c 12 -f -o $OUT/${TAG}_step $B > $OUT/${TAG}_step.log 2>&1
+    -s 52 -c 26 --csv --log-file $OUT/${TAG}_launches.csv $B > $OUT/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
+timeout 500 ncu --set full --clock-control none --import-source on -s 52 -c 13 -f -o $OUT/${TAG}_step $B > $OUT/${TAG}_step.log 2>&1
 echo "ncu full rc=$?"
