@@ -313,6 +313,10 @@ def extra_paths(torch, dist, api, peak, rank, world, plan, timed, skip):
     out = {}
     if "slide" not in skip:
         _fenced(out, "whole_slide", lambda: BC.whole_slide(torch, dist, rank, world, peak=peak))
+    if "slide_ws" not in skip:
+        # the same slide through postproc = 1 (process(): EDT, markers, watershed), own rows + overlap rows per rank
+        _fenced(out, "whole_slide_watershed", lambda: BC.whole_slide(torch, dist, rank, world, peak=peak, postproc=1,
+                                                                     steps=2))
     if "targets" not in skip:
         _fenced(out, "targets", lambda: BC.targets_config2(torch, dist, rank, world, peak=peak))
     if "config3" not in skip:

@@ -31,6 +31,9 @@ SIGNATURES = {
     "cdnet_edt_workspace_bytes": (c_size_t, [c_int] * 3),
     "cdnet_edt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cdnet_ws_postproc_workspace_bytes": (c_size_t, [c_int] * 3),
+    "cdnet_shard_ws_relabel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "cdnet_shard_ws_process": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_size_t, c_void_p]),
     "cdnet_ws_postproc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_size_t, c_void_p]),
     "cdnet_dam_postproc_workspace_bytes": (c_size_t, [c_int] * 3),
@@ -89,7 +92,7 @@ SIGNATURES = {
 }
 
 E_BADARG, E_WORKSPACE = 1, 2
-S_DDM_CONSTANT, S_WS_OVERFLOW, S_NO_BACKGROUND, S_CLASS_RANGE = 1, 2, 16, 32
+S_DDM_CONSTANT, S_WS_OVERFLOW, S_NO_BACKGROUND, S_CLASS_RANGE, S_SHARD_OVERFLOW = 1, 2, 16, 32, 64
 S_WS_CONTESTED_SHIFT = 8  # status >> 8: watershed pixels two equal-priority age-0 markers compete for (cdnet_b200.h)
 
 _lib = None

@@ -489,6 +489,53 @@ extern "C" int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t
     return ws_process_launch(pred01, labels, status, B, H, W, min_size, ws_flag, ws, ws_bytes, st);
 }
 
+// process() on the extended tile of a row-sharded slide (cdnet_b200/sharded.py, postproc = 1): rows [own_lo, own_hi)
+// are the rank's own, the rest is overlap.  Also reports the largest marker id per row (before small markers are
+// dropped), from which the ranks number the markers of the whole slide, and CDNET_S_SHARD_OVERFLOW.
+extern "C" int cdnet_shard_ws_process(const uint8_t* pred01, int32_t* labels, int32_t* marker_rowmax, int32_t* status,
+                                      int H, int W, int own_lo, int own_hi, int min_size, void* ws, size_t ws_bytes,
+                                      void* stream) {
+    if (!pred01 || !labels || !marker_rowmax || !status || bad_dims(1, H, W) || own_lo < 0 || own_hi > H ||
+        own_lo >= own_hi)
+        return CDNET_E_BADARG;
+    if (ws_bytes < ws_process_workspace(1, H, W)) return CDNET_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    CDNET_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    return ws_process_launch(pred01, labels, status, 1, H, W, min_size, 1, ws, ws_bytes, st, marker_rowmax, own_lo, own_hi);
+}
+
+// tile-local marker ids of a rank's own rows -> slide-global ids, one pass.  sc = {markers that start above the own
+// rows, markers that start on them (= owned), markers owned by the lower ranks} on the device; an owned id l maps to
+// sc[2] + l - sc[0]; any other id was adopted from a row neighbour through lut (0 = nobody claimed it -> err).
+__global__ void __launch_bounds__(256) k_shard_ws_relabel(const int32_t* __restrict__ labels, const int32_t* __restrict__ sc,
+                                                          const int32_t* __restrict__ lut, int32_t* __restrict__ out,
+                                                          int32_t* __restrict__ err, size_t n) {
+    const int above = sc[0], owned = sc[1], off = sc[2];
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = labels[i];
+        int g = 0;
+        if (l > above && l <= above + owned) g = off + l - above;
+        else if (l > 0) {
+            g = lut[l];
+            bad = bad || g == 0;
+        }
+        out[i] = g;
+    }
+    if (bad) *err = 1;
+}
+
+extern "C" int cdnet_shard_ws_relabel(const int32_t* labels, const int32_t* scalars, const int32_t* lut, int32_t* out,
+                                      int32_t* err, int rows, int W, void* stream) {
+    if (!labels || !scalars || !lut || !out || !err || rows <= 0 || W <= 0) return CDNET_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)rows * W;
+    const size_t blocks = (n + 1023) / 1024;
+    CDNET_LAUNCH(k_shard_ws_relabel, (unsigned)(blocks > 148u * 16 ? 148u * 16 : blocks), 256, 0, st, labels, scalars, lut, out,
+                 err, n);
+    return last_error();
+}
+
 // ---- whole-slide shard pieces of the DAM chain (cdnet_b200/sharded.py) -----------------------------
 // max of the shard's own point-map rows as an order-preserving uint32 (the host all-reduces MAX)
 extern "C" int cdnet_shard_point_max(const float* point, uint32_t* pmax, size_t n, void* stream) {

@@ -148,6 +148,39 @@ __global__ void __launch_bounds__(kBX* kBY) k_ws_contested(const uint8_t* __rest
     if (lane == 0 && m) atomicAdd(status + b, __popc(m) << 8);
 }
 
+// rowmax[b][y] = largest marker id on row y.  Ids are handed out in raster order of the components' first pixels, so
+// max(rowmax[0..y]) = number of marker components that start on rows 0..y
+__global__ void __launch_bounds__(kBX* kBY) k_label_rowmax(const int* __restrict__ labels, int* __restrict__ rowmax,
+                                                           int H, int W) {
+    PX_COORDS
+    const int l = inb ? labels[tile + p] : 0;
+    const int m = __reduce_max_sync(0xffffffffu, l);  // a warp covers 32 pixels of one row (kBX = 128)
+    if (lane == 0 && m > 0) atomicMax(rowmax + (size_t)b * H + y, m);
+}
+
+// Row-sharded callers hand in an extended tile and use the rows [own_lo, own_hi) only.  A 4-connected component of
+// the mask that touches those rows must lie inside the tile completely, or its distance normalisation and markers
+// are not the slide's: a component that reaches an outer row of the tile (0 when own_lo > 0, H-1 when own_hi < H)
+// and the own rows sets CDNET_S_SHARD_OVERFLOW.  L holds flat roots = first raster pixel of the component.
+// step 0: clear the marks of the components on row own_hi-1; 1: mark those on row H-1; 2: test (both seams).
+__global__ void __launch_bounds__(256) k_shard_overflow(const uint8_t* __restrict__ pred, const int* __restrict__ L,
+                                                        int* __restrict__ mark, int32_t* __restrict__ status, int H,
+                                                        int W, int own_lo, int own_hi, int step) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    if (x >= W) return;
+    const size_t tile = (size_t)b * H * W;
+    const int pb = (own_hi - 1) * W + x, pl = (H - 1) * W + x, pt = own_lo * W + x;
+    bool bad = false;
+    if (own_hi < H) {
+        if (step == 0 && pred[tile + pb]) mark[tile + L[tile + pb]] = 0;
+        if (step == 1 && pred[tile + pl]) mark[tile + L[tile + pl]] = 1;
+        if (step == 2 && pred[tile + pb]) bad = mark[tile + L[tile + pb]] == 1;
+    }
+    if (step == 2 && own_lo > 0 && pred[tile + pt]) bad = bad || L[tile + pt] < W;  // root on row 0
+    if (bad) atomicOr(status + b, CDNET_S_SHARD_OVERFLOW);
+}
+
 __global__ void __launch_bounds__(kBX* kBY) k_bbox_init(int* __restrict__ ymax, int* __restrict__ xmin,
                                                         int* __restrict__ xmax, int H, int W) {
     PX_COORDS
@@ -414,7 +447,8 @@ __global__ void k_state_mask(const uint8_t* __restrict__ state, uint8_t* __restr
 }
 
 int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W, int min_size,
-                      int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st, int32_t* marker_rowmax, int own_lo,
+                      int own_hi) {
     const size_t n = (size_t)B * H * W;
     if (n >= 4294967296ull) return CDNET_E_BADARG;  // root list holds 32-bit batch-global pixel indices
     CDNET_RANGE("process(): EDT, markers, watershed, remove small");
@@ -448,6 +482,10 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     if (rc) return rc;
     CDNET_CUDA_OK(cudaMemsetAsync(D, 0, n * 4, st));
     CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, status, H, W);
+    if (marker_rowmax && status && (own_lo > 0 || own_hi < H))
+        for (int step = 0; step < 3; ++step)  // E is free until the flood
+            CDNET_LAUNCH(k_shard_overflow, dim3(ceil_div(W, 256), B), 256, 0, st, pred01, A, E, status, H, W, own_lo,
+                         own_hi, step);
     // 2. uint8 distance, its negation, markers (:25-26, :39-41, :47)
     CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, H, W);
     // 3. fill holes, cross erosion, label, remove small (:42-46)
@@ -456,6 +494,11 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     CDNET_LAUNCH(k_erode_cross, px_grid(B, H, W), px_block(), 0, st, state, mk, H, W);
     rc = ccl_label_launch(mk, labels, nullptr, C, Bp, rowcnt, B, H, W, 4, st);
     if (rc) return rc;
+    if (marker_rowmax) {
+        // markers of all sizes: the small ones dropped next keep their ids reserved (:46 leaves gaps)
+        CDNET_CUDA_OK(cudaMemsetAsync(marker_rowmax, 0, sizeof(int32_t) * (size_t)B * H, st));
+        CDNET_LAUNCH(k_label_rowmax, px_grid(B, H, W), px_block(), 0, st, labels, marker_rowmax, H, W);
+    }
     rc = remove_small_labels_launch(labels, counts, B, H, W, min_size, st);
     if (rc) return rc;
     // 4. flood (:47)

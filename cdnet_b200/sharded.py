@@ -266,6 +266,63 @@ class CudaBackend(object):
                                        out_dtype=getattr(self.torch, out_dtype))
         return t[0]
 
+    # -- postproc = 1: process() on own rows + overlap, slide-global marker ids
+    def ws_process(self, inside_ext, own_lo, own_hi, min_size):
+        """-> (labels int32 [He,W] with tile-local marker ids, rowmax int32 [He], status int32 [1])"""
+        from ._cabi import check
+        He, W = inside_ext.shape
+        labels = self.empty((He, W), "int32")
+        rowmax = self.empty((He,), "int32")
+        status = self.empty((1,), "int32")
+        ws = self.api._workspace(self.L.cdnet_ws_postproc_workspace_bytes(1, He, W), self.dev)
+        check(self.L.cdnet_shard_ws_process(inside_ext.data_ptr(), labels.data_ptr(), rowmax.data_ptr(),
+                                            status.data_ptr(), He, W, int(own_lo), int(own_hi), int(min_size),
+                                            ws.data_ptr(), ws.numel(), self._st()), "shard_ws_process")
+        return labels, rowmax, status
+
+    def marker_ranges(self, rowmax, own_lo, own_hi):
+        """markers that start above the own rows, markers that start on them: two [1] int32 device tensors"""
+        t = self.torch
+        a = rowmax[:own_lo].max().reshape(1) if own_lo > 0 else self.zeros((1,), "int32")
+        b = t.maximum(a, rowmax[:own_hi].max().reshape(1))
+        return a, b - a
+
+    def ws_own_ids(self, labels, scalars):
+        """slide-global id of the markers this rank owns (local ids above+1 .. above+owned), 0 elsewhere; scalars =
+        [above, owned, offset] on the device"""
+        t = self.torch
+        above, owned, off = scalars[0], scalars[1], scalars[2]
+        mine = (labels > above) & (labels <= above + owned)
+        return t.where(mine, labels - above + off, t.zeros_like(labels))
+
+    def ws_adopt(self, lut, local_rows, global_rows):
+        """lut[local id] = the owner's id, read where the neighbour's own rows overlap this tile"""
+        t = self.torch
+        l, g = local_rows.reshape(-1), global_rows.reshape(-1)
+        ok = (l > 0) & (g > 0)
+        zero = t.zeros_like(l)
+        lut.index_copy_(0, t.where(ok, l, zero).long(), t.where(ok, g, zero))   # entry 0 stays 0
+
+    def ws_relabel(self, labels_own, scalars, lut, out):
+        """final labels of the own rows into `out` (a [Hl,W] view); -> [1] int32, 1 if a label found no owner"""
+        from ._cabi import check
+        Hl, W = labels_own.shape
+        assert labels_own.is_contiguous() and out.is_contiguous()
+        err = self.zeros((1,), "int32")
+        check(self.L.cdnet_shard_ws_relabel(labels_own.data_ptr(), scalars.data_ptr(), lut.data_ptr(), out.data_ptr(),
+                                            err.data_ptr(), Hl, W, self._st()), "shard_ws_relabel")
+        return err
+
+    def pack_status_ws(self, flags, ws_status, unresolved):
+        """[flags word, error bits] like pack_status: 4 = a nucleus reaches beyond the overlap, 8 = no background,
+        16 = unresolved marker id, 32 = watershed queue overflow"""
+        t = self.torch
+        from ._cabi import S_NO_BACKGROUND, S_SHARD_OVERFLOW, S_WS_OVERFLOW
+        w = ws_status.reshape(-1)[:1]
+        err = (((w & S_SHARD_OVERFLOW) != 0).to(t.int32) * 4 + ((w & S_NO_BACKGROUND) != 0).to(t.int32) * 8 +
+               unresolved.reshape(-1)[:1] * 16 + ((w & S_WS_OVERFLOW) != 0).to(t.int32) * 32)
+        return t.cat([flags.reshape(-1)[:1].to(t.int32), err.to(t.int32)])
+
     # -- seam rounds (csrc/seam.cu)
     def seam_init(self, sh, world, W):
         sh.cap = 4 * W + 1
@@ -371,10 +428,100 @@ def _seam_tables(be, comm, S, valid_of, attr_of, round_id):
     return comm.allgather_tensor(be, tables)
 
 
-def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64",
-                      timings=None, defer_checks=False):
-    """Direction-aware post-processing (test_dam.py:455-563, postproc = 0) of an H x W slide whose rows
-    are partitioned over comm.world ranks.
+def _check_flags(flags, n_maps):
+    for t in range(n_maps):
+        f = (flags >> (3 * t)) & 7
+        if f in (0, 1, 2, 4):
+            raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
+
+
+def _watershed_tail(S, comm, be, W, r, out_dtype, K, halo, _mark, n_maps):
+    """postproc = 1 after the boost: inside mask of the own rows -> process() -> dilation (test_dam.py:559-563).
+
+    Why overlap + ownership is exact: process() treats every 4-connected component of the mask on its own (distance
+    normalised by the component's maximum :24-26, markers inside it :39-46, flooding confined to the mask :47), apart
+    from the marker numbering of :44, which is the raster order of the markers' first pixels over the slide.  A
+    component that touches a rank's rows and stays inside its extended tile is therefore segmented there exactly as on
+    the whole slide, with tile-local ids; the kernel reports when a component does not stay inside.  Ids: a marker
+    belongs to the rank whose own rows hold its first pixel; tile-local ids are raster ordered too, so the owner's
+    slide-global id is (markers owned by lower ranks) + (rank among its own).  Labels of the own rows that belong to a
+    neighbour's marker are read off the neighbour's labels on the overlap rows, where both tiles show the same
+    regions."""
+    _mark("phase 3: watershed")
+    h_in = halo(lambda sh, a, b: sh.inside_own[a:b], K)
+    counts = []
+    for sh, (ia, ib) in zip(S, h_in):
+        sh.kt = ia.shape[-2] if ia is not None else 0
+        kb = ib.shape[-2] if ib is not None else 0
+        sh.inw = be.empty((sh.kt + sh.Hl + kb, W), "uint8")
+        sh.inw[sh.kt:sh.kt + sh.Hl] = sh.inside_own
+        if ia is not None:
+            sh.inw[:sh.kt] = ia
+        if ib is not None:
+            sh.inw[sh.kt + sh.Hl:] = ib
+        # min_size 10: what the DAM path passes to process() (test_dam.py:559)
+        sh.wl, rowmax, sh.wstat = be.ws_process(sh.inw, sh.kt, sh.kt + sh.Hl, 10)
+        sh.n_above, sh.n_owned = be.marker_ranges(rowmax, sh.kt, sh.kt + sh.Hl)
+        counts.append(sh.n_owned)
+    g_cnt = comm.allgather_tensor(be, counts)
+    _mark("phase 4: marker ids")
+    top = lambda sh, a, b: slice(sh.kt + a, sh.kt + b)
+    for sh, gc in zip(S, g_cnt):
+        sh.scal = be.stack([sh.n_above.reshape(()), sh.n_owned.reshape(()), be.exclusive_offset(gc, sh.rank).reshape(())])
+    # the owners' ids on the K rows either side of every seam (only those rows are ever looked at)
+    h_ids = halo(lambda sh, a, b: be.ws_own_ids(sh.wl[top(sh, a, b)], sh.scal), K)
+    packed = []
+    for sh, (la, lb) in zip(S, h_ids):
+        lut = be.zeros((sh.wl.shape[0] * W // 2 + 2,), "int32")   # more entries than 4-connected components
+        if la is not None:
+            be.ws_adopt(lut, sh.wl[:sh.kt], la)
+        if lb is not None:
+            be.ws_adopt(lut, sh.wl[sh.kt + sh.Hl:], lb)
+        # final labels land in the middle of the buffer the dilation reads, with room for the neighbours' rows
+        sh.pt = r if sh.has_top else 0
+        sh.big = be.empty((sh.pt + sh.Hl + (r if sh.has_bottom else 0), W), "int32")
+        sh.final = sh.big[sh.pt:sh.pt + sh.Hl]
+        unresolved = be.ws_relabel(sh.wl[sh.kt:sh.kt + sh.Hl], sh.scal, lut, sh.final)
+        packed.append(be.pack_status_ws(sh.flags, sh.wstat, unresolved))
+        del lut
+    g_stat = comm.allgather_tensor(be, packed)
+    _mark("phase 6: dilation")
+    outs = []
+    h_lab = halo(lambda sh, a, b: sh.final[a:b], r) if r > 0 else [(None, None)] * len(S)
+    for sh, (la, lb) in zip(S, h_lab):
+        if la is not None:
+            sh.big[:sh.pt] = la
+        if lb is not None:
+            sh.big[sh.pt + sh.Hl:] = lb
+        outs.append(be.dilate(sh.big, r, out_dtype)[sh.pt:sh.pt + sh.Hl])
+    _mark("end")
+
+    def check():
+        # every rank looks at the error bits of ALL ranks, so that either all of them raise or none does
+        h = np.asarray(be.to_host(g_stat[0])).reshape(-1, 2)
+        _check_flags(int(h[:1, 0].astype(np.int32).view(np.uint32)[0]), n_maps)
+        err = int(np.bitwise_or.reduce(h[:, 1]))
+        if err & 8:
+            raise ValueError("the mask of a shard has no background pixel (postproc_other.py:18-19 raises there)")
+        if err & 4:
+            raise RuntimeError("whole-slide watershed: a nucleus reaches beyond the %d overlap rows of a shard; "
+                               "raise `overlap` (or use fewer ranks)" % K)
+        if err & 16:
+            raise RuntimeError("whole-slide watershed: a label of a shard found no owner")
+        if err & 32:
+            raise RuntimeError("watershed queue overflow")
+    return outs, check
+
+
+def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype=None,
+                      timings=None, defer_checks=False, postproc=0, overlap=128):
+    """Direction-aware post-processing (test_dam.py:455-563) of an H x W slide whose rows are partitioned over
+    comm.world ranks.  postproc = 0: fill holes / remove small / label (exact for any component, seam union-find).
+    postproc = 1: process() = marker-controlled watershed (test_dam.py:559, postproc_other.py:32-48); every rank
+    runs it on its own rows plus `overlap` rows of each neighbour and the ranks agree on slide-global marker ids --
+    exact as long as no nucleus that touches a rank's rows reaches beyond its overlap rows, RuntimeError otherwise
+    (the distance normalisation of a nucleus needs the whole nucleus).  out_dtype defaults to the reference's: int64
+    for postproc 0, int32 for postproc 1.
 
     shards: one dict per LOCAL rank (comm.local_ranks order), either with the rank's OWN rows as numpy or
     backend arrays -- dcm uint8 [T,Hl,W] (T = 1 or 8), prob float32 [3,Hl,W], point float32 [1,Hl,W] -- or
@@ -388,6 +535,14 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
     graph (SlidePlan)."""
     G = comm.world
     parts = row_partition(H, G)
+    postproc = int(postproc)
+    if postproc not in (0, 1):
+        raise ValueError("whole-slide post-processing supports postproc 0 and 1")
+    if out_dtype is None:
+        out_dtype = "int64" if postproc == 0 else "int32"
+    if postproc == 1 and G > 1 and min(b - a for a, b in parts) < max(int(overlap), int(radius), 1):
+        raise ValueError("whole-slide watershed: shards need at least overlap = %d rows each (H = %d over %d ranks)"
+                         % (int(overlap), H, G))
     if G > 1 and min(b - a for a, b in parts) < max(2, int(radius)):
         # phase 6 fetches radius-1 label rows from each row neighbour only: a shard thinner than the radius would need
         # rows from two shards away
@@ -403,6 +558,14 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
             import torch
             torch.cuda.synchronize()
             _marks.append((name, time.perf_counter()))
+
+    def _report():
+        if timings is not None:
+            for i in range(len(_marks) - 1):
+                timings[_marks[i][0]] = 1e3 * (_marks[i + 1][1] - _marks[i][1])
+        if _timing and timings is None and S and S[0].rank == 0:
+            print("shard timing (ms):", ", ".join("%s %.2f" % (_marks[i][0], 1e3 * (_marks[i + 1][1] - _marks[i][1]))
+                                                  for i in range(len(_marks) - 1)), flush=True)
 
     _mark("phase 0: set-up")
     S = []
@@ -477,6 +640,13 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         # prob needs no halo (the boost is pointwise in prob); its ghost rows are never looked at
         sh.inside = be.boost(sh.codes, sh.flags, sh.point_ext.reshape(sh.He, W), pmax, sh.prob_ext, n_maps)
         sh.inside_own = sh.inside[sh.lo:sh.lo + sh.Hl]
+    if postproc == 1:
+        outs, check = _watershed_tail(S, comm, be, W, int(radius), out_dtype, int(overlap), halo, _mark, n_maps)
+        _report()
+        if defer_checks:
+            return outs, check
+        check()
+        return outs
     h_in = halo(lambda sh, a, b: sh.inside_own[a:b], 1)
     for sh, (ia, ib) in zip(S, h_in):
         fill_ghosts(sh, sh.inside, ia, ib)
@@ -545,12 +715,7 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         out = be.dilate(sh.lab_big, r, out_dtype)[top:top + sh.Hl]
         outs.append(out)
     _mark("end")
-    if timings is not None:
-        for i in range(len(_marks) - 1):
-            timings[_marks[i][0]] = 1e3 * (_marks[i + 1][1] - _marks[i][1])
-    if _timing and timings is None and S and S[0].rank == 0:
-        print("shard timing (ms):", ", ".join("%s %.2f" % (_marks[i][0], 1e3 * (_marks[i + 1][1] - _marks[i][1]))
-                                              for i in range(len(_marks) - 1)), flush=True)
+    _report()
     # ---- the only host round trip: status of the whole slide (one small tensor, packed while enqueueing)
     packed = [be.pack_status(sh.flags, sh.tables) for sh in S] if hasattr(be, "pack_status") else None
 
@@ -561,10 +726,7 @@ def postprocess_slide(shards, comm, H, W, be, direction_classes=9, min_area=20, 
         else:
             flags = be.flags_to_host(S[0].flags)
             err = max(be.seam_errors(sh.tables) for sh in S)
-        for t in range(n_maps):
-            f = (flags >> (3 * t)) & 7
-            if f in (0, 1, 2, 4):
-                raise AssertionError("constant direction map: generate_dd_map is NaN (test_dam.py:535)")
+        _check_flags(flags, n_maps)
         if err & 1:
             raise RuntimeError("seam pixels were classified differently by two neighbouring ranks")
         if err & 2:
@@ -584,16 +746,19 @@ class SlidePlan(object):
     capturable) is recorded once and replayed.  `bufs` are the rank's extended buffers (alloc_shard_buffers); fill the
     dcm / prob / point views, call run(), read `labels` ([Hl, W], the rank's own rows).  CUDA backend only."""
 
-    def __init__(self, bufs, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype="int64"):
+    def __init__(self, bufs, comm, H, W, be, direction_classes=9, min_area=20, radius=2, out_dtype=None, postproc=0,
+                 overlap=128):
         import torch
         self.torch, self.be = torch, be
         args = ([bufs], comm, H, W, be, direction_classes, min_area, radius, out_dtype)
-        postprocess_slide(*args)  # eager warm-up: scratch memory, kernel attributes, NCCL channels
+        kw = dict(postproc=postproc, overlap=overlap)
+        postprocess_slide(*args, **kw)  # eager warm-up: scratch memory, kernel attributes, NCCL channels
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the graph's private pool holds the step's intermediates from here on
         self.graph = torch.cuda.CUDAGraph()
         # thread_local: the NCCL watchdog thread may query events while this thread captures
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            outs, self._check = postprocess_slide(*args, defer_checks=True)
+            outs, self._check = postprocess_slide(*args, defer_checks=True, **kw)
         self.labels = outs[0]
 
     def launch(self):

@@ -41,6 +41,7 @@ extern "C" {
                                       * EQUAL priority and different labels compete for (their pop order is where
                                       * scikit-image's heap and this build's raster order may differ; 0 = the result
                                       * does not depend on that order to first order).  Flags live in bits 0..7. */
+#define CDNET_S_SHARD_OVERFLOW 64 /* cdnet_shard_ws_process: a nucleus reaches beyond the overlap rows of the tile */
 #define CDNET_S_CLASS_RANGE 32   /* cdnet_direction_one_hot: a class id outside [0, C); the reference's
                                   * `target_direction_temp[j, k]` raises IndexError (train_util_dam.py:138) */
 #define CDNET_S_PAIR_OVERFLOW 4 /* cdnet_label_pairs: more distinct (true, pred) pairs than `cap` */
@@ -121,6 +122,20 @@ int cdnet_edt(const uint8_t* mask, int32_t* d2, double* dist, int B, int H, int 
 size_t cdnet_ws_postproc_workspace_bytes(int B, int H, int W);
 int cdnet_ws_postproc(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W,
                       int min_size, int ws_flag, void* ws, size_t ws_bytes, void* stream);
+/* process() (ws = 1) on the extended tile [H, W] of one rank of a row-sharded slide (cdnet_b200/sharded.py,
+ * postproc = 1): rows [own_lo, own_hi) are the rank's own, the rows around them overlap the neighbours' so that every
+ * nucleus touching the own rows is seen whole.  marker_rowmax int32 [H] receives the largest marker id per row as
+ * postproc_other.py:44 numbers them -- before remove_small_objects (:46), whose gaps stay -- so that
+ * max(marker_rowmax[0..y]) = markers that start on rows 0..y; status (required) also gets CDNET_S_SHARD_OVERFLOW when
+ * a 4-connected component of the mask touches both the own rows and an outer overlap row (overlap too small). */
+int cdnet_shard_ws_process(const uint8_t* pred01, int32_t* labels, int32_t* marker_rowmax, int32_t* status, int H, int W,
+                           int own_lo, int own_hi, int min_size, void* ws, size_t ws_bytes, void* stream);
+/* Own rows of that tile: tile-local marker ids -> slide-global ids.  scalars int32 [3] on the device = {markers that
+ * start above the own rows, markers that start on them, markers owned by lower ranks}; lut int32 [> largest local id]
+ * holds the ids adopted from the row neighbours (0 = none); err int32 [1] is set to 1 (never cleared) when a label has
+ * neither.  labels / out: int32 [rows, W]. */
+int cdnet_shard_ws_relabel(const int32_t* labels, const int32_t* scalars, const int32_t* lut, int32_t* out, int32_t* err,
+                           int rows, int W, void* stream);
 
 /* ---- direction-aware inference post-processing, test_dam.py:455-563 ----------------------------
  * dcm:   uint8   [B,n_maps,H,W]  n_maps = 8: the 8 TTA direction-argmax maps (prob_dcm ...

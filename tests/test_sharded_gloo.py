@@ -155,3 +155,51 @@ def test_slide_many_ranks_small_shards(seed, H, W, G):
     outs = sharded.postprocess_slide(_split(dcm, prob, point, H, G), sharded.SimComm(G), H, W, NumpyBackend(), 9, 20, 2)
     got = np.concatenate(outs, axis=0)
     assert np.array_equal(got, ref), int((got != ref).sum())
+
+
+def _worker_watershed(rank, world, port, H, W, overlap, seed, q):
+    """postproc = 1 over gloo with the product's CudaBackend (kernels under the SIMT emulator)"""
+    import torch.distributed as dist
+    from simt import emulated_api
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        with emulated_api():
+            d = synth.postproc_inputs(seed, H, W, 60)
+            mine = _split(d["dcm"], d["prob"], d["point"], H, world)[rank]
+            be = sharded.CudaBackend()
+            try:
+                out = sharded.postprocess_slide([mine], sharded.DistComm(), H, W, be, 9, 20, 2, postproc=1,
+                                                overlap=overlap)[0]
+                q.put((rank, be.to_host(out)))
+            except RuntimeError as e:
+                q.put((rank, str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.simt
+@pytest.mark.parametrize("world,overlap", [(2, 48), (3, 40), (2, 4)])
+def test_slide_watershed_gloo_with_emulated_kernels(world, overlap):
+    """overlap 4 is far too small for the nuclei: EVERY rank must raise (the error word is all-gathered), none may
+    run ahead into the next collective"""
+    import torch.multiprocessing as mp
+    H, W = 240, 200
+    port = 33500 + (os.getpid() % 2000) + world + overlap
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_watershed, args=(r, world, port, H, W, overlap, 35, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    if overlap < 8:
+        assert all(isinstance(v, str) and "overlap" in v for v in res.values()), res
+        return
+    d = synth.postproc_inputs(35, H, W, 60)
+    ref = O.dam_postprocess(d["prob"].copy(), d["point"], d["dcm"], 9, 20, 2, 1, literal=False)["pred_labeled"]
+    got = np.concatenate([res[r] for r in range(world)], axis=0)
+    assert got.dtype == ref.dtype and np.array_equal(got, ref), int((got != ref).sum())

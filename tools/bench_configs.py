@@ -70,13 +70,15 @@ def fill_slide_rows(bands, dst, r0, r1):
         y += take
 
 
-def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(8000, 6000), peak=None):
+def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(8000, 6000), peak=None, postproc=0,
+                overlap=128):
     from cdnet_b200 import api, sharded
     be = sharded.CudaBackend()
     comm = sharded.DistComm() if world > 1 else sharded.SimComm(1)
     out = {"workload": "configs[4]: %dx%d synthetic prediction map (P1: 1 direction map u8 + prob f32[3] + point f32), "
-                       "row-partitioned over %d rank(s), sharded.postprocess_slide over %s, postproc=0, min_area=20, "
-                       "radius=2" % (H, W, world, "NCCL" if world > 1 else "one process"),
+                       "row-partitioned over %d rank(s), sharded.postprocess_slide over %s, postproc=%d%s, min_area=20, "
+                       "radius=2" % (H, W, world, "NCCL" if world > 1 else "one process", postproc,
+                                     " (watershed; %d overlap rows per seam)" % overlap if postproc else ""),
            "n_gpus": world, "scaling": "strong", "alg_bytes_per_px": 21.0}
     bands = slide_bands(torch, max(W, verify_hw[1]), 1)
 
@@ -87,12 +89,13 @@ def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(
         bw = [{k: b[k][..., :w] for k in b} for b in bands] if w != bands[0]["dcm"].shape[-1] else bands
         bufs = sharded.alloc_shard_buffers(be, rank, world, h, w, 1)
         fill_slide_rows(bw, bufs, r0, r1)
-        eager = lambda tm=None: sharded.postprocess_slide([bufs], comm, h, w, be, 9, 20, 2, timings=tm)[0]
+        eager = lambda tm=None: sharded.postprocess_slide([bufs], comm, h, w, be, 9, 20, 2, timings=tm, postproc=postproc,
+                                                          overlap=overlap)[0]
         step = eager
         if use_graph:
             # the whole step (kernels, torch ops, NCCL all-gathers) recorded once in a CUDA graph and replayed
             try:
-                plan = sharded.SlidePlan(bufs, comm, h, w, be, 9, 20, 2)
+                plan = sharded.SlidePlan(bufs, comm, h, w, be, 9, 20, 2, postproc=postproc, overlap=overlap)
                 step = lambda tm=None: plan.run() if tm is None else eager(tm)
                 graph_state["used"] = True
             except Exception as e:  # noqa: BLE001
@@ -145,7 +148,8 @@ def whole_slide(torch, dist, rank, world, H=40000, W=40000, steps=3, verify_hw=(
                  "prob": torch.empty((3, hv, wv), dtype=torch.float32, device="cuda"),
                  "point": torch.empty((1, hv, wv), dtype=torch.float32, device="cuda")}
         fill_slide_rows([{k: b[k][..., :wv] for k in b} for b in bands], whole, 0, hv)
-        single, _ = api.dam_postprocess_cuda(whole["dcm"][None], whole["prob"][None], whole["point"][None], 9, 20, 2, 0)
+        single, _ = api.dam_postprocess_cuda(whole["dcm"][None], whole["prob"][None], whole["point"][None], 9, 20, 2,
+                                             postproc)
         ok = bool(torch.equal(single[0], full))
         out["verify"] = {"slide": [hv, wv], "n_labels": int(single.max().item()),
                          "reference": "api.dam_postprocess_cuda on rank 0 alone (unsharded tile path)"}
