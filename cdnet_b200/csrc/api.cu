@@ -1,6 +1,7 @@
 // api.cu -- library-level entry points: version, device check, launch counter and the optional
 // per-launch CUDA-event profiler that bench.py uses for the live roofline numbers.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -12,6 +13,11 @@
 namespace cdnet {
 unsigned long long g_launches = 0;
 int g_prof_on = 0;
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) on = getenv("CDNET_NO_PDL") ? 0 : 1;
+    return on == 1;
+}
 
 struct ProfRec {
     const char* name;

@@ -27,6 +27,18 @@ void prof_end(cudaStream_t st);
         if (::cdnet::g_prof_on) ::cdnet::prof_end((stream));                      \
         ++::cdnet::g_launches;                                                    \
     } while (0)
+// The same, as a programmatic dependent launch (PDL): the grid may be scheduled while the previous kernel of the stream
+// drains, and its blocks wait in pdl_wait() until that kernel has completed and its writes are visible.  Saves the
+// launch gap and the tail of every boundary of a chain of short kernels.  Every kernel launched this way calls
+// pdl_wait() before its first global access (and before any early return); the kernel in front of it calls
+// pdl_trigger().  Off under the per-launch profiler and with CDNET_NO_PDL=1.
+#define CDNET_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                        \
+    do {                                                                                                \
+        if (::cdnet::g_prof_on) ::cdnet::prof_begin(#kernel, (stream));                                 \
+        ::cdnet::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__);    \
+        if (::cdnet::g_prof_on) ::cdnet::prof_end((stream));                                            \
+        ++::cdnet::g_launches;                                                                          \
+    } while (0)
 // dynamic shared memory of the running block, viewed as `type name[]`
 #define CDNET_DYN_SHARED(type, name) extern __shared__ type name[]
 // pins a 64-bit value in one register pair (stops ptxas from rematerialising it per use)
@@ -47,6 +59,29 @@ static inline void nvtx_mark(const char* name) { nvtxMarkA(name); }
 #else
 #define CDNET_RANGE(name) ((void)0)
 static inline void nvtx_mark(const char*) {}
+#endif
+
+#if defined(__CUDACC__)
+bool pdl_enabled();  // api.cu
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_enabled() && !g_prof_on) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through last_error()
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+static inline void pdl_wait() {}
+static inline void pdl_trigger() {}
 #endif
 
 #define CDNET_CUDA_OK(expr)                                 \
@@ -147,10 +182,27 @@ __device__ __forceinline__ int uf_find_c(int* L, int p) {
     return p;
 }
 
+// both finds of a union at once: the two chains of dependent loads overlap instead of following each other
+__device__ __forceinline__ void uf_find2_c(int* L, int& a, int& b) {
+    int qa = L[a], qb = L[b];
+    while (qa != a || qb != b) {
+        const int ga = L[qa], gb = L[qb];
+        if (qa != a) {
+            if (ga != qa) L[a] = ga;
+            a = qa;
+            qa = ga;
+        }
+        if (qb != b) {
+            if (gb != qb) L[b] = gb;
+            b = qb;
+            qb = gb;
+        }
+    }
+}
+
 __device__ __forceinline__ void uf_union_c(int* L, int a, int b) {
     for (;;) {
-        a = uf_find_c(L, a);
-        b = uf_find_c(L, b);
+        uf_find2_c(L, a, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
         const int old = atomicMin(L + a, b);  // a > b: hang a under b

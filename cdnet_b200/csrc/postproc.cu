@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
     __shared__ uint8_t s_lo[256], s_hi[256];
     __shared__ float s_thr;
     __shared__ int s_const, s_div;
+    pdl_wait();  // no-ops unless launched as a programmatic dependent (common.cuh)
+    pdl_trigger();
     const int b = blockIdx.z;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     if (PREP) {
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(256) k_boost_inside4(const uint16_t* __restric
 // word), the gate threshold and the constant-map flag -- what every block of k_boost_inside4<false> recomputes for itself
 __global__ void __launch_bounds__(256) k_boost_prep(const uint32_t* __restrict__ flags, const unsigned int* __restrict__ pmax,
                                                     int32_t* __restrict__ status, BoostPrep* __restrict__ prep, int n_maps) {
+    pdl_trigger();
     const int b = blockIdx.x, tid = threadIdx.x;
     const uint32_t fl = flags[b];
     int bad = 0, lo = 0, hi = 0;
@@ -433,7 +436,7 @@ extern "C" int cdnet_dam_postproc(const uint8_t* dcm, int n_maps, float* prob, c
     }
     if (W % 4 == 0 && ((uintptr_t)prob & 15) == 0 && ((uintptr_t)point & 15) == 0) {
         CDNET_LAUNCH(k_boost_prep, B, 256, 0, st, flags, pmax, status, prep, n_maps);
-        CDNET_LAUNCH(k_boost_inside4<true>, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes,
+        CDNET_LAUNCH_PDL(k_boost_inside4<true>, dim3(ceil_div(W, 256), ceil_div(H, 4 * kBoostRows), B), dim3(64, 4), 0, st, codes,
                      flags, point, pmax, prob, inside, status, H, W, write_prob, n_maps, prep);
     } else {
         CDNET_LAUNCH(k_boost_inside, dim3(ceil_div(W, 64), ceil_div(H, 4), B), dim3(64, 4), 0, st, codes, flags, point,

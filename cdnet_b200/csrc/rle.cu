@@ -75,6 +75,8 @@ __device__ __forceinline__ uint32_t left_bits(const uint32_t* __restrict__ row, 
 }
 
 #define RLE_ROW_COORDS                                          \
+    pdl_wait();                                                 \
+    pdl_trigger();                                              \
     const int lane = threadIdx.x & 31;                          \
     const int y = blockIdx.x * kRleWarps + (threadIdx.x >> 5);  \
     const int b = blockIdx.y;                                   \
@@ -86,6 +88,7 @@ __device__ __forceinline__ uint32_t left_bits(const uint32_t* __restrict__ row, 
     (void)tile; (void)nchunks; (void)rowbits; (void)lane;
 
 static inline dim3 rle_grid(int B, int H) { return dim3(ceil_div(H, kRleWarps), B); }
+static inline dim3 link_grid(int B, int H, int mod_lo) { return dim3(ceil_div(ceil_div(H, mod_lo), 2), B); }
 
 // 32 mask bytes -> 32 bits
 __device__ __forceinline__ uint32_t nz_nibble(uint32_t w) {  // 4 bytes -> 4 bits (bit i = byte i != 0)
@@ -154,9 +157,14 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __re
 // pixel position inside the group, ~30-cycle hops, no global atomics), then every run start is written out already
 // pointing at the root of its group-local tree.  What is left for global memory are the links across the group seams
 // (k_rle_link on rows y % kRleWarps == 0): an eighth of the unions, on trees of depth one.
-__device__ __forceinline__ int sm_find(const int* P, int p) {
+__device__ __forceinline__ int sm_find(int* P, int p) {  // path halving with plain stores, like uf_find_c
     int q = P[p];
-    while (q != p) { p = q; q = P[p]; }
+    while (q != p) {
+        const int g = P[q];
+        if (g != q) P[p] = g;
+        p = q;
+        q = g;
+    }
     return p;
 }
 __device__ __forceinline__ void sm_union(int* P, int a, int b) {
@@ -171,14 +179,19 @@ __device__ __forceinline__ void sm_union(int* P, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack_link(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M,
-                                                                  int* __restrict__ C, int* __restrict__ P,
-                                                                  int* __restrict__ A, int H, int W) {
-    __shared__ int s_par[kRleWarps * 1024];
-    __shared__ uint32_t s_m[kRleWarps][32], s_t[kRleWarps][32];
-    __shared__ int s_c[kRleWarps][32];
+template <int ROWS>
+__global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M,
+                                                             int* __restrict__ C, int* __restrict__ P,
+                                                             int* __restrict__ A, int H, int W) {
+    pdl_wait();
+    pdl_trigger();
+    CDNET_DYN_SHARED(int, s_dyn);  // ROWS * (1024 + 96) words
+    int* s_par = s_dyn;
+    uint32_t(*s_m)[32] = reinterpret_cast<uint32_t(*)[32]>(s_dyn + ROWS * 1024);
+    uint32_t(*s_t)[32] = reinterpret_cast<uint32_t(*)[32]>(s_dyn + ROWS * 1024 + ROWS * 32);
+    int(*s_c)[32] = reinterpret_cast<int(*)[32]>(s_dyn + ROWS * 1024 + ROWS * 64);
     const int lane = threadIdx.x & 31, rw = threadIdx.x >> 5;
-    const int y0 = blockIdx.x * kRleWarps, y = y0 + rw;
+    const int y0 = blockIdx.x * ROWS, y = y0 + rw;
     const int b = blockIdx.y;
     const size_t tile = (size_t)b * H * W;
     const int NW = (W + 31) >> 5;  // <= 32
@@ -261,19 +274,55 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack_link(const uint8_t*
 // (rows inside groups of 8, the seams of those inside groups of 64, the remaining seams) keep the trees shallow and the
 // atomics spread out: the one huge component of a tile -- its background -- is then assembled from a few dozen
 // sub-trees instead of being fought over by every row at once.
-__global__ void __launch_bounds__(32 * kRleWarps) k_rle_link(const uint32_t* __restrict__ M, const int* __restrict__ C,
-                                                             int* __restrict__ P, int H, int W, int mod_lo, int mod_hi) {
-    RLE_ROW_COORDS
-    if (y == 0 || (y % mod_lo) != 0 || (mod_hi && (y % mod_hi) == 0)) return;
+constexpr int kLinkWarps = 2;  // few warps per block: the seam rows of a launch spread over all SMs
+__global__ void __launch_bounds__(32 * kLinkWarps) k_rle_link(const uint32_t* __restrict__ M, const int* __restrict__ C,
+                                                              int* __restrict__ P, int H, int W, int mod_lo, int mod_hi) {
+    pdl_wait();
+    pdl_trigger();
+    // one warp per candidate row y = mod_lo, 2 mod_lo, ..
+    const int lane = threadIdx.x & 31;
+    const int y = (blockIdx.x * kLinkWarps + (threadIdx.x >> 5) + 1) * mod_lo;
+    const int b = blockIdx.y;
+    if (y >= H || (mod_hi && (y % mod_hi) == 0)) return;
+    const size_t tile = (size_t)b * H * W;
+    const int NW = (W + 31) >> 5;
+    const size_t rowbits = ((size_t)b * H + y) * NW;
     int* Pt = P + tile;
     for (int wj = lane; wj < NW; wj += 32) {
         const RowScan cur = row_load(M + rowbits, C + rowbits, NW, W, wj);
         const RowScan prv = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
         uint32_t e = ~(cur.m ^ prv.m) & cur.valid & (cur.t | prv.t);
         while (e) {
-            const int k = __ffs(e) - 1;
-            e &= e - 1;
-            uf_union_c(Pt, y * W + run_start(cur, k), (y - 1) * W + run_start(prv, k));
+            // four events per round: the first two hops of their eight find chains are independent loads.  A union of
+            // two ancestors unites the same sets, so the unions start from the grandparents.
+            int ea[4], eb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ea[i] = eb[i] = -1;
+                if (e) {
+                    const int k = __ffs(e) - 1;
+                    e &= e - 1;
+                    ea[i] = y * W + run_start(cur, k);
+                    eb[i] = (y - 1) * W + run_start(prv, k);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (ea[i] >= 0) {
+                    ea[i] = Pt[ea[i]];
+                    eb[i] = Pt[eb[i]];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (ea[i] >= 0) {
+                    ea[i] = Pt[ea[i]];
+                    eb[i] = Pt[eb[i]];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (ea[i] >= 0 && ea[i] != eb[i]) uf_union_c(Pt, ea[i], eb[i]);
         }
     }
 }
@@ -282,6 +331,8 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_link(const uint32_t* __r
 // (the words of the first and last row, the first and last pixel of every other row)
 __global__ void __launch_bounds__(256) k_rle_touch(const uint32_t* __restrict__ M, const int* __restrict__ C,
                                                    int* __restrict__ P, int* __restrict__ A, int H, int W) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.y;
     const int NW = (W + 31) >> 5;
     const size_t tile = (size_t)b * H * W;
@@ -452,10 +503,13 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_diag(const uint32_t* __r
 }
 
 // surviving roots of a row: foreground run starts that are their own parent and whose component is large enough
+// The counting pass leaves the roots it found (and the removed ones) as two bit-planes, so that the assigning pass does
+// not repeat the sparse parent / area loads.
 template <bool ASSIGN>
 __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* __restrict__ M, const int* __restrict__ P,
-                                                               int* __restrict__ A, int* __restrict__ rowcnt, int min_area,
-                                                               int H, int W) {
+                                                               int* __restrict__ A, int* __restrict__ rowcnt,
+                                                               uint32_t* __restrict__ RB, uint32_t* __restrict__ DB,
+                                                               int min_area, int H, int W) {
     RLE_ROW_COORDS
     const int* Pt = P + tile;
     int* At = A + tile;
@@ -471,8 +525,14 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
     for (int ch = 0; ch < nchunks; ++ch) {
         const int wj = ch * 32 + lane;
         const bool in = wj < NW;
-        const RowScan r = row_word(in ? M[rowbits + wj] : 0u, (in && wj > 0) ? M[rowbits + wj - 1] : 0u, -1, W, wj);
-        uint32_t s = r.t & r.m, roots = 0, dead = 0;
+        uint32_t roots = 0, dead = 0;
+        if (ASSIGN) {
+            roots = in ? RB[rowbits + wj] : 0u;
+            dead = in ? DB[rowbits + wj] : 0u;
+        }
+        const RowScan r = ASSIGN ? row_word(0u, 0u, -1, W, wj)
+                                 : row_word(in ? M[rowbits + wj] : 0u, (in && wj > 0) ? M[rowbits + wj - 1] : 0u, -1, W, wj);
+        uint32_t s = ASSIGN ? 0u : (r.t & r.m);
         while (s) {
             // four run starts per round: their parent and area loads are independent of each other
             int kk[4], pv[4], av[4];
@@ -494,6 +554,10 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
                     else dead |= 1u << kk[i];
                 }
             }
+        }
+        if (!ASSIGN && in) {
+            RB[rowbits + wj] = roots;
+            DB[rowbits + wj] = dead;
         }
         const int n = __popc(roots);
         int incl = n;
@@ -536,6 +600,8 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
                                                     const uint32_t* __restrict__ F, const int* __restrict__ P,
                                                     const int* __restrict__ A, OUT* __restrict__ out, int H, int W,
                                                     int chunk_px, int halo) {
+    pdl_wait();
+    pdl_trigger();
     CDNET_DYN_SHARED(int, s_lab);  // [(kLabRows + 2 R)][kLabTW]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.z;
@@ -704,14 +770,14 @@ static int rle_labels_launch(const uint32_t* M, const int* C, const uint32_t* F,
         attr_done = true;
     }
     dim3 grid(ceil_div(W, chunk_px), ceil_div(H, kLabRows), B);
-    CDNET_LAUNCH((k_rle_labels<R, OUT>), grid, 256, smem, st, M, C, F, P, A, out, H, W, chunk_px, halo);
+    CDNET_LAUNCH_PDL((k_rle_labels<R, OUT>), grid, 256, smem, st, M, C, F, P, A, out, H, W, chunk_px, halo);
     return last_error();
 }
 
 size_t rle_tail_workspace(int B, int H, int W) {
     const size_t n = (size_t)B * H * W;
     const size_t nbits = (size_t)B * H * ((W + 31) / 32) * sizeof(uint32_t);
-    return 2 * pad256(n * 4) + 3 * pad256(nbits) + pad256((size_t)B * H * 4);
+    return 2 * pad256(n * 4) + 5 * pad256(nbits) + pad256((size_t)B * H * 4);
 }
 
 bool rle_tail_supported(int radius) {
@@ -731,6 +797,8 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
     uint32_t* M = ar.take<uint32_t>(nbits);
     uint32_t* F = ar.take<uint32_t>(nbits);
     int* C = ar.take<int>(nbits);
+    uint32_t* RB = ar.take<uint32_t>(nbits);
+    uint32_t* DB = ar.take<uint32_t>(nbits);
     int* rowcnt = ar.take<int>((size_t)B * H);
     if (!ar.ok) return CDNET_E_WORKSPACE;
     const dim3 grid = rle_grid(B, H);
@@ -739,37 +807,55 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
     static int fused = -1;  // CDNET_RLE_NO_LOCAL=1: every link through global memory
     if (fused < 0) fused = getenv("CDNET_RLE_NO_LOCAL") ? 0 : 1;
     if (fused && W <= 1024) {
-        CDNET_LAUNCH(k_rle_pack_link, grid, threads, 0, st, inside, M, C, P, A, H, W);
+        // rows per block of the shared-memory union-find (CDNET_RLE_PACK_ROWS = 8 | 16 | 32); the seams between the
+        // blocks are what k_rle_link joins through global memory afterwards
+        // Default: as many rows as still give every SM two blocks (measured on 14 x 1000^2, whole step: 32 rows 0.288 ms,
+        // 16 rows 0.306 ms, 8 rows 0.305 ms; a single 1000^2 tile keeps 8 rows = 125 blocks).
+        static int prow_env = -1;
+        if (prow_env < 0) {
+            const char* e = getenv("CDNET_RLE_PACK_ROWS");
+            prow_env = e ? atoi(e) : 0;
+            if (prow_env != 8 && prow_env != 16 && prow_env != 32) prow_env = 0;
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1120 * 4));
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1120 * 4));
+        }
+        const long long rows_total = (long long)B * H;
+        const int prow = prow_env ? prow_env : (rows_total >= 32LL * 296 ? 32 : (rows_total >= 16LL * 296 ? 16 : 8));
+        const dim3 pgrid(ceil_div(H, prow), B);
+        const size_t psm = (size_t)prow * 1120 * sizeof(int);
+        if (prow == 8) CDNET_LAUNCH_PDL(k_rle_pack_link<8>, pgrid, 256, psm, st, inside, M, C, P, A, H, W);
+        else if (prow == 16) CDNET_LAUNCH_PDL(k_rle_pack_link<16>, pgrid, 512, psm, st, inside, M, C, P, A, H, W);
+        else CDNET_LAUNCH_PDL(k_rle_pack_link<32>, pgrid, 1024, psm, st, inside, M, C, P, A, H, W);
         // the seams between the groups in one launch (CDNET_RLE_SEAM_PHASES=2 links the seams inside super-groups of 64
         // rows first: measured slower on B200, 0.057 vs 0.042 ms for 14 x 1000^2)
         static int seam2 = -1;
         if (seam2 < 0) { const char* e = getenv("CDNET_RLE_SEAM_PHASES"); seam2 = (e && atoi(e) == 2) ? 1 : 0; }
-        if (H > kRleWarps) {
-            if (seam2 && H > 64) {
-                CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, kRleWarps, 64);
-                CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 64, 0);
+        if (H > prow) {
+            if (seam2 && H > 64 && prow < 64) {
+                CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, prow), 32 * kLinkWarps, 0, st, M, C, P, H, W, prow, 64);
+                CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 64), 32 * kLinkWarps, 0, st, M, C, P, H, W, 64, 0);
             } else {
-                CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, kRleWarps, 0);
+                CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, prow), 32 * kLinkWarps, 0, st, M, C, P, H, W, prow, 0);
             }
         }
     } else {
-        CDNET_LAUNCH(k_rle_pack, grid, threads, 0, st, inside, M, C, P, A, H, W);
+        CDNET_LAUNCH_PDL(k_rle_pack, grid, threads, 0, st, inside, M, C, P, A, H, W);
         static int phases = 0;  // CDNET_RLE_LINK_PHASES=3: rows inside groups of 8, then of 64, then the rest (slower on B200)
         if (!phases) { const char* e = getenv("CDNET_RLE_LINK_PHASES"); phases = (e && atoi(e) == 3) ? 3 : 1; }
         if (phases == 1 || H <= 8) {
-            CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 1, 0);
+            CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 1), 32 * kLinkWarps, 0, st, M, C, P, H, W, 1, 0);
         } else {
-            CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 1, 8);
-            CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 8, 64);
-            if (H > 64) CDNET_LAUNCH(k_rle_link, grid, threads, 0, st, M, C, P, H, W, 64, 0);
+            CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 1), 32 * kLinkWarps, 0, st, M, C, P, H, W, 1, 8);
+            CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 8), 32 * kLinkWarps, 0, st, M, C, P, H, W, 8, 64);
+            if (H > 64) CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 64), 32 * kLinkWarps, 0, st, M, C, P, H, W, 64, 0);
         }
     }
-    CDNET_LAUNCH(k_rle_touch, dim3(ceil_div(2 * ((W + 31) / 32) + 2 * (H > 2 ? H - 2 : 0) + 1, 256), B), 256, 0, st, M, C, P, A, H, W);
-    CDNET_LAUNCH(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
-    CDNET_LAUNCH(k_rle_area, grid, threads, 0, st, M, C, F, P, A, H, W);
-    CDNET_LAUNCH(k_rle_diag, grid, threads, 0, st, M, C, F, P, A, min_area, H, W);
-    CDNET_LAUNCH(k_rle_number<false>, grid, threads, 0, st, M, P, A, rowcnt, min_area, H, W);
-    CDNET_LAUNCH(k_rle_number<true>, grid, threads, 0, st, M, P, A, rowcnt, min_area, H, W);
+    CDNET_LAUNCH_PDL(k_rle_touch, dim3(ceil_div(2 * ((W + 31) / 32) + 2 * (H > 2 ? H - 2 : 0) + 1, 256), B), 256, 0, st, M, C, P, A, H, W);
+    CDNET_LAUNCH_PDL(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
+    CDNET_LAUNCH_PDL(k_rle_area, grid, threads, 0, st, M, C, F, P, A, H, W);
+    CDNET_LAUNCH_PDL(k_rle_diag, grid, threads, 0, st, M, C, F, P, A, min_area, H, W);
+    CDNET_LAUNCH_PDL(k_rle_number<false>, grid, threads, 0, st, M, P, A, rowcnt, RB, DB, min_area, H, W);
+    CDNET_LAUNCH_PDL(k_rle_number<true>, grid, threads, 0, st, M, P, A, rowcnt, RB, DB, min_area, H, W);
     if (out_elem_bytes == 4) {
         if (radius == 0) return rle_labels_launch<0, int32_t>(M, C, F, P, A, (int32_t*)out, B, H, W, st);
         if (radius == 1) return rle_labels_launch<1, int32_t>(M, C, F, P, A, (int32_t*)out, B, H, W, st);

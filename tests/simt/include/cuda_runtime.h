@@ -128,6 +128,8 @@ int lane_id();
         ::simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); }, #kernel); \
         ++::cdnet::g_launches;                                                                        \
     } while (0)
+// programmatic dependent launch only changes WHEN a kernel may start; the emulator runs launches back to back anyway
+#define CDNET_LAUNCH_PDL CDNET_LAUNCH
 #ifdef CDNET_SIMT_ASAN  // tests/simt/build.py --asan: poisoned gaps between the workspace slices (common.cuh Arena)
 extern "C" void __asan_poison_memory_region(void const volatile*, size_t);
 extern "C" void __asan_unpoison_memory_region(void const volatile*, size_t);

@@ -200,6 +200,34 @@ def test_run_based_tail_fuzz(kernel_api):
                                                                         int((got != ref).sum()))
 
 
+@pytest.mark.parametrize("B,H,W", [(5, 1000, 96), (12, 800, 64)])
+def test_run_based_tail_block_rows(kernel_api, B, H, W):
+    """batches with enough rows switch k_rle_pack_link to 16- and 32-row blocks (shared-memory union-find over more
+    rows, fewer seams for k_rle_link): 4 736+ rows -> 16, 9 472+ rows -> 32; labels must not change"""
+    import torch
+    from scipy import ndimage as ndi
+    from oracle import restate as O
+    rng = np.random.default_rng(B * 1000 + W)
+    prob = np.zeros((B, 3, H, W), np.float32)
+    prob[:, 0] = 0.5
+    for b in range(B):
+        if b % 3 == 0:
+            m = rng.random((H, W)) < 0.55                      # one-pixel structure, nested holes
+        elif b % 3 == 1:
+            m = ndi.binary_dilation(rng.random((H, W)) < 0.02, iterations=3) & (rng.random((H, W)) < 0.97)
+        else:
+            yy, xx = np.mgrid[0:H, 0:W]                        # a snake through every block seam + pinholes
+            m = (((yy // 5) % 2 == 0) | ((xx < 3) & ((yy // 10) % 2 == 0)) | ((xx >= W - 3) & ((yy // 10) % 2 == 1)))
+            m &= rng.random((H, W)) < 0.98
+        prob[b, 1] = m
+    got, _ = kernel_api.plain_postprocess_cuda(to_dev(kernel_api, torch.from_numpy(prob)), 5, 2, 0)
+    got = got.cpu().numpy()
+    for b in range(B):
+        ref = O.plain_postprocess(prob[b].copy(), 5, 2, 0)
+        ref = ref["pred_labeled"] if isinstance(ref, dict) else ref
+        assert np.array_equal(got[b], ref), (b, int((got[b] != ref).sum()))
+
+
 def test_edt_large_components(kernel_api):
     """the distance transform away from nucleus scale: a 1000-pixel-wide blob, a tile with a single background pixel,
     columns / rows without any, a frame-to-frame band -- the scans beyond the fast kernels' cut-off (csrc/edt.cu)"""
