@@ -12,8 +12,8 @@
 //   k_rle_pack     mask bytes -> bit-plane M; parent[start] = start, aux[start] = 0 at every run start
 //   k_rle_link     runs of equal value that overlap in adjacent rows are united (4-connectivity; foreground AND
 //                  background components in one forest; the root is the component's first raster pixel)
-//   k_rle_touch    background components that reach the image frame are flagged at their root
-//   k_rle_holes    bit-plane F = M | (background runs whose component is not flagged) = binary_fill_holes(M)
+//                  background runs on the image frame hang below the special root -1 ("outside") from the start
+//   k_rle_holes    bit-plane F = M | (background runs whose component never reached -1) = binary_fill_holes(M)
 //   k_rle_fill     hole runs are united with the foreground runs they touch (left / right / above / below)
 //   k_rle_area     per-component pixel counts (one atomicAdd per filled segment of a word); flattens the run starts
 //   k_rle_diag     components with area >= min_area that touch only diagonally are united (8-connectivity of the
@@ -33,6 +33,7 @@
 namespace cdnet {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kOutside = -1;  // the special root of background that touches the image frame (see rf_find)
 constexpr int kRleWarps = 8;  // rows per block, one warp per row
 
 struct RowScan {
@@ -88,6 +89,7 @@ __device__ __forceinline__ uint32_t left_bits(const uint32_t* __restrict__ row, 
     (void)tile; (void)nchunks; (void)rowbits; (void)lane;
 
 static inline dim3 rle_grid(int B, int H) { return dim3(ceil_div(H, kRleWarps), B); }
+static inline size_t pack_smem(int rows) { return (size_t)rows * 96 * 4 + ((size_t)rows * 1024 + 2) * 2; }
 static inline dim3 link_grid(int B, int H, int mod_lo) { return dim3(ceil_div(ceil_div(H, mod_lo), 2), B); }
 
 // 32 mask bytes -> 32 bits
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __re
     const bool vec = (W % 8 == 0) && (((uintptr_t)mask & 7) == 0);
     uint32_t carry_word = 0;  // last word of the previous chunk
     int carry_start = -1;     // latest run start of the previous chunks
+    uint32_t last_word = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
         const int wj = ch * 32 + lane;
         const int x0 = wj * 32;
@@ -146,10 +149,15 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __re
             const int k = __ffs(t) - 1;
             t &= t - 1;
             const int gid = y * W + r.wx + k;
-            P[tile + gid] = gid;
+            const bool frame_bg = !((r.m >> k) & 1u) && (y == 0 || y == H - 1 || gid == y * W);
+            P[tile + gid] = frame_bg ? kOutside : gid;
             A[tile + gid] = 0;
         }
+        last_word = __shfl_sync(kFull, r.m, (NW - 1) & 31);  // meaningful after the last chunk
     }
+    // the last run of the row, if background, touches the frame too
+    __syncwarp();
+    if (lane == 0 && !((last_word >> ((W - 1) & 31)) & 1u)) P[tile + y * W + carry_start] = kOutside;
 }
 
 // ---- tiles up to 1024 columns: pack + the links INSIDE groups of kRleWarps rows in one kernel ---------------------
@@ -157,9 +165,20 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __re
 // pixel position inside the group, ~30-cycle hops, no global atomics), then every run start is written out already
 // pointing at the root of its group-local tree.  What is left for global memory are the links across the group seams
 // (k_rle_link on rows y % kRleWarps == 0): an eighth of the unions, on trees of depth one.
-__device__ __forceinline__ int sm_find(int* P, int p) {  // path halving with plain stores, like uf_find_c
+// The forest of the link phase knows one special root, kOutside = -1: a background run that touches the image frame is
+// born with it as its parent.  Hooking always goes to the smaller index, so -1 wins every union it takes part in, and
+//   * "is this background run a hole?" is "does its find() end at a real root?" -- no frame-flag pass;
+//   * the one huge component of a tile, its background, is never assembled: its runs hang two hops below -1, and a
+//     union of two runs that are both outside finds equal roots and touches no atomic.
+// Foreground runs never meet -1 (only runs of equal value are united before the holes are known).
+
+// path halving with plain stores: parents only ever point at smaller indices of the same tree, so a stale store can at
+// worst undo a little compression (shared or global memory)
+__device__ __forceinline__ int rf_find(int* P, int p) {
+    if (p < 0) return kOutside;
     int q = P[p];
     while (q != p) {
+        if (q < 0) return kOutside;
         const int g = P[q];
         if (g != q) P[p] = g;
         p = q;
@@ -167,13 +186,57 @@ __device__ __forceinline__ int sm_find(int* P, int p) {  // path halving with pl
     }
     return p;
 }
-__device__ __forceinline__ void sm_union(int* P, int a, int b) {
+
+// both finds of a union at once: the two chains of dependent loads overlap
+__device__ __forceinline__ void rf_find2(int* P, int& a, int& b) {
+    int qa = a >= 0 ? P[a] : a, qb = b >= 0 ? P[b] : b;
+    while (qa != a || qb != b) {
+        const int ga = (qa != a && qa >= 0) ? P[qa] : qa;
+        const int gb = (qb != b && qb >= 0) ? P[qb] : qb;
+        if (qa != a) {
+            if (qa >= 0 && ga != qa) P[a] = ga;
+            a = qa;
+            qa = ga;
+        }
+        if (qb != b) {
+            if (qb >= 0 && gb != qb) P[b] = gb;
+            b = qb;
+            qb = gb;
+        }
+    }
+}
+
+__device__ __forceinline__ void rf_union(int* P, int a, int b) {
     for (;;) {
-        a = sm_find(P, a);
-        b = sm_find(P, b);
+        rf_find2(P, a, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
-        const int old = atomicMin(P + a, b);
+        const int old = atomicMin(P + a, b);  // a > b >= -1: hang a under b
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// The group-local forest of k_rle_pack_link: 16-bit parents in shared memory (32 rows x 1024 positions + 1 fit), slot 0
+// = outside (a root that is smaller than every other, so it wins every union by itself), slot 1 + row * 1024 + x = the
+// run that starts at (row, x).  Hooking is a compare-and-swap of a root's self-link.
+__device__ __forceinline__ int sf_find(unsigned short* P, int p) {
+    int q = P[p];
+    while (q != p) {
+        const int g = P[q];
+        if (g != q) P[p] = (unsigned short)g;
+        p = q;
+        q = g;
+    }
+    return p;
+}
+__device__ __forceinline__ void sf_union(unsigned short* P, int a, int b) {
+    for (;;) {
+        a = sf_find(P, a);
+        b = sf_find(P, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicCAS(P + a, (unsigned short)a, (unsigned short)b);  // a > b: hang root a under b
         if (old == a) return;
         a = old;
     }
@@ -185,11 +248,12 @@ __global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __re
                                                              int* __restrict__ A, int H, int W) {
     pdl_wait();
     pdl_trigger();
-    CDNET_DYN_SHARED(int, s_dyn);  // ROWS * (1024 + 96) words
-    int* s_par = s_dyn;
-    uint32_t(*s_m)[32] = reinterpret_cast<uint32_t(*)[32]>(s_dyn + ROWS * 1024);
-    uint32_t(*s_t)[32] = reinterpret_cast<uint32_t(*)[32]>(s_dyn + ROWS * 1024 + ROWS * 32);
-    int(*s_c)[32] = reinterpret_cast<int(*)[32]>(s_dyn + ROWS * 1024 + ROWS * 64);
+    CDNET_DYN_SHARED(int, s_dyn);  // ROWS * 96 words, then ROWS * 1024 + 2 16-bit parents
+    uint32_t(*s_m)[32] = reinterpret_cast<uint32_t(*)[32]>(s_dyn);
+    uint32_t(*s_t)[32] = reinterpret_cast<uint32_t(*)[32]>(s_dyn + ROWS * 32);
+    int(*s_c)[32] = reinterpret_cast<int(*)[32]>(s_dyn + ROWS * 64);
+    unsigned short* s_par = reinterpret_cast<unsigned short*>(s_dyn + ROWS * 96);
+    if (threadIdx.x == 0) s_par[0] = 0;  // outside
     const int lane = threadIdx.x & 31, rw = threadIdx.x >> 5;
     const int y0 = blockIdx.x * ROWS, y = y0 + rw;
     const int b = blockIdx.y;
@@ -236,8 +300,22 @@ __global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __re
         while (t) {
             const int k = __ffs(t) - 1;
             t &= t - 1;
-            const int li = rw * 1024 + r.wx + k;
-            s_par[li] = li;
+            const int li = 1 + rw * 1024 + r.wx + k;
+            s_par[li] = (unsigned short)li;
+        }
+        // background runs on the image frame start out below kOutside: every background run of the first and the last
+        // row, the first and the last run of the others
+        __syncwarp();
+        if (y == 0 || y == H - 1) {
+            uint32_t t0 = r.t & ~r.m;
+            while (t0) {
+                const int k = __ffs(t0) - 1;
+                t0 &= t0 - 1;
+                s_par[1 + rw * 1024 + r.wx + k] = 0;
+            }
+        } else {
+            if (lane == 0 && !(r.m & 1u)) s_par[1 + rw * 1024] = 0;
+            if (lane == ((W - 1) >> 5) && !((r.m >> ((W - 1) & 31)) & 1u)) s_par[1 + rw * 1024 + run_start(r, (W - 1) & 31)] = 0;
         }
     }
     s_m[rw][lane] = r.m;
@@ -253,7 +331,7 @@ __global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __re
         while (e) {
             const int k = __ffs(e) - 1;
             e &= e - 1;
-            sm_union(s_par, rw * 1024 + run_start(r, k), (rw - 1) * 1024 + run_start(prv, k));
+            sf_union(s_par, 1 + rw * 1024 + run_start(r, k), 1 + (rw - 1) * 1024 + run_start(prv, k));
         }
     }
     __syncthreads();
@@ -262,9 +340,9 @@ __global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __re
         while (t) {
             const int k = __ffs(t) - 1;
             t &= t - 1;
-            const int root = sm_find(s_par, rw * 1024 + r.wx + k);
+            const int root = sf_find(s_par, 1 + rw * 1024 + r.wx + k) - 1;
             const int gid = y * W + r.wx + k;
-            P[tile + gid] = (y0 + (root >> 10)) * W + (root & 1023);
+            P[tile + gid] = root < 0 ? kOutside : (y0 + (root >> 10)) * W + (root & 1023);
             A[tile + gid] = 0;
         }
     }
@@ -296,9 +374,11 @@ __global__ void __launch_bounds__(32 * kLinkWarps) k_rle_link(const uint32_t* __
             // four events per round: the first two hops of their eight find chains are independent loads.  A union of
             // two ancestors unites the same sets, so the unions start from the grandparents.
             int ea[4], eb[4];
+            bool ev[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                ea[i] = eb[i] = -1;
+                ev[i] = e != 0;
+                ea[i] = eb[i] = kOutside;
                 if (e) {
                     const int k = __ffs(e) - 1;
                     e &= e - 1;
@@ -307,58 +387,22 @@ __global__ void __launch_bounds__(32 * kLinkWarps) k_rle_link(const uint32_t* __
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (ea[i] >= 0) {
-                    ea[i] = Pt[ea[i]];
-                    eb[i] = Pt[eb[i]];
-                }
-            }
+            for (int hop = 0; hop < 2; ++hop) {
+                int na[4], nb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (ea[i] >= 0) {
-                    ea[i] = Pt[ea[i]];
-                    eb[i] = Pt[eb[i]];
+                for (int i = 0; i < 4; ++i) {
+                    na[i] = ea[i] >= 0 ? Pt[ea[i]] : kOutside;
+                    nb[i] = eb[i] >= 0 ? Pt[eb[i]] : kOutside;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ea[i] = na[i];
+                    eb[i] = nb[i];
                 }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (ea[i] >= 0 && ea[i] != eb[i]) uf_union_c(Pt, ea[i], eb[i]);
-        }
-    }
-}
-
-// background components that reach the image frame are flagged at their root: one thread per frame position
-// (the words of the first and last row, the first and last pixel of every other row)
-__global__ void __launch_bounds__(256) k_rle_touch(const uint32_t* __restrict__ M, const int* __restrict__ C,
-                                                   int* __restrict__ P, int* __restrict__ A, int H, int W) {
-    pdl_wait();
-    pdl_trigger();
-    const int b = blockIdx.y;
-    const int NW = (W + 31) >> 5;
-    const size_t tile = (size_t)b * H * W;
-    int* Pt = P + tile;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < 2 * NW) {
-        const int y = i < NW ? 0 : H - 1, wj = i < NW ? i : i - NW;
-        if (i >= NW && H == 1) return;
-        const size_t rowbits = ((size_t)b * H + y) * NW;
-        const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
-        uint32_t s = r.t & ~r.m;  // every background run of the first / last row
-        while (s) {
-            const int k = __ffs(s) - 1;
-            s &= s - 1;
-            A[tile + uf_find_c(Pt, y * W + r.wx + k)] = 1;
-        }
-    } else if (i < 2 * NW + 2 * (H - 2)) {
-        const int j = i - 2 * NW;
-        const int y = 1 + (j >> 1);
-        const size_t rowbits = ((size_t)b * H + y) * NW;
-        if (j & 1) {
-            const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, NW - 1);
-            const int k = (W - 1) & 31;
-            if (!((r.m >> k) & 1u)) A[tile + uf_find_c(Pt, y * W + run_start(r, k))] = 1;
-        } else if (!(M[rowbits] & 1u)) {
-            A[tile + uf_find_c(Pt, y * W)] = 1;
+                if (ev[i] && ea[i] != eb[i]) rf_union(Pt, ea[i], eb[i]);
         }
     }
 }
@@ -432,15 +476,15 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) root[i] = par[i] >= 0 ? Pt[par[i]] : -1;
+        for (int i = 0; i < 4; ++i) root[i] = par[i] >= 0 ? Pt[par[i]] : kOutside;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (root[i] >= 0 && root[i] != par[i]) root[i] = uf_find_c(Pt, root[i]);
+            if (root[i] >= 0 && root[i] != par[i]) root[i] = rf_find(Pt, root[i]);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (root[i] >= 0 && A[tile + root[i]] == 0) hole |= seg4[i];
+            if (seg4[i] && root[i] >= 0) hole |= seg4[i];  // its component never reached kOutside
         for_each_segment(rest, [&](int k0, uint32_t seg) {  // more than four background segments in one word
-            if (A[tile + uf_find_c(Pt, y * W + run_start(r, k0))] == 0) hole |= seg;
+            if (rf_find(Pt, y * W + run_start(r, k0)) >= 0) hole |= seg;
         });
         F[rowbits + wj] = r.m | hole;
         if (hole) for_each_segment(hole, [&](int k0, uint32_t seg) { rle_join_hole(M, C, Pt, r, seg, k0, y, H, W, NW, rowbits, wj); });
@@ -809,20 +853,20 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
     if (fused && W <= 1024) {
         // rows per block of the shared-memory union-find (CDNET_RLE_PACK_ROWS = 8 | 16 | 32); the seams between the
         // blocks are what k_rle_link joins through global memory afterwards
-        // Default: as many rows as still give every SM two blocks (measured on 14 x 1000^2, whole step: 32 rows 0.288 ms,
-        // 16 rows 0.306 ms, 8 rows 0.305 ms; a single 1000^2 tile keeps 8 rows = 125 blocks).
+        // Default: 16 rows when that still gives every SM two blocks, else 8 (measured on 14 x 1000^2, whole step: 16 rows
+        // 0.274 ms, 32 rows 0.278 ms, 8 rows 0.277 ms; a single 1000^2 tile keeps 8 rows = 125 blocks).
         static int prow_env = -1;
         if (prow_env < 0) {
             const char* e = getenv("CDNET_RLE_PACK_ROWS");
             prow_env = e ? atoi(e) : 0;
             if (prow_env != 8 && prow_env != 16 && prow_env != 32) prow_env = 0;
-            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1120 * 4));
-            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1120 * 4));
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(16)));
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(32)));
         }
         const long long rows_total = (long long)B * H;
-        const int prow = prow_env ? prow_env : (rows_total >= 32LL * 296 ? 32 : (rows_total >= 16LL * 296 ? 16 : 8));
+        const int prow = prow_env ? prow_env : (rows_total >= 16LL * 296 ? 16 : 8);
         const dim3 pgrid(ceil_div(H, prow), B);
-        const size_t psm = (size_t)prow * 1120 * sizeof(int);
+        const size_t psm = pack_smem(prow);
         if (prow == 8) CDNET_LAUNCH_PDL(k_rle_pack_link<8>, pgrid, 256, psm, st, inside, M, C, P, A, H, W);
         else if (prow == 16) CDNET_LAUNCH_PDL(k_rle_pack_link<16>, pgrid, 512, psm, st, inside, M, C, P, A, H, W);
         else CDNET_LAUNCH_PDL(k_rle_pack_link<32>, pgrid, 1024, psm, st, inside, M, C, P, A, H, W);
@@ -850,7 +894,6 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
             if (H > 64) CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 64), 32 * kLinkWarps, 0, st, M, C, P, H, W, 64, 0);
         }
     }
-    CDNET_LAUNCH_PDL(k_rle_touch, dim3(ceil_div(2 * ((W + 31) / 32) + 2 * (H > 2 ? H - 2 : 0) + 1, 256), B), 256, 0, st, M, C, P, A, H, W);
     CDNET_LAUNCH_PDL(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
     CDNET_LAUNCH_PDL(k_rle_area, grid, threads, 0, st, M, C, F, P, A, H, W);
     CDNET_LAUNCH_PDL(k_rle_diag, grid, threads, 0, st, M, C, F, P, A, min_area, H, W);

@@ -266,6 +266,10 @@ SIMT_INT_ATOMICS(unsigned)
 SIMT_INT_ATOMICS(long long)
 SIMT_INT_ATOMICS(unsigned long long)
 #undef SIMT_INT_ATOMICS
+static inline unsigned short atomicCAS(unsigned short* p, unsigned short cmp, unsigned short v) {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
 static inline float atomicAdd(float* p, float v) {
     unsigned* u = (unsigned*)p;
     unsigned old = __atomic_load_n(u, __ATOMIC_RELAXED), nw;

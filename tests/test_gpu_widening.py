@@ -202,8 +202,8 @@ def test_run_based_tail_fuzz(kernel_api):
 
 @pytest.mark.parametrize("B,H,W", [(5, 1000, 96), (12, 800, 64)])
 def test_run_based_tail_block_rows(kernel_api, B, H, W):
-    """batches with enough rows switch k_rle_pack_link to 16- and 32-row blocks (shared-memory union-find over more
-    rows, fewer seams for k_rle_link): 4 736+ rows -> 16, 9 472+ rows -> 32; labels must not change"""
+    """batches with 4 736+ rows switch k_rle_pack_link to 16-row blocks (shared-memory union-find over more rows, fewer
+    seams for k_rle_link; CDNET_RLE_PACK_ROWS=32 for 32-row blocks); labels must not change"""
     import torch
     from scipy import ndimage as ndi
     from oracle import restate as O
