@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcdnet_b200.so")
+# CDNET_B200_LIB: another build of the SAME library (tools/build_variant.py: compile-time tunings side by side on one box)
+LIB_PATH = os.environ.get("CDNET_B200_LIB") or os.path.join(_HERE, "libcdnet_b200.so")
 
 c_int, c_size_t, c_void_p = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
 
