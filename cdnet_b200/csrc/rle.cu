@@ -34,6 +34,9 @@ namespace cdnet {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kOutside = -1;  // the special root of background that touches the image frame (see rf_find)
+// parent and aux (area, then id) of a run start sit side by side: node i = words 2 i, 2 i + 1 of ONE plane, so that the
+// sparse accesses that need both (numbering, labels, the first store) touch one sector instead of two
+constexpr int kNS = 2;
 constexpr int kRleWarps = 8;  // rows per block, one warp per row
 
 struct RowScan {
@@ -150,14 +153,13 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __re
             t &= t - 1;
             const int gid = y * W + r.wx + k;
             const bool frame_bg = !((r.m >> k) & 1u) && (y == 0 || y == H - 1 || gid == y * W);
-            P[tile + gid] = frame_bg ? kOutside : gid;
-            A[tile + gid] = 0;
+            *(int2*)(P + kNS * (tile + gid)) = make_int2(frame_bg ? kOutside : gid, 0);
         }
         last_word = __shfl_sync(kFull, r.m, (NW - 1) & 31);  // meaningful after the last chunk
     }
     // the last run of the row, if background, touches the frame too
     __syncwarp();
-    if (lane == 0 && !((last_word >> ((W - 1) & 31)) & 1u)) P[tile + y * W + carry_start] = kOutside;
+    if (lane == 0 && !((last_word >> ((W - 1) & 31)) & 1u)) P[kNS * (tile + y * W + carry_start)] = kOutside;
 }
 
 // ---- tiles up to 1024 columns: pack + the links INSIDE groups of kRleWarps rows in one kernel ---------------------
@@ -176,30 +178,40 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_pack(const uint8_t* __re
 // worst undo a little compression (shared or global memory)
 __device__ __forceinline__ int rf_find(int* P, int p) {
     if (p < 0) return kOutside;
-    int q = P[p];
+    int q = P[kNS * p];
     while (q != p) {
         if (q < 0) return kOutside;
-        const int g = P[q];
-        if (g != q) P[p] = g;
+        const int g = P[kNS * q];
+        if (g != q) P[kNS * p] = g;
         p = q;
         q = g;
     }
     return p;
 }
 
+// read-only walk (foreground runs after the link phase: never outside)
+__device__ __forceinline__ int rf_find_ro(const int* P, int p) {
+    int q = P[kNS * p];
+    while (q != p) {
+        p = q;
+        q = P[kNS * p];
+    }
+    return p;
+}
+
 // both finds of a union at once: the two chains of dependent loads overlap
 __device__ __forceinline__ void rf_find2(int* P, int& a, int& b) {
-    int qa = a >= 0 ? P[a] : a, qb = b >= 0 ? P[b] : b;
+    int qa = a >= 0 ? P[kNS * a] : a, qb = b >= 0 ? P[kNS * b] : b;
     while (qa != a || qb != b) {
-        const int ga = (qa != a && qa >= 0) ? P[qa] : qa;
-        const int gb = (qb != b && qb >= 0) ? P[qb] : qb;
+        const int ga = (qa != a && qa >= 0) ? P[kNS * qa] : qa;
+        const int gb = (qb != b && qb >= 0) ? P[kNS * qb] : qb;
         if (qa != a) {
-            if (qa >= 0 && ga != qa) P[a] = ga;
+            if (qa >= 0 && ga != qa) P[kNS * a] = ga;
             a = qa;
             qa = ga;
         }
         if (qb != b) {
-            if (qb >= 0 && gb != qb) P[b] = gb;
+            if (qb >= 0 && gb != qb) P[kNS * b] = gb;
             b = qb;
             qb = gb;
         }
@@ -211,7 +223,7 @@ __device__ __forceinline__ void rf_union(int* P, int a, int b) {
         rf_find2(P, a, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
-        const int old = atomicMin(P + a, b);  // a > b >= -1: hang a under b
+        const int old = atomicMin(P + kNS * a, b);  // a > b >= -1: hang a under b
         if (old == a) return;
         a = old;
     }
@@ -342,8 +354,7 @@ __global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __re
             t &= t - 1;
             const int root = sf_find(s_par, 1 + rw * 1024 + r.wx + k) - 1;
             const int gid = y * W + r.wx + k;
-            P[tile + gid] = root < 0 ? kOutside : (y0 + (root >> 10)) * W + (root & 1023);
-            A[tile + gid] = 0;
+            *(int2*)(P + kNS * (tile + gid)) = make_int2(root < 0 ? kOutside : (y0 + (root >> 10)) * W + (root & 1023), 0);
         }
     }
 }
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(32 * kLinkWarps) k_rle_link(const uint32_t* __
     const size_t tile = (size_t)b * H * W;
     const int NW = (W + 31) >> 5;
     const size_t rowbits = ((size_t)b * H + y) * NW;
-    int* Pt = P + tile;
+    int* Pt = P + kNS * tile;
     for (int wj = lane; wj < NW; wj += 32) {
         const RowScan cur = row_load(M + rowbits, C + rowbits, NW, W, wj);
         const RowScan prv = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
@@ -391,8 +402,8 @@ __global__ void __launch_bounds__(32 * kLinkWarps) k_rle_link(const uint32_t* __
                 int na[4], nb[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    na[i] = ea[i] >= 0 ? Pt[ea[i]] : kOutside;
-                    nb[i] = eb[i] >= 0 ? Pt[eb[i]] : kOutside;
+                    na[i] = ea[i] >= 0 ? Pt[kNS * ea[i]] : kOutside;
+                    nb[i] = eb[i] >= 0 ? Pt[kNS * eb[i]] : kOutside;
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -433,19 +444,19 @@ __device__ __noinline__ void rle_join_hole(const uint32_t* __restrict__ M, const
     const int me = y * W + sx;
     // a hole never touches the frame: it has a left and a right neighbour, a row above and a row below
     const int k1 = 31 - __clz(seg);  // last bit of the segment
-    if (sx >= r.wx) uf_union_c(Pt, me, y * W + (k0 ? run_start(r, k0 - 1) : r.cin));  // the run starts here: left
+    if (sx >= r.wx) rf_union(Pt, me, y * W + (k0 ? run_start(r, k0 - 1) : r.cin));  // the run starts here: left
     if (k1 < 31) {
-        if ((r.valid >> (k1 + 1)) & 1u) uf_union_c(Pt, me, y * W + r.wx + k1 + 1);     // the run ends here: right
+        if ((r.valid >> (k1 + 1)) & 1u) rf_union(Pt, me, y * W + r.wx + k1 + 1);     // the run ends here: right
     } else if (wj + 1 < NW && (M[rowbits + wj + 1] & 1u)) {
-        uf_union_c(Pt, me, y * W + r.wx + 32);
+        rf_union(Pt, me, y * W + r.wx + 32);
     }
     if (y > 0) {
         const RowScan up = row_load(M + rowbits - NW, C + rowbits - NW, NW, W, wj);
-        for_each_segment(up.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y - 1) * W + run_start(up, j0)); });
+        for_each_segment(up.m & seg, [&](int j0, uint32_t) { rf_union(Pt, me, (y - 1) * W + run_start(up, j0)); });
     }
     if (y + 1 < H) {
         const RowScan dn = row_load(M + rowbits + NW, C + rowbits + NW, NW, W, wj);
-        for_each_segment(dn.m & seg, [&](int j0, uint32_t) { uf_union_c(Pt, me, (y + 1) * W + run_start(dn, j0)); });
+        for_each_segment(dn.m & seg, [&](int j0, uint32_t) { rf_union(Pt, me, (y + 1) * W + run_start(dn, j0)); });
     }
 }
 
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __
                                                               int* __restrict__ P, const int* __restrict__ A,
                                                               uint32_t* __restrict__ F, int H, int W) {
     RLE_ROW_COORDS
-    int* Pt = P + tile;
+    int* Pt = P + kNS * tile;
     for (int wj = lane; wj < NW; wj += 32) {
         const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
         uint32_t hole = 0;
@@ -472,11 +483,11 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_holes(const uint32_t* __
                 const int len = inv ? (__ffs(inv) - 1) : (32 - k0);
                 seg4[i] = (len >= 32 ? kFull : ((1u << len) - 1u)) << k0;
                 rest &= ~seg4[i];
-                par[i] = Pt[y * W + run_start(r, k0)];
+                par[i] = Pt[kNS * (y * W + run_start(r, k0))];
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) root[i] = par[i] >= 0 ? Pt[par[i]] : kOutside;
+        for (int i = 0; i < 4; ++i) root[i] = par[i] >= 0 ? Pt[kNS * par[i]] : kOutside;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (root[i] >= 0 && root[i] != par[i]) root[i] = rf_find(Pt, root[i]);
@@ -495,7 +506,7 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_area(const uint32_t* __r
                                                              const uint32_t* __restrict__ F, int* __restrict__ P,
                                                              int* __restrict__ A, int H, int W) {
     RLE_ROW_COORDS
-    int* Pt = P + tile;
+    int* Pt = P + kNS * tile;
     for (int wj = lane; wj < NW; wj += 32) {
         const uint32_t f = F[rowbits + wj];
         if (!f) continue;
@@ -504,9 +515,9 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_area(const uint32_t* __r
         for_each_segment(f, [&](int k0, uint32_t seg) {
             const int sx = run_start(r, k0);
             const int s = y * W + sx;
-            const int root = uf_find_c(Pt, s);
-            if (sx >= r.wx && root != s) Pt[s] = root;  // flatten the starts that live in this word
-            atomicAdd(A + tile + root, __popc(seg));
+            const int root = rf_find(Pt, s);
+            if (sx >= r.wx && root != s) Pt[kNS * s] = root;  // flatten the starts that live in this word
+            atomicAdd(A + kNS * (tile + root), __popc(seg));
         });
     }
 }
@@ -516,8 +527,8 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_diag(const uint32_t* __r
                                                              const int* __restrict__ A, int min_area, int H, int W) {
     RLE_ROW_COORDS
     if (y == 0) return;
-    int* Pt = P + tile;
-    const int* At = A + tile;
+    int* Pt = P + kNS * tile;
+    const int* At = A + kNS * tile;
     for (int wj = lane; wj < NW; wj += 32) {
         const uint32_t fc = F[rowbits + wj], fp = F[rowbits - NW + wj];
         const uint32_t fcl = left_bits(F + rowbits, NW, wj, fc), fpl = left_bits(F + rowbits - NW, NW, wj, fp);
@@ -532,16 +543,16 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_diag(const uint32_t* __r
         while (dl) {
             const int k = __ffs(dl) - 1;
             dl &= dl - 1;
-            const int ra = uf_find(Pt, y * W + run_start(cur, k));
-            const int rb = uf_find(Pt, (y - 1) * W + (k ? run_start(prv, k - 1) : prv.cin));
-            if (ra != rb && At[ra] >= min_area && At[rb] >= min_area) uf_union(Pt, ra, rb);
+            const int ra = rf_find_ro(Pt, y * W + run_start(cur, k));
+            const int rb = rf_find_ro(Pt, (y - 1) * W + (k ? run_start(prv, k - 1) : prv.cin));
+            if (ra != rb && At[kNS * ra] >= min_area && At[kNS * rb] >= min_area) rf_union(Pt, ra, rb);
         }
         while (dr) {
             const int k = __ffs(dr) - 1;
             dr &= dr - 1;
-            const int ra = uf_find(Pt, (y - 1) * W + run_start(prv, k));
-            const int rb = uf_find(Pt, y * W + (k ? run_start(cur, k - 1) : cur.cin));
-            if (ra != rb && At[ra] >= min_area && At[rb] >= min_area) uf_union(Pt, ra, rb);
+            const int ra = rf_find_ro(Pt, (y - 1) * W + run_start(prv, k));
+            const int rb = rf_find_ro(Pt, y * W + (k ? run_start(cur, k - 1) : cur.cin));
+            if (ra != rb && At[kNS * ra] >= min_area && At[kNS * rb] >= min_area) rf_union(Pt, ra, rb);
         }
     }
 }
@@ -555,8 +566,8 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
                                                                uint32_t* __restrict__ RB, uint32_t* __restrict__ DB,
                                                                int min_area, int H, int W) {
     RLE_ROW_COORDS
-    const int* Pt = P + tile;
-    int* At = A + tile;
+    const int* Pt = P + kNS * tile;
+    int* At = A + kNS * tile;
     int running = 0;
     if (ASSIGN) {
         // id base of this row = surviving roots of the rows above (the per-row counts of a tile are a few KB in L2:
@@ -588,8 +599,9 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int gid = y * W + r.wx + max(kk[i], 0);
-                pv[i] = kk[i] >= 0 ? Pt[gid] : -1;
-                av[i] = kk[i] >= 0 ? At[gid] : 0;
+                const int2 node = kk[i] >= 0 ? *(const int2*)(Pt + kNS * gid) : make_int2(-1, 0);
+                pv[i] = node.x;
+                av[i] = node.y;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -615,12 +627,12 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
             while (roots) {
                 const int k = __ffs(roots) - 1;
                 roots &= roots - 1;
-                At[y * W + r.wx + k] = id++;
+                At[kNS * (y * W + r.wx + k)] = id++;
             }
             while (dead) {  // removed components label their pixels 0
                 const int k = __ffs(dead) - 1;
                 dead &= dead - 1;
-                At[y * W + r.wx + k] = 0;
+                At[kNS * (y * W + r.wx + k)] = 0;
             }
         }
         running += __shfl_sync(kFull, incl, 31);
@@ -653,8 +665,8 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
     const int NW = (W + 31) >> 5;
     const int w0 = blockIdx.x * (chunk_px >> 5) - halo;  // first word of the staged window (may be -1)
     const size_t tile = (size_t)b * H * W;
-    const int* Pt = P + tile;
-    const int* At = A + tile;
+    const int* Pt = P + kNS * tile;
+    const int* At = A + kNS * tile;
     constexpr int SR = kLabRows + 2 * R;
     // zero padding columns
     for (int i = threadIdx.x; i < SR * 2 * kLabPad; i += 256) {
@@ -698,19 +710,18 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
         // the look-ups of the four segments are issued together: parent of the run start (the area pass left it pointing
         // at its root, the diagonal pass may have re-rooted that) -> root -> id.  Three rounds of independent loads
         // instead of up to twelve dependent ones.
-        int par[4], root[4];
+        int par[4];
+        int2 node[4];
 #pragma unroll
-        for (int sgi = 0; sgi < 4; ++sgi) par[sgi] = sidx[sgi] >= 0 ? Pt[sidx[sgi]] : -1;
+        for (int sgi = 0; sgi < 4; ++sgi) par[sgi] = sidx[sgi] >= 0 ? Pt[kNS * sidx[sgi]] : -1;
+        // parent and id sit side by side: when the parent is the root (the common case) its node holds the answer
 #pragma unroll
-        for (int sgi = 0; sgi < 4; ++sgi) root[sgi] = par[sgi] >= 0 ? Pt[par[sgi]] : -1;
+        for (int sgi = 0; sgi < 4; ++sgi) node[sgi] = par[sgi] >= 0 ? *(const int2*)(Pt + kNS * par[sgi]) : make_int2(-1, 0);
 #pragma unroll
         for (int sgi = 0; sgi < 4; ++sgi) {
-            if (root[sgi] >= 0 && root[sgi] != par[sgi]) root[sgi] = uf_find(Pt, root[sgi]);  // rare: a longer chain
-            slab[sgi] = 0;
+            slab[sgi] = node[sgi].y;
+            if (par[sgi] >= 0 && node[sgi].x != par[sgi]) slab[sgi] = At[kNS * rf_find_ro(Pt, node[sgi].x)];  // rare: a longer chain
         }
-#pragma unroll
-        for (int sgi = 0; sgi < 4; ++sgi)
-            if (root[sgi] >= 0) slab[sgi] = At[root[sgi]];
         // the row is zero-filled with 128-bit stores (skewed by the lane: each quarter-warp covers all 32 banks), then
         // only the pixels of labelled segments are written -- a quarter of a tile is nucleus, not all of it
 #pragma unroll
@@ -726,7 +737,7 @@ __global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__
         while (rest) {  // more than four segments in one word: rare
             const int pbit = __ffs(rest) - 1;
             rest &= rest - 1;
-            dst[32 * lane + pbit] = At[uf_find(Pt, y * W + run_start(r, pbit))];
+            dst[32 * lane + pbit] = At[kNS * rf_find_ro(Pt, y * W + run_start(r, pbit))];
         }
     }
     __syncthreads();
@@ -836,8 +847,8 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
     const size_t n = (size_t)B * H * W;
     const size_t nbits = (size_t)B * H * ((W + 31) / 32);
     Arena ar(ws, ws_bytes);
-    int* P = ar.take<int>(n);
-    int* A = ar.take<int>(n);
+    int* P = ar.take<int>(kNS * n);  // nodes: parent at 2 i, aux at 2 i + 1
+    int* A = P + 1;
     uint32_t* M = ar.take<uint32_t>(nbits);
     uint32_t* F = ar.take<uint32_t>(nbits);
     int* C = ar.take<int>(nbits);
