@@ -236,7 +236,9 @@ __device__ __forceinline__ int sf_find(unsigned short* P, int p) {
     int q = P[p];
     while (q != p) {
         const int g = P[q];
+#ifndef CDNET_SF_NO_HALVING
         if (g != q) P[p] = (unsigned short)g;
+#endif
         p = q;
         q = g;
     }

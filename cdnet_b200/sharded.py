@@ -246,7 +246,7 @@ class CudaBackend(object):
         """-> (idmap, n_owned [1] int32 on the device)"""
         from ._cabi import check
         He, W = keep.shape
-        idmap = self.empty((He, W), "int32")
+        idmap = self.zeros((He, W), "int32")  # only root pixels are written; add_offset reads the whole plane
         rowcnt = self.empty((He,), "int32")
         n = self.zeros((1,), "int32")
         check(self.L.cdnet_shard_label_stage4(L.data_ptr(), keep.data_ptr(), excluded.data_ptr(), idmap.data_ptr(),
@@ -341,7 +341,7 @@ class CudaBackend(object):
 
     def seam_export(self, sh, valid, attr, round_id, nb_gid):
         from ._cabi import check
-        tbl = self.empty((sh.cap, 4), "int32")
+        tbl = self.zeros((sh.cap, 4), "int32")  # the whole table travels (all-gather): no undefined tail
         check(self.L.cdnet_seam_export(sh.L.data_ptr(), valid.data_ptr() if valid is not None else None,
                                        attr.data_ptr() if attr is not None else None, sh.emitted.data_ptr(),
                                        int(round_id), int(sh.off), sh.He, sh.L.shape[1], 1 if sh.has_top else 0,
@@ -358,7 +358,7 @@ class CudaBackend(object):
 
     def seam_ids_export(self, sh, gathered, idmap, round_id, W):
         from ._cabi import check
-        tbl2 = self.empty((sh.cap, 4), "int32")
+        tbl2 = self.zeros((sh.cap, 4), "int32")
         check(self.L.cdnet_seam_ids_export(gathered.data_ptr(), sh.world, sh.cap, sh.rank, int(sh.off), sh.r0 * W,
                                            sh.r1 * W, idmap.data_ptr(), sh.emitted.data_ptr(), int(round_id),
                                            tbl2.data_ptr(), sh.seam_ws.data_ptr(), sh.seam_ws.numel(), self._st()),
