@@ -646,6 +646,9 @@ __global__ void __launch_bounds__(32 * kRleWarps) k_rle_number(const uint32_t* _
 // A block owns TR output rows of one column chunk.  Phase 1: warp per staged row, lane per pixel of a 32-pixel
 // word: label = id of the root of the pixel's run (F bit set) or 0; the row goes to shared memory (4 zero columns
 // of padding left and right).  Phase 2: max over disk(R) from shared memory, 4 pixels per thread, written as OUT.
+#ifndef CDNET_LAB_MINB
+#define CDNET_LAB_MINB 4  // resident blocks per SM the register allocation aims at
+#endif
 #ifndef CDNET_LAB_ROWS
 #define CDNET_LAB_ROWS 4
 #endif
@@ -654,7 +657,7 @@ constexpr int kLabPad = 4;
 constexpr int kLabTW = 1024 + 2 * kLabPad;
 
 template <int R, typename OUT>
-__global__ void __launch_bounds__(256) k_rle_labels(const uint32_t* __restrict__ M, const int* __restrict__ C,
+__global__ void __launch_bounds__(256, CDNET_LAB_MINB) k_rle_labels(const uint32_t* __restrict__ M, const int* __restrict__ C,
                                                     const uint32_t* __restrict__ F, const int* __restrict__ P,
                                                     const int* __restrict__ A, OUT* __restrict__ out, int H, int W,
                                                     int chunk_px, int halo) {

@@ -158,3 +158,56 @@ def test_sharded_watershed_overflow_is_reported(kernel_api):
     with pytest.raises(ValueError, match="overlap"):
         sharded.postprocess_slide(shards, sharded.SimComm(3), H, W, sharded.CudaBackend(), 9, 20, 2, postproc=1,
                                   overlap=128)
+
+
+def test_shard_ws_process_entry(kernel_api):
+    """cdnet_shard_ws_process through the C ABI: labels == the oracle's process(); marker_rowmax == the per-row maximum
+    of label4(markers) BEFORE remove_small_objects (postproc_other.py:44 vs :46); the overflow bit for a component that
+    reaches from an outer overlap row into the own rows, and only then"""
+    import torch
+    from scipy import ndimage as ndi
+    from cdnet_b200 import _cabi, synth
+    from oracle import restate as O
+    be = __import__("cdnet_b200.sharded", fromlist=["CudaBackend"]).CudaBackend()
+    d = synth.postproc_inputs(71, 180, 200, 40)
+    pred = (np.argmax(d["prob"], axis=0) == 1).astype(np.uint8)
+    ref, parts = O.process(pred.astype(np.float64).copy(), min_size=10, return_parts=True, literal=False)
+    marker0 = ndi.binary_erosion(ndi.binary_fill_holes(parts["dist"] > 125), iterations=1)
+    rowmax_ref = O.label4(marker0).max(axis=1)
+    labels, rowmax, status = be.ws_process(to_dev(kernel_api, torch.from_numpy(pred)), 0, 180, 10)
+    assert int(status[0]) & 0xff == 0
+    assert np.array_equal(labels.cpu().numpy(), ref)
+    assert np.array_equal(rowmax.cpu().numpy(), rowmax_ref)
+    # own rows [60, 120): nuclei are small, nothing reaches row 0 or row 179 from there
+    _, _, status = be.ws_process(to_dev(kernel_api, torch.from_numpy(pred)), 60, 120, 10)
+    assert not int(status[0]) & _cabi.S_SHARD_OVERFLOW
+    for col, rows in ((20, slice(0, 70)), (150, slice(110, 180))):   # a bar from the top / bottom edge into the own rows
+        p2 = pred.copy()
+        p2[rows, col:col + 3] = 1
+        _, _, status = be.ws_process(to_dev(kernel_api, torch.from_numpy(p2)), 60, 120, 10)
+        assert int(status[0]) & _cabi.S_SHARD_OVERFLOW
+    p2 = pred.copy()
+    p2[0:55, 20:23] = 1      # ends before the own rows: fine
+    p2[58:125, 90:93] = 1    # crosses the own rows but stays inside the tile: fine
+    _, _, status = be.ws_process(to_dev(kernel_api, torch.from_numpy(p2)), 60, 120, 10)
+    assert not int(status[0]) & _cabi.S_SHARD_OVERFLOW
+
+
+def test_shard_ws_relabel_entry(kernel_api):
+    """cdnet_shard_ws_relabel: owned ids by arithmetic, adopted ids through the table, err for an id without owner"""
+    import torch
+    be = __import__("cdnet_b200.sharded", fromlist=["CudaBackend"]).CudaBackend()
+    rng = np.random.default_rng(5)
+    lab = rng.integers(0, 40, size=(37, 53)).astype(np.int32)
+    above, owned, off = 10, 20, 1000
+    lut = np.zeros(64, np.int32)
+    lut[1:11] = 500 + np.arange(10)       # adopted from above
+    lut[31:40] = 2000 + np.arange(9)      # adopted from below
+    want = np.where((lab > above) & (lab <= above + owned), lab - above + off, lut[lab]).astype(np.int32)
+    dev = lambda a: to_dev(kernel_api, torch.from_numpy(a))
+    out = be.empty(lab.shape, "int32")
+    err = be.ws_relabel(dev(lab), dev(np.array([above, owned, off], np.int32)), dev(lut), out)
+    assert int(err[0]) == 0 and np.array_equal(out.cpu().numpy(), want)
+    lut[35] = 0
+    err = be.ws_relabel(dev(lab), dev(np.array([above, owned, off], np.int32)), dev(lut), out)
+    assert int(err[0]) == 1
