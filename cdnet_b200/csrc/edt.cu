@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(128) k_edt_cols_far(const uint8_t* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) k_edt_rows(const int* __restrict__ g2, int* __restrict__ d2, int H, int W) {
+// rowflag[b * H + y] != 0: row y holds a pixel that k_edt_rows_far has to finish
+__global__ void __launch_bounds__(256) k_edt_rows(const int* __restrict__ g2, int* __restrict__ d2, int* __restrict__ rowflag,
+                                                  int H, int W) {
     const int x = blockIdx.x * 64 + threadIdx.x;
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int b = blockIdx.z;
@@ -92,20 +94,25 @@ __global__ void __launch_bounds__(256) k_edt_rows(const int* __restrict__ g2, in
             if (x - k >= 0) best = min(best, kk + min(G[x - k], kInf - kk));
             if (x + k < W) best = min(best, kk + min(G[x + k], kInf - kk));
         }
-        if (k > kcut && kcut < kmax && k * k < best) best = -1;  // unfinished: k_edt_rows_far completes it
+        if (k > kcut && kcut < kmax && k * k < best) {  // unfinished: k_edt_rows_far completes it
+            best = -1;
+            rowflag[(size_t)b * H + y] = 1;
+        }
     }
     d2[tile + (size_t)y * W + x] = best;
 }
 
 // one warp per 32 consecutive pixels of a row; the (rare) marked pixels are finished one after the other, 32 offsets
 // at a time
-__global__ void __launch_bounds__(256) k_edt_rows_far(const int* __restrict__ g2, int* __restrict__ d2, int H, int W) {
+__global__ void __launch_bounds__(256) k_edt_rows_far(const int* __restrict__ g2, int* __restrict__ d2,
+                                                      const int* __restrict__ rowflag, int H, int W) {
     const int lane = threadIdx.x & 31;
     const int x0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
     const int b = blockIdx.z;
     if (x0 >= W) return;
     const size_t tile = (size_t)b * H * W;
     for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    if (!rowflag[(size_t)b * H + y]) continue;  // nothing left in this row (every row of a tile of nuclei)
     const int* G = g2 + tile + (size_t)y * W;
     int* D = d2 + tile + (size_t)y * W;
     const int mine = (x0 + lane < W) ? D[x0 + lane] : 0;
@@ -137,15 +144,17 @@ __global__ void k_sqrt_f64(const int* __restrict__ d2, double* __restrict__ dist
         dist[i] = __dsqrt_rn((double)d2[i]);
 }
 
-int edt_launch(const uint8_t* mask, int32_t* d2, int32_t* g2, int B, int H, int W, cudaStream_t st) {
+int edt_launch(const uint8_t* mask, int32_t* d2, int32_t* g2, int32_t* rowflag, int B, int H, int W, cudaStream_t st) {
     dim3 block(64, 4), grid(ceil_div(W, 64), ceil_div(H, 4), B);
     // the column flags borrow the head of d2, which pass 2 overwrites afterwards
     int* colflag = d2;
     CDNET_CUDA_OK(cudaMemsetAsync(colflag, 0, sizeof(int) * (size_t)B * W, st));
     CDNET_LAUNCH(k_edt_cols, grid, block, 0, st, mask, g2, colflag, H, W);
     if (H > kFar + 1) CDNET_LAUNCH(k_edt_cols_far, dim3(ceil_div(W, 128), B), 128, 0, st, mask, g2, colflag, H, W);
-    CDNET_LAUNCH(k_edt_rows, grid, block, 0, st, g2, d2, H, W);
-    if (W > kFar + 1) CDNET_LAUNCH(k_edt_rows_far, dim3(ceil_div(W, 256), H < 65535 ? H : 65535, B), 256, 0, st, g2, d2, H, W);
+    if (W > kFar + 1) CDNET_CUDA_OK(cudaMemsetAsync(rowflag, 0, sizeof(int) * (size_t)B * H, st));
+    CDNET_LAUNCH(k_edt_rows, grid, block, 0, st, g2, d2, rowflag, H, W);
+    if (W > kFar + 1)
+        CDNET_LAUNCH(k_edt_rows_far, dim3(ceil_div(W, 256), H < 65535 ? H : 65535, B), 256, 0, st, g2, d2, rowflag, H, W);
     return last_error();
 }
 
@@ -155,7 +164,7 @@ using namespace cdnet;
 
 extern "C" size_t cdnet_edt_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0 || (double)H * W >= 2147483648.0) return 0;
-    return pad256((size_t)B * H * W * 4);
+    return pad256((size_t)B * H * W * 4) + pad256((size_t)B * H * 4);
 }
 
 extern "C" int cdnet_edt(const uint8_t* mask, int32_t* d2, double* dist, int B, int H, int W, void* ws, size_t ws_bytes,
@@ -164,9 +173,10 @@ extern "C" int cdnet_edt(const uint8_t* mask, int32_t* d2, double* dist, int B, 
     Arena ar(ws, ws_bytes);
     const size_t n = (size_t)B * H * W;
     int32_t* g2 = ar.take<int32_t>(n);
+    int32_t* rowflag = ar.take<int32_t>((size_t)B * H);
     if (!ar.ok) return CDNET_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = edt_launch(mask, d2, g2, B, H, W, st);
+    int rc = edt_launch(mask, d2, g2, rowflag, B, H, W, st);
     if (rc) return rc;
     if (dist) {
         const size_t blocks = (n + 1023) / 1024;

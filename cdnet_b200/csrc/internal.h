@@ -49,7 +49,8 @@ size_t ws_process_workspace(int B, int H, int W);
 int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, int B, int H, int W, int min_size,
                       int ws_flag, void* ws, size_t ws_bytes, cudaStream_t st, int32_t* marker_rowmax = nullptr,
                       int own_lo = 0, int own_hi = 0);
-int edt_launch(const uint8_t* mask, int32_t* d2, int32_t* g2, int B, int H, int W, cudaStream_t st);
+// rowflag: int32 [B * H] scratch (rows with pixels left for the far pass)
+int edt_launch(const uint8_t* mask, int32_t* d2, int32_t* g2, int32_t* rowflag, int B, int H, int W, cudaStream_t st);
 // squared distance reported where a tile has no background pixel at all (edt.cu)
 constexpr int kEdtInf = 1 << 30;
 

@@ -478,7 +478,7 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     // 1. components of pred (:37) and the exact EDT of the mask (:24 for all instances at once)
     rc = ccl_forest_launch(pred01, A, B, H, W, 4, st);
     if (rc) return rc;
-    rc = edt_launch(pred01, C, Bp, B, H, W, st);
+    rc = edt_launch(pred01, C, Bp, rowcnt, B, H, W, st);  // rowcnt is free until the markers are labelled
     if (rc) return rc;
     CDNET_CUDA_OK(cudaMemsetAsync(D, 0, n * 4, st));
     CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, status, H, W);
