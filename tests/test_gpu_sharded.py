@@ -211,3 +211,28 @@ def test_shard_ws_relabel_entry(kernel_api):
     lut[35] = 0
     err = be.ws_relabel(dev(lab), dev(np.array([above, owned, off], np.int32)), dev(lut), out)
     assert int(err[0]) == 1
+
+
+@pytest.mark.parametrize("G,radius,overlap,out_dtype", [(2, 0, 60, "int64"), (5, 1, 44, "int32"), (3, 2, 52, "int64")])
+def test_sharded_watershed_radius_and_dtype(kernel_api, G, radius, overlap, out_dtype):
+    """postproc = 1 with every dilation radius of the reference and both output types; a crowded slide (touching nuclei
+    that the watershed splits, small markers dropped next to the seams) so that marker ids with gaps cross the seams"""
+    import torch
+    from cdnet_b200 import sharded, synth
+    H, W = 330, 300
+    d = synth.postproc_inputs(90 + G, H, W, 160)
+    dcm, prob, point = d["dcm"].copy(), d["prob"], d["point"]
+    single, _ = kernel_api.dam_postprocess_cuda(to_dev(kernel_api, torch.from_numpy(dcm)[None]),
+                                                to_dev(kernel_api, torch.from_numpy(prob)[None]),
+                                                to_dev(kernel_api, torch.from_numpy(point)[None]), 9, 20, radius, 1,
+                                                out_dtype=getattr(torch, out_dtype))
+    single = single[0].cpu().numpy()
+    ids = np.unique(single)
+    assert len(ids) > 30 and ids.max() > len(ids)          # gaps in the numbering (markers dropped as too small)
+    parts = sharded.row_partition(H, G)
+    shards = [dict(dcm=dcm[:, a:b].copy(), prob=prob[:, a:b].copy(), point=point[:, a:b].copy()) for a, b in parts]
+    outs = sharded.postprocess_slide(shards, sharded.SimComm(G), H, W, sharded.CudaBackend(), 9, 20, radius,
+                                     out_dtype=out_dtype, postproc=1, overlap=overlap)
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    assert got.dtype == single.dtype
+    assert np.array_equal(got, single), int((got != single).sum())

@@ -200,6 +200,52 @@ def test_run_based_tail_fuzz(kernel_api):
                                                                         int((got != ref).sum()))
 
 
+def test_run_based_tail_frame_cases(kernel_api):
+    """background and the image frame (the run-based tail hangs frame-touching background below an 'outside' root):
+    all background, all foreground, a ring whose inside reaches the frame only through a corner pixel / a diagonal gap
+    (background is 4-connected for binary_fill_holes: a diagonal gap does not open a hole), holes on the first and
+    last row / column, every radius"""
+    from oracle import restate as O
+    cases = {}
+    for (H, W) in ((40, 70), (33, 1030)):
+        z = np.zeros((H, W), bool)
+        cases["zeros_%d" % W] = z
+        cases["ones_%d" % W] = ~z
+        ring = z.copy()
+        ring[5:25, 5:30] = True
+        ring[8:22, 8:27] = False
+        cases["ring_%d" % W] = ring
+        gap = ring.copy()
+        gap[5, 5] = False                      # corner of the ring removed: the hole touches outside diagonally only
+        cases["ring_diag_gap_%d" % W] = gap
+        leak = ring.copy()
+        leak[5:8, 15] = False                  # a real 4-connected leak: no hole any more
+        cases["ring_leak_%d" % W] = leak
+        edge = z.copy()
+        edge[0:12, 40:60] = True
+        edge[0:6, 45:50] = False               # notch open to the first row: not a hole
+        edge[8:10, 52:55] = False              # a hole next to it
+        edge[H - 10:H, 0:15] = True
+        edge[H - 5:H - 2, 0:4] = False         # notch open to the first column
+        edge[H - 8:H - 6, 6:9] = False         # hole
+        edge[10:30, W - 12:W] = True
+        edge[15:20, W - 3:W] = False           # notch open to the last column
+        cases["frame_notches_%d" % W] = edge
+        corner = ~z
+        corner[0, 0] = False                   # one background pixel, in the corner
+        corner[H // 2, W // 2] = False         # and one enclosed
+        cases["corner_%d" % W] = corner
+    for name, m in cases.items():
+        prob = np.zeros((3,) + m.shape, np.float32)
+        prob[0] = 0.5
+        prob[1] = m
+        for radius in (0, 1, 2):
+            ref = O.plain_postprocess(prob.copy(), 4, radius, 0)
+            ref = ref["pred_labeled"] if isinstance(ref, dict) else ref
+            got = kernel_api.plain_postprocess(prob.copy(), 4, radius, 0)
+            assert np.array_equal(got, ref), (name, radius, int((got != ref).sum()))
+
+
 @pytest.mark.parametrize("B,H,W", [(5, 1000, 96), (12, 800, 64)])
 def test_run_based_tail_block_rows(kernel_api, B, H, W):
     """batches with 4 736+ rows switch k_rle_pack_link to 16-row blocks (shared-memory union-find over more rows, fewer
