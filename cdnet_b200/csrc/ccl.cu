@@ -894,17 +894,56 @@ __global__ void k_label_hist(const int* __restrict__ labels, int* __restrict__ c
     const int b = blockIdx.y;
     const int* Lb = labels + (size_t)b * plane;
     int* cb = counts + (size_t)b * (plane + 1);
+    if ((plane & 3) == 0 && (((uintptr_t)Lb) & 15) == 0) {
+        // 128-bit loads; equal neighbours inside the quad share one atomic (a quad inside a nucleus: one)
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < plane / 4; q += (size_t)gridDim.x * blockDim.x) {
+            const int4 v = *(const int4*)(Lb + 4 * q);
+            if ((v.x | v.y | v.z | v.w) == 0) continue;
+            const int vs[4] = {v.x, v.y, v.z, v.w};
+            int cur = vs[0], c = 1;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                if (vs[k] == cur) { ++c; continue; }
+                if (cur > 0) atomicAdd(cb + cur, c);
+                cur = vs[k];
+                c = 1;
+            }
+            if (cur > 0) atomicAdd(cb + cur, c);
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((plane + 31) & ~size_t(31));
          i += (size_t)gridDim.x * blockDim.x) {
         const int v = i < plane ? Lb[i] : 0;
+        const unsigned nz = __ballot_sync(0xffffffffu, v > 0);
+        if (!nz) continue;  // 32 unlabelled pixels: most of a tile
+        const int lane = threadIdx.x & 31, first = __ffs(nz) - 1;
+        const int v0 = __shfl_sync(0xffffffffu, v, first);
+        if (__all_sync(0xffffffffu, v <= 0 || v == v0)) {  // one label among them: the inside of a nucleus
+            if (lane == first) atomicAdd(cb + v0, __popc(nz));
+            continue;
+        }
         const unsigned peers = __match_any_sync(0xffffffffu, v);
-        if (v > 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(cb + v, __popc(peers));
+        if (v > 0 && lane == (__ffs(peers) - 1)) atomicAdd(cb + v, __popc(peers));
     }
 }
 __global__ void k_label_drop_small(int* __restrict__ labels, const int* __restrict__ counts, size_t plane, int min_size) {
     const int b = blockIdx.y;
     int* Lb = labels + (size_t)b * plane;
     const int* cb = counts + (size_t)b * (plane + 1);
+    if ((plane & 3) == 0 && (((uintptr_t)Lb) & 15) == 0) {  // 128-bit loads; a quad is stored only when it changes
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < plane / 4; q += (size_t)gridDim.x * blockDim.x) {
+            int4 v = *(const int4*)(Lb + 4 * q);
+            if ((v.x | v.y | v.z | v.w) == 0) continue;
+            bool ch = false;
+            if (v.x > 0 && cb[v.x] < min_size) { v.x = 0; ch = true; }
+            if (v.y > 0 && cb[v.y] < min_size) { v.y = 0; ch = true; }
+            if (v.z > 0 && cb[v.z] < min_size) { v.z = 0; ch = true; }
+            if (v.w > 0 && cb[v.w] < min_size) { v.w = 0; ch = true; }
+            if (ch) *(int4*)(Lb + 4 * q) = v;
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
         const int v = Lb[i];
         if (v > 0 && cb[v] < min_size) Lb[i] = 0;

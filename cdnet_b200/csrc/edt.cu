@@ -153,8 +153,14 @@ int edt_launch(const uint8_t* mask, int32_t* d2, int32_t* g2, int32_t* rowflag, 
     if (H > kFar + 1) CDNET_LAUNCH(k_edt_cols_far, dim3(ceil_div(W, 128), B), 128, 0, st, mask, g2, colflag, H, W);
     if (W > kFar + 1) CDNET_CUDA_OK(cudaMemsetAsync(rowflag, 0, sizeof(int) * (size_t)B * H, st));
     CDNET_LAUNCH(k_edt_rows, grid, block, 0, st, g2, d2, rowflag, H, W);
-    if (W > kFar + 1)
-        CDNET_LAUNCH(k_edt_rows_far, dim3(ceil_div(W, 256), H < 65535 ? H : 65535, B), 256, 0, st, g2, d2, rowflag, H, W);
+    if (W > kFar + 1) {
+        // ~4 000 blocks that loop over the rows: most rows are skipped by their flag, and a block per row would spend the
+        // launch on nothing (56 000 blocks for 14 tiles of 1000^2: 38 us)
+        const int per_tile = ceil_div(W, 256) * B;
+        int gy = 4096 / per_tile;
+        gy = gy < 1 ? 1 : (gy > H ? H : gy);
+        CDNET_LAUNCH(k_edt_rows_far, dim3(ceil_div(W, 256), gy, B), 256, 0, st, g2, d2, rowflag, H, W);
+    }
     return last_error();
 }
 

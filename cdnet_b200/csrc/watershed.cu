@@ -47,11 +47,19 @@ __global__ void __launch_bounds__(kBX* kBY) k_comp_stats(const uint8_t* __restri
         Lt[p] = r;
         d = d2[tile + p];
     }
-    if (r >= 0) {
+    // a warp covers 32 pixels of one row: mostly background, or the inside of ONE nucleus -- then one atomic serves all
+    const unsigned act = __ballot_sync(0xffffffffu, r >= 0);
+    if (!act) return;
+    const int first = __ffs(act) - 1;
+    const int r0 = __shfl_sync(0xffffffffu, r, first);
+    if (__all_sync(0xffffffffu, r < 0 || r == r0)) {
+        const int m = __reduce_max_sync(0xffffffffu, r >= 0 ? d : 0);
+        if (lane == first) atomicMax(maxd2 + tile + r0, m);
+    } else if (r >= 0) {
         atomicMax(maxd2 + tile + r, d);
-        if (d >= kEdtInf && status && !(__ldcg(status + b) & CDNET_S_NO_BACKGROUND))
-            atomicOr(status + b, CDNET_S_NO_BACKGROUND);
     }
+    if (r >= 0 && d >= kEdtInf && status && !(__ldcg(status + b) & CDNET_S_NO_BACKGROUND))
+        atomicOr(status + b, CDNET_S_NO_BACKGROUND);
 }
 
 // dist = uint8(255 * (sqrt(d2) / sqrt(max d2)))  (postproc_other.py:24-26, f64, truncating);
@@ -73,6 +81,37 @@ __global__ void __launch_bounds__(kBX* kBY) k_dist_marker(const uint8_t* __restr
     marker0[tile + p] = dist > 125;
 }
 
+// the same, four pixels per thread (W % 4 == 0, 16-byte aligned planes): 32- and 128-bit accesses, and a thread that sees
+// four background pixels -- most of them -- touches neither the label nor the distance plane
+__global__ void __launch_bounds__(256) k_dist_marker4(const uint8_t* __restrict__ pred, const int* __restrict__ L,
+                                                      const int* __restrict__ d2, const int* __restrict__ maxd2,
+                                                      uint8_t* __restrict__ val, uint8_t* __restrict__ marker0, size_t plane,
+                                                      size_t nquads) {
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = 4 * q;
+        const size_t tile = (i / plane) * plane;
+        const uint32_t pw = *(const uint32_t*)(pred + i);
+        uint32_t vw = 0, mw = 0;
+        if (pw) {
+            const int4 lv = *(const int4*)(L + i);
+            const int4 dv = *(const int4*)(d2 + i);
+            const int ls[4] = {lv.x, lv.y, lv.z, lv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if ((pw >> (8 * k)) & 0xffu) {
+                    const double d = __dsqrt_rn((double)ds[k]);
+                    const double dm = __dsqrt_rn((double)maxd2[tile + ls[k]]);
+                    const uint32_t dist = (uint32_t)(uint8_t)(int)__dmul_rn(255.0, __ddiv_rn(d, dm));
+                    vw |= ((0u - dist) & 0xffu) << (8 * k);
+                    mw |= (uint32_t)(dist > 125u) << (8 * k);
+                }
+            }
+        }
+        *(uint32_t*)(val + i) = vw;
+        *(uint32_t*)(marker0 + i) = mw;
+    }
+}
+
 // binary_erosion(iterations=1): cross structure, border_value 0 (postproc_other.py:43)
 __global__ void __launch_bounds__(kBX* kBY) k_erode_cross(const uint8_t* __restrict__ state, uint8_t* __restrict__ out,
                                                           int H, int W) {
@@ -84,18 +123,71 @@ __global__ void __launch_bounds__(kBX* kBY) k_erode_cross(const uint8_t* __restr
     out[tile + p] = k;
 }
 
+// four pixels per thread (W % 4 == 0, aligned planes): the cross is an AND of five byte-words
+__global__ void __launch_bounds__(256) k_erode_cross4(const uint8_t* __restrict__ state, uint8_t* __restrict__ out, int H,
+                                                      int W, size_t nquads) {
+    const int WQ = W >> 2;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
+        const int xq = (int)(q % WQ);
+        const int y = (int)((q / WQ) % H);
+        const size_t i = 4 * q;
+        auto nz = [](uint32_t w) { return ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) >> 7) & 0x01010101u; };
+        uint32_t r = 0;
+        const uint32_t c = nz(*(const uint32_t*)(state + i));
+        if (c && y > 0 && y + 1 < H) {
+            const uint32_t up = nz(*(const uint32_t*)(state + i - W)), dn = nz(*(const uint32_t*)(state + i + W));
+            const uint32_t lf = xq > 0 ? (uint32_t)(state[i - 1] != 0) : 0u;           // border_value 0
+            const uint32_t rt = xq + 1 < WQ ? (uint32_t)(state[i + 4] != 0) : 0u;
+            r = c & up & dn & ((c << 8) | lf) & ((c >> 8) | (rt << 24));
+        }
+        *(uint32_t*)(out + i) = r;
+    }
+}
+
 // out <- markers * mask (skimage watershed's input validation); bounding box of every component of
 // pred, keyed by its root
 __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restrict__ pred, const int* __restrict__ L,
                                                          int* __restrict__ out, int* __restrict__ ymax,
                                                          int* __restrict__ xmin, int* __restrict__ xmax,
                                                          unsigned int* __restrict__ rootlist, int* __restrict__ nroots,
+                                                         const uint8_t* __restrict__ val, int32_t* __restrict__ status,
                                                          int H, int W) {
     PX_COORDS
     int r = -1;
+    bool contested = false;
     if (inb) {
-        if (pred[tile + p]) r = L[tile + p];
-        else out[tile + p] = 0;
+        if (pred[tile + p]) {
+            r = L[tile + p];
+            // Diagnostic for the one place where parity with scikit-image is unpinned: pixels that
+            // two age-0 markers of EQUAL priority compete for.  skimage's heap pops such markers in an order that depends
+            // on its internal heap mechanics; this build pops them in raster order.  A mask pixel without a marker is
+            // counted when the smallest priority among its 4-neighbouring marker pixels is held by markers of two
+            // different labels (first-order exposure: whichever of them is popped first labels the pixel).  The count
+            // lands in status bits 8..31.  Marker pixels outside the mask are being zeroed by their own threads right
+            // now, so a neighbour counts only where the mask is set (markers * mask).
+            if (status && out[tile + p] == 0) {
+                int best = 256, lab = 0;
+                const int dy[4] = {-1, 0, 0, 1}, dx[4] = {0, -1, 1, 0};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int yy = y + dy[k], xx = x + dx[k];
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    const int q = yy * W + xx;
+                    if (!pred[tile + q]) continue;
+                    const int l = out[tile + q];
+                    if (l <= 0) continue;
+                    const int v = val[tile + q];
+                    if (v < best) { best = v; lab = l; contested = false; }
+                    else if (v == best && l != lab) contested = true;
+                }
+            }
+        } else {
+            out[tile + p] = 0;
+        }
+    }
+    {
+        const unsigned mc = __ballot_sync(0xffffffffu, contested);
+        if (lane == 0 && mc) atomicAdd(status + b, __popc(mc) << 8);
     }
     {
         // compact list of component roots: the flood kernel hands them out to persistent warps
@@ -106,7 +198,12 @@ __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restri
         basei = __shfl_sync(0xffffffffu, basei, 0);
         if (is_root) rootlist[basei + __popc(m & ((1u << lane) - 1))] = (unsigned int)(tile + p);
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, r);
+    // bounding boxes: one set of atomics per (warp, component).  A warp is 32 pixels of one row -- mostly no component
+    // at all, or one; only a mixed warp pays for the match
+    const unsigned act = __ballot_sync(0xffffffffu, r >= 0);
+    if (!act) return;
+    const int r0 = __shfl_sync(0xffffffffu, r, __ffs(act) - 1);
+    const unsigned peers = __all_sync(0xffffffffu, r < 0 || r == r0) ? act : __match_any_sync(0xffffffffu, r);
     if (r >= 0) {
         const int first = __ffs(peers) - 1, last = 31 - __clz(peers);
         if (lane == first) {
@@ -115,37 +212,6 @@ __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restri
         }
         if (lane == last) atomicMax(xmax + tile + r, x);
     }
-}
-
-// Diagnostic for the one place where parity with scikit-image is unpinned: pixels that two
-// age-0 markers of EQUAL priority compete for.  skimage's heap pops such markers in an order that depends on its
-// internal heap mechanics; this build pops them in raster order.  A mask pixel without a marker is counted when the
-// smallest priority among its 4-neighbouring marker pixels is held by markers of two different labels (first-order
-// exposure: whichever of them is popped first labels the pixel).  The count lands in status bits 8..31.
-__global__ void __launch_bounds__(kBX* kBY) k_ws_contested(const uint8_t* __restrict__ pred, const int* __restrict__ marker,
-                                                           const uint8_t* __restrict__ val, int32_t* __restrict__ status,
-                                                           int H, int W) {
-    PX_COORDS
-    bool hit = false;
-    if (inb && pred[tile + p] && marker[tile + p] == 0) {
-        int best = 256, lab = 0;
-        bool two = false;
-        const int dy[4] = {-1, 0, 0, 1}, dx[4] = {0, -1, 1, 0};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int yy = y + dy[k], xx = x + dx[k];
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const int q = yy * W + xx;
-            const int l = marker[tile + q];
-            if (l <= 0) continue;
-            const int v = val[tile + q];
-            if (v < best) { best = v; lab = l; two = false; }
-            else if (v == best && l != lab) two = true;
-        }
-        hit = two;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0 && m) atomicAdd(status + b, __popc(m) << 8);
 }
 
 // rowmax[b][y] = largest marker id on row y.  Ids are handed out in raster order of the components' first pixels, so
@@ -487,11 +553,22 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
             CDNET_LAUNCH(k_shard_overflow, dim3(ceil_div(W, 256), B), 256, 0, st, pred01, A, E, status, H, W, own_lo,
                          own_hi, step);
     // 2. uint8 distance, its negation, markers (:25-26, :39-41, :47)
-    CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, H, W);
+    if (W % 4 == 0 && (((uintptr_t)pred01 | (uintptr_t)val | (uintptr_t)mk) & 3) == 0) {
+        const size_t nq = n / 4, blocks = (nq + 255) / 256;
+        CDNET_LAUNCH(k_dist_marker4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, pred01, A, C, D, val, mk,
+                     (size_t)H * W, nq);
+    } else {
+        CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, H, W);
+    }
     // 3. fill holes, cross erosion, label, remove small (:42-46)
     rc = fill_holes_state_launch(mk, state, C, Bp, B, H, W, st);
     if (rc) return rc;
-    CDNET_LAUNCH(k_erode_cross, px_grid(B, H, W), px_block(), 0, st, state, mk, H, W);
+    if (W % 4 == 0 && (((uintptr_t)state | (uintptr_t)mk) & 3) == 0) {
+        const size_t nq = n / 4, blocks = (nq + 255) / 256;
+        CDNET_LAUNCH(k_erode_cross4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, state, mk, H, W, nq);
+    } else {
+        CDNET_LAUNCH(k_erode_cross, px_grid(B, H, W), px_block(), 0, st, state, mk, H, W);
+    }
     rc = ccl_label_launch(mk, labels, nullptr, C, Bp, rowcnt, B, H, W, 4, st);
     if (rc) return rc;
     if (marker_rowmax) {
@@ -507,8 +584,8 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     // of roots, rowcnt[1] = work-stealing cursor
     unsigned int* rootlist = (unsigned int*)counts;
     CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, 2 * sizeof(int32_t), st));
-    CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, H, W);
-    if (status) CDNET_LAUNCH(k_ws_contested, px_grid(B, H, W), px_block(), 0, st, pred01, labels, val, status, H, W);
+    CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, val, status,
+                 H, W);
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;
