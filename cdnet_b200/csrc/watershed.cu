@@ -62,6 +62,44 @@ __global__ void __launch_bounds__(kBX* kBY) k_comp_stats(const uint8_t* __restri
         atomicOr(status + b, CDNET_S_NO_BACKGROUND);
 }
 
+// four pixels per thread (W % 4 == 0, aligned planes); pixels of one quad that share a root share the atomic
+__global__ void __launch_bounds__(256) k_comp_stats4(const uint8_t* __restrict__ pred, int* __restrict__ L,
+                                                     const int* __restrict__ d2, int* __restrict__ maxd2,
+                                                     int32_t* __restrict__ status, size_t plane, size_t nquads) {
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = 4 * q;
+        const uint32_t pw = *(const uint32_t*)(pred + i);
+        if (!pw) continue;
+        const size_t b = i / plane, tile = b * plane;
+        int* Lt = L + tile;
+        const int p0 = (int)(i - tile);
+        const int4 dv = *(const int4*)(d2 + i);
+        const int ds[4] = {dv.x, dv.y, dv.z, dv.w};
+        int4 lv = *(const int4*)(L + i);
+        int rs[4] = {lv.x, lv.y, lv.z, lv.w};
+        int cur = -1, m = 0;
+        bool inf = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((pw >> (8 * k)) & 0xffu)) continue;
+            int r = rs[k];                       // the pixel's parent: walk on from there
+            if (r != p0 + k) r = uf_find(Lt, r);
+            rs[k] = r;
+            inf = inf || ds[k] >= kEdtInf;
+            if (r != cur) {
+                if (cur >= 0) atomicMax(maxd2 + tile + cur, m);
+                cur = r;
+                m = ds[k];
+            } else {
+                m = max(m, ds[k]);
+            }
+        }
+        if (cur >= 0) atomicMax(maxd2 + tile + cur, m);
+        *(int4*)(L + i) = make_int4(rs[0], rs[1], rs[2], rs[3]);  // background entries are written back unchanged
+        if (inf && status && !(__ldcg(status + b) & CDNET_S_NO_BACKGROUND)) atomicOr(status + b, CDNET_S_NO_BACKGROUND);
+    }
+}
+
 // dist = uint8(255 * (sqrt(d2) / sqrt(max d2)))  (postproc_other.py:24-26, f64, truncating);
 // val = (uint8)(-dist) (:47); marker0 = dist > 125 (:39-41)
 __global__ void __launch_bounds__(kBX* kBY) k_dist_marker(const uint8_t* __restrict__ pred, const int* __restrict__ L,
@@ -245,6 +283,116 @@ __global__ void __launch_bounds__(256) k_shard_overflow(const uint8_t* __restric
     }
     if (step == 2 && own_lo > 0 && pred[tile + pt]) bad = bad || L[tile + pt] < W;  // root on row 0
     if (bad) atomicOr(status + b, CDNET_S_SHARD_OVERFLOW);
+}
+
+// one quad of k_flood_prep4
+__device__ __forceinline__ void flood_prep_quad(const uint8_t* __restrict__ pred, const int* __restrict__ L,
+                                                int* __restrict__ out, int* __restrict__ ymax, int* __restrict__ xmin,
+                                                int* __restrict__ xmax, unsigned int* s_roots, int* s_n,
+                                                const uint8_t* __restrict__ val, int32_t* __restrict__ status, int H, int W,
+                                                size_t plane, size_t q) {
+    {
+        const size_t i = 4 * q;
+        const uint32_t pw = *(const uint32_t*)(pred + i);
+        if (!pw) {
+            *(int4*)(out + i) = make_int4(0, 0, 0, 0);
+            return;
+        }
+        const size_t b = i / plane, tile = b * plane;
+        const int p0 = (int)(i - tile), y = p0 / W, x0 = p0 - y * W;
+        const int4 lv = *(const int4*)(L + i);
+        const int4 ov4 = *(const int4*)(out + i);
+        const int ls[4] = {lv.x, lv.y, lv.z, lv.w};
+        int ov[4] = {ov4.x, ov4.y, ov4.z, ov4.w};
+        const uint32_t left = x0 > 0 ? pred[i - 1] : 0u, right = x0 + 4 < W ? pred[i + 4] : 0u;
+        const uint32_t below = y + 1 < H ? *(const uint32_t*)(pred + i + W) : 0u;
+        int ncont = 0;
+        bool need = false;  // a mask pixel without a marker
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((pw >> (8 * k)) & 0xffu)) {
+                ov[k] = 0;  // markers * mask
+                continue;
+            }
+            const int r = ls[k], x = x0 + k;
+            if (r == p0 + k) s_roots[atomicAdd(s_n, 1)] = (unsigned int)(tile + p0 + k);
+            const uint32_t lf = k ? ((pw >> (8 * (k - 1))) & 0xffu) : left;
+            const uint32_t rt = k < 3 ? ((pw >> (8 * (k + 1))) & 0xffu) : right;
+            if (!lf) atomicMin(xmin + tile + r, x);
+            if (!rt) atomicMax(xmax + tile + r, x);
+            if (!((below >> (8 * k)) & 0xffu)) atomicMax(ymax + tile + r, y);
+            need = need || ov[k] == 0;
+        }
+        if (status && need) {
+            // tie exposure (see k_flood_prep): the markers around the quad arrive as quads too, gated by the mask
+            // (markers * mask); values are fetched only next to a marker
+            const uint32_t above = y > 0 ? *(const uint32_t*)(pred + i - W) : 0u;
+            const int4 zero4 = make_int4(0, 0, 0, 0);
+            const int4 upo = above ? *(const int4*)(out + i - W) : zero4;
+            const int4 dno = below ? *(const int4*)(out + i + W) : zero4;
+            const int ups[4] = {upo.x, upo.y, upo.z, upo.w}, dns[4] = {dno.x, dno.y, dno.z, dno.w};
+            const int os[4] = {ov4.x, ov4.y, ov4.z, ov4.w};
+            const int lfo = left ? out[i - 1] : 0, rto = right ? out[i + 4] : 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!((pw >> (8 * k)) & 0xffu) || os[k] != 0) continue;
+                int nl[4];
+                nl[0] = ((above >> (8 * k)) & 0xffu) ? ups[k] : 0;
+                nl[1] = k ? (((pw >> (8 * (k - 1))) & 0xffu) ? os[k > 0 ? k - 1 : 0] : 0) : lfo;
+                nl[2] = k < 3 ? (((pw >> (8 * (k + 1))) & 0xffu) ? os[k < 3 ? k + 1 : 3] : 0) : rto;
+                nl[3] = ((below >> (8 * k)) & 0xffu) ? dns[k] : 0;
+                if (nl[0] <= 0 && nl[1] <= 0 && nl[2] <= 0 && nl[3] <= 0) continue;
+                const ptrdiff_t off[4] = {-(ptrdiff_t)W, -1, 1, (ptrdiff_t)W};
+                int best = 256, lab = 0;
+                bool two = false;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (nl[d] <= 0) continue;
+                    const int v = val[(ptrdiff_t)(i + k) + off[d]];
+                    if (v < best) { best = v; lab = nl[d]; two = false; }
+                    else if (v == best && nl[d] != lab) two = true;
+                }
+                ncont += two;
+            }
+        }
+        *(int4*)(out + i) = make_int4(ov[0], ov[1], ov[2], ov[3]);
+        if (ncont) atomicAdd(status + b, ncont << 8);
+    }
+}
+
+// k_flood_prep, four pixels per thread (W % 4 == 0, aligned planes).  Quads without a mask pixel -- most -- are one
+// 128-bit store.  The bounding box needs atomics only where the component ends: x_min where the left neighbour is not
+// mask (in a 4-connected labelling a mask neighbour is the same component), x_max / y_max likewise.
+__global__ void __launch_bounds__(256) k_flood_prep4(const uint8_t* __restrict__ pred, const int* __restrict__ L,
+                                                     int* __restrict__ out, int* __restrict__ ymax,
+                                                     int* __restrict__ xmin, int* __restrict__ xmax,
+                                                     unsigned int* __restrict__ rootlist, int* __restrict__ nroots,
+                                                     const uint8_t* __restrict__ val, int32_t* __restrict__ status, int H,
+                                                     int W, size_t nquads) {
+    // The compact list of component roots (work items of k_flood) is filled through ONE counter: thousands of returning
+    // atomics on one address serialise (~17 ns each: they WERE this kernel's run time), so a block collects its roots in
+    // shared memory and reserves list space once per ~1000 roots.
+    __shared__ unsigned int s_roots[2048];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const size_t plane = (size_t)H * W;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t iters = (nquads + stride - 1) / stride;  // the same for every thread: the flush below has barriers
+    for (size_t it = 0; it < iters; ++it) {
+        const size_t q = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (q < nquads) flood_prep_quad(pred, L, out, ymax, xmin, xmax, s_roots, &s_n, val, status, H, W, plane, q);
+        __syncthreads();
+        if (s_n > 1024 || it + 1 == iters) {  // at most 512 roots join per round (neighbours share a root)
+            const int cnt = s_n;
+            if (threadIdx.x == 0 && cnt) s_base = atomicAdd(nroots, cnt);
+            __syncthreads();
+            for (int j = threadIdx.x; j < cnt; j += blockDim.x) rootlist[s_base + j] = s_roots[j];
+            __syncthreads();
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kBX* kBY) k_bbox_init(int* __restrict__ ymax, int* __restrict__ xmin,
@@ -547,7 +695,13 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     rc = edt_launch(pred01, C, Bp, rowcnt, B, H, W, st);  // rowcnt is free until the markers are labelled
     if (rc) return rc;
     CDNET_CUDA_OK(cudaMemsetAsync(D, 0, n * 4, st));
-    CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, status, H, W);
+    if (W % 4 == 0 && (((uintptr_t)pred01) & 3) == 0) {
+        const size_t nq = n / 4, blocks = (nq + 255) / 256;
+        CDNET_LAUNCH(k_comp_stats4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, pred01, A, C, D, status,
+                     (size_t)H * W, nq);
+    } else {
+        CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, status, H, W);
+    }
     if (marker_rowmax && status && (own_lo > 0 || own_hi < H))
         for (int step = 0; step < 3; ++step)  // E is free until the flood
             CDNET_LAUNCH(k_shard_overflow, dim3(ceil_div(W, 256), B), 256, 0, st, pred01, A, E, status, H, W, own_lo,
@@ -584,8 +738,15 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     // of roots, rowcnt[1] = work-stealing cursor
     unsigned int* rootlist = (unsigned int*)counts;
     CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, 2 * sizeof(int32_t), st));
-    CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, val, status,
-                 H, W);
+    if (W % 4 == 0 && (((uintptr_t)pred01) & 3) == 0) {
+        const size_t nq = n / 4, blocks = (nq + 255) / 256;
+        // a small grid: every block flushes its roots with one atomic at the end (plus one per ~1000 roots)
+        CDNET_LAUNCH(k_flood_prep4, (unsigned)(blocks > 148u * 8 ? 148u * 8 : blocks), 256, 0, st, pred01, A, labels, Bp, C, D,
+                     rootlist, rowcnt, val, status, H, W, nq);
+    } else {
+        CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, val,
+                     status, H, W);
+    }
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;

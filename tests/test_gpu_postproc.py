@@ -201,3 +201,36 @@ def test_direction_argmax_handoff(kernel_api):
         clear = (top2[0] - top2[1]) > 1e-6   # an exact tie-break is a property of torch's kernels, not ours
         assert torch.equal(cls[i].long()[clear], torch.argmax(d, dim=0)[clear])
         assert torch.allclose(prob[i], p, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed,H,W", [(22, 200, 320), (22, 200, 323), (24, 200, 320), (24, 200, 323)])
+def test_watershed_tie_counter_exact(kernel_api, seed, H, W):
+    """the tie-exposure count (status >> 8) against a numpy restatement on the oracle's markers and priorities, on the
+    4-pixels-per-thread kernel (W % 4 == 0) and on the scalar one; noisy blobs whose fragmented markers do produce ties
+    (1 .. 7 per mask)"""
+    import torch
+    from scipy import ndimage as ndi
+    from oracle import restate as O
+    rng = np.random.default_rng(seed)
+    pred = ndi.binary_dilation(rng.random((H, W)) < 0.006, iterations=7)
+    pred &= rng.random((H, W)) < 0.97
+    _, parts = O.process(pred.astype(np.float64).copy(), min_size=10, return_parts=True, literal=False)
+    marker = parts["marker"] * pred
+    val = (-parts["dist"]).astype(np.uint8).astype(np.int32)
+    want = 0
+    for y, x in zip(*np.nonzero(pred & (marker == 0))):
+        best, labs = 256, set()
+        for dy, dx in ((-1, 0), (0, -1), (0, 1), (1, 0)):
+            yy, xx = y + dy, x + dx
+            if 0 <= yy < H and 0 <= xx < W and marker[yy, xx] > 0:
+                v = val[yy, xx]
+                if v < best:
+                    best, labs = v, {marker[yy, xx]}
+                elif v == best:
+                    labs.add(marker[yy, xx])
+        want += len(labs) > 1
+    assert want > 0
+    _, status = kernel_api.process_cuda(to_dev(kernel_api, torch.from_numpy(pred.astype(np.uint8))[None]), 10, True,
+                                        return_status=True)
+    got = int(kernel_api.ws_contested_pixels(status)[0])
+    assert got == want, (got, want)
