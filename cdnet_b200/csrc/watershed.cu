@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restri
                                                          int* __restrict__ out, int* __restrict__ ymax,
                                                          int* __restrict__ xmin, int* __restrict__ xmax,
                                                          unsigned int* __restrict__ rootlist, int* __restrict__ nroots,
-                                                         const uint8_t* __restrict__ val, int32_t* __restrict__ status,
-                                                         int H, int W) {
+                                                         int* __restrict__ flag, const uint8_t* __restrict__ val,
+                                                         int32_t* __restrict__ status, int H, int W) {
     PX_COORDS
     int r = -1;
     bool contested = false;
@@ -228,13 +228,15 @@ __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restri
         if (lane == 0 && mc) atomicAdd(status + b, __popc(mc) << 8);
     }
     {
-        // compact list of component roots: the flood kernel hands them out to persistent warps
-        const bool is_root = r == p;
-        const unsigned m = __ballot_sync(0xffffffffu, is_root);
+        // compact list of the components that hold a marker (the others stay unlabelled: nothing to flood) -- the flood
+        // kernel hands them out to persistent warps.  The first marker pixel to raise its component's flag enters it.
+        bool rep = false;
+        if (r >= 0 && out[tile + p] > 0 && __ldcg(flag + tile + r) == 0) rep = atomicExch(flag + tile + r, 1) == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, rep);
         int basei = 0;
         if (lane == 0 && m) basei = atomicAdd(nroots, __popc(m));
         basei = __shfl_sync(0xffffffffu, basei, 0);
-        if (is_root) rootlist[basei + __popc(m & ((1u << lane) - 1))] = (unsigned int)(tile + p);
+        if (rep) rootlist[basei + __popc(m & ((1u << lane) - 1))] = (unsigned int)(tile + r);
     }
     // bounding boxes: one set of atomics per (warp, component).  A warp is 32 pixels of one row -- mostly no component
     // at all, or one; only a mixed warp pays for the match
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(256) k_shard_overflow(const uint8_t* __restric
 __device__ __forceinline__ void flood_prep_quad(const uint8_t* __restrict__ pred, const int* __restrict__ L,
                                                 int* __restrict__ out, int* __restrict__ ymax, int* __restrict__ xmin,
                                                 int* __restrict__ xmax, unsigned int* s_roots, int* s_n,
-                                                const uint8_t* __restrict__ val, int32_t* __restrict__ status, int H, int W,
+                                                int* __restrict__ flag, const uint8_t* __restrict__ val, int32_t* __restrict__ status, int H, int W,
                                                 size_t plane, size_t q) {
     {
         const size_t i = 4 * q;
@@ -315,7 +317,9 @@ __device__ __forceinline__ void flood_prep_quad(const uint8_t* __restrict__ pred
                 continue;
             }
             const int r = ls[k], x = x0 + k;
-            if (r == p0 + k) s_roots[atomicAdd(s_n, 1)] = (unsigned int)(tile + p0 + k);
+            // (a plain look first: after the component's first marker pixel the flag is up and no atomic is needed)
+            if (ov[k] > 0 && __ldcg(flag + tile + r) == 0 && atomicExch(flag + tile + r, 1) == 0)
+                s_roots[atomicAdd(s_n, 1)] = (unsigned int)(tile + r);
             const uint32_t lf = k ? ((pw >> (8 * (k - 1))) & 0xffu) : left;
             const uint32_t rt = k < 3 ? ((pw >> (8 * (k + 1))) & 0xffu) : right;
             if (!lf) atomicMin(xmin + tile + r, x);
@@ -367,9 +371,9 @@ __global__ void __launch_bounds__(256) k_flood_prep4(const uint8_t* __restrict__
                                                      int* __restrict__ out, int* __restrict__ ymax,
                                                      int* __restrict__ xmin, int* __restrict__ xmax,
                                                      unsigned int* __restrict__ rootlist, int* __restrict__ nroots,
-                                                     const uint8_t* __restrict__ val, int32_t* __restrict__ status, int H,
-                                                     int W, size_t nquads) {
-    // The compact list of component roots (work items of k_flood) is filled through ONE counter: thousands of returning
+                                                     int* __restrict__ flag, const uint8_t* __restrict__ val,
+                                                     int32_t* __restrict__ status, int H, int W, size_t nquads) {
+    // The compact list of the components with a marker (work items of k_flood) is filled through ONE counter: thousands of returning
     // atomics on one address serialise (~17 ns each: they WERE this kernel's run time), so a block collects its roots in
     // shared memory and reserves list space once per ~1000 roots.
     __shared__ unsigned int s_roots[2048];
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(256) k_flood_prep4(const uint8_t* __restrict__
     const size_t iters = (nquads + stride - 1) / stride;  // the same for every thread: the flush below has barriers
     for (size_t it = 0; it < iters; ++it) {
         const size_t q = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if (q < nquads) flood_prep_quad(pred, L, out, ymax, xmin, xmax, s_roots, &s_n, val, status, H, W, plane, q);
+        if (q < nquads) flood_prep_quad(pred, L, out, ymax, xmin, xmax, s_roots, &s_n, flag, val, status, H, W, plane, q);
         __syncthreads();
         if (s_n > 1024 || it + 1 == iters) {  // at most 512 roots join per round (neighbours share a root)
             const int cnt = s_n;
@@ -738,13 +742,14 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     // of roots, rowcnt[1] = work-stealing cursor
     unsigned int* rootlist = (unsigned int*)counts;
     CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, 2 * sizeof(int32_t), st));
+    CDNET_CUDA_OK(cudaMemsetAsync(E, 0, n * 4, st));  // "component is on the list" flags, keyed by root (free until the flood)
     if (W % 4 == 0 && (((uintptr_t)pred01) & 3) == 0) {
         const size_t nq = n / 4, blocks = (nq + 255) / 256;
         // a small grid: every block flushes its roots with one atomic at the end (plus one per ~1000 roots)
         CDNET_LAUNCH(k_flood_prep4, (unsigned)(blocks > 148u * 8 ? 148u * 8 : blocks), 256, 0, st, pred01, A, labels, Bp, C, D,
-                     rootlist, rowcnt, val, status, H, W, nq);
+                     rootlist, rowcnt, E, val, status, H, W, nq);
     } else {
-        CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, val,
+        CDNET_LAUNCH(k_flood_prep, px_grid(B, H, W), px_block(), 0, st, pred01, A, labels, Bp, C, D, rootlist, rowcnt, E, val,
                      status, H, W);
     }
     static int n_sm = 0;
