@@ -37,6 +37,8 @@ size_t rle_tail_workspace(int B, int H, int W);
 bool rle_tail_supported(int radius);
 int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
                     void* ws, size_t ws_bytes, cudaStream_t st);
+// plain 4-connected labelling with raster-first ids through the run-based kernels (workspace: rle_tail_workspace)
+int rle_label4_launch(const uint8_t* mask, int32_t* labels, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // morph.cu ----------------------------------------------------------------------------------------
 int label_dilate_launch(const int32_t* labels, void* out, int out_elem_bytes, int B, int H, int W, int radius,

@@ -847,8 +847,10 @@ bool rle_tail_supported(int radius) {
 }
 
 // inside (0 / non-zero bytes) -> out = dilation(label8(remove_small(fill_holes(inside), min_area)), disk(radius))
-int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
-                    void* ws, size_t ws_bytes, cudaStream_t st) {
+// label4: plain 4-connected labelling of the mask (no hole filling, no size filter, no diagonal joins, no dilation) with
+// the same raster-first numbering -- what process() needs for its markers (postproc_other.py:44)
+static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
+                     bool label4, void* ws, size_t ws_bytes, cudaStream_t st) {
     const size_t n = (size_t)B * H * W;
     const size_t nbits = (size_t)B * H * ((W + 31) / 32);
     Arena ar(ws, ws_bytes);
@@ -910,6 +912,12 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
             if (H > 64) CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 64), 32 * kLinkWarps, 0, st, M, C, P, H, W, 64, 0);
         }
     }
+    if (label4) {
+        // every foreground root survives (aux is still 0 >= 0); the filled plane is the mask itself
+        CDNET_LAUNCH_PDL(k_rle_number<false>, grid, threads, 0, st, M, P, A, rowcnt, RB, DB, 0, H, W);
+        CDNET_LAUNCH_PDL(k_rle_number<true>, grid, threads, 0, st, M, P, A, rowcnt, RB, DB, 0, H, W);
+        return rle_labels_launch<0, int32_t>(M, C, M, P, A, (int32_t*)out, B, H, W, st);
+    }
     CDNET_LAUNCH_PDL(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
     CDNET_LAUNCH_PDL(k_rle_area, grid, threads, 0, st, M, C, F, P, A, H, W);
     CDNET_LAUNCH_PDL(k_rle_diag, grid, threads, 0, st, M, C, F, P, A, min_area, H, W);
@@ -923,6 +931,15 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
     if (radius == 0) return rle_labels_launch<0, long long>(M, C, F, P, A, (long long*)out, B, H, W, st);
     if (radius == 1) return rle_labels_launch<1, long long>(M, C, F, P, A, (long long*)out, B, H, W, st);
     return rle_labels_launch<2, long long>(M, C, F, P, A, (long long*)out, B, H, W, st);
+}
+
+int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    return rle_chain(inside, out, out_elem_bytes, B, H, W, min_area, radius, false, ws, ws_bytes, st);
+}
+
+int rle_label4_launch(const uint8_t* mask, int32_t* labels, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return rle_chain(mask, labels, 4, B, H, W, 0, 0, true, ws, ws_bytes, st);
 }
 
 }  // namespace cdnet

@@ -727,7 +727,16 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     } else {
         CDNET_LAUNCH(k_erode_cross, px_grid(B, H, W), px_block(), 0, st, state, mk, H, W);
     }
-    rc = ccl_label_launch(mk, labels, nullptr, C, Bp, rowcnt, B, H, W, 4, st);
+    // label the markers (:44).  Bp .. E are free here and lie back to back in the workspace: room for the run-based
+    // labelling (node plane + bit-planes); tiny tiles, where the 256-byte padding of its slices does not fit, and
+    // CDNET_NO_RLE=1 take the pixel-parent kernels
+    {
+        const size_t span = (size_t)((char*)E - (char*)Bp) + pad256(n * 4);
+        if (rle_tail_supported(0) && span >= rle_tail_workspace(B, H, W))
+            rc = rle_label4_launch(mk, labels, B, H, W, Bp, span, st);
+        else
+            rc = ccl_label_launch(mk, labels, nullptr, C, Bp, rowcnt, B, H, W, 4, st);
+    }
     if (rc) return rc;
     if (marker_rowmax) {
         // markers of all sizes: the small ones dropped next keep their ids reserved (:46 leaves gaps)
