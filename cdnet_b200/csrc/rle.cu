@@ -256,7 +256,10 @@ __device__ __forceinline__ void sf_union(unsigned short* P, int a, int b) {
     }
 }
 
-template <int ROWS>
+// ERODED: the input is not a byte mask but a bit-plane (the filled plane F of a previous chain, passed through `mask`),
+// eroded on the fly with the cross structure and a zero border -- binary_erosion(iterations=1) of postproc_other.py:43
+// between the hole filling and the labelling of the markers, without ever leaving the bit domain.
+template <int ROWS, bool ERODED = false>
 __global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M,
                                                              int* __restrict__ C, int* __restrict__ P,
                                                              int* __restrict__ A, int H, int W) {
@@ -280,7 +283,16 @@ __global__ void __launch_bounds__(32 * ROWS) k_rle_pack_link(const uint8_t* __re
         const bool vec = (W % 8 == 0) && (((uintptr_t)mask & 7) == 0);
         const int x0 = lane * 32;
         uint32_t word = 0;
-        if (x0 < W) {
+        if (ERODED) {
+            const uint32_t* Fp = reinterpret_cast<const uint32_t*>(mask) + ((size_t)b * H + y) * NW;
+            const uint32_t c = lane < NW ? Fp[lane] : 0u;
+            const uint32_t lw = __shfl_up_sync(kFull, c, 1), rw_ = __shfl_down_sync(kFull, c, 1);
+            if (lane < NW && y > 0 && y + 1 < H) {
+                const uint32_t left = (c << 1) | (lane ? (lw >> 31) : 0u);                  // bit k = pixel k - 1
+                const uint32_t right = (c >> 1) | (lane + 1 < NW ? (rw_ << 31) : 0u);       // bit k = pixel k + 1
+                word = c & Fp[lane - NW] & Fp[lane + NW] & left & right;                    // pixels beyond W are 0 in F
+            }
+        } else if (x0 < W) {
             if (vec) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -849,8 +861,15 @@ bool rle_tail_supported(int radius) {
 // inside (0 / non-zero bytes) -> out = dilation(label8(remove_small(fill_holes(inside), min_area)), disk(radius))
 // label4: plain 4-connected labelling of the mask (no hole filling, no size filter, no diagonal joins, no dilation) with
 // the same raster-first numbering -- what process() needs for its markers (postproc_other.py:44)
+// markers: fill_holes -> cross erosion -> label4 (postproc_other.py:42-44) as two chains that meet in the bit domain
+enum { kChainTail = 0, kChainLabel4 = 1, kChainMarkers = 2 };
+static bool rle_fused_path(int W) {
+    static int fused = -1;  // CDNET_RLE_NO_LOCAL=1: every link through global memory
+    if (fused < 0) fused = getenv("CDNET_RLE_NO_LOCAL") ? 0 : 1;
+    return fused && W <= 1024;
+}
 static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
-                     bool label4, void* ws, size_t ws_bytes, cudaStream_t st) {
+                     int mode, void* ws, size_t ws_bytes, cudaStream_t st) {
     const size_t n = (size_t)B * H * W;
     const size_t nbits = (size_t)B * H * ((W + 31) / 32);
     Arena ar(ws, ws_bytes);
@@ -866,9 +885,11 @@ static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B
     const dim3 grid = rle_grid(B, H);
     const int threads = 32 * kRleWarps;
     CDNET_RANGE("run-based tail (rle.cu)");
-    static int fused = -1;  // CDNET_RLE_NO_LOCAL=1: every link through global memory
-    if (fused < 0) fused = getenv("CDNET_RLE_NO_LOCAL") ? 0 : 1;
-    if (fused && W <= 1024) {
+    if (mode == kChainMarkers && !rle_fused_path(W)) return CDNET_E_BADARG;  // callers ask rle_markers_supported first
+    const uint8_t* src = inside;
+    bool eroded = false;
+second_chain:
+    if (rle_fused_path(W)) {
         // rows per block of the shared-memory union-find (CDNET_RLE_PACK_ROWS = 8 | 16 | 32); the seams between the
         // blocks are what k_rle_link joins through global memory afterwards
         // Default: 16 rows when that still gives every SM two blocks, else 8 (measured on 14 x 1000^2, whole step: 16 rows
@@ -878,16 +899,24 @@ static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B
             const char* e = getenv("CDNET_RLE_PACK_ROWS");
             prow_env = e ? atoi(e) : 0;
             if (prow_env != 8 && prow_env != 16 && prow_env != 32) prow_env = 0;
-            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(16)));
-            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(32)));
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(16)));
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(32)));
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(16)));
+            CDNET_CUDA_OK(cudaFuncSetAttribute(k_rle_pack_link<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(32)));
         }
         const long long rows_total = (long long)B * H;
         const int prow = prow_env ? prow_env : (rows_total >= 16LL * 296 ? 16 : 8);
         const dim3 pgrid(ceil_div(H, prow), B);
         const size_t psm = pack_smem(prow);
-        if (prow == 8) CDNET_LAUNCH_PDL(k_rle_pack_link<8>, pgrid, 256, psm, st, inside, M, C, P, A, H, W);
-        else if (prow == 16) CDNET_LAUNCH_PDL(k_rle_pack_link<16>, pgrid, 512, psm, st, inside, M, C, P, A, H, W);
-        else CDNET_LAUNCH_PDL(k_rle_pack_link<32>, pgrid, 1024, psm, st, inside, M, C, P, A, H, W);
+        if (eroded) {
+            if (prow == 8) CDNET_LAUNCH_PDL((k_rle_pack_link<8, true>), pgrid, 256, psm, st, src, M, C, P, A, H, W);
+            else if (prow == 16) CDNET_LAUNCH_PDL((k_rle_pack_link<16, true>), pgrid, 512, psm, st, src, M, C, P, A, H, W);
+            else CDNET_LAUNCH_PDL((k_rle_pack_link<32, true>), pgrid, 1024, psm, st, src, M, C, P, A, H, W);
+        } else {
+            if (prow == 8) CDNET_LAUNCH_PDL((k_rle_pack_link<8, false>), pgrid, 256, psm, st, src, M, C, P, A, H, W);
+            else if (prow == 16) CDNET_LAUNCH_PDL((k_rle_pack_link<16, false>), pgrid, 512, psm, st, src, M, C, P, A, H, W);
+            else CDNET_LAUNCH_PDL((k_rle_pack_link<32, false>), pgrid, 1024, psm, st, src, M, C, P, A, H, W);
+        }
         // the seams between the groups in one launch (CDNET_RLE_SEAM_PHASES=2 links the seams inside super-groups of 64
         // rows first: measured slower on B200, 0.057 vs 0.042 ms for 14 x 1000^2)
         static int seam2 = -1;
@@ -901,7 +930,7 @@ static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B
             }
         }
     } else {
-        CDNET_LAUNCH_PDL(k_rle_pack, grid, threads, 0, st, inside, M, C, P, A, H, W);
+        CDNET_LAUNCH_PDL(k_rle_pack, grid, threads, 0, st, src, M, C, P, A, H, W);
         static int phases = 0;  // CDNET_RLE_LINK_PHASES=3: rows inside groups of 8, then of 64, then the rest (slower on B200)
         if (!phases) { const char* e = getenv("CDNET_RLE_LINK_PHASES"); phases = (e && atoi(e) == 3) ? 3 : 1; }
         if (phases == 1 || H <= 8) {
@@ -912,7 +941,14 @@ static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B
             if (H > 64) CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 64), 32 * kLinkWarps, 0, st, M, C, P, H, W, 64, 0);
         }
     }
-    if (label4) {
+    if (mode == kChainMarkers && !eroded) {
+        // first chain done up to the filled plane F; the second chain reads it back through the erosion
+        CDNET_LAUNCH_PDL(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
+        src = reinterpret_cast<const uint8_t*>(F);
+        eroded = true;
+        goto second_chain;
+    }
+    if (mode != kChainTail) {
         // every foreground root survives (aux is still 0 >= 0); the filled plane is the mask itself
         CDNET_LAUNCH_PDL(k_rle_number<false>, grid, threads, 0, st, M, P, A, rowcnt, RB, DB, 0, H, W);
         CDNET_LAUNCH_PDL(k_rle_number<true>, grid, threads, 0, st, M, P, A, rowcnt, RB, DB, 0, H, W);
@@ -935,11 +971,17 @@ static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B
 
 int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
                     void* ws, size_t ws_bytes, cudaStream_t st) {
-    return rle_chain(inside, out, out_elem_bytes, B, H, W, min_area, radius, false, ws, ws_bytes, st);
+    return rle_chain(inside, out, out_elem_bytes, B, H, W, min_area, radius, kChainTail, ws, ws_bytes, st);
 }
 
 int rle_label4_launch(const uint8_t* mask, int32_t* labels, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st) {
-    return rle_chain(mask, labels, 4, B, H, W, 0, 0, true, ws, ws_bytes, st);
+    return rle_chain(mask, labels, 4, B, H, W, 0, 0, kChainLabel4, ws, ws_bytes, st);
+}
+
+bool rle_markers_supported(int W) { return rle_tail_supported(0) && rle_fused_path(W); }
+
+int rle_markers_launch(const uint8_t* marker0, int32_t* labels, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return rle_chain(marker0, labels, 4, B, H, W, 0, 0, kChainMarkers, ws, ws_bytes, st);
 }
 
 }  // namespace cdnet

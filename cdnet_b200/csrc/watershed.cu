@@ -718,24 +718,28 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     } else {
         CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, H, W);
     }
-    // 3. fill holes, cross erosion, label, remove small (:42-46)
-    rc = fill_holes_state_launch(mk, state, C, Bp, B, H, W, st);
-    if (rc) return rc;
-    if (W % 4 == 0 && (((uintptr_t)state | (uintptr_t)mk) & 3) == 0) {
-        const size_t nq = n / 4, blocks = (nq + 255) / 256;
-        CDNET_LAUNCH(k_erode_cross4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, state, mk, H, W, nq);
-    } else {
-        CDNET_LAUNCH(k_erode_cross, px_grid(B, H, W), px_block(), 0, st, state, mk, H, W);
-    }
-    // label the markers (:44).  Bp .. E are free here and lie back to back in the workspace: room for the run-based
-    // labelling (node plane + bit-planes); tiny tiles, where the 256-byte padding of its slices does not fit, and
-    // CDNET_NO_RLE=1 take the pixel-parent kernels
+    // 3. fill holes, cross erosion, label, remove small (:42-46).  Bp .. E are free here and lie back to back in the
+    // workspace: room for the run-based kernels (node plane + bit-planes).  Tiles up to 1024 columns do all three steps
+    // there -- the filled bit-plane of one chain is eroded as the next chain packs it; wider tiles fill and erode on the
+    // pixel-parent kernels and only label on runs; tiny tiles, where the 256-byte padding of the run kernels' slices does
+    // not fit, and CDNET_NO_RLE=1 stay on the pixel-parent kernels altogether
     {
         const size_t span = (size_t)((char*)E - (char*)Bp) + pad256(n * 4);
-        if (rle_tail_supported(0) && span >= rle_tail_workspace(B, H, W))
-            rc = rle_label4_launch(mk, labels, B, H, W, Bp, span, st);
-        else
-            rc = ccl_label_launch(mk, labels, nullptr, C, Bp, rowcnt, B, H, W, 4, st);
+        const bool room = span >= rle_tail_workspace(B, H, W);
+        if (room && rle_markers_supported(W)) {
+            rc = rle_markers_launch(mk, labels, B, H, W, Bp, span, st);
+        } else {
+            rc = fill_holes_state_launch(mk, state, C, Bp, B, H, W, st);
+            if (rc) return rc;
+            if (W % 4 == 0 && (((uintptr_t)state | (uintptr_t)mk) & 3) == 0) {
+                const size_t nq = n / 4, blocks = (nq + 255) / 256;
+                CDNET_LAUNCH(k_erode_cross4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, state, mk, H, W, nq);
+            } else {
+                CDNET_LAUNCH(k_erode_cross, px_grid(B, H, W), px_block(), 0, st, state, mk, H, W);
+            }
+            if (room && rle_tail_supported(0)) rc = rle_label4_launch(mk, labels, B, H, W, Bp, span, st);
+            else rc = ccl_label_launch(mk, labels, nullptr, C, Bp, rowcnt, B, H, W, 4, st);
+        }
     }
     if (rc) return rc;
     if (marker_rowmax) {
