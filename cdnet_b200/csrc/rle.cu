@@ -36,7 +36,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kOutside = -1;  // the special root of background that touches the image frame (see rf_find)
 // parent and aux (area, then id) of a run start sit side by side: node i = words 2 i, 2 i + 1 of ONE plane, so that the
 // sparse accesses that need both (numbering, labels, the first store) touch one sector instead of two
-constexpr int kNS = 2;
+constexpr size_t kNS = 2;  // size_t: 2 * (pixel index) leaves the int range on tiles beyond 2^30 pixels (a 40 000^2 slide)
 constexpr int kRleWarps = 8;  // rows per block, one warp per row
 
 struct RowScan {
