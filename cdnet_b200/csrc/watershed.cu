@@ -105,20 +105,15 @@ __global__ void __launch_bounds__(256) k_comp_stats4(const uint8_t* __restrict__
 __global__ void __launch_bounds__(kBX* kBY) k_dist_marker(const uint8_t* __restrict__ pred, const int* __restrict__ L,
                                                           const int* __restrict__ d2, const int* __restrict__ maxd2,
                                                           uint8_t* __restrict__ val, uint8_t* __restrict__ marker0,
-                                                          int* __restrict__ flag, int H, int W) {
+                                                          int H, int W) {
     PX_COORDS
     if (!inb) return;
     uint8_t dist = 0;
     if (pred[tile + p]) {
-        const int root = L[tile + p];
         const double d = __dsqrt_rn((double)d2[tile + p]);
-        const double dm = __dsqrt_rn((double)maxd2[tile + root]);
+        const double dm = __dsqrt_rn((double)maxd2[tile + L[tile + p]]);
         const double s = __dmul_rn(255.0, __ddiv_rn(d, dm));
         dist = (uint8_t)(int)s;
-        // flag[root]: the component holds a marker candidate.  Hole filling, erosion and the size filter can only take
-        // candidates away inside the component, so an unflagged component can never hold a marker: it stays off the
-        // flood's work list (every writer stores the same 1)
-        if (dist > 125) flag[tile + root] = 1;
     }
     val[tile + p] = (uint8_t)(0u - (unsigned)dist);
     marker0[tile + p] = dist > 125;
@@ -128,8 +123,8 @@ __global__ void __launch_bounds__(kBX* kBY) k_dist_marker(const uint8_t* __restr
 // four background pixels -- most of them -- touches neither the label nor the distance plane
 __global__ void __launch_bounds__(256) k_dist_marker4(const uint8_t* __restrict__ pred, const int* __restrict__ L,
                                                       const int* __restrict__ d2, const int* __restrict__ maxd2,
-                                                      uint8_t* __restrict__ val, uint8_t* __restrict__ marker0,
-                                                      int* __restrict__ flag, size_t plane, size_t nquads) {
+                                                      uint8_t* __restrict__ val, uint8_t* __restrict__ marker0, size_t plane,
+                                                      size_t nquads) {
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
         const size_t i = 4 * q;
         const size_t tile = (i / plane) * plane;
@@ -147,7 +142,6 @@ __global__ void __launch_bounds__(256) k_dist_marker4(const uint8_t* __restrict_
                     const uint32_t dist = (uint32_t)(uint8_t)(int)__dmul_rn(255.0, __ddiv_rn(d, dm));
                     vw |= ((0u - dist) & 0xffu) << (8 * k);
                     mw |= (uint32_t)(dist > 125u) << (8 * k);
-                    if (dist > 125u) flag[tile + ls[k]] = 1;  // see k_dist_marker
                 }
             }
         }
@@ -194,7 +188,7 @@ __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restri
                                                          int* __restrict__ out, int* __restrict__ ymax,
                                                          int* __restrict__ xmin, int* __restrict__ xmax,
                                                          unsigned int* __restrict__ rootlist, int* __restrict__ nroots,
-                                                         const int* __restrict__ flag, const uint8_t* __restrict__ val,
+                                                         int* __restrict__ flag, const uint8_t* __restrict__ val,
                                                          int32_t* __restrict__ status, int H, int W) {
     PX_COORDS
     int r = -1;
@@ -234,9 +228,10 @@ __global__ void __launch_bounds__(kBX* kBY) k_flood_prep(const uint8_t* __restri
         if (lane == 0 && mc) atomicAdd(status + b, __popc(mc) << 8);
     }
     {
-        // compact list of the components that may hold a marker (flag, k_dist_marker; the others stay unlabelled: nothing
-        // to flood) -- the flood kernel hands them out to persistent warps
-        const bool rep = r == p && flag[tile + r] != 0;
+        // compact list of the components that hold a marker (the others stay unlabelled: nothing to flood) -- the flood
+        // kernel hands them out to persistent warps.  The first marker pixel to raise its component's flag enters it.
+        bool rep = false;
+        if (r >= 0 && out[tile + p] > 0 && __ldcg(flag + tile + r) == 0) rep = atomicExch(flag + tile + r, 1) == 0;
         const unsigned m = __ballot_sync(0xffffffffu, rep);
         int basei = 0;
         if (lane == 0 && m) basei = atomicAdd(nroots, __popc(m));
@@ -296,7 +291,7 @@ __global__ void __launch_bounds__(256) k_shard_overflow(const uint8_t* __restric
 __device__ __forceinline__ void flood_prep_quad(const uint8_t* __restrict__ pred, const int* __restrict__ L,
                                                 int* __restrict__ out, int* __restrict__ ymax, int* __restrict__ xmin,
                                                 int* __restrict__ xmax, unsigned int* s_roots, int* s_n,
-                                                const int* __restrict__ flag, const uint8_t* __restrict__ val, int32_t* __restrict__ status, int H, int W,
+                                                int* __restrict__ flag, const uint8_t* __restrict__ val, int32_t* __restrict__ status, int H, int W,
                                                 size_t plane, size_t q) {
     {
         const size_t i = 4 * q;
@@ -322,7 +317,9 @@ __device__ __forceinline__ void flood_prep_quad(const uint8_t* __restrict__ pred
                 continue;
             }
             const int r = ls[k], x = x0 + k;
-            if (r == p0 + k && flag[tile + r] != 0) s_roots[atomicAdd(s_n, 1)] = (unsigned int)(tile + r);
+            // (a plain look first: after the component's first marker pixel the flag is up and no atomic is needed)
+            if (ov[k] > 0 && __ldcg(flag + tile + r) == 0 && atomicExch(flag + tile + r, 1) == 0)
+                s_roots[atomicAdd(s_n, 1)] = (unsigned int)(tile + r);
             const uint32_t lf = k ? ((pw >> (8 * (k - 1))) & 0xffu) : left;
             const uint32_t rt = k < 3 ? ((pw >> (8 * (k + 1))) & 0xffu) : right;
             if (!lf) atomicMin(xmin + tile + r, x);
@@ -374,7 +371,7 @@ __global__ void __launch_bounds__(256) k_flood_prep4(const uint8_t* __restrict__
                                                      int* __restrict__ out, int* __restrict__ ymax,
                                                      int* __restrict__ xmin, int* __restrict__ xmax,
                                                      unsigned int* __restrict__ rootlist, int* __restrict__ nroots,
-                                                     const int* __restrict__ flag, const uint8_t* __restrict__ val,
+                                                     int* __restrict__ flag, const uint8_t* __restrict__ val,
                                                      int32_t* __restrict__ status, int H, int W, size_t nquads) {
     // The compact list of the components with a marker (work items of k_flood) is filled through ONE counter: thousands of returning
     // atomics on one address serialise (~17 ns each: they WERE this kernel's run time), so a block collects its roots in
@@ -713,23 +710,21 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
         for (int step = 0; step < 3; ++step)  // E is free until the flood
             CDNET_LAUNCH(k_shard_overflow, dim3(ceil_div(W, 256), B), 256, 0, st, pred01, A, E, status, H, W, own_lo,
                          own_hi, step);
-    // 2. uint8 distance, its negation, markers (:25-26, :39-41, :47); E = "component holds a marker candidate" flags, keyed by
-    // root, untouched from here to the flood
-    CDNET_CUDA_OK(cudaMemsetAsync(E, 0, n * 4, st));
+    // 2. uint8 distance, its negation, markers (:25-26, :39-41, :47)
     if (W % 4 == 0 && (((uintptr_t)pred01 | (uintptr_t)val | (uintptr_t)mk) & 3) == 0) {
         const size_t nq = n / 4, blocks = (nq + 255) / 256;
         CDNET_LAUNCH(k_dist_marker4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, pred01, A, C, D, val, mk,
-                     E, (size_t)H * W, nq);
+                     (size_t)H * W, nq);
     } else {
-        CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, E, H, W);
+        CDNET_LAUNCH(k_dist_marker, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, val, mk, H, W);
     }
-    // 3. fill holes, cross erosion, label, remove small (:42-46).  Bp .. D are free here and lie back to back in the
+    // 3. fill holes, cross erosion, label, remove small (:42-46).  Bp .. E are free here and lie back to back in the
     // workspace: room for the run-based kernels (node plane + bit-planes).  Tiles up to 1024 columns do all three steps
     // there -- the filled bit-plane of one chain is eroded as the next chain packs it; wider tiles fill and erode on the
     // pixel-parent kernels and only label on runs; tiny tiles, where the 256-byte padding of the run kernels' slices does
     // not fit, and CDNET_NO_RLE=1 stay on the pixel-parent kernels altogether
     {
-        const size_t span = (size_t)((char*)E - (char*)Bp);  // Bp, C, D
+        const size_t span = (size_t)((char*)E - (char*)Bp) + pad256(n * 4);
         const bool room = span >= rle_tail_workspace(B, H, W);
         if (room && rle_markers_supported(W)) {
             rc = rle_markers_launch(mk, labels, B, H, W, Bp, span, st);
@@ -760,6 +755,7 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
     // of roots, rowcnt[1] = work-stealing cursor
     unsigned int* rootlist = (unsigned int*)counts;
     CDNET_CUDA_OK(cudaMemsetAsync(rowcnt, 0, 2 * sizeof(int32_t), st));
+    CDNET_CUDA_OK(cudaMemsetAsync(E, 0, n * 4, st));  // "component is on the list" flags, keyed by root (free until the flood)
     if (W % 4 == 0 && (((uintptr_t)pred01) & 3) == 0) {
         const size_t nq = n / 4, blocks = (nq + 255) / 256;
         // a small grid: every block flushes its roots with one atomic at the end (plus one per ~1000 roots)
