@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cdnet_b200 import api, synth
 tiles = [synth.postproc_inputs(100 + i, 1000, 1000) for i in range(14)]
-plan = api.DamPostprocessPlan(14, 1000, 1000, 9, 20, 2, 0)
+plan = api.DamPostprocessPlan(14, 1000, 1000, 9, 20, 2, 0, write_prob=True)  # what bench.py times as e2e
 for i, t in enumerate(tiles):
     plan.h_dcm[i], plan.h_prob[i], plan.h_point[i] = t["dcm"], t["prob"], t["point"]
 plan.run()
