@@ -40,8 +40,6 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
 // plain 4-connected labelling with raster-first ids through the run-based kernels (workspace: rle_tail_workspace)
 int rle_label4_launch(const uint8_t* mask, int32_t* labels, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st);
 // label4(binary_erosion(binary_fill_holes(marker0))) (postproc_other.py:42-44) in the bit domain; tiles up to 1024 columns
-int rle_forest_launch(const uint8_t* mask, int32_t* L, const int32_t* d2, int32_t* maxd2, int32_t* status, int B, int H, int W,
-                      void* ws, size_t ws_bytes, cudaStream_t st);  // per-pixel root plane + max d2 per component
 bool rle_markers_supported(int W);
 int rle_markers_launch(const uint8_t* marker0, int32_t* labels, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st);
 

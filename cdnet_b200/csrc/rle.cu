@@ -861,76 +861,15 @@ bool rle_tail_supported(int radius) {
 // inside (0 / non-zero bytes) -> out = dilation(label8(remove_small(fill_holes(inside), min_area)), disk(radius))
 // label4: plain 4-connected labelling of the mask (no hole filling, no size filter, no diagonal joins, no dilation) with
 // the same raster-first numbering -- what process() needs for its markers (postproc_other.py:44)
-// forest mode: after pack + link every foreground pixel receives the root of its run's component (= the component's
-// first raster pixel, what the pixel-parent forest of ccl.cu delivers) and the component's maximum of d2 is collected at
-// the root -- k_comp_stats of watershed.cu on runs.  Four pixels per thread (W % 4 == 0: a quad lies inside one word of
-// the bit-plane); background pixels get their own index, like the pixel forest's initial state.
-__global__ void __launch_bounds__(256) k_rle_paint(const uint8_t* __restrict__ pred, const uint32_t* __restrict__ M,
-                                                   const int* __restrict__ C, const int* __restrict__ P,
-                                                   const int* __restrict__ d2, int* __restrict__ L,
-                                                   int* __restrict__ maxd2, int32_t* __restrict__ status, int H, int W,
-                                                   size_t nquads) {
-    pdl_wait();
-    pdl_trigger();
-    const size_t plane = (size_t)H * W;
-    const int NW = (W + 31) >> 5;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = 4 * q;
-        const size_t b = i / plane, tile = b * plane;
-        const int p0 = (int)(i - tile);
-        const uint32_t pw = *(const uint32_t*)(pred + i);
-        if (!pw) {
-            *(int4*)(L + i) = make_int4(p0, p0 + 1, p0 + 2, p0 + 3);
-            continue;
-        }
-        const int y = p0 / W, x0 = p0 - y * W;
-        const size_t rowbits = (b * H + y) * NW;
-        const int wj = x0 >> 5, bit0 = x0 & 31;
-        const RowScan r = row_load(M + rowbits, C + rowbits, NW, W, wj);
-        const int* Pt = P + kNS * tile;
-        const int4 dv = *(const int4*)(d2 + i);
-        const int ds[4] = {dv.x, dv.y, dv.z, dv.w};
-        int rs[4] = {p0, p0 + 1, p0 + 2, p0 + 3};
-        int last_start = -2, root = -1, cur = -1, m = 0;
-        bool inf = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!((pw >> (8 * k)) & 0xffu)) continue;
-            const int start = run_start(r, bit0 + k);
-            if (start != last_start) {
-                last_start = start;
-                root = rf_find_ro(Pt, y * W + start);
-            }
-            rs[k] = root;
-            inf = inf || ds[k] >= kEdtInf;
-            if (root != cur) {
-                if (cur >= 0) atomicMax(maxd2 + tile + cur, m);
-                cur = root;
-                m = ds[k];
-            } else {
-                m = max(m, ds[k]);
-            }
-        }
-        if (cur >= 0) atomicMax(maxd2 + tile + cur, m);
-        *(int4*)(L + i) = make_int4(rs[0], rs[1], rs[2], rs[3]);
-        if (inf && status && !(__ldcg(status + b) & CDNET_S_NO_BACKGROUND)) atomicOr(status + b, CDNET_S_NO_BACKGROUND);
-    }
-}
-
 // markers: fill_holes -> cross erosion -> label4 (postproc_other.py:42-44) as two chains that meet in the bit domain
-enum { kChainTail = 0, kChainLabel4 = 1, kChainMarkers = 2, kChainForest = 3 };
+enum { kChainTail = 0, kChainLabel4 = 1, kChainMarkers = 2 };
 static bool rle_fused_path(int W) {
     static int fused = -1;  // CDNET_RLE_NO_LOCAL=1: every link through global memory
     if (fused < 0) fused = getenv("CDNET_RLE_NO_LOCAL") ? 0 : 1;
     return fused && W <= 1024;
 }
-struct ForestOut {  // kChainForest only
-    const int32_t* d2;
-    int32_t* maxd2;
-    int32_t* status;
-};
 static int rle_chain(const uint8_t* inside, void* out, int out_elem_bytes, int B, int H, int W, int min_area, int radius,
-                     int mode, void* ws, size_t ws_bytes, cudaStream_t st, const ForestOut* fo = nullptr) {
+                     int mode, void* ws, size_t ws_bytes, cudaStream_t st) {
     const size_t n = (size_t)B * H * W;
     const size_t nbits = (size_t)B * H * ((W + 31) / 32);
     Arena ar(ws, ws_bytes);
@@ -1002,12 +941,6 @@ second_chain:
             if (H > 64) CDNET_LAUNCH_PDL(k_rle_link, link_grid(B, H, 64), 32 * kLinkWarps, 0, st, M, C, P, H, W, 64, 0);
         }
     }
-    if (mode == kChainForest) {
-        const size_t nq = n / 4, blocks = (nq + 255) / 256;
-        CDNET_LAUNCH_PDL(k_rle_paint, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, inside, M, C, P, fo->d2,
-                         (int*)out, fo->maxd2, fo->status, H, W, nq);
-        return last_error();
-    }
     if (mode == kChainMarkers && !eroded) {
         // first chain done up to the filled plane F; the second chain reads it back through the erosion
         CDNET_LAUNCH_PDL(k_rle_holes, grid, threads, 0, st, M, C, P, A, F, H, W);
@@ -1043,14 +976,6 @@ int rle_tail_launch(const uint8_t* inside, void* out, int out_elem_bytes, int B,
 
 int rle_label4_launch(const uint8_t* mask, int32_t* labels, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st) {
     return rle_chain(mask, labels, 4, B, H, W, 0, 0, kChainLabel4, ws, ws_bytes, st);
-}
-
-// forest of the 4-connected components of `mask` as a per-pixel root plane L (root = first raster pixel), with the maximum
-// of d2 per component at maxd2[root] (zeroed by the caller) and CDNET_S_NO_BACKGROUND; W % 4 == 0, 4-byte aligned mask
-int rle_forest_launch(const uint8_t* mask, int32_t* L, const int32_t* d2, int32_t* maxd2, int32_t* status, int B, int H, int W,
-                      void* ws, size_t ws_bytes, cudaStream_t st) {
-    const ForestOut fo = {d2, maxd2, status};
-    return rle_chain(mask, L, 4, B, H, W, 0, 0, kChainForest, ws, ws_bytes, st, &fo);
 }
 
 bool rle_markers_supported(int W) { return rle_tail_supported(0) && rle_fused_path(W); }

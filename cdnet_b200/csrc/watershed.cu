@@ -694,26 +694,17 @@ int ws_process_launch(const uint8_t* pred01, int32_t* labels, int32_t* status, i
         return remove_small_labels_launch(labels, counts, B, H, W, min_size, st);
     }
     // 1. components of pred (:37) and the exact EDT of the mask (:24 for all instances at once)
+    rc = ccl_forest_launch(pred01, A, B, H, W, 4, st);
+    if (rc) return rc;
     rc = edt_launch(pred01, C, Bp, rowcnt, B, H, W, st);  // rowcnt is free until the markers are labelled
     if (rc) return rc;
     CDNET_CUDA_OK(cudaMemsetAsync(D, 0, n * 4, st));
-    // forest + per-component maximum of d2: on runs where the tile allows four pixels per thread (scratch: E .. state,
-    // all free until the distance kernel), else on the pixel-parent kernels
-    const size_t span1 = (size_t)((char*)rowcnt - (char*)E);
-    const bool quads = W % 4 == 0 && (((uintptr_t)pred01) & 3) == 0;
-    if (quads && rle_tail_supported(0) && span1 >= rle_tail_workspace(B, H, W)) {
-        rc = rle_forest_launch(pred01, A, C, D, status, B, H, W, E, span1, st);
-        if (rc) return rc;
+    if (W % 4 == 0 && (((uintptr_t)pred01) & 3) == 0) {
+        const size_t nq = n / 4, blocks = (nq + 255) / 256;
+        CDNET_LAUNCH(k_comp_stats4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, pred01, A, C, D, status,
+                     (size_t)H * W, nq);
     } else {
-        rc = ccl_forest_launch(pred01, A, B, H, W, 4, st);
-        if (rc) return rc;
-        if (quads) {
-            const size_t nq = n / 4, blocks = (nq + 255) / 256;
-            CDNET_LAUNCH(k_comp_stats4, (unsigned)(blocks > (1u << 20) ? (1u << 20) : blocks), 256, 0, st, pred01, A, C, D,
-                         status, (size_t)H * W, nq);
-        } else {
-            CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, status, H, W);
-        }
+        CDNET_LAUNCH(k_comp_stats, px_grid(B, H, W), px_block(), 0, st, pred01, A, C, D, status, H, W);
     }
     if (marker_rowmax && status && (own_lo > 0 || own_hi < H))
         for (int step = 0; step < 3; ++step)  // E is free until the flood
